@@ -1,0 +1,185 @@
+/*
+ * sgmcmc_b200.h -- C ABI of libsgmcmc_b200.so, the B200 (sm_100a) SG-MCMC engine.
+ *
+ * This is the drop-in boundary for the sampler hot path of MFreidank/pysgmcmc.
+ * The reference has no FFI of its own (pure Python on TensorFlow 1.x); each
+ * entry point below replaces the TensorFlow graph region cited next to it and
+ * is what a binding for that path would call (ctypes stub: INTEGRATION.md).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never
+ *     allocates or frees caller-visible memory and keeps no global state besides
+ *     a thread-local error string and the launch-tuning knobs;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all calls are asynchronous and stream ordered;
+ *   - state is laid out [C chains x D params] row-major, flattened; `n` = C*D;
+ *   - return value: 0 on success, <0 on error (SGMCMC_E_*), message via
+ *     sgmcmc_last_error();
+ *   - noise: `z` != NULL -> N(0,1) draws are READ from z (same layout as theta);
+ *     `z` == NULL -> generated in-kernel: Philox4x32-10, counter =
+ *     ((elem_offset+e)/4, step), key = seed, Box-Muller (see oracle/philox.py).
+ *     `elem_offset` (multiple of 4) is the global flat index of element 0, so a
+ *     shard of chains reproduces the stream of the un-sharded run.
+ */
+#ifndef SGMCMC_B200_H
+#define SGMCMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGMCMC_OK 0
+#define SGMCMC_E_INVALID (-1)   /* bad argument (NULL pointer, negative size, ...) */
+#define SGMCMC_E_ALIGN (-2)     /* pointer not aligned to the element size       */
+#define SGMCMC_E_CUDA (-3)      /* CUDA launch / runtime error                   */
+#define SGMCMC_E_UNSUPPORTED (-4)
+
+#define SGMCMC_SAMPLER_SGHMC 0
+#define SGMCMC_SAMPLER_SGLD 1
+#define SGMCMC_SAMPLER_RSGHMC 2
+
+#define SGMCMC_TARGET_BANANA 0  /* diagnostics/objective_functions.py:49-59 */
+#define SGMCMC_TARGET_GMM1 1    /* :89-90 */
+#define SGMCMC_TARGET_GMM2 2    /* :93-94 */
+#define SGMCMC_TARGET_GMM3 3    /* :97-98 */
+
+int sgmcmc_version(void);
+const char* sgmcmc_last_error(void);
+
+/* Launch tuning for the element-wise update kernels (threads per CTA in
+ * {128,256,512}, float4 groups per thread in {1,2,4}); 0 keeps the current value. */
+int sgmcmc_set_update_tuning(int threads, int unroll);
+
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t sgmcmc_launch_count(void);
+
+/* ---- K1: SGHMC update, replaces pysgmcmc/samplers/sghmc.py:165-251 ----------------
+ * burn_in != 0: adapts tau/g/v_hat and computes minv from the OLD v_hat; if
+ *               store_minv != 0 the minv used is also written to `minv`.
+ * burn_in == 0: `minv` is READ (the mass matrix frozen by
+ *               samplers/base_classes.py:448-454); tau/g/v_hat are not touched.
+ * grad = d cost / d theta at the old theta.  epsilon is the UNSCALED step size. */
+int sgmcmc_sghmc_step_f32(float* theta, float* v, float* tau, float* g, float* v_hat, float* minv,
+                          const float* grad, const float* z, int64_t n,
+                          float epsilon, float mdecay, float scale_grad,
+                          int burn_in, int store_minv,
+                          uint64_t seed, uint64_t step, uint64_t elem_offset, void* stream);
+int sgmcmc_sghmc_step_f64(double* theta, double* v, double* tau, double* g, double* v_hat, double* minv,
+                          const double* grad, const double* z, int64_t n,
+                          double epsilon, double mdecay, double scale_grad,
+                          int burn_in, int store_minv,
+                          uint64_t seed, uint64_t step, uint64_t elem_offset, void* stream);
+
+/* ---- K2: SGLD update, replaces pysgmcmc/samplers/sgld.py:149-213 ------------------ */
+int sgmcmc_sgld_step_f32(float* theta, float* tau, float* g, float* v_hat, float* minv,
+                         const float* grad, const float* z, int64_t n,
+                         float epsilon, float A, float scale_grad,
+                         int burn_in, int store_minv,
+                         uint64_t seed, uint64_t step, uint64_t elem_offset, void* stream);
+int sgmcmc_sgld_step_f64(double* theta, double* tau, double* g, double* v_hat, double* minv,
+                         const double* grad, const double* z, int64_t n,
+                         double epsilon, double A, double scale_grad,
+                         int burn_in, int store_minv,
+                         uint64_t seed, uint64_t step, uint64_t elem_offset, void* stream);
+
+/* ---- K3: relativistic SGHMC update, replaces
+ * pysgmcmc/samplers/relativistic_sghmc.py:120-140 (element-wise momentum).
+ * grad_cost = d cost / d theta (the kernel negates it, :100-103). */
+int sgmcmc_rsghmc_step_f32(float* theta, float* p, const float* grad_cost, const float* z, int64_t n,
+                           float epsilon, float mass, float speed_of_light, float D, float Bhat,
+                           uint64_t seed, uint64_t step, uint64_t elem_offset, void* stream);
+int sgmcmc_rsghmc_step_f64(double* theta, double* p, const double* grad_cost, const double* z, int64_t n,
+                           double epsilon, double mass, double speed_of_light, double D, double Bhat,
+                           uint64_t seed, uint64_t step, uint64_t elem_offset, void* stream);
+
+/* The engine's N(0,1) stream written out (replaces tf.random_normal,
+ * samplers/base_classes.py:218-220; also the test hook for the in-kernel noise). */
+int sgmcmc_normal_fill_f32(float* out, int64_t n, uint64_t seed, uint64_t step,
+                           uint64_t elem_offset, void* stream);
+
+/* ---- K6: whole chains on a built-in target, many steps per launch -----------------
+ * One thread owns one chain (D = 2 for banana, 1 for gmm*): gradient of the target
+ * (diagnostics/objective_functions.py:49-98), the sampler update and the noise are
+ * fused; `n_steps` steps run inside one launch with the state in registers.
+ * Steps [0, n_burn_in) adapt (and the last of them stores minv), the rest use the
+ * frozen minv; adapt_forever != 0 reproduces burn_in_steps == 0
+ * (samplers/base_classes.py:449).  Unused state pointers may be NULL
+ * (SGLD: a1; RSGHMC: tau,g,v_hat,minv; a1 is V for SGHMC and p for RSGHMC).
+ * z: NULL or [n_steps, C, D].  Outputs (either may be NULL): every keep_every-th
+ * step s (s+1 divisible by keep_every) writes theta (post-update) to
+ * trace[(s+1)/keep_every-1, C, D] and the cost at the pre-update point to
+ * cost_trace[(s+1)/keep_every-1, C]  -- the (sample, cost) pair next(sampler)
+ * returns (samplers/base_classes.py:298-300). */
+typedef struct {
+  float epsilon;
+  float mdecay;          /* SGHMC */
+  float scale_grad;      /* SGHMC, SGLD */
+  float A;               /* SGLD */
+  float mass, speed_of_light, D, Bhat;   /* RSGHMC */
+} sgmcmc_hyper_t;
+
+int sgmcmc_target_chains_run_f32(int sampler, int target,
+                                 float* theta, float* a1, float* tau, float* g, float* v_hat,
+                                 float* minv, const float* z, float* trace, float* cost_trace,
+                                 int64_t n_chains, int64_t n_steps, int64_t n_burn_in,
+                                 int adapt_forever, int64_t keep_every,
+                                 const sgmcmc_hyper_t* hyper,
+                                 uint64_t seed, uint64_t step0, uint64_t chain_offset, void* stream);
+
+/* ---- K7: minibatch start indices, replaces pysgmcmc/data_batches.py:104-120 -------
+ * One MT19937 stream per chain, bit-exact with numpy.random.RandomState(seed).
+ * state: uint32 [625, n_streams] (624 words + position, stream-minor). */
+int sgmcmc_mt19937_seed(uint32_t* state, const uint32_t* seeds, int64_t n_streams, void* stream);
+/* starts[s, j] = the (s+1)-th future value of rng_j.randint(0, max_inclusive + 1). */
+int sgmcmc_mt19937_starts(uint32_t* state, int32_t* starts, int64_t n_streams, int64_t n_steps,
+                          uint32_t max_inclusive, void* stream);
+
+/* ---- K4: BNN cost and gradient, replaces
+ * pysgmcmc/models/bayesian_neural_network.py:28-69 (get_default_net), :77-141
+ * (priors), :337-388 (negative_log_likelihood) and tf.gradients over it.
+ * Network n_in -> 50 -> 50 -> 50 -> 1 (tanh), flat per-chain layout
+ * W1 b1 W2 b2 W3 b3 W4 b4 rho (D = 50*n_in + 5202).  Chain j reads the minibatch
+ * rows X[starts[j] : starts[j]+batch], y[...] (data_batches.py:120-123).
+ * batch_size_cfg is the constant the reference divides the data term by (:377).
+ * cost [C]; grad [C, D] (may be NULL); mse [C] (may be NULL). */
+int sgmcmc_bnn_nll_grad_f32(const float* theta, const float* X, const float* y,
+                            const int32_t* starts, float* cost, float* grad, float* mse,
+                            int64_t n_chains, int n_in, int batch, float batch_size_cfg,
+                            int64_t n_examples, void* stream);
+
+/* ---- K5: fused BNN-SGHMC chains: K4 + K1 for `n_steps` steps in one launch,
+ * the whole next(sampler) of the BNN path (samplers/base_classes.py:408-456 driving
+ * sghmc.py:165-251 over bayesian_neural_network.py:337-388).
+ * starts: int32 [n_steps, C] (from sgmcmc_mt19937_starts).  Same burn-in / noise /
+ * trace conventions as sgmcmc_target_chains_run_f32; z is NULL or [n_steps, C, D]. */
+int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float* v_hat, float* minv,
+                             const float* X, const float* y, const int32_t* starts,
+                             const float* z, float* trace, float* cost_trace,
+                             int64_t n_chains, int n_in, int batch, float batch_size_cfg,
+                             int64_t n_examples, int64_t n_steps, int64_t n_burn_in,
+                             int adapt_forever, int64_t keep_every,
+                             float epsilon, float mdecay, float scale_grad,
+                             uint64_t seed, uint64_t step0, uint64_t chain_offset, void* stream);
+
+/* ---- K10: BNN predictive, replaces bayesian_neural_network.py:535-557 -------------
+ * out[k, i, 0] = f(x_i; theta_k), out[k, i, 1] = rho_k  for n_nets stored samples. */
+int sgmcmc_bnn_predict_f32(const float* theta, const float* X, float* out,
+                           int64_t n_nets, int n_in, int64_t n_points, void* stream);
+
+/* ---- K8: per-chain moments and lagged variogram sums for R-hat / ESS --------------
+ * (formulas: pysgmcmc/diagnostics/sampler_diagnostics.py:76-82,153-161).
+ * trace: float [n_draws, C, D].  sums: double [3, D] = sum_j mean_j, sum_j mean_j^2,
+ * sum_j var_j (ddof=1) over the C local chains -- the quantities all-reduced across
+ * GPUs.  variogram: double [n_lags, D], sum over chains and draws of
+ * (x[i] - x[i-t])^2 for t = lag0 .. lag0+n_lags-1.  Either output may be NULL. */
+int sgmcmc_chain_moments_f32(const float* trace, double* sums, int64_t n_draws, int64_t n_chains,
+                             int64_t n_dims, void* stream);
+int sgmcmc_variogram_f32(const float* trace, double* variogram, int64_t n_draws, int64_t n_chains,
+                         int64_t n_dims, int64_t lag0, int64_t n_lags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGMCMC_B200_H */

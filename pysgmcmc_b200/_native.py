@@ -1,0 +1,108 @@
+"""ctypes binding of libsgmcmc_b200.so (the C ABI in include/sgmcmc_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsgmcmc_b200.so")
+
+SAMPLER_SGHMC, SAMPLER_SGLD, SAMPLER_RSGHMC = 0, 1, 2
+TARGET_IDS = {"banana": 0, "gmm1": 1, "gmm2": 2, "gmm3": 3}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Hyper(Structure):
+    """sgmcmc_hyper_t"""
+    _fields_ = [("epsilon", c_float), ("mdecay", c_float), ("scale_grad", c_float), ("A", c_float),
+                ("mass", c_float), ("speed_of_light", c_float), ("D", c_float), ("Bhat", c_float)]
+
+
+_P = c_void_p  # every device pointer / stream crosses the ABI as an integer address
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); must mirror include/sgmcmc_b200.h
+SIGNATURES = {
+    "sgmcmc_version": [],
+    "sgmcmc_last_error": [],
+    "sgmcmc_set_update_tuning": [c_int, c_int],
+    "sgmcmc_launch_count": [],
+    "sgmcmc_sghmc_step_f32": [_P] * 8 + [c_int64, c_float, c_float, c_float, c_int, c_int,
+                                         c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_sghmc_step_f64": [_P] * 8 + [c_int64, c_double, c_double, c_double, c_int, c_int,
+                                         c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_sgld_step_f32": [_P] * 7 + [c_int64, c_float, c_float, c_float, c_int, c_int,
+                                        c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_sgld_step_f64": [_P] * 7 + [c_int64, c_double, c_double, c_double, c_int, c_int,
+                                        c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_rsghmc_step_f32": [_P] * 4 + [c_int64] + [c_float] * 5 + [c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_rsghmc_step_f64": [_P] * 4 + [c_int64] + [c_double] * 5 + [c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_normal_fill_f32": [_P, c_int64, c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_target_chains_run_f32": [c_int, c_int] + [_P] * 9 + [c_int64, c_int64, c_int64, c_int, c_int64,
+                                                                POINTER(Hyper), c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_mt19937_seed": [_P, _P, c_int64, _P],
+    "sgmcmc_mt19937_starts": [_P, _P, c_int64, c_int64, c_uint32, _P],
+    "sgmcmc_bnn_nll_grad_f32": [_P] * 7 + [c_int64, c_int, c_int, c_float, c_int64, _P],
+    "sgmcmc_bnn_sghmc_run_f32": [_P] * 12 + [c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
+                                             c_int, c_int64, c_float, c_float, c_float,
+                                             c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_bnn_predict_f32": [_P, _P, _P, c_int64, c_int, c_int64, _P],
+    "sgmcmc_chain_moments_f32": [_P, _P, c_int64, c_int64, c_int64, _P],
+    "sgmcmc_variogram_f32": [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
+}
+_RESTYPES = {"sgmcmc_last_error": c_char_p, "sgmcmc_launch_count": c_int64}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every symbol of the header."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "libsgmcmc_b200.so is not built (%s). Run `python -m pysgmcmc_b200.build` "
+            "(needs nvcc); there is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the .so does not export it
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise NativeError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.sgmcmc_last_error()
+        raise NativeError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else "?"))
+    return rc
+
+
+def launch_count():
+    return int(load().sgmcmc_launch_count())
+
+
+def ptr(t):
+    """Device address of a torch tensor (None -> NULL). The tensor must be contiguous CUDA memory."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("expected a CUDA tensor; the engine has no CPU path")
+    if not t.is_contiguous():
+        raise NativeError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return s.cuda_stream

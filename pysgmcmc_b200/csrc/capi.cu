@@ -1,0 +1,59 @@
+// Library-level plumbing of the C ABI: version, thread-local error string, launch
+// counter and the launch-tuning knobs of the streaming kernels.
+#include <atomic>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace sgmcmc {
+
+static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_threads{256};
+static std::atomic<int> g_unroll{2};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return SGMCMC_OK;
+}
+
+int tuning_threads() { return g_threads.load(std::memory_order_relaxed); }
+int tuning_unroll() { return g_unroll.load(std::memory_order_relaxed); }
+
+}  // namespace sgmcmc
+
+extern "C" {
+
+int sgmcmc_version(void) { return 100; /* 0.1.0 */ }
+
+const char* sgmcmc_last_error(void) { return sgmcmc::g_error; }
+
+int64_t sgmcmc_launch_count(void) { return (int64_t)sgmcmc::g_launches.load(); }
+
+int sgmcmc_set_update_tuning(int threads, int unroll) {
+  if (threads != 0) {
+    if (threads != 128 && threads != 256 && threads != 512)
+      return sgmcmc::set_error(SGMCMC_E_INVALID, "threads must be 128, 256 or 512 (got %d)", threads);
+    sgmcmc::g_threads.store(threads);
+  }
+  if (unroll != 0) {
+    if (unroll != 1 && unroll != 2 && unroll != 4)
+      return sgmcmc::set_error(SGMCMC_E_INVALID, "unroll must be 1, 2 or 4 (got %d)", unroll);
+    sgmcmc::g_unroll.store(unroll);
+  }
+  return SGMCMC_OK;
+}
+
+}  // extern "C"

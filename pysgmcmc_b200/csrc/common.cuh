@@ -1,0 +1,119 @@
+// Shared device/host helpers for libsgmcmc_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sgmcmc_b200.h"
+
+namespace sgmcmc {
+
+// ---- error plumbing (capi.cu) ------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch();
+int tuning_threads();
+int tuning_unroll();
+
+#define SG_REQUIRE(cond, code, ...)                          \
+  do {                                                       \
+    if (!(cond)) return ::sgmcmc::set_error(code, __VA_ARGS__); \
+  } while (0)
+
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- IEEE round-to-nearest arithmetic that the compiler may NOT contract -----------
+// TensorFlow evaluates the reference's update op by op (no FMA), so parity with the
+// float32 oracle needs every product and sum rounded on its own.  The intrinsics
+// below are never fused, independent of -fmad.
+template <typename T>
+struct ieee;
+
+template <>
+struct ieee<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
+};
+
+template <>
+struct ieee<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double min(double a, double b) { return fmin(a, b); }
+};
+
+// safe_divide(x, y) = x / (y + (2*sign(y)*c + c)), c = 1e-16  (tensor_utils.py:269).
+// (2*sign*c + c) evaluates to fl(3c) for y>0, c for y==0, -c for y<0.
+template <typename T>
+__device__ __forceinline__ T safe_den(T y) {
+  const T c = (T)1e-16;
+  const T c3 = ieee<T>::add(ieee<T>::mul((T)2.0, c), c);
+  const T off = (y > (T)0) ? c3 : ((y < (T)0) ? -c : c);
+  return ieee<T>::add(y, off);   // NaN y stays NaN
+}
+template <typename T>
+__device__ __forceinline__ T safe_divide(T x, T y) {
+  return ieee<T>::div(x, safe_den(y));
+}
+// safe_sqrt(x) = sqrt(clip(x, 0, inf))  (tensor_utils.py:319-323)
+template <typename T>
+__device__ __forceinline__ T safe_sqrt(T x) {
+  return ieee<T>::sqrt(ieee<T>::max(x, (T)0));
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011) + Box-Muller: the engine's noise stream ----
+// Restated for the tests in oracle/philox.py (pinned there by Random123 vectors).
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ float u32_to_unit_open(uint32_t x) {
+  // float32(x) * 2^-32 + 2^-33 in (0, 1]; the product is exact, one rounding in the add
+  return __fadd_rn(__fmul_rn(__uint2float_rn(x), 2.3283064365386963e-10f), 1.1641532182693481e-10f);
+}
+
+// Four N(0,1) draws for elements 4*group .. 4*group+3 of step `step`.
+__device__ __forceinline__ void normal4(uint64_t group, uint64_t step, uint64_t seed, float out[4]) {
+  const Philox4 r = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), (uint32_t)step,
+                                  (uint32_t)(step >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u0 = u32_to_unit_open(r.x), u1 = u32_to_unit_open(r.y);
+  const float u2 = u32_to_unit_open(r.z), u3 = u32_to_unit_open(r.w);
+  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  out[0] = r0 * c0; out[1] = r0 * s0; out[2] = r1 * c1; out[3] = r1 * s1;
+}
+
+// ---- streaming global memory access (single-use data: do not keep it in L1) --------
+template <typename V>
+__device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V>
+__device__ __forceinline__ void st_stream(V* p, const V& v) { __stcs(p, v); }
+
+}  // namespace sgmcmc

@@ -1,0 +1,142 @@
+"""Minibatch generation -- same interface as pysgmcmc/data_batches.py:10-206, plus the
+on-device index generator the B200 engine uses for many chains.
+
+* `generate_batches` / `generate_shuffled_batches`: host generators, identical
+  behaviour to the reference (NumPy ``RandomState`` stream, contiguous slices,
+  ``feed_dict`` of placeholders).
+* `DeviceBatchGenerator`: one MT19937 stream PER CHAIN on the GPU (kernel K7,
+  csrc/mt19937.cu), producing the same ``start`` sequence
+  ``RandomState(seed_j).randint(0, N - B + 1)`` bit for bit; it yields start indices
+  only -- the BNN kernels slice the device-resident dataset themselves.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import _native
+from .placeholders import Placeholder
+
+
+def generate_batches(x, y, x_placeholder, y_placeholder, batch_size=20, seed=None):
+    """Infinite generator of random minibatches (data_batches.py:10-129).
+
+    Yields ``{x_placeholder: x[start:start+B], y_placeholder: y[start:start+B].reshape(-1, 1)}``
+    with ``start = rng.randint(0, N - B + 1)``.
+
+    >>> import numpy as np
+    >>> from pysgmcmc_b200.placeholders import placeholder
+    >>> N, D = 100, 3
+    >>> x = np.asarray([np.random.uniform(-10, 10, D) for _ in range(N)])
+    >>> y = np.asarray([np.random.choice([0., 1.]) for _ in range(N)])
+    >>> xp, yp = placeholder(), placeholder()
+    >>> batch_dict = next(generate_batches(x, y, xp, yp, 20))
+    >>> batch_dict[xp].shape, batch_dict[yp].shape
+    ((20, 3), (20, 1))
+    """
+    # Sanitize inputs
+    assert(isinstance(batch_size, int)), "generate_batches: batch size must be an integer."
+    assert(batch_size > 0), "generate_batches: batch size must be greater than zero."
+    assert(seed is None or isinstance(seed, int)), "generate_batches: seed must be an integer or `None`"
+    assert seed is None or (0 <= seed <= 2 ** 32 - 1)
+    assert(y.shape[0] == x.shape[0]), "Not exactly one label per datapoint!"
+
+    n_examples = x.shape[0]
+
+    if seed is None:
+        seed = np.random.randint(1, 100000)
+
+    rng = np.random.RandomState()
+    rng.seed(seed)
+
+    initial_batch_size = batch_size
+    batch_size = min(initial_batch_size, n_examples)
+
+    if initial_batch_size != batch_size:
+        logging.error("Not enough datapoints to form a minibatch. "
+                      "Batchsize was set to %s", batch_size)
+
+    while True:
+        start = rng.randint(0, (n_examples - batch_size + 1))
+        minibatch_x = x[start:start + batch_size]
+        minibatch_y = y[start:start + batch_size, None]
+        yield {x_placeholder: minibatch_x, y_placeholder: minibatch_y.reshape(-1, 1)}
+
+
+def generate_shuffled_batches(x, y, x_placeholder, y_placeholder, batch_size=20, seed=None):
+    """`generate_batches` with the rows of every batch shuffled, x and y alike
+    (data_batches.py:132-206)."""
+    if seed is None:
+        seed = np.random.randint(1, 100000)
+
+    rng_x, rng_y = np.random.RandomState(), np.random.RandomState()
+    rng_x.seed(seed)
+    rng_y.seed(seed)
+
+    for batch in generate_batches(x, y, x_placeholder, y_placeholder, batch_size, seed):
+        # like the reference, this shuffles the slice VIEWS, i.e. permutes the rows of
+        # the caller's x and y in place (pairs stay matched): data_batches.py:203-205
+        rng_x.shuffle(batch[x_placeholder])
+        rng_y.shuffle(batch[y_placeholder])
+        yield batch
+
+
+class DeviceBatchGenerator(object):
+    """Per-chain minibatch start indices generated on the GPU (K7).
+
+    Chain j draws from ``numpy.random.RandomState(seeds[j])`` exactly as
+    `generate_batches` would with ``seed=seeds[j]``.  ``next(gen)`` yields
+    ``{gen.starts_placeholder: int32 tensor [C]}``; `next_block(n)` returns the next
+    ``n`` steps at once as ``[n, C]`` for the multi-step fused kernel.
+    """
+
+    def __init__(self, n_examples, batch_size=20, seeds=None, n_chains=None, seed=None,
+                 device="cuda:0", block=256):
+        assert isinstance(batch_size, int) and batch_size > 0
+        if seeds is None:
+            assert n_chains is not None
+            if seed is None:
+                seed = int(np.random.randint(1, 100000))
+            # chain j continues the reference's convention "one generator per seed"
+            seeds = (np.arange(n_chains, dtype=np.uint64) + np.uint64(seed)) % np.uint64(2 ** 32)
+        seeds = np.asarray(seeds, dtype=np.uint64)
+        assert ((0 <= seeds) & (seeds <= 2 ** 32 - 1)).all()
+        self.n_examples = int(n_examples)
+        self.batch_size = min(int(batch_size), self.n_examples)       # data_batches.py:111
+        if self.batch_size != batch_size:
+            logging.error("Not enough datapoints to form a minibatch. "
+                          "Batchsize was set to %s", self.batch_size)
+        self.n_chains = int(seeds.shape[0])
+        self.device = torch.device(device)
+        self.seeds = torch.as_tensor(seeds.astype(np.int64), device=self.device).to(torch.int32)
+        self.state = torch.empty((625, self.n_chains), dtype=torch.int32, device=self.device)
+        self.starts_placeholder = Placeholder("minibatch_starts")
+        self.block = int(block)
+        self._buf = None
+        self._pos = 0
+        with torch.cuda.device(self.device):
+            _native.call("sgmcmc_mt19937_seed", _native.ptr(self.state), _native.ptr(self.seeds),
+                         self.n_chains, _native.stream_ptr())
+
+    def next_block(self, n_steps):
+        """Start indices of the next `n_steps` steps: int32 ``[n_steps, C]``."""
+        assert self._buf is None or self._pos == self._buf.shape[0], \
+            "next_block cannot be mixed with a partially consumed next() block"
+        out = torch.empty((n_steps, self.n_chains), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.call("sgmcmc_mt19937_starts", _native.ptr(self.state), _native.ptr(out),
+                         self.n_chains, n_steps, self.n_examples - self.batch_size,
+                         _native.stream_ptr())
+        return out
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._buf is None or self._pos == self._buf.shape[0]:
+            self._buf = None
+            self._buf = self.next_block(self.block)
+            self._pos = 0
+        row = self._buf[self._pos]
+        self._pos += 1
+        return {self.starts_placeholder: row}

@@ -1,0 +1,63 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports
+exactly the entry points include/sgmcmc_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pysgmcmc_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sgmcmc_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sgmcmc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    names = declared_functions()
+    for required in ("sgmcmc_sghmc_step_f32", "sgmcmc_sgld_step_f32", "sgmcmc_rsghmc_step_f32",
+                     "sgmcmc_bnn_nll_grad_f32", "sgmcmc_bnn_sghmc_run_f32", "sgmcmc_mt19937_starts",
+                     "sgmcmc_target_chains_run_f32", "sgmcmc_chain_moments_f32"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_native.LIB_PATH), "run `python -m pysgmcmc_b200.build` first"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(lib, name), "libsgmcmc_b200.so does not export %s" % name
+
+
+def test_python_binding_covers_the_header():
+    assert sorted(_native.SIGNATURES) == declared_functions()
+    _native.load()
+
+
+def test_version_and_error_reporting_without_gpu():
+    lib = _native.load()
+    assert lib.sgmcmc_version() >= 100
+    assert lib.sgmcmc_set_update_tuning(100, 0) == -1          # SGMCMC_E_INVALID
+    assert b"threads" in lib.sgmcmc_last_error()
+    assert lib.sgmcmc_set_update_tuning(256, 2) == 0
+    with pytest.raises(_native.NativeError):
+        _native.call("sgmcmc_set_update_tuning", 0, 3)
+    # argument validation happens before any CUDA call
+    assert lib.sgmcmc_sghmc_step_f32(None, None, None, None, None, None, None, None, 16,
+                                     0.01, 0.05, 1.0, 1, 0, 0, 0, 0, None) == -1
+    assert lib.sgmcmc_sghmc_step_f32(None, None, None, None, None, None, None, None, 16,
+                                     0.01, 0.05, 1.0, 1, 0, 0, 0, 2, None) == -1   # elem_offset % 4
+    assert lib.sgmcmc_mt19937_starts(None, None, 4, 4, 10, None) == -1
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pysgmcmc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
