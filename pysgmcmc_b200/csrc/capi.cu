@@ -10,7 +10,7 @@ namespace sgmcmc {
 static thread_local char g_error[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_threads{256};
-static std::atomic<int> g_unroll{2};
+static std::atomic<int> g_unroll{1};
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -49,8 +49,8 @@ int sgmcmc_set_update_tuning(int threads, int unroll) {
     sgmcmc::g_threads.store(threads);
   }
   if (unroll != 0) {
-    if (unroll != 1 && unroll != 2 && unroll != 4)
-      return sgmcmc::set_error(SGMCMC_E_INVALID, "unroll must be 1, 2 or 4 (got %d)", unroll);
+    if (unroll != 1 && unroll != 2)
+      return sgmcmc::set_error(SGMCMC_E_INVALID, "unroll must be 1 or 2 (got %d)", unroll);
     sgmcmc::g_unroll.store(unroll);
   }
   return SGMCMC_OK;

@@ -129,23 +129,30 @@ __device__ __forceinline__ void sgld_apply(T& theta, T minv_t, T grad, T z, cons
 }
 
 // ---- relativistic SGHMC: relativistic_sghmc.py:120-135 ----------------------------------
-template <typename T>
+// UNIT: mass == 1 and speed_of_light == 1 (the reference's defaults).  x / 1 and 1 * x are
+// exact in IEEE arithmetic, so skipping them is bit-identical and saves two of the four
+// divisions per element.
+template <typename T, bool UNIT>
 __device__ __forceinline__ T rel_velocity(T p, const RsghmcScalars<T>& s) {
   using F = ieee<T>;
   // eps * p / (m * sqrt(p*p / (m^2 c^2) + 1))
-  return F::div(F::mul(s.eps, p),
-                F::mul(s.m, F::sqrt(F::add(F::div(F::mul(p, p), s.m2c2), (T)1))));
+  if constexpr (UNIT) {
+    return F::div(F::mul(s.eps, p), F::sqrt(F::add(F::mul(p, p), (T)1)));
+  } else {
+    return F::div(F::mul(s.eps, p),
+                  F::mul(s.m, F::sqrt(F::add(F::div(F::mul(p, p), s.m2c2), (T)1))));
+  }
 }
-template <typename T>
+template <typename T, bool UNIT = false>
 __device__ __forceinline__ void rsghmc_apply(T& theta, T& p, T grad_cost, T z,
                                              const RsghmcScalars<T>& s) {
   using F = ieee<T>;
   const T grad = -grad_cost;                                                       // :100-103
-  const T p_grad = rel_velocity(p, s);                                             // :123
+  const T p_grad = rel_velocity<T, UNIT>(p, s);                                    // :123
   const T n = F::mul(s.noise_sigma, z);                                            // :125
   const T p_t = F::add(p, F::sub(F::add(F::mul(s.eps, grad), n), F::mul(s.D, p_grad)));   // :126-129
   p = p_t;
-  theta = F::add(theta, rel_velocity(p_t, s));                                     // :131-135
+  theta = F::add(theta, rel_velocity<T, UNIT>(p_t, s));                            // :131-135
 }
 
 }  // namespace sgmcmc

@@ -187,7 +187,7 @@ __global__ void sgld_update_kernel(T* __restrict__ theta, T* __restrict__ tau, T
 // ------------------------------------------------------------------------------------
 // K3  relativistic SGHMC
 // ------------------------------------------------------------------------------------
-template <typename T, bool EXT_Z, bool ALIGNED, int UNROLL>
+template <typename T, bool UNIT, bool EXT_Z, bool ALIGNED, int UNROLL>
 __global__ void rsghmc_update_kernel(T* __restrict__ theta, T* __restrict__ p,
                                      const T* __restrict__ grad, const T* __restrict__ z, int64_t n,
                                      RsghmcScalars<T> s, NoiseArgs na) {
@@ -212,7 +212,7 @@ __global__ void rsghmc_update_kernel(T* __restrict__ theta, T* __restrict__ p,
     if (valid[u] > 0) {
       const int64_t gi = base + (int64_t)u * blockDim.x;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) rsghmc_apply(th[u].v[i], pp[u].v[i], gr[u].v[i], zz[u].v[i], s);
+      for (int i = 0; i < 4; ++i) rsghmc_apply<T, UNIT>(th[u].v[i], pp[u].v[i], gr[u].v[i], zz[u].v[i], s);
       store_pack<T, ALIGNED>(theta, gi, valid[u], th[u]);
       store_pack<T, ALIGNED>(p, gi, valid[u], pp[u]);
     }
@@ -242,10 +242,9 @@ static inline LaunchShape launch_shape(int64_t n) {
   LaunchShape ls;
   ls.threads = tuning_threads();
   ls.unroll = tuning_unroll();
-  // register budget: the float kernels use up to ~200 registers at unroll 4 and the
-  // double kernels are only instantiated at unroll 1 (see SG_DISPATCH_UNROLL)
+  // the double kernels are only instantiated at unroll 1 (see SG_DISPATCH_UNROLL) and
+  // need up to ~170 registers per thread
   if (sizeof(T) == 8) { ls.unroll = 1; if (ls.threads > 256) ls.threads = 256; }
-  if (ls.unroll == 4 && ls.threads > 256) ls.threads = 256;
   const int64_t n_groups = (n + 3) / 4;
   const int64_t per_block = (int64_t)ls.threads * ls.unroll;
   ls.blocks = (unsigned)((n_groups + per_block - 1) / per_block);
@@ -257,9 +256,8 @@ static inline LaunchShape launch_shape(int64_t n) {
     constexpr int U = 1; __VA_ARGS__;                                   \
   } else {                                                              \
     switch (UN) {                                                       \
-      case 1: { constexpr int U = 1; __VA_ARGS__; } break;              \
       case 2: { constexpr int U = 2; __VA_ARGS__; } break;              \
-      default: { constexpr int U = 4; __VA_ARGS__; } break;             \
+      default: { constexpr int U = 1; __VA_ARGS__; } break;             \
     }                                                                   \
   }
 
@@ -366,10 +364,12 @@ static int rsghmc_step(T* theta, T* p, const T* grad, const T* z, int64_t n, T e
   const LaunchShape ls = launch_shape<T>(n);
   cudaStream_t st = (cudaStream_t)stream;
   const bool ext_z = z != nullptr;
+  const bool unit = mass == (T)1 && c == (T)1;
   SG_DISPATCH_UNROLL(ls.unroll,
     SG_DISPATCH_BOOL(aligned, AL,
       SG_DISPATCH_BOOL(ext_z, EZ,
-        rsghmc_update_kernel<T, EZ, AL, U><<<ls.blocks, ls.threads, 0, st>>>(theta, p, grad, z, n, s, na))))
+        SG_DISPATCH_BOOL(unit, UN1,
+          rsghmc_update_kernel<T, UN1, EZ, AL, U><<<ls.blocks, ls.threads, 0, st>>>(theta, p, grad, z, n, s, na)))))
   return check_launch("rsghmc_update_kernel");
 }
 

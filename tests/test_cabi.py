@@ -43,7 +43,7 @@ def test_version_and_error_reporting_without_gpu():
     assert lib.sgmcmc_version() >= 100
     assert lib.sgmcmc_set_update_tuning(100, 0) == -1          # SGMCMC_E_INVALID
     assert b"threads" in lib.sgmcmc_last_error()
-    assert lib.sgmcmc_set_update_tuning(256, 2) == 0
+    assert lib.sgmcmc_set_update_tuning(256, 1) == 0
     with pytest.raises(_native.NativeError):
         _native.call("sgmcmc_set_update_tuning", 0, 3)
     # argument validation happens before any CUDA call

@@ -34,6 +34,13 @@ CLS = {"sghmc": SGHMCSampler, "sgld": SGLDSampler, "rsghmc": RelativisticSGHMCSa
 RTOL, ATOL = 1e-5, 2e-5
 
 
+def as_matrix(sample, C):
+    """(list of per-parameter [C] tensors | unwrapped single tensor) -> [C, D] numpy."""
+    if isinstance(sample, (list, tuple)):
+        return torch.stack([t.reshape(C) for t in sample], dim=1).cpu().numpy()
+    return sample.reshape(C, -1).cpu().numpy()
+
+
 def make_params(theta0):
     """theta0 [C, D] -> list of D tensors of shape [C] (scalar parameters with a chain axis)."""
     return [torch.tensor(theta0[:, d].copy(), device=DEV) for d in range(theta0.shape[1])]
@@ -90,7 +97,7 @@ def test_golden_trajectories(case, fused):
         np.testing.assert_allclose(cost.cpu().numpy(), want_cost, rtol=2e-5, atol=ATOL,
                                    err_msg="%s cost at step %d" % (name, step))
         if step in MG.CHECKPOINTS:
-            got = torch.stack(list(sample), dim=1).cpu().numpy()
+            got = as_matrix(sample, theta0.shape[0])
             np.testing.assert_allclose(got, g[name + "/theta"][k], rtol=RTOL, atol=ATOL,
                                        err_msg="%s theta at step %d" % (name, step))
             k += 1
@@ -116,8 +123,7 @@ def test_multi_step_run_equals_per_step(method, target):
     for s in range(steps):
         sample, cost = next(b)
         if (s + 1) % 4 == 0:
-            kept.append((torch.stack(list(sample), dim=1) if isinstance(sample, list)
-                         else sample.reshape(C, D), cost))
+            kept.append((torch.as_tensor(as_matrix(sample, C), device=DEV), cost))
     assert torch.equal(trace, torch.stack([k[0] for k in kept]))
     assert torch.equal(costs, torch.stack([k[1] for k in kept]))
     assert torch.equal(a._theta, b._theta)
@@ -214,7 +220,7 @@ def test_float64_generic_path():
     for step in range(1, 101):
         z = z_rng.standard_normal(theta0.shape)
         sample, cost = s.__next__(feed_dict={s.noise: z})
-    got = torch.stack(list(sample), dim=1).cpu().numpy()
+    got = as_matrix(sample, C)
     np.testing.assert_allclose(got, g[name + "/theta"][3], rtol=1e-10, atol=1e-12)
 
 

@@ -94,7 +94,7 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peak, which = peak_gbs()
-    tunings = [(t, u) for t in (128, 256, 512) for u in (1, 2, 4)] if args.sweep_tuning else [(0, 0)]
+    tunings = [(t, u) for t in (128, 256, 512) for u in (1, 2)] if args.sweep_tuning else [(0, 0)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for size in args.sizes.split(","):
         n = int(float(size))
@@ -116,7 +116,7 @@ def main():
                                   "Gelem_steps_per_s": round(n / ms / 1e6, 2)}), flush=True)
             del fn, keep
             torch.cuda.empty_cache()
-    _native.call("sgmcmc_set_update_tuning", 256, 2)
+    _native.call("sgmcmc_set_update_tuning", 256, 1)
 
 
 if __name__ == "__main__":
