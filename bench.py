@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Headline benchmark: chain-steps/s of BNN-SGHMC (BASELINE.json `metric`) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], one GPU's shard; weak scaling over GPUs):
+  8192 chains per GPU of the BOHAMIANN BNN (1-50-50-50-1 tanh MLP, Gaussian likelihood,
+  D = 5252 parameters per chain) sampled with burn-in / mass-adapting SGHMC on synthetic
+  sinc regression, N = 20 000 points, minibatch 20, eps = 0.01, mdecay = 0.05,
+  scale_grad = N; every chain has its own MT19937 minibatch stream and Philox noise
+  substream.  A "step" is one sampler step of every chain: on-device minibatch start
+  indices (K7), BNN cost + gradient (K4) and the fused SGHMC update (K1), all burn-in steps
+  (the 44 B/element variant of the update).
+
+`value`   : chain-steps/s with everything resident in HBM (CUDA events, max over ranks).
+`e2e`     : the same metric through the C ABI with HOST buffers every step: minibatch start
+            indices come from pinned host memory (H2D), the per-chain cost goes back to
+            pinned host memory (D2H) and every 100th step the whole sample does too (the
+            thinning of BayesianNeuralNetwork.train, bayesian_neural_network.py:510-531).
+`roofline`: the dominant kernel of the step, timed launch by launch with CUDA events.
+`cpu_baseline` / `--impl reference`: the reference cannot run on this image (TensorFlow 1.x);
+            the CPU arm is the NumPy restatement in oracle/ ("port"), vectorised over chains
+            and spread over the host cores with a thread pool.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_EXAMPLES, BATCH, N_IN, D = 20000, 20, 1, 5252
+EPS, MDECAY = 0.01, 0.05
+SAMPLE_STEPS = 100                      # thinning of BayesianNeuralNetwork (default sample_steps)
+FLOP_PER_CHAIN_STEP_K4 = 2 * 305000.0   # fwd 102 k + bwd 203 k FFMA
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12    # 74.4: 148 SMs x 128 lanes x 2 x max clock
+BYTES_PER_ELEM_K1_BURN_IN = 44
+
+
+def synthetic_sinc(n=N_EXAMPLES, seed=1):
+    """Config 3 inputs: X ~ U(0,1) drawn row-wise from RandomState(1)
+    (tests/utils.py:24-29), y = sinc(10x - 5) (tests/utils.py:32-33), both z-normalised."""
+    rng = np.random.RandomState(seed)
+    X = np.array([rng.uniform(0.0, 1.0, N_IN) for _ in range(n)])
+    y = np.sinc(X * 10 - 5).sum(axis=1)
+    X = (X - X.mean(axis=0)) / X.std(axis=0)
+    y = (y - y.mean()) / y.std()
+    return X.astype(np.float32), y.astype(np.float32)
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------
+def cpu_chain_steps_per_s(n_chains, n_steps, warmup, cores):
+    """NumPy oracle (oracle/bnn.py + oracle/samplers.py), `n_chains` chains split over
+    `cores` threads (NumPy releases the GIL inside its kernels)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import bnn, samplers
+    X, y = synthetic_sinc()
+    shards = np.array_split(np.arange(n_chains), cores)
+
+    def make(shard):
+        theta = bnn.init_theta(len(shard), seed=1 + int(shard[0]))
+        rng = np.random.RandomState(100 + int(shard[0]))
+        holder = {}
+
+        def cost_and_grad(th):
+            Xb, yb = bnn.gather_minibatch(X, y, holder["s"], BATCH)
+            c, g, _ = bnn.nll_and_grad(th, Xb, yb, n_examples=N_EXAMPLES)
+            return c, g
+        chain = samplers.OracleChain("sghmc", theta, cost_and_grad, epsilon=EPS, burn_in_steps=10 ** 9,
+                                     mdecay=MDECAY, scale_grad=float(N_EXAMPLES))
+
+        def run(k):
+            for _ in range(k):
+                holder["s"] = rng.randint(0, N_EXAMPLES - BATCH + 1, size=len(shard))
+                chain.next(rng.standard_normal((len(shard), D)).astype(np.float32))
+        return run
+    runners = [make(s) for s in shards if len(s)]
+    with ThreadPoolExecutor(max_workers=len(runners)) as pool:
+        list(pool.map(lambda r: r(warmup), runners))
+        t0 = time.perf_counter()
+        list(pool.map(lambda r: r(n_steps), runners))
+        dt = time.perf_counter() - t0
+    return n_chains * n_steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    n_chains = 64 * cores
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 2))
+    value, dt = cpu_chain_steps_per_s(n_chains, steps, warmup, cores)
+    sample = ("%d chains x %d steps of the same BNN-SGHMC workload (NumPy oracle port, %d threads); "
+              "reference TF 1.x is not installable on this image" % (n_chains, steps, cores))
+    line = {
+        "impl": "reference", "metric": "chain-steps/s (BNN SGHMC)", "value": value, "unit": "chain-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(n_chains, 1),
+        "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(chains_per_gpu, n_gpus):
+    return {"workload": "BNN-SGHMC burn-in steps: BOHAMIANN 1-50-50-50-1 tanh MLP (D=5252), sinc "
+                        "regression N=20000, minibatch 20, eps=0.01, mdecay=0.05, scale_grad=N",
+            "chains_per_gpu": chains_per_gpu, "chains_total": chains_per_gpu * n_gpus,
+            "params_per_chain": D, "parallelism": "chains sharded over %d GPU(s), no data-path collective" % n_gpus,
+            "l2": "state is %.2f GB per GPU, larger than the 126 MB L2 (no flush needed)" %
+                  (chains_per_gpu * D * 4 * 6 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------
+# clocks during the timed region (NVML, 20 ms period)
+# ------------------------------------------------------------------------------------
+class ClockSampler(object):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.nv is not None:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "n_samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pysgmcmc_b200 import Session, _native
+    from pysgmcmc_b200.data_batches import DeviceBatchGenerator
+    from pysgmcmc_b200.models.bnn_cost import BayesianNeuralNetworkNLL, default_net_params
+    from pysgmcmc_b200.samplers import SGHMCSampler
+    from pysgmcmc_b200.stepsize_schedules import ConstantStepsizeSchedule
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    C, K, W = args.chains_per_gpu, args.steps, args.warmup
+    X, y = synthetic_sinc()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def build():
+        chain0 = rank * C                                   # global id of this rank's first chain
+        seeds = (np.arange(C, dtype=np.uint64) + np.uint64(chain0 + 1)) % np.uint64(2 ** 32)
+        gen = DeviceBatchGenerator(N_EXAMPLES, BATCH, seeds=seeds, device=dev, block=256)
+        nll = BayesianNeuralNetworkNLL(N_EXAMPLES, BATCH, X=X, y=y,
+                                       starts_placeholder=gen.starts_placeholder, device=dev)
+        params = default_net_params(N_IN, n_chains=C, seed=1 + rank, device=dev)
+        sampler = SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen,
+                               stepsize_schedule=ConstantStepsizeSchedule(EPS),
+                               burn_in_steps=10 ** 9, mdecay=MDECAY, scale_grad=float(N_EXAMPLES), seed=1,
+                               session=Session(device=dev, n_chains=C, output="torch", chain_offset=chain0))
+        return sampler, gen, nll
+
+    # ---- device-resident throughput: `value` -------------------------------------------
+    sampler, gen, nll = build()
+    sampler.run(W)
+    barrier()
+    launches0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        sampler.run(K)
+        e1.record()
+        barrier()
+    launches = _native.launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = C * world * K / (ms / 1e3)
+    assert bool(torch.isfinite(sampler._theta).all()), "chains diverged"
+
+    # ---- per-kernel timing (rank 0): which kernel dominates, and its roofline -----------
+    roofline, kernels = None, None
+    if rank == 0:
+        kernels = per_kernel_times(sampler, gen, nll, torch, _native, n=30)
+        peak, which = measured_peaks()
+        k1_gbs = BYTES_PER_ELEM_K1_BURN_IN * C * D / (kernels["k1_sghmc_update_ms"] * 1e6)
+        k4_tf = FLOP_PER_CHAIN_STEP_K4 * C / (kernels["k4_bnn_nll_grad_ms"] * 1e9)
+        r_k1 = {"kernel": "sghmc_update_kernel (K1, burn-in)", "bound": "hbm", "achieved": k1_gbs,
+                "peak": peak, "peak_source": which, "unit": "GB/s", "frac": k1_gbs / peak,
+                "frac_of_nominal_8TBps": k1_gbs / 8000.0, "traffic": None,
+                "algorithmic_bytes_per_launch": BYTES_PER_ELEM_K1_BURN_IN * C * D,
+                "ms_per_launch": kernels["k1_sghmc_update_ms"]}
+        r_k4 = {"kernel": "bnn_nll_grad_kernel (K4)", "bound": "fp32", "achieved": k4_tf,
+                "peak": FP32_PEAK_TFLOPS, "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 x 1.965 GHz",
+                "unit": "TFLOP/s", "frac": k4_tf / FP32_PEAK_TFLOPS, "traffic": None,
+                "algorithmic_flops_per_launch": FLOP_PER_CHAIN_STEP_K4 * C,
+                "ms_per_launch": kernels["k4_bnn_nll_grad_ms"]}
+        dominant_is_k4 = kernels["k4_bnn_nll_grad_ms"] >= kernels["k1_sghmc_update_ms"]
+        roofline = dict(r_k4 if dominant_is_k4 else r_k1)
+        roofline["share_of_step"] = (kernels["k4_bnn_nll_grad_ms"] if dominant_is_k4
+                                     else kernels["k1_sghmc_update_ms"]) / kernels["step_ms"]
+        roofline["other_kernel"] = r_k1 if dominant_is_k4 else r_k4
+
+    # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------
+    e2e = end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks)
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_chains, cpu_steps = 64 * cores, 10
+        cpu_value, cpu_dt = cpu_chain_steps_per_s(cpu_chains, cpu_steps, 1, cores)
+        cpu = {"value": cpu_value, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+               "sample": "%d chains x %d steps of the same workload, NumPy oracle port on %d threads "
+                         "(%.1f s); TF 1.x reference not installable" % (cpu_chains, cpu_steps, cores, cpu_dt)}
+    else:
+        cpu = None
+    line = {
+        "metric": "chain-steps/s (BNN SGHMC)", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(C, world),
+        "clocks": clocks.summary(),
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def per_kernel_times(sampler, gen, nll, torch, _native, n=30):
+    """Average launch duration of K7 / K4 / K1, each bracketed by CUDA events on the
+    launching stream, over `n` consecutive sampler steps (state > L2, so every launch is
+    cold in L2 like in the timed region)."""
+    C = sampler.n_chains
+    starts = gen.next_block(n)
+    grad = sampler._grad if sampler._grad is not None else torch.empty_like(sampler._theta)
+    cost = torch.empty(C, device=sampler.device)
+    st = _native.stream_ptr()
+    p = _native.ptr
+    arrs = sampler._arrays()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
+    t7a, t7b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t7a.record()
+    gen.next_block(256)
+    t7b.record()
+    for s in range(n):
+        ev[s][0].record()
+        _native.call("sgmcmc_bnn_nll_grad_f32", p(sampler._theta), p(nll.X), p(nll.y), p(starts[s]), p(cost),
+                     p(grad), None, C, N_IN, BATCH, float(BATCH), N_EXAMPLES, st)
+        ev[s][1].record()
+        _native.call("sgmcmc_sghmc_step_f32", *[p(a) for a in arrs], p(grad), None, C * D, EPS, MDECAY,
+                     float(N_EXAMPLES), 1, 0, 1, sampler.n_iterations + s, sampler._elem_offset, st)
+        ev[s][2].record()
+    torch.cuda.synchronize()
+    sampler.n_iterations += n
+    k4 = float(np.mean([ev[s][0].elapsed_time(ev[s][1]) for s in range(n)]))
+    k1 = float(np.mean([ev[s][1].elapsed_time(ev[s][2]) for s in range(n)]))
+    k7 = t7a.elapsed_time(t7b) / 256.0
+    return {"k4_bnn_nll_grad_ms": k4, "k1_sghmc_update_ms": k1, "k7_mt19937_starts_ms_per_step": k7,
+            "step_ms": k4 + k1 + k7, "launches_timed": n}
+
+
+def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks):
+    """K steps through sgmcmc_bnn_sghmc_run_f32 with host buffers: per step the minibatch
+    start indices are copied from pinned host memory, the per-chain cost is copied back to
+    pinned host memory and the host waits for it (what `sample, cost = next(sampler)`
+    means); every SAMPLE_STEPS-th step the whole sample [C, D] is copied back as well."""
+    K_e = min(K, 300)
+    rng = np.random.RandomState(7)
+    host_starts = torch.from_numpy(
+        rng.randint(0, N_EXAMPLES - BATCH + 1, size=(W + K_e, C)).astype(np.int32)).pin_memory()
+    host_cost = torch.empty(C, dtype=torch.float32).pin_memory()
+    host_sample = torch.empty((C, D), dtype=torch.float32).pin_memory()
+    dev_starts = torch.empty(C, dtype=torch.int32, device=dev)
+    grad = sampler._grad if sampler._grad is not None else torch.empty_like(sampler._theta)
+    cost = torch.empty(C, device=dev)
+    p = _native.ptr
+    arrs = sampler._arrays()
+    st = _native.stream_ptr()
+
+    def step(s):
+        dev_starts.copy_(host_starts[s], non_blocking=True)
+        _native.call("sgmcmc_bnn_sghmc_run_f32", *[p(a) for a in arrs], p(nll.X), p(nll.y), p(dev_starts),
+                     None, None, None, p(grad), p(cost), C, N_IN, BATCH, float(BATCH), N_EXAMPLES,
+                     1, 1, 1, 1, EPS, MDECAY, float(N_EXAMPLES), 1, sampler.n_iterations,
+                     sampler.session.chain_offset, st)
+        host_cost.copy_(cost, non_blocking=True)
+        if (s + 1) % SAMPLE_STEPS == 0:
+            host_sample.copy_(sampler._theta, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller holds (sample, cost) now
+        sampler.n_iterations += 1
+    for s in range(W):
+        step(s)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(W, W + K_e):
+        step(s)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+    n_samples = sum(1 for s in range(W, W + K_e) if (s + 1) % SAMPLE_STEPS == 0)
+    return {"value": C * world * K_e / (ms / 1e3), "unit": "chain-steps/s", "steps": K_e,
+            "ms_per_step": ms / K_e, "wall_ms_per_step": wall_ms / K_e,
+            "h2d_bytes_per_step": C * 4, "d2h_bytes_per_step": C * 4 + n_samples * C * D * 4 / K_e,
+            "api": "sgmcmc_bnn_sghmc_run_f32 (C ABI), one call per step, pinned host buffers, host sync per step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains-per-gpu", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,14 +150,18 @@ int sgmcmc_bnn_nll_grad_f32(const float* theta, const float* X, const float* y,
                             int64_t n_chains, int n_in, int batch, float batch_size_cfg,
                             int64_t n_examples, void* stream);
 
-/* ---- K5: fused BNN-SGHMC chains: K4 + K1 for `n_steps` steps in one launch,
- * the whole next(sampler) of the BNN path (samplers/base_classes.py:408-456 driving
- * sghmc.py:165-251 over bayesian_neural_network.py:337-388).
- * starts: int32 [n_steps, C] (from sgmcmc_mt19937_starts).  Same burn-in / noise /
- * trace conventions as sgmcmc_target_chains_run_f32; z is NULL or [n_steps, C, D]. */
+/* ---- K5: BNN-SGHMC chains: K4 + K1 for `n_steps` steps in one call with no host
+ * synchronisation -- the whole next(sampler) of the BNN path
+ * (samplers/base_classes.py:408-456 driving sghmc.py:165-251 over
+ * bayesian_neural_network.py:337-388).
+ * starts: int32 [n_steps, C] (from sgmcmc_mt19937_starts; NULL: every minibatch starts at
+ * row 0).  Same burn-in / noise / trace conventions as sgmcmc_target_chains_run_f32; z is
+ * NULL or [n_steps, C, D].  grad_scratch [C, D] and cost_scratch [C] are caller-owned
+ * work buffers (the gradient and cost of the last step are left in them). */
 int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float* v_hat, float* minv,
                              const float* X, const float* y, const int32_t* starts,
                              const float* z, float* trace, float* cost_trace,
+                             float* grad_scratch, float* cost_scratch,
                              int64_t n_chains, int n_in, int batch, float batch_size_cfg,
                              int64_t n_examples, int64_t n_steps, int64_t n_burn_in,
                              int adapt_forever, int64_t keep_every,

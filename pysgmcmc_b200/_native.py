@@ -47,7 +47,7 @@ SIGNATURES = {
     "sgmcmc_mt19937_seed": [_P, _P, c_int64, _P],
     "sgmcmc_mt19937_starts": [_P, _P, c_int64, c_int64, c_uint32, _P],
     "sgmcmc_bnn_nll_grad_f32": [_P] * 7 + [c_int64, c_int, c_int, c_float, c_int64, _P],
-    "sgmcmc_bnn_sghmc_run_f32": [_P] * 12 + [c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
+    "sgmcmc_bnn_sghmc_run_f32": [_P] * 14 + [c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
                                              c_int, c_int64, c_float, c_float, c_float,
                                              c_uint64, c_uint64, c_uint64, _P],
     "sgmcmc_bnn_predict_f32": [_P, _P, _P, c_int64, c_int, c_int64, _P],

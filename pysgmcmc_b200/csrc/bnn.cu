@@ -1,5 +1,593 @@
-#include "common.cuh"
+// K4: per-chain fused BNN cost + gradient (the BOHAMIANN network n_in-50-50-50-1, tanh,
+// Gaussian likelihood with a learned log-variance; pysgmcmc/models/
+// bayesian_neural_network.py:28-69, :77-141, :337-388 and tf.gradients over it),
+// K5: the host-side pipeline K4 -> K1 for `n_steps` steps of BNN-SGHMC,
+// K10: the forward pass over stored networks for the predictive.
+//
+// Work decomposition (K4).  A chain's step is 8 small GEMMs over a 20-row minibatch
+// (305 k FFMA).  A CTA owns NC chains; TPC = 50 / COLS threads cooperate on one chain and
+// thread u owns COLS of the 50 hidden units.  Every phase is "weights stationary in
+// registers": the thread loads its column (forward, dW) or row (dH) of the 50x50 kernel
+// straight from global memory into 50 registers per owned unit and streams the
+// activations of the minibatch from shared memory with 128-bit broadcast loads, four
+// batch rows in flight.  Activations (3 x B x 50) and one dZ buffer live in shared memory
+// (17 KB per chain); the gradient leaves in registers-to-global coalesced stores, so the
+// only HBM traffic is theta in and grad out (42 KB per chain-step).
+// The kernel is bound by the FP32 pipe and by shared-memory operand bandwidth, not by
+// HBM or tensor cores (DESIGN.md "K4").
+#include "sampler_math.cuh"
+
+namespace sgmcmc {
+
+constexpr int HID = 50;      // hidden width of get_default_net (bayesian_neural_network.py:30-49)
+constexpr int HS = 52;       // row stride of the activation buffers: rows stay 16-byte aligned
+constexpr int ROWS = 4;      // batch rows in flight per thread
+
+struct BnnLayout {
+  int n_in, D;
+  int oW1, ob1, oW2, ob2, oW3, ob3, oW4, ob4, orho;
+};
+
+static BnnLayout make_layout(int n_in) {
+  BnnLayout L;
+  L.n_in = n_in;
+  int o = 0;
+  L.oW1 = o; o += n_in * HID;
+  L.ob1 = o; o += HID;
+  L.oW2 = o; o += HID * HID;
+  L.ob2 = o; o += HID;
+  L.oW3 = o; o += HID * HID;
+  L.ob3 = o; o += HID;
+  L.oW4 = o; o += HID;
+  L.ob4 = o; o += 1;
+  L.orho = o; o += 1;
+  L.D = o;
+  return L;
+}
+
+struct BnnArgs {
+  const float* theta;     // [C, D]
+  const float* X;         // [N, n_in]
+  const float* y;         // [N]
+  const int32_t* starts;  // [C] (NULL: every chain starts at row 0)
+  float* cost;            // [C]
+  float* grad;            // [C, D] or NULL
+  float* mse;             // [C] or NULL
+  int64_t n_chains;
+  int batch;              // rows actually in the minibatch
+  float inv_bs;           // 1 / configured batch size          (:377)
+  float inv_n;            // 1 / n_examples                     (:380)
+  float prior_den_inv;    // 1 / (D + 3e-16)   safe_divide in weight_prior_log_like (:141)
+  BnnLayout L;
+};
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx + rcp.approx): |error| ~ 2e-7,
+// saturates correctly at +-1.  3000 activations per chain-step make the libm tanhf
+// (~25 instructions) a third of the kernel; this is 6.
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+// acc[r][c] += sum_k act[row r][k] * w[c][k]  for ROWS rows of a [B x HS] activation buffer
+template <int COLS>
+__device__ __forceinline__ void dot_rows(const float* __restrict__ act, int i0, int n_rows,
+                                         const float (&w)[COLS][HID], float (&acc)[ROWS][COLS]) {
+  const float* rp[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) rp[r] = act + (i0 + (r < n_rows ? r : 0)) * HS;
+#pragma unroll
+  for (int k4 = 0; k4 < HID / 4; ++k4) {
+    float4 h[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) h[r] = *reinterpret_cast<const float4*>(rp[r] + 4 * k4);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        acc[r][c] = fmaf(h[r].x, w[c][4 * k4 + 0], acc[r][c]);
+        acc[r][c] = fmaf(h[r].y, w[c][4 * k4 + 1], acc[r][c]);
+        acc[r][c] = fmaf(h[r].z, w[c][4 * k4 + 2], acc[r][c]);
+        acc[r][c] = fmaf(h[r].w, w[c][4 * k4 + 3], acc[r][c]);
+      }
+  }
+  {  // k = 48, 49
+    float2 h[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) h[r] = *reinterpret_cast<const float2*>(rp[r] + HID - 2);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        acc[r][c] = fmaf(h[r].x, w[c][HID - 2], acc[r][c]);
+        acc[r][c] = fmaf(h[r].y, w[c][HID - 1], acc[r][c]);
+      }
+  }
+}
+
+// One dense tanh layer, forward: out[i][j] = tanh(b[j] + sum_k in[i][k] W[k][j]) for the
+// thread's columns j; returns sum of squares of the weights it touched (weight prior).
+template <int COLS, int TPC>
+__device__ __forceinline__ float layer_forward(const float* __restrict__ th, int oW, int ob,
+                                               const float* __restrict__ in, float* __restrict__ out,
+                                               int batch, int u) {
+  float w[COLS][HID], b[COLS];
+  float sq = 0.0f;
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const int j = u + c * TPC;
+#pragma unroll
+    for (int k = 0; k < HID; ++k) {
+      w[c][k] = __ldg(th + oW + k * HID + j);
+      sq = fmaf(w[c][k], w[c][k], sq);
+    }
+    b[c] = __ldg(th + ob + j);
+    sq = fmaf(b[c], b[c], sq);
+  }
+  for (int i0 = 0; i0 < batch; i0 += ROWS) {
+    const int n_rows = min(ROWS, batch - i0);
+    float acc[ROWS][COLS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[r][c] = b[c];
+    dot_rows<COLS>(in, i0, n_rows, w, acc);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+      if (r < n_rows) {
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) out[(i0 + r) * HS + u + c * TPC] = fast_tanh(acc[r][c]);
+      }
+  }
+  return sq;
+}
+
+// dZ_prev[i][j] = (sum_m dZ[i][m] W[j][m]) * (1 - H_prev[i][j]^2), for the thread's units j
+template <int COLS, int TPC>
+__device__ __forceinline__ void layer_backward_data(const float* __restrict__ th, int oW,
+                                                    const float* __restrict__ dz,
+                                                    const float* __restrict__ h_prev,
+                                                    float* __restrict__ dz_prev, int batch, int u) {
+  float w[COLS][HID];
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const float2* row = reinterpret_cast<const float2*>(th + oW + (u + c * TPC) * HID);
+#pragma unroll
+    for (int m = 0; m < HID / 2; ++m) {
+      const float2 v = __ldg(row + m);
+      w[c][2 * m] = v.x;
+      w[c][2 * m + 1] = v.y;
+    }
+  }
+  for (int i0 = 0; i0 < batch; i0 += ROWS) {
+    const int n_rows = min(ROWS, batch - i0);
+    float acc[ROWS][COLS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[r][c] = 0.0f;
+    dot_rows<COLS>(dz, i0, n_rows, w, acc);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+      if (r < n_rows) {
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+          const int idx = (i0 + r) * HS + u + c * TPC;
+          const float h = h_prev[idx];
+          dz_prev[idx] = acc[r][c] * fmaf(-h, h, 1.0f);
+        }
+      }
+  }
+}
+
+// dW[k][j] = sum_i H_prev[i][k] dZ[i][j], db[j] = sum_i dZ[i][j]  (+ weight-prior term),
+// written to grad for the thread's columns j.
+template <int COLS, int TPC>
+__device__ __forceinline__ void layer_backward_weights(const float* __restrict__ th,
+                                                       float* __restrict__ gr, int oW, int ob,
+                                                       const float* __restrict__ h_prev,
+                                                       const float* __restrict__ dz, int batch, int u,
+                                                       float pscale) {
+  float acc[COLS][HID], db[COLS];
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    db[c] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < HID; ++k) acc[c][k] = 0.0f;
+  }
+  for (int i = 0; i < batch; ++i) {
+    float d[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      d[c] = dz[i * HS + u + c * TPC];
+      db[c] += d[c];
+    }
+    const float* rp = h_prev + i * HS;
+#pragma unroll
+    for (int k4 = 0; k4 < HID / 4; ++k4) {
+      const float4 h = *reinterpret_cast<const float4*>(rp + 4 * k4);
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        acc[c][4 * k4 + 0] = fmaf(h.x, d[c], acc[c][4 * k4 + 0]);
+        acc[c][4 * k4 + 1] = fmaf(h.y, d[c], acc[c][4 * k4 + 1]);
+        acc[c][4 * k4 + 2] = fmaf(h.z, d[c], acc[c][4 * k4 + 2]);
+        acc[c][4 * k4 + 3] = fmaf(h.w, d[c], acc[c][4 * k4 + 3]);
+      }
+    }
+    const float2 h = *reinterpret_cast<const float2*>(rp + HID - 2);
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      acc[c][HID - 2] = fmaf(h.x, d[c], acc[c][HID - 2]);
+      acc[c][HID - 1] = fmaf(h.y, d[c], acc[c][HID - 1]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const int j = u + c * TPC;
+#pragma unroll
+    for (int k = 0; k < HID; ++k)
+      gr[oW + k * HID + j] = fmaf(__ldg(th + oW + k * HID + j), pscale, acc[c][k]);
+    gr[ob + j] = fmaf(__ldg(th + ob + j), pscale, db[c]);
+  }
+}
+
+template <int COLS, int NC>
+struct BnnShape {
+  static constexpr int TPC = HID / COLS;
+  static constexpr int THREADS = ((NC * TPC + 31) / 32) * 32;
+};
+
+// shared memory per chain, in floats
+__host__ __device__ inline int bnn_smem_floats(int batch, int n_in) {
+  const int x = ((batch * n_in + 3) / 4) * 4;
+  const int yb = ((batch + 3) / 4) * 4;
+  return x + 2 * yb + 4 * batch * HS + 64;   // X, Y, df, H1, H2, H3, E, scratch[64]
+}
+
+template <int COLS, int NC, bool WANT_GRAD>
+__global__ void __launch_bounds__(BnnShape<COLS, NC>::THREADS)
+bnn_nll_grad_kernel(BnnArgs a) {
+  constexpr int TPC = BnnShape<COLS, NC>::TPC;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int lc = tid / TPC;            // chain slot in this CTA
+  const int u = tid - lc * TPC;        // unit group of this thread
+  const int64_t chain = (int64_t)blockIdx.x * NC + lc;
+  const bool active = lc < NC && chain < a.n_chains;
+  const int batch = a.batch, n_in = a.L.n_in;
+  const BnnLayout L = a.L;
+
+  const int per_chain = bnn_smem_floats(batch, n_in);
+  float* sX = smem + (size_t)(lc < NC ? lc : 0) * per_chain;
+  float* sY = sX + ((batch * n_in + 3) / 4) * 4;
+  float* sDf = sY + ((batch + 3) / 4) * 4;
+  float* H1 = sDf + ((batch + 3) / 4) * 4;
+  float* H2 = H1 + batch * HS;
+  float* H3 = H2 + batch * HS;
+  float* E = H3 + batch * HS;
+  float* scr = E + batch * HS;         // [64]
+
+  const float* th = a.theta + (active ? chain : 0) * L.D;
+  float* gr = (WANT_GRAD && a.grad != nullptr) ? a.grad + (active ? chain : 0) * L.D : nullptr;
+  float sq = 0.0f;                     // this thread's share of sum(theta^2)
+
+  // ---- P0: stage the minibatch rows X[start : start+B], y[start : start+B] ----
+  if (active) {
+    const int64_t start = a.starts != nullptr ? a.starts[chain] : 0;
+    for (int t = u; t < batch * n_in; t += TPC) sX[t] = __ldg(a.X + start * n_in + t);
+    for (int t = u; t < batch; t += TPC) sY[t] = __ldg(a.y + start + t);
+  }
+  __syncthreads();
+
+  // ---- P1: layer 1 forward (n_in -> 50) ----
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int j = u + c * TPC;
+      const float b = __ldg(th + L.ob1 + j);
+      sq = fmaf(b, b, sq);
+      for (int i = 0; i < batch; ++i) H1[i * HS + j] = b;
+      for (int m = 0; m < n_in; ++m) {
+        const float w = __ldg(th + L.oW1 + m * HID + j);
+        sq = fmaf(w, w, sq);
+        for (int i = 0; i < batch; ++i) H1[i * HS + j] = fmaf(sX[i * n_in + m], w, H1[i * HS + j]);
+      }
+      for (int i = 0; i < batch; ++i) H1[i * HS + j] = fast_tanh(H1[i * HS + j]);
+    }
+  }
+  __syncthreads();
+  // ---- P2, P3: layers 2 and 3 forward ----
+  if (active) sq += layer_forward<COLS, TPC>(th, L.oW2, L.ob2, H1, H2, batch, u);
+  __syncthreads();
+  if (active) sq += layer_forward<COLS, TPC>(th, L.oW3, L.ob3, H2, H3, batch, u);
+  __syncthreads();
+
+  // ---- P4: head f[i] = H3[i,:] . W4 + b4 : per-thread partials, reduced through E ----
+  float w4[COLS];
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      w4[c] = __ldg(th + L.oW4 + u + c * TPC);
+      sq = fmaf(w4[c], w4[c], sq);
+    }
+    for (int i = 0; i < batch; ++i) {
+      float p = 0.0f;
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) p = fmaf(H3[i * HS + u + c * TPC], w4[c], p);
+      E[i * HS + u] = p;
+    }
+    scr[u] = sq;
+  }
+  __syncthreads();
+  if (active) {
+    const float b4 = __ldg(th + L.ob4), rho = __ldg(th + L.orho);
+    const float e_rho = expf(rho);
+    const float fvi = 1.0f / (e_rho + 1e-16f);                       // :368
+    for (int i = u; i < batch; i += TPC) {
+      float f = b4;
+      for (int t = 0; t < TPC; ++t) f += E[i * HS + t];
+      const float diff = sY[i] - f;
+      sDf[i] = -(diff * fvi) * a.inv_bs;                             // d cost / d f_i
+      sY[i] = diff * diff;                                           // squared error (:370)
+    }
+  }
+  __syncthreads();
+  if (active && u == 0) {
+    // scalar tail of the cost (:372-388) and the rho / b4 gradients, one thread per chain
+    const float b4 = __ldg(th + L.ob4), rho = __ldg(th + L.orho);
+    const float e_rho = expf(rho);
+    const float fvi = 1.0f / (e_rho + 1e-16f);
+    float sse = 0.0f, sdf = 0.0f, total_sq = fmaf(b4, b4, rho * rho);
+    for (int i = 0; i < batch; ++i) { sse += sY[i]; sdf += sDf[i]; }
+    for (int t = 0; t < TPC; ++t) total_sq += scr[t];
+    const float log_like_data = (-sse * (0.5f * fvi) - 0.5f * rho * (float)batch) * a.inv_bs;
+    const float lv_den = 0.02f + 3e-16f;                             // safe_divide(., 2 * var)
+    const float dl = rho - logf(1e-6f);
+    const float lv = -(dl * dl) / lv_den - 0.5f * logf(0.01f);       // :102-107
+    const float wp = (-0.5f * total_sq) * a.prior_den_inv;           // :131-141
+    a.cost[chain] = -(log_like_data + (lv + wp) * a.inv_n);
+    if (a.mse != nullptr) a.mse[chain] = sse / (float)batch;
+    if (gr != nullptr) {
+      const float pscale = a.prior_den_inv * a.inv_n;
+      const float drho_data = -(0.5f * sse * e_rho * fvi * fvi - 0.5f * (float)batch) * a.inv_bs;
+      gr[L.orho] = drho_data + (2.0f * dl / lv_den) * a.inv_n + rho * pscale;
+      gr[L.ob4] = sdf + b4 * pscale;
+    }
+  }
+  if (gr == nullptr) return;           // cost only (uniform across the CTA)
+
+  const float pscale = a.prior_den_inv * a.inv_n;
+  // ---- P5: layer 4 backward: dW4, dZ3 = (df W4^T) * (1 - H3^2) in place over H3 ----
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int j = u + c * TPC;
+      float dw = 0.0f;
+      for (int i = 0; i < batch; ++i) {
+        const float h = H3[i * HS + j], df = sDf[i];
+        dw = fmaf(h, df, dw);
+        H3[i * HS + j] = (df * w4[c]) * fmaf(-h, h, 1.0f);
+      }
+      gr[L.oW4 + j] = fmaf(w4[c], pscale, dw);
+    }
+  }
+  __syncthreads();
+  // ---- layer 3 backward: dZ2 -> E (needs old W3 rows), then dW3 from H2 and dZ3 ----
+  if (active) layer_backward_data<COLS, TPC>(th, L.oW3, H3, H2, E, batch, u);
+  if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW3, L.ob3, H2, H3, batch, u, pscale);
+  __syncthreads();
+  // ---- layer 2 backward: dZ1 -> H3 (dZ3 is dead), then dW2 from H1 and dZ2 ----
+  if (active) layer_backward_data<COLS, TPC>(th, L.oW2, E, H1, H3, batch, u);
+  if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW2, L.ob2, H1, E, batch, u, pscale);
+  __syncthreads();
+  // ---- layer 1 backward: dW1 = X^T dZ1, db1 ----
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int j = u + c * TPC;
+      float db = 0.0f;
+      for (int i = 0; i < batch; ++i) db += H3[i * HS + j];
+      gr[L.ob1 + j] = fmaf(__ldg(th + L.ob1 + j), pscale, db);
+      for (int m = 0; m < n_in; ++m) {
+        float dw = 0.0f;
+        for (int i = 0; i < batch; ++i) dw = fmaf(sX[i * n_in + m], H3[i * HS + j], dw);
+        gr[L.oW1 + m * HID + j] = fmaf(__ldg(th + L.oW1 + m * HID + j), pscale, dw);
+      }
+    }
+  }
+}
+
+// ---- K10: forward only, one "chain" = (stored network k, block of <= PB test points) ----
+constexpr int PB = 32;
+template <int COLS, int NC>
+__global__ void __launch_bounds__(BnnShape<COLS, NC>::THREADS)
+bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X, float* __restrict__ out,
+                   int64_t n_nets, int64_t n_points, BnnLayout L) {
+  constexpr int TPC = BnnShape<COLS, NC>::TPC;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int lc = tid / TPC, u = tid - lc * TPC;
+  const int64_t blocks_per_net = (n_points + PB - 1) / PB;
+  const int64_t item = (int64_t)blockIdx.x * NC + lc;
+  const bool active = lc < NC && item < n_nets * blocks_per_net;
+  const int64_t net = active ? item / blocks_per_net : 0;
+  const int64_t p0 = active ? (item % blocks_per_net) * PB : 0;
+  const int batch = active ? (int)min((int64_t)PB, n_points - p0) : 0;
+  const int n_in = L.n_in;
+  const int per_chain = bnn_smem_floats(PB, n_in);
+  float* sX = smem + (size_t)(lc < NC ? lc : 0) * per_chain;
+  float* H1 = sX + ((PB * n_in + 3) / 4) * 4 + 2 * PB;
+  float* H2 = H1 + PB * HS;
+  float* H3 = H2 + PB * HS;
+  float* E = H3 + PB * HS;
+  const float* th = theta + net * L.D;
+  if (active)
+    for (int t = u; t < batch * n_in; t += TPC) sX[t] = __ldg(X + p0 * n_in + t);
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int j = u + c * TPC;
+      const float b = __ldg(th + L.ob1 + j);
+      for (int i = 0; i < batch; ++i) {
+        float z = b;
+        for (int m = 0; m < n_in; ++m) z = fmaf(sX[i * n_in + m], __ldg(th + L.oW1 + m * HID + j), z);
+        H1[i * HS + j] = fast_tanh(z);
+      }
+    }
+  }
+  __syncthreads();
+  if (active) layer_forward<COLS, TPC>(th, L.oW2, L.ob2, H1, H2, batch, u);
+  __syncthreads();
+  if (active) layer_forward<COLS, TPC>(th, L.oW3, L.ob3, H2, H3, batch, u);
+  __syncthreads();
+  if (active) {
+    for (int i = 0; i < batch; ++i) {
+      float p = 0.0f;
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) p = fmaf(H3[i * HS + u + c * TPC], __ldg(th + L.oW4 + u + c * TPC), p);
+      E[i * HS + u] = p;
+    }
+  }
+  __syncthreads();
+  if (active) {
+    const float b4 = __ldg(th + L.ob4), rho = __ldg(th + L.orho);
+    for (int i = u; i < batch; i += TPC) {
+      float f = b4;
+      for (int t = 0; t < TPC; ++t) f += E[i * HS + t];
+      out[(net * n_points + p0 + i) * 2 + 0] = f;
+      out[(net * n_points + p0 + i) * 2 + 1] = rho;     // "ones_like(layer_4) * output_bias" (:63-67)
+    }
+  }
+}
+
+// launch configuration shared by the entry points below
+constexpr int K4_COLS = 1;
+constexpr int K4_NC = 5;
+
+static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
+  using Shape = BnnShape<K4_COLS, K4_NC>;
+  const size_t smem = (size_t)K4_NC * bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
+  SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED,
+             "minibatch of %d rows x %d inputs needs %zu B of shared memory per CTA (max 232448)",
+             a.batch, a.L.n_in, smem);
+  const unsigned blocks = (unsigned)((a.n_chains + K4_NC - 1) / K4_NC);
+  if (a.grad != nullptr) {
+    auto k = bnn_nll_grad_kernel<K4_COLS, K4_NC, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<blocks, Shape::THREADS, smem, st>>>(a);
+  } else {
+    auto k = bnn_nll_grad_kernel<K4_COLS, K4_NC, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<blocks, Shape::THREADS, smem, st>>>(a);
+  }
+  return check_launch("bnn_nll_grad_kernel");
+}
+
+static int make_bnn_args(BnnArgs& a, const float* theta, const float* X, const float* y,
+                         const int32_t* starts, float* cost, float* grad, float* mse, int64_t n_chains,
+                         int n_in, int batch, float batch_size_cfg, int64_t n_examples) {
+  SG_REQUIRE(n_chains >= 0, SGMCMC_E_INVALID, "n_chains must be >= 0");
+  SG_REQUIRE(theta && X && y && cost, SGMCMC_E_INVALID, "bnn: theta, X, y and cost must not be NULL");
+  SG_REQUIRE(n_in >= 1 && n_in <= 64, SGMCMC_E_UNSUPPORTED, "bnn: n_in must be in [1, 64] (got %d)", n_in);
+  SG_REQUIRE(batch >= 1 && batch <= 256, SGMCMC_E_UNSUPPORTED, "bnn: batch must be in [1, 256] (got %d)", batch);
+  SG_REQUIRE(batch_size_cfg > 0 && n_examples >= 1, SGMCMC_E_INVALID, "bnn: batch_size_cfg and n_examples must be > 0");
+  a.theta = theta; a.X = X; a.y = y; a.starts = starts; a.cost = cost; a.grad = grad; a.mse = mse;
+  a.n_chains = n_chains; a.batch = batch;
+  a.L = make_layout(n_in);
+  SG_REQUIRE(aligned_to(theta, 8) && (a.L.D % 2 == 0), SGMCMC_E_ALIGN, "bnn: theta must be 8-byte aligned");
+  a.inv_bs = 1.0f / batch_size_cfg;
+  a.inv_n = 1.0f / (float)n_examples;
+  a.prior_den_inv = 1.0f / ((float)a.L.D + 3e-16f);
+  return SGMCMC_OK;
+}
+
+// trace[k] <- theta, cost_trace[k] <- cost (device-to-device, stream ordered)
+static int snapshot(float* trace, float* cost_trace, int64_t k, const float* theta, const float* cost,
+                    int64_t n_chains, int64_t D, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  if (trace != nullptr)
+    e = cudaMemcpyAsync(trace + k * n_chains * D, theta, sizeof(float) * n_chains * D, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess && cost_trace != nullptr)
+    e = cudaMemcpyAsync(cost_trace + k * n_chains, cost, sizeof(float) * n_chains, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "snapshot copy: %s", cudaGetErrorString(e));
+  return SGMCMC_OK;
+}
+
+}  // namespace sgmcmc
+
 using namespace sgmcmc;
-extern "C" int sgmcmc_bnn_nll_grad_f32(const float*, const float*, const float*, const int32_t*, float*, float*, float*, int64_t, int, int, float, int64_t, void*) { return set_error(SGMCMC_E_UNSUPPORTED, "not built yet"); }
-extern "C" int sgmcmc_bnn_sghmc_run_f32(float*, float*, float*, float*, float*, float*, const float*, const float*, const int32_t*, const float*, float*, float*, int64_t, int, int, float, int64_t, int64_t, int64_t, int, int64_t, float, float, float, uint64_t, uint64_t, uint64_t, void*) { return set_error(SGMCMC_E_UNSUPPORTED, "not built yet"); }
-extern "C" int sgmcmc_bnn_predict_f32(const float*, const float*, float*, int64_t, int, int64_t, void*) { return set_error(SGMCMC_E_UNSUPPORTED, "not built yet"); }
+
+extern "C" int sgmcmc_bnn_nll_grad_f32(const float* theta, const float* X, const float* y,
+                                       const int32_t* starts, float* cost, float* grad, float* mse,
+                                       int64_t n_chains, int n_in, int batch, float batch_size_cfg,
+                                       int64_t n_examples, void* stream) {
+  BnnArgs a;
+  if (int rc = make_bnn_args(a, theta, X, y, starts, cost, grad, mse, n_chains, n_in, batch,
+                             batch_size_cfg, n_examples))
+    return rc;
+  if (n_chains == 0) return SGMCMC_OK;
+  return launch_nll_grad(a, (cudaStream_t)stream);
+}
+
+// K5: `n_steps` steps of BNN-SGHMC for all chains, driven from C with no host
+// synchronisation: per step K4 (cost + gradient at the old theta, minibatch
+// starts[s, :]) then K1 (fused SGHMC update), plus a device-to-device snapshot of
+// (theta, cost) every keep_every-th step.  The gradient goes through the caller's
+// `grad_scratch` [C, D]; a single-kernel variant that keeps it on chip is round-2 work
+// (DESIGN.md "K5").
+extern "C" int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float* v_hat,
+                                        float* minv, const float* X, const float* y,
+                                        const int32_t* starts, const float* z, float* trace,
+                                        float* cost_trace, float* grad_scratch, float* cost_scratch,
+                                        int64_t n_chains, int n_in, int batch,
+                                        float batch_size_cfg, int64_t n_examples, int64_t n_steps,
+                                        int64_t n_burn_in, int adapt_forever, int64_t keep_every,
+                                        float epsilon, float mdecay, float scale_grad, uint64_t seed,
+                                        uint64_t step0, uint64_t chain_offset, void* stream) {
+  SG_REQUIRE(n_steps >= 0 && n_burn_in >= 0 && keep_every >= 1, SGMCMC_E_INVALID,
+             "bnn_sghmc_run: n_steps, n_burn_in must be >= 0 and keep_every >= 1");
+  SG_REQUIRE(grad_scratch && cost_scratch, SGMCMC_E_INVALID, "bnn_sghmc_run: scratch buffers must not be NULL");
+  SG_REQUIRE(v && tau && g && v_hat && minv, SGMCMC_E_INVALID, "bnn_sghmc_run: state arrays must not be NULL");
+  BnnArgs a;
+  if (int rc = make_bnn_args(a, theta, X, y, starts, cost_scratch, grad_scratch, nullptr, n_chains, n_in,
+                             batch, batch_size_cfg, n_examples))
+    return rc;
+  const int64_t D = a.L.D, n = n_chains * D;
+  SG_REQUIRE((chain_offset * (uint64_t)D) % 4 == 0, SGMCMC_E_INVALID, "chain_offset * D must be a multiple of 4");
+  if (n_chains == 0) return SGMCMC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    a.starts = starts != nullptr ? starts + s * n_chains : nullptr;
+    if (int rc = launch_nll_grad(a, st)) return rc;
+    const int burn_in = adapt_forever || s < n_burn_in;
+    const int store_minv = burn_in && (s == n_burn_in - 1 || (adapt_forever && s == n_steps - 1));
+    if (int rc = sgmcmc_sghmc_step_f32(theta, v, tau, g, v_hat, minv, grad_scratch,
+                                       z != nullptr ? z + s * n : nullptr, n, epsilon, mdecay, scale_grad,
+                                       burn_in, store_minv, seed, step0 + (uint64_t)s,
+                                       chain_offset * (uint64_t)D, stream))
+      return rc;
+    if ((s + 1) % keep_every == 0)
+      if (int rc = snapshot(trace, cost_trace, (s + 1) / keep_every - 1, theta, cost_scratch, n_chains, D, st))
+        return rc;
+  }
+  return SGMCMC_OK;
+}
+
+extern "C" int sgmcmc_bnn_predict_f32(const float* theta, const float* X, float* out, int64_t n_nets,
+                                      int n_in, int64_t n_points, void* stream) {
+  SG_REQUIRE(n_nets >= 0 && n_points >= 0, SGMCMC_E_INVALID, "negative size");
+  if (n_nets == 0 || n_points == 0) return SGMCMC_OK;
+  SG_REQUIRE(theta && X && out, SGMCMC_E_INVALID, "bnn_predict: NULL pointer");
+  SG_REQUIRE(n_in >= 1 && n_in <= 64, SGMCMC_E_UNSUPPORTED, "bnn: n_in must be in [1, 64] (got %d)", n_in);
+  const BnnLayout L = make_layout(n_in);
+  using Shape = BnnShape<K4_COLS, K4_NC>;
+  const size_t smem = (size_t)K4_NC * bnn_smem_floats(PB, n_in) * sizeof(float);
+  SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED, "bnn_predict: n_in too large for shared memory");
+  auto k = bnn_predict_kernel<K4_COLS, K4_NC>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t items = n_nets * ((n_points + PB - 1) / PB);
+  k<<<(unsigned)((items + K4_NC - 1) / K4_NC), Shape::THREADS, smem, (cudaStream_t)stream>>>(
+      theta, X, out, n_nets, n_points, L);
+  return check_launch("bnn_predict_kernel");
+}

@@ -1,0 +1,189 @@
+"""The BNN cost function of the hot path as a sampler `cost_fun`:
+negative log likelihood of the BOHAMIANN network (n_in-50-50-50-1 tanh MLP with a learned
+log-variance), i.e. pysgmcmc/models/bayesian_neural_network.py:28-69 (`get_default_net`),
+:77-141 (priors) and :337-388 (`negative_log_likelihood`).
+
+* ``native_cost_and_grad`` runs kernel K4 (csrc/bnn.cu) for all chains at once;
+  `SGHMCSampler` recognises the object and drives K4 + K1 from C (K5) without returning
+  to Python between steps.
+* ``__call__(params)`` is the same cost written in differentiable torch ops: it serves
+  float64 samplers, SGLD / relativistic samplers (generic autograd path) and the
+  full-dataset logging of `BayesianNeuralNetwork.train`.
+
+Flat per-chain layout = ``tf.trainable_variables()`` order of the reference:
+W1[n_in,50] b1[50] W2[50,50] b2[50] W3[50,50] b3[50] W4[50,1] b4[1] rho[1,1].
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import _native
+from ..placeholders import Placeholder
+from ..tensor_utils import safe_divide
+
+HIDDEN = 50
+
+
+def parameter_shapes(n_in):
+    return [(n_in, HIDDEN), (HIDDEN,), (HIDDEN, HIDDEN), (HIDDEN,), (HIDDEN, HIDDEN), (HIDDEN,),
+            (HIDDEN, 1), (1,), (1, 1)]
+
+
+def n_parameters(n_in):
+    return sum(int(np.prod(s)) for s in parameter_shapes(n_in))
+
+
+def default_net_params(n_in, n_chains=None, seed=None, dtype=torch.float32, device="cuda:0"):
+    """Initial parameters of `get_default_net` (bayesian_neural_network.py:28-61): kernels
+    ~ truncated normal(0, sqrt(1.3 / fan_in)) (tf.contrib `variance_scaling_initializer`
+    with factor=1.0: FAN_IN, truncated at two standard deviations and rescaled), zero
+    biases, log-variance log(1e-3).  TensorFlow's random stream cannot be reproduced
+    (and the reference pins none, tests/bayesian_neural_network/test_seeding.py:14-46 only
+    asks for same seed -> same net), so the draws come from a seeded torch generator.
+
+    Returns a list of 9 tensors (with a leading chain axis when `n_chains` is given).
+    """
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed))
+    lead = () if n_chains is None else (n_chains,)
+    out = []
+    for shp in parameter_shapes(n_in):
+        if len(shp) == 2 and shp != (1, 1):
+            std = math.sqrt(1.3 / shp[0])
+            w = torch.empty(lead + shp, dtype=torch.float64)
+            torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=gen)
+            out.append((w * std).to(dtype))
+        elif shp == (1, 1):
+            out.append(torch.full(lead + shp, math.log(1e-3), dtype=dtype))
+        else:
+            out.append(torch.zeros(lead + shp, dtype=dtype))
+    return [p.to(device) for p in out]
+
+
+def network_output(params, X):
+    """`get_default_net` in torch ops: returns ``[..., n_points, 2]`` = (mean, log variance).
+    `params` may carry a leading chain axis (then X is ``[C, B, n_in]`` or ``[B, n_in]``)."""
+    W1, b1, W2, b2, W3, b3, W4, b4, rho = params
+    chains = W1.dim() == 3
+    bias = (lambda b: b[:, None, :]) if chains else (lambda b: b)
+    h = torch.tanh(X @ W1 + bias(b1))
+    h = torch.tanh(h @ W2 + bias(b2))
+    h = torch.tanh(h @ W3 + bias(b3))
+    f = h @ W4 + bias(b4)
+    return torch.cat([f, torch.ones_like(f) * rho], dim=-1)
+
+
+def log_variance_prior_log_like(log_var, mean=1e-6, var=0.01, dtype=None):
+    """bayesian_neural_network.py:77-107 (log_var: ``[..., B, 1]``)."""
+    return (safe_divide(-torch.square(log_var - math.log(mean)),
+                        torch.as_tensor(2.0 * var, dtype=log_var.dtype, device=log_var.device))
+            - 0.5 * math.log(var)).sum(dim=-1).mean(dim=-1)
+
+
+def weight_prior_log_like(parameters, wdecay=1.0, dtype=None, chains=False):
+    """bayesian_neural_network.py:110-141."""
+    log_like, n_params = 0.0, 0.0
+    for p in parameters:
+        sq = -wdecay * 0.5 * torch.square(p)
+        log_like = log_like + (sq.reshape(p.shape[0], -1).sum(dim=1) if chains else sq.sum())
+        n_params += float(np.prod(p.shape[1:] if chains else p.shape))
+    return safe_divide(log_like, torch.as_tensor(n_params, dtype=log_like.dtype, device=log_like.device))
+
+
+class BayesianNeuralNetworkNLL(object):
+    """Cost function object: ``cost = -log_like`` of :337-388.
+
+    Two ways to supply the minibatch, mirroring the reference's feed mechanism:
+
+    * device-resident data + on-device start indices (`DeviceBatchGenerator`): pass the
+      whole (normalised) dataset `X`, `y` and the generator's ``starts_placeholder``;
+      chain j uses rows ``X[starts[j] : starts[j] + batch_size]``;
+    * host minibatches (`generate_batches`): pass ``x_placeholder`` / ``y_placeholder``;
+      every step the fed ``(B, n_in)`` / ``(B, 1)`` arrays are uploaded and used by all
+      chains (the reference's single-chain behaviour).
+    """
+
+    def __init__(self, n_examples, batch_size=20, n_in=None, X=None, y=None, starts_placeholder=None,
+                 x_placeholder=None, y_placeholder=None, n_chains=None, device="cuda:0",
+                 dtype=torch.float32):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.n_examples = int(n_examples)
+        self.batch_size = int(batch_size)               # the CONFIGURED constant of :377
+        self.n_chains = n_chains
+        self.x_placeholder, self.y_placeholder = x_placeholder, y_placeholder
+        self.starts_placeholder = starts_placeholder
+        if X is not None:
+            self.X = torch.as_tensor(np.asarray(X) if not isinstance(X, torch.Tensor) else X
+                                     ).to(self.device, dtype).reshape(len(X), -1).contiguous()
+            self.y = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y
+                                     ).to(self.device, dtype).reshape(-1).contiguous()
+            self.n_in = self.X.shape[1]
+        else:
+            assert x_placeholder is not None and y_placeholder is not None and n_in is not None
+            self.X = self.y = None
+            self.n_in = int(n_in)
+        self.actual_batch = min(self.batch_size, self.n_examples)    # data_batches.py:111
+        self.n_params = n_parameters(self.n_in)
+        self.bnn_native = True
+        self._cost = None
+        self.last_mse = None
+
+    # ---- where the current minibatch comes from ---------------------------------------
+    def _device_batch(self):
+        """(X, y, starts or None, batch) for the native kernels."""
+        if self.X is not None:
+            starts = None
+            if self.starts_placeholder is not None and self.starts_placeholder.value is not None:
+                starts = self.starts_placeholder.tensor(self.device, torch.int32).contiguous()
+            batch = self.actual_batch if starts is not None else min(self.X.shape[0], 256)
+            return self.X, self.y, starts, batch
+        xb = self.x_placeholder.tensor(self.device, torch.float32).reshape(-1, self.n_in).contiguous()
+        yb = self.y_placeholder.tensor(self.device, torch.float32).reshape(-1).contiguous()
+        return xb, yb, None, xb.shape[0]
+
+    def _torch_batch(self):
+        if self.X is not None:
+            if self.starts_placeholder is not None and self.starts_placeholder.value is not None:
+                starts = self.starts_placeholder.tensor(self.device, torch.int64)
+                idx = starts[:, None] + torch.arange(self.actual_batch, device=self.device)[None, :]
+                return self.X[idx].to(self.dtype), self.y[idx].to(self.dtype)
+            return self.X.to(self.dtype), self.y.to(self.dtype)
+        xb = self.x_placeholder.tensor(self.device, self.dtype).reshape(-1, self.n_in)
+        yb = self.y_placeholder.tensor(self.device, self.dtype).reshape(-1)
+        return xb, yb
+
+    # ---- native path (K4) ---------------------------------------------------------------
+    def native_cost_and_grad(self, theta, grad_out, want_mse=False):
+        C, D = theta.shape
+        assert D == self.n_params, "parameter layout does not match the %d-input network" % self.n_in
+        X, y, starts, batch = self._device_batch()
+        assert starts is None or starts.shape[0] == C
+        if self._cost is None or self._cost.shape[0] != C:
+            self._cost = torch.empty(C, dtype=torch.float32, device=self.device)
+        mse = torch.empty(C, dtype=torch.float32, device=self.device) if want_mse else None
+        with torch.cuda.device(self.device):
+            _native.call("sgmcmc_bnn_nll_grad_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(y),
+                         _native.ptr(starts), _native.ptr(self._cost), _native.ptr(grad_out),
+                         _native.ptr(mse), C, self.n_in, batch, float(self.batch_size),
+                         self.n_examples, _native.stream_ptr())
+        self.last_mse = mse
+        return self._cost
+
+    # ---- generic differentiable path ------------------------------------------------------
+    def __call__(self, params, *_):
+        params = list(params)
+        chains = params[0].dim() == 3
+        X, Y = self._torch_batch()
+        out = network_output(params, X)
+        f_mean, f_log_var = out[..., 0:1], out[..., 1:2]
+        Y = Y.reshape(f_mean.shape)
+        f_var_inv = 1.0 / (torch.exp(f_log_var) + 1e-16)
+        mse = torch.square(Y - f_mean)
+        log_like = (-mse * (0.5 * f_var_inv) - 0.5 * f_log_var).sum(dim=(-1, -2))
+        log_like = log_like / self.batch_size
+        log_like = log_like + log_variance_prior_log_like(f_log_var) / self.n_examples
+        log_like = log_like + weight_prior_log_like(params, chains=chains) / self.n_examples
+        self.last_mse = mse.mean(dim=(-1, -2)).detach()
+        return -log_like

@@ -77,7 +77,36 @@ class SGHMCSampler(BurnInMCMCSampler):
         self._target_run(1, 1 if adapt else 0, 1, z, None, cost, epsilon)
         return cost[0] if self.multi_chain else cost[0, 0]
 
+    def _bnn_run_ok(self):
+        """The BNN cost with device-resident data: K4 + K1 can be driven from C (K5)."""
+        from ..data_batches import DeviceBatchGenerator
+        cf = self.cost_fun
+        return (getattr(cf, "bnn_native", False) and self.dtype == torch.float32 and self.session.fused
+                and getattr(cf, "X", None) is not None
+                and type(self.stepsize_schedule) is ConstantStepsizeSchedule
+                and (self.batch_generator is None or isinstance(self.batch_generator, DeviceBatchGenerator)))
+
+    def _can_run_fused(self):
+        return super()._can_run_fused() or self._bnn_run_ok()
+
     def _launch_fused_run(self, n_steps, keep_every, trace, costs):
-        self._target_run(n_steps, min(n_steps, self._burn_in_remaining()), keep_every, None, trace,
-                         costs, float(next(self.stepsize_schedule)))
+        epsilon = float(next(self.stepsize_schedule))
+        n_burn_in = min(n_steps, self._burn_in_remaining())
+        if self._native_target is not None:
+            self._target_run(n_steps, n_burn_in, keep_every, None, trace, costs, epsilon)
+        else:
+            cf = self.cost_fun
+            starts = None if self.batch_generator is None else self.batch_generator.next_block(n_steps)
+            batch = cf.actual_batch if starts is not None else min(cf.X.shape[0], 256)
+            if self._grad is None:
+                self._grad = torch.empty_like(self._theta)
+            cost_scratch = torch.empty(self.n_chains, dtype=self.dtype, device=self.device)
+            _native.call("sgmcmc_bnn_sghmc_run_f32", *[_native.ptr(a) for a in self._arrays()],
+                         _native.ptr(cf.X), _native.ptr(cf.y), _native.ptr(starts), None,
+                         _native.ptr(trace), _native.ptr(costs), _native.ptr(self._grad),
+                         _native.ptr(cost_scratch), self.n_chains, cf.n_in, batch, float(cf.batch_size),
+                         cf.n_examples, n_steps, n_burn_in, int(self.burn_in_steps == 0), keep_every,
+                         epsilon, self.mdecay, self.scale_grad, self._noise_seed, self.n_iterations,
+                         self.session.chain_offset, self._stream())
+            self.cost = cost_scratch
         self.n_iterations += n_steps

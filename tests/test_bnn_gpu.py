@@ -1,0 +1,277 @@
+"""GPU parity tests of the BNN path: K4 (cost + gradient), K5 (BNN-SGHMC steps driven from
+C), K10 (predictive forward) and the sampler classes on top, against the oracle.
+
+Tolerances: K4 accumulates 50-term dot products with FMA in fp32 and evaluates tanh on the
+SFU (|error| ~ 2e-7 per activation), the oracle is float64.  Cost: rtol 2e-6.  Gradient:
+|g - g_ref| <= 2e-5 * max|g_ref| per chain (element-wise rtol is meaningless for the many
+entries that are ~1e-8 of the largest one).  Trajectories (injected noise, scale_grad = N as
+BayesianNeuralNetwork.train sets it): 1e-5 relative to max|theta| after 200 steps.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bnn as obnn, mt19937 as omt, samplers as osamplers
+from pysgmcmc_b200 import Session, _native
+from pysgmcmc_b200.data_batches import DeviceBatchGenerator
+from pysgmcmc_b200.models.bnn_cost import (BayesianNeuralNetworkNLL, default_net_params,
+                                           n_parameters, network_output, parameter_shapes)
+from pysgmcmc_b200.samplers import SGHMCSampler, SGLDSampler
+from pysgmcmc_b200.stepsize_schedules import ConstantStepsizeSchedule
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def sinc_data(N, n_in=1, seed=1):
+    rng = np.random.RandomState(seed)
+    X = np.array([rng.uniform(0.0, 1.0, n_in) for _ in range(N)])      # tests/utils.py:24-29
+    y = np.sinc(X * 10 - 5).sum(axis=1)                                 # tests/utils.py:32-33
+    X = (X - X.mean(axis=0)) / X.std(axis=0)                            # base_model.py:125-133
+    y = (y - y.mean()) / y.std()
+    return X, y
+
+
+def k4(theta, X, y, starts, batch, bs_cfg, N, want_grad=True, n_in=1):
+    C = theta.shape[0]
+    t = torch.as_tensor(theta, dtype=torch.float32, device=DEV).contiguous()
+    Xd = torch.as_tensor(X, dtype=torch.float32, device=DEV).contiguous()
+    yd = torch.as_tensor(y, dtype=torch.float32, device=DEV).contiguous()
+    sd = None if starts is None else torch.as_tensor(starts, dtype=torch.int32, device=DEV)
+    cost = torch.empty(C, device=DEV)
+    mse = torch.empty(C, device=DEV)
+    grad = torch.full_like(t, float("nan")) if want_grad else None
+    _native.call("sgmcmc_bnn_nll_grad_f32", _native.ptr(t), _native.ptr(Xd), _native.ptr(yd),
+                 _native.ptr(sd), _native.ptr(cost), _native.ptr(grad), _native.ptr(mse), C, n_in, batch,
+                 float(bs_cfg), N, _native.stream_ptr())
+    torch.cuda.synchronize()
+    return cost.cpu().numpy(), None if grad is None else grad.cpu().numpy(), mse.cpu().numpy()
+
+
+def assert_grad_close(got, want, tol=2e-5):
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    err = np.abs(got - want) / scale
+    assert np.isfinite(got).all()
+    assert err.max() <= tol, "max |dg| / max|g| = %.3g" % err.max()
+
+
+def test_k4_golden_file():
+    g = np.load(os.path.join(GOLDEN, "bnn_nll.npz"))
+    cost, grad, mse = k4(g["theta"], g["X"], g["y"], g["starts"], 20, 20, g["X"].shape[0])
+    np.testing.assert_allclose(cost, g["cost"], rtol=2e-6)
+    np.testing.assert_allclose(mse, g["mse"], rtol=2e-5)
+    assert_grad_close(grad, g["grad"])
+
+
+@pytest.mark.parametrize("C", [1, 4, 5, 6, 37, 1000])
+@pytest.mark.parametrize("n_in,batch,N", [(1, 20, 20000), (1, 7, 50), (3, 20, 300), (1, 32, 100), (2, 1, 10)])
+def test_k4_matches_oracle(C, n_in, batch, N):
+    """Ragged cases: chain counts that do not fill a CTA, batches that are not a multiple of
+    the 4-row blocking, several input features, batch == 1."""
+    if C == 1000 and n_in != 1:
+        pytest.skip("large C covered for the headline shape only")
+    rng = np.random.RandomState(C * 31 + batch)
+    X, y = sinc_data(N, n_in, seed=3)
+    theta = obnn.init_theta(C, n_in=n_in, seed=C, dtype=np.float64)
+    theta += 0.1 * rng.standard_normal(theta.shape)
+    starts = rng.randint(0, N - batch + 1, size=C)
+    Xb, yb = obnn.gather_minibatch(X, y, starts, batch)
+    wc, wg, wm = obnn.nll_and_grad(theta, Xb, yb, n_examples=N, batch_size=20, n_in=n_in)
+    cost, grad, mse = k4(theta, X, y, starts, batch, 20, N, n_in=n_in)
+    np.testing.assert_allclose(cost, wc, rtol=3e-6)
+    np.testing.assert_allclose(mse, wm, rtol=3e-5)
+    assert_grad_close(grad, wg)
+    # cost-only launch (grad == NULL) gives the same cost
+    cost2, _, _ = k4(theta, X, y, starts, batch, 20, N, want_grad=False, n_in=n_in)
+    assert np.array_equal(cost, cost2)
+
+
+def test_k4_reference_prior_golden_inside_the_cost():
+    """With zero residual the cost reduces to the two priors the reference pins with golden
+    vectors (tests/bayesian_neural_network/test_priors.py): check K4 against them."""
+    g = np.load(os.path.join(GOLDEN, "bnn_priors.npz"))
+    theta = np.concatenate([g["w%d" % i].ravel() for i in range(9)])[None, :]
+    X = np.zeros((20, 1))
+    f, rho, _ = obnn.forward(theta, X[None])
+    y = f[0]
+    N = 100
+    cost, _, mse = k4(theta, X, y, None, 20, 20, N)
+    lv = obnn.log_variance_prior_log_like(np.full((20, 1), rho[0]))
+    wp = float(g["expected_weights"])
+    expect = -(-0.5 * rho[0] + lv / N + wp / N)
+    assert abs(mse[0]) < 1e-10
+    np.testing.assert_allclose(cost[0], expect, rtol=2e-6)
+
+
+def test_k4_full_size_properties():
+    """8192 chains (one GPU's shard of config 4): identical chains give identical results
+    whatever CTA slot they land in, and the gradient is linear in the residual scale."""
+    C, N = 8192, 20000
+    X, y = sinc_data(N)
+    theta1 = obnn.init_theta(1, seed=7, dtype=np.float64)
+    theta = np.repeat(theta1, C, axis=0)
+    starts = np.full(C, 1234)
+    cost, grad, _ = k4(theta, X, y, starts, 20, 20, N)
+    assert (cost == cost[0]).all() and (grad == grad[0]).all()
+    Xb, yb = obnn.gather_minibatch(X, y, starts[:1], 20)
+    wc, wg, _ = obnn.nll_and_grad(theta1, Xb, yb, n_examples=N)
+    np.testing.assert_allclose(cost[0], wc[0], rtol=3e-6)
+    assert_grad_close(grad[:1], wg)
+
+
+def test_k10_predict_matches_oracle():
+    rng = np.random.RandomState(2)
+    n_nets, n_points = 7, 77
+    theta = obnn.init_theta(n_nets, seed=4, dtype=np.float64) + 0.05 * rng.standard_normal((n_nets, 5252))
+    X = rng.uniform(-2, 2, size=(n_points, 1))
+    t = torch.as_tensor(theta, dtype=torch.float32, device=DEV)
+    out = torch.empty((n_nets, n_points, 2), device=DEV)
+    _native.call("sgmcmc_bnn_predict_f32", _native.ptr(t), _native.ptr(torch.as_tensor(X, dtype=torch.float32, device=DEV)),
+                 _native.ptr(out), n_nets, 1, n_points, _native.stream_ptr())
+    f, rho, _ = obnn.forward(theta, np.repeat(X[None], n_nets, axis=0))
+    np.testing.assert_allclose(out[..., 0].cpu().numpy(), f, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(out[..., 1].cpu().numpy(), np.repeat(rho[:, None], n_points, 1), rtol=1e-6)
+
+
+def test_torch_cost_equals_oracle_and_k4():
+    """The differentiable torch restatement used by the generic path agrees with both."""
+    C, N = 3, 200
+    X, y = sinc_data(N)
+    theta = obnn.init_theta(C, seed=2, dtype=np.float64) + 0.05 * np.random.RandomState(0).standard_normal((C, 5252))
+    starts = np.array([0, 17, 180])
+    ph = type("P", (), {})
+    from pysgmcmc_b200.placeholders import Placeholder
+    sp = Placeholder("starts")
+    sp.value = torch.as_tensor(starts, dtype=torch.int32, device=DEV)
+    nll = BayesianNeuralNetworkNLL(N, 20, X=X, y=y, starts_placeholder=sp, device=DEV, dtype=torch.float64)
+    params, off = [], 0
+    for shp in parameter_shapes(1):
+        n = int(np.prod(shp))
+        params.append(torch.tensor(theta[:, off:off + n].reshape((C,) + shp), device=DEV, requires_grad=True))
+        off += n
+    cost = nll(params)
+    Xb, yb = obnn.gather_minibatch(X, y, starts, 20)
+    wc, wg, _ = obnn.nll_and_grad(theta, Xb, yb, n_examples=N)
+    np.testing.assert_allclose(cost.detach().cpu().numpy(), wc, rtol=1e-12)
+    grads = torch.autograd.grad(cost.sum(), params)
+    got = np.concatenate([gr.reshape(C, -1).cpu().numpy() for gr in grads], axis=1)
+    np.testing.assert_allclose(got, wg, rtol=1e-8, atol=1e-14)
+
+
+def oracle_bnn_chain(theta0, X, y, seeds, N, batch, steps, burn, z_seed, eps=0.01):
+    C, D = theta0.shape
+    streams = [omt.MT19937(int(s)) for s in seeds]
+    holder = {}
+
+    def cost_and_grad(theta):
+        Xb, yb = obnn.gather_minibatch(X, y, holder["starts"], batch)
+        c, g, _ = obnn.nll_and_grad(theta, Xb.astype(np.float32), yb.astype(np.float32), n_examples=N)
+        return c, g
+    chain = osamplers.OracleChain("sghmc", theta0, cost_and_grad, epsilon=eps, burn_in_steps=burn,
+                                  scale_grad=float(N))
+    zr = np.random.RandomState(z_seed)
+    costs = []
+    for s in range(steps):
+        holder["starts"] = np.array([st.bounded(N - batch) for st in streams])
+        z = zr.standard_normal((C, D)).astype(np.float32)
+        theta, c = chain.next(z)
+        costs.append(c)
+    return theta, np.stack(costs), chain
+
+
+def test_bnn_sghmc_sampler_trajectory_matches_oracle():
+    """next(sampler) on the BNN cost with per-chain on-device minibatch streams and
+    injected noise, 200 steps across the burn-in boundary, vs the fp32 oracle."""
+    C, N, batch, steps, burn = 6, 2000, 20, 200, 120
+    X, y = sinc_data(N)
+    theta0 = obnn.init_theta(C, seed=11, dtype=np.float32)
+    seeds = np.arange(C) + 40
+    want_theta, want_cost, chain = oracle_bnn_chain(theta0, X, y, seeds, N, batch, steps, burn, z_seed=9)
+
+    gen = DeviceBatchGenerator(N, batch, seeds=seeds, device=DEV, block=64)
+    nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+    params, off = [], 0
+    for shp in parameter_shapes(1):
+        n = int(np.prod(shp))
+        params.append(torch.tensor(theta0[:, off:off + n].reshape((C,) + shp), device=DEV))
+        off += n
+    sampler = SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen, burn_in_steps=burn,
+                           scale_grad=float(N), stepsize_schedule=ConstantStepsizeSchedule(0.01),
+                           session=Session(device=DEV, n_chains=C, output="torch"))
+    zr = np.random.RandomState(9)
+    for s in range(steps):
+        z = zr.standard_normal((C, 5252)).astype(np.float32)
+        sample, cost = sampler.__next__(feed_dict={sampler.noise: z})
+        np.testing.assert_allclose(cost.cpu().numpy(), want_cost[s], rtol=1e-4, err_msg="step %d" % s)
+    got = sampler._theta.cpu().numpy()
+    scale = np.abs(want_theta).max()
+    assert np.abs(got - want_theta).max() <= 1e-5 * scale
+    np.testing.assert_allclose(sampler._state_array("minv").cpu().numpy(), chain.minv, rtol=1e-4)
+    assert not sampler.is_burning_in
+
+
+def test_bnn_sghmc_run_equals_per_step_and_oracle():
+    """sampler.run(n) (K5: K4+K1 driven from C, Philox noise, device minibatch streams) ==
+    n x next(sampler), bit for bit; thinned trace and costs are the same pairs."""
+    C, N, batch, steps, burn = 10, 2000, 20, 60, 25
+    X, y = sinc_data(N)
+
+    def build():
+        gen = DeviceBatchGenerator(N, batch, n_chains=C, seed=5, device=DEV, block=16)
+        nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+        params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+        return SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen, burn_in_steps=burn,
+                            scale_grad=float(N), seed=77,
+                            session=Session(device=DEV, n_chains=C, output="torch"))
+    a, b = build(), build()
+    trace, costs = a.run(steps, keep_every=5)
+    assert a.n_iterations == steps and trace.shape == (steps // 5, C, 5252)
+    for s in range(steps):
+        sample, cost = next(b)
+        if (s + 1) % 5 == 0:
+            k = (s + 1) // 5 - 1
+            assert torch.equal(trace[k], b._theta), "trace at step %d" % s
+            assert torch.equal(costs[k], cost), "cost at step %d" % s
+    for name in ("v", "tau", "g", "v_hat", "minv"):
+        assert torch.equal(a._state_array(name), b._state_array(name)), name
+    assert torch.isfinite(a._theta).all()
+
+
+def test_reference_style_host_batches_single_chain():
+    """Reference wiring: generate_batches feeding placeholders, one chain, numpy outputs."""
+    from pysgmcmc_b200.data_batches import generate_batches
+    from pysgmcmc_b200.placeholders import placeholder
+    N, batch = 300, 20
+    X, y = sinc_data(N)
+    xp, yp = placeholder(name="X_Minibatch"), placeholder(name="Y_Minibatch")
+    nll = BayesianNeuralNetworkNLL(N, batch, n_in=1, x_placeholder=xp, y_placeholder=yp, device=DEV)
+    params = default_net_params(1, seed=1, device=DEV)
+    sampler = SGHMCSampler(params=params, cost_fun=nll,
+                           batch_generator=generate_batches(X, y, xp, yp, batch, seed=1),
+                           burn_in_steps=5, scale_grad=float(N), seed=1, session=Session(device=DEV))
+    theta0 = np.concatenate([p.detach().cpu().numpy().ravel() for p in params])[None, :]
+    start = np.random.RandomState(1).randint(0, N - batch + 1)
+    wc, _, _ = obnn.nll_and_grad(theta0.astype(np.float64), X[None, start:start + batch],
+                                 y[None, start:start + batch], n_examples=N)
+    sample, cost = next(sampler)
+    assert isinstance(sample, list) and [s.shape for s in sample] == parameter_shapes(1)
+    np.testing.assert_allclose(cost, wc[0], rtol=1e-5)
+    for _ in range(10):
+        sample, cost = next(sampler)
+    assert np.isfinite(cost) and all(np.isfinite(s).all() for s in sample)
+
+
+def test_sgld_on_bnn_cost_uses_generic_update_kernel():
+    C, N = 4, 500
+    X, y = sinc_data(N)
+    gen = DeviceBatchGenerator(N, 20, n_chains=C, seed=2, device=DEV)
+    nll = BayesianNeuralNetworkNLL(N, 20, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+    s = SGLDSampler(params=default_net_params(1, n_chains=C, seed=2, device=DEV), cost_fun=nll,
+                    batch_generator=gen, burn_in_steps=3, scale_grad=float(N),
+                    session=Session(device=DEV, n_chains=C, output="torch"))
+    for _ in range(6):
+        sample, cost = next(s)
+    assert torch.isfinite(cost).all() and cost.shape == (C,)
