@@ -21,7 +21,7 @@ Workload (BASELINE.json configs[3], one GPU's shard; weak scaling over GPUs):
 `roofline`: the dominant kernel of the step, timed launch by launch with CUDA events.
 `cpu_baseline` / `--impl reference`: the reference cannot run on this image (TensorFlow 1.x);
             the CPU arm is the NumPy restatement in oracle/ ("port"), vectorised over chains
-            and spread over the host cores with a thread pool.
+            and spread over the host cores with one process per core.
 """
 import argparse
 import json
@@ -65,38 +65,43 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------
-def cpu_chain_steps_per_s(n_chains, n_steps, warmup, cores):
-    """NumPy oracle (oracle/bnn.py + oracle/samplers.py), `n_chains` chains split over
-    `cores` threads (NumPy releases the GIL inside its kernels)."""
-    from concurrent.futures import ThreadPoolExecutor
+def _cpu_worker(job):
+    """One host process: `n` chains of the NumPy oracle (oracle/bnn.py + oracle/samplers.py),
+    vectorised over its chains; returns the seconds its timed steps took."""
+    first_chain, n, n_steps, warmup = job
     from oracle import bnn, samplers
     X, y = synthetic_sinc()
-    shards = np.array_split(np.arange(n_chains), cores)
+    theta = bnn.init_theta(n, seed=1 + first_chain)
+    rng = np.random.RandomState(100 + first_chain)
+    holder = {}
 
-    def make(shard):
-        theta = bnn.init_theta(len(shard), seed=1 + int(shard[0]))
-        rng = np.random.RandomState(100 + int(shard[0]))
-        holder = {}
+    def cost_and_grad(th):
+        Xb, yb = bnn.gather_minibatch(X, y, holder["s"], BATCH)
+        c, g, _ = bnn.nll_and_grad(th, Xb, yb, n_examples=N_EXAMPLES)
+        return c, g
+    chain = samplers.OracleChain("sghmc", theta, cost_and_grad, epsilon=EPS, burn_in_steps=10 ** 9,
+                                 mdecay=MDECAY, scale_grad=float(N_EXAMPLES))
 
-        def cost_and_grad(th):
-            Xb, yb = bnn.gather_minibatch(X, y, holder["s"], BATCH)
-            c, g, _ = bnn.nll_and_grad(th, Xb, yb, n_examples=N_EXAMPLES)
-            return c, g
-        chain = samplers.OracleChain("sghmc", theta, cost_and_grad, epsilon=EPS, burn_in_steps=10 ** 9,
-                                     mdecay=MDECAY, scale_grad=float(N_EXAMPLES))
+    def run(k):
+        for _ in range(k):
+            holder["s"] = rng.randint(0, N_EXAMPLES - BATCH + 1, size=n)
+            chain.next(rng.standard_normal((n, D)).astype(np.float32))
+    run(warmup)
+    t0 = time.perf_counter()
+    run(n_steps)
+    return time.perf_counter() - t0
 
-        def run(k):
-            for _ in range(k):
-                holder["s"] = rng.randint(0, N_EXAMPLES - BATCH + 1, size=len(shard))
-                chain.next(rng.standard_normal((len(shard), D)).astype(np.float32))
-        return run
-    runners = [make(s) for s in shards if len(s)]
-    with ThreadPoolExecutor(max_workers=len(runners)) as pool:
-        list(pool.map(lambda r: r(warmup), runners))
-        t0 = time.perf_counter()
-        list(pool.map(lambda r: r(n_steps), runners))
-        dt = time.perf_counter() - t0
-    return n_chains * n_steps / dt, dt
+
+def cpu_chain_steps_per_s(n_chains, n_steps, warmup, cores):
+    """The oracle port on all host cores: `n_chains` chains split over `cores` processes
+    (spawned, so no CUDA state is inherited); throughput = all chain-steps / slowest worker."""
+    import multiprocessing as mp
+    per = n_chains // cores
+    jobs = [(i * per, per, n_steps, warmup) for i in range(cores)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        times = pool.map(_cpu_worker, jobs)
+    dt = max(times)
+    return per * cores * n_steps / dt, dt
 
 
 def run_reference(args):
@@ -108,7 +113,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 20))
     warmup = max(1, min(args.warmup, 2))
     value, dt = cpu_chain_steps_per_s(n_chains, steps, warmup, cores)
-    sample = ("%d chains x %d steps of the same BNN-SGHMC workload (NumPy oracle port, %d threads); "
+    sample = ("%d chains x %d steps of the same BNN-SGHMC workload (NumPy oracle port, %d processes); "
               "reference TF 1.x is not installable on this image" % (n_chains, steps, cores))
     line = {
         "impl": "reference", "metric": "chain-steps/s (BNN SGHMC)", "value": value, "unit": "chain-steps/s",
@@ -278,10 +283,10 @@ def run_b200(args):
         return
     cores = len(os.sched_getaffinity(0))
     if world == 1 and not args.no_cpu_baseline:
-        cpu_chains, cpu_steps = 64 * cores, 10
+        cpu_chains, cpu_steps = 64 * cores, 400
         cpu_value, cpu_dt = cpu_chain_steps_per_s(cpu_chains, cpu_steps, 1, cores)
         cpu = {"value": cpu_value, "unit": "chain-steps/s", "cores": cores, "kind": "port",
-               "sample": "%d chains x %d steps of the same workload, NumPy oracle port on %d threads "
+               "sample": "%d chains x %d steps of the same workload, NumPy oracle port on %d processes "
                          "(%.1f s); TF 1.x reference not installable" % (cpu_chains, cpu_steps, cores, cpu_dt)}
     else:
         cpu = None
