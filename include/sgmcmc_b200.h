@@ -53,6 +53,10 @@ const char* sgmcmc_last_error(void);
  * Measured on B200 (profiles/): 256 x 1 is fastest; more groups per thread cost occupancy. */
 int sgmcmc_set_update_tuning(int threads, int unroll);
 
+/* Launch shape of the BNN kernel K4 (units per thread, chains per CTA, rows in flight):
+ * 0 is the default; the others exist for the sweeps recorded under profiles/. */
+int sgmcmc_set_bnn_tuning(int variant);
+
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t sgmcmc_launch_count(void);
 

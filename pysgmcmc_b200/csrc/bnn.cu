@@ -20,8 +20,8 @@
 namespace sgmcmc {
 
 constexpr int HID = 50;      // hidden width of get_default_net (bayesian_neural_network.py:30-49)
-constexpr int HS = 52;       // row stride of the activation buffers: rows stay 16-byte aligned
-constexpr int ROWS = 4;      // batch rows in flight per thread
+constexpr int HS = 52;       // row stride of the activation buffers: rows stay 16-byte aligned;
+                             // columns 50, 51 are zero padding so every k-loop is 13 float4 steps
 
 struct BnnLayout {
   int n_in, D;
@@ -69,49 +69,48 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
-// acc[r][c] += sum_k act[row r][k] * w[c][k]  for ROWS rows of a [B x HS] activation buffer
-template <int COLS>
+// acc[r][c] += sum_k act[row r][k] * w[c][k]  for ROWS rows of a [B x HS] activation buffer.
+// The 128-bit broadcast loads of step k4+1 are issued before the FFMAs of step k4
+// (software pipelining: the shared-memory latency was the top stall in the ncu source view).
+template <int COLS, int ROWS>
 __device__ __forceinline__ void dot_rows(const float* __restrict__ act, int i0, int n_rows,
-                                         const float (&w)[COLS][HID], float (&acc)[ROWS][COLS]) {
-  const float* rp[ROWS];
+                                         const float (&w)[COLS][HS], float (&acc)[ROWS][COLS]) {
+  const float4* rp[ROWS];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) rp[r] = act + (i0 + (r < n_rows ? r : 0)) * HS;
+  for (int r = 0; r < ROWS; ++r)
+    rp[r] = reinterpret_cast<const float4*>(act + (i0 + (r < n_rows ? r : 0)) * HS);
+  float4 hc[ROWS], hn[ROWS];
 #pragma unroll
-  for (int k4 = 0; k4 < HID / 4; ++k4) {
-    float4 h[ROWS];
+  for (int r = 0; r < ROWS; ++r) hc[r] = rp[r][0];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) h[r] = *reinterpret_cast<const float4*>(rp[r] + 4 * k4);
+  for (int k4 = 0; k4 < HS / 4; ++k4) {
+    if (k4 + 1 < HS / 4) {
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-      for (int c = 0; c < COLS; ++c) {
-        acc[r][c] = fmaf(h[r].x, w[c][4 * k4 + 0], acc[r][c]);
-        acc[r][c] = fmaf(h[r].y, w[c][4 * k4 + 1], acc[r][c]);
-        acc[r][c] = fmaf(h[r].z, w[c][4 * k4 + 2], acc[r][c]);
-        acc[r][c] = fmaf(h[r].w, w[c][4 * k4 + 3], acc[r][c]);
-      }
-  }
-  {  // k = 48, 49
-    float2 h[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) h[r] = *reinterpret_cast<const float2*>(rp[r] + HID - 2);
+      for (int r = 0; r < ROWS; ++r) hn[r] = rp[r][k4 + 1];
+    }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int c = 0; c < COLS; ++c) {
-        acc[r][c] = fmaf(h[r].x, w[c][HID - 2], acc[r][c]);
-        acc[r][c] = fmaf(h[r].y, w[c][HID - 1], acc[r][c]);
+        acc[r][c] = fmaf(hc[r].x, w[c][4 * k4 + 0], acc[r][c]);
+        acc[r][c] = fmaf(hc[r].y, w[c][4 * k4 + 1], acc[r][c]);
+        acc[r][c] = fmaf(hc[r].z, w[c][4 * k4 + 2], acc[r][c]);
+        acc[r][c] = fmaf(hc[r].w, w[c][4 * k4 + 3], acc[r][c]);
       }
+    if (k4 + 1 < HS / 4) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) hc[r] = hn[r];
+    }
   }
 }
 
 // One dense tanh layer, forward: out[i][j] = tanh(b[j] + sum_k in[i][k] W[k][j]) for the
 // thread's columns j; returns sum of squares of the weights it touched (weight prior).
-template <int COLS, int TPC>
+template <int COLS, int TPC, int ROWS>
 __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int oW, int ob,
                                                const float* __restrict__ in, float* __restrict__ out,
                                                int batch, int u) {
-  float w[COLS][HID], b[COLS];
+  float w[COLS][HS], b[COLS];
   float sq = 0.0f;
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
@@ -121,6 +120,7 @@ __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int
       w[c][k] = __ldg(th + oW + k * HID + j);
       sq = fmaf(w[c][k], w[c][k], sq);
     }
+    w[c][HID] = w[c][HID + 1] = 0.0f;
     b[c] = __ldg(th + ob + j);
     sq = fmaf(b[c], b[c], sq);
   }
@@ -131,7 +131,7 @@ __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int c = 0; c < COLS; ++c) acc[r][c] = b[c];
-    dot_rows<COLS>(in, i0, n_rows, w, acc);
+    dot_rows<COLS, ROWS>(in, i0, n_rows, w, acc);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
       if (r < n_rows) {
@@ -143,12 +143,12 @@ __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int
 }
 
 // dZ_prev[i][j] = (sum_m dZ[i][m] W[j][m]) * (1 - H_prev[i][j]^2), for the thread's units j
-template <int COLS, int TPC>
+template <int COLS, int TPC, int ROWS>
 __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th, int oW,
                                                     const float* __restrict__ dz,
                                                     const float* __restrict__ h_prev,
                                                     float* __restrict__ dz_prev, int batch, int u) {
-  float w[COLS][HID];
+  float w[COLS][HS];
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
     const float2* row = reinterpret_cast<const float2*>(th + oW + (u + c * TPC) * HID);
@@ -158,6 +158,7 @@ __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th
       w[c][2 * m] = v.x;
       w[c][2 * m + 1] = v.y;
     }
+    w[c][HID] = w[c][HID + 1] = 0.0f;
   }
   for (int i0 = 0; i0 < batch; i0 += ROWS) {
     const int n_rows = min(ROWS, batch - i0);
@@ -166,7 +167,7 @@ __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int c = 0; c < COLS; ++c) acc[r][c] = 0.0f;
-    dot_rows<COLS>(dz, i0, n_rows, w, acc);
+    dot_rows<COLS, ROWS>(dz, i0, n_rows, w, acc);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
       if (r < n_rows) {
@@ -188,24 +189,34 @@ __device__ __forceinline__ void layer_backward_weights(const float* __restrict__
                                                        const float* __restrict__ h_prev,
                                                        const float* __restrict__ dz, int batch, int u,
                                                        float pscale) {
-  float acc[COLS][HID], db[COLS];
+  float acc[COLS][HS], db[COLS];
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
     db[c] = 0.0f;
 #pragma unroll
-    for (int k = 0; k < HID; ++k) acc[c][k] = 0.0f;
+    for (int k = 0; k < HS; ++k) acc[c][k] = 0.0f;
   }
+  // flat (row, k4) walk with a one-step look-ahead on the broadcast loads
+  const float4* hp = reinterpret_cast<const float4*>(h_prev);
+  float4 hc = hp[0];
+  float dn[COLS];
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) dn[c] = dz[u + c * TPC];
   for (int i = 0; i < batch; ++i) {
     float d[COLS];
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
-      d[c] = dz[i * HS + u + c * TPC];
+      d[c] = dn[c];
       db[c] += d[c];
     }
-    const float* rp = h_prev + i * HS;
+    const int inext = i + 1 < batch ? i + 1 : i;
 #pragma unroll
-    for (int k4 = 0; k4 < HID / 4; ++k4) {
-      const float4 h = *reinterpret_cast<const float4*>(rp + 4 * k4);
+    for (int c = 0; c < COLS; ++c) dn[c] = dz[inext * HS + u + c * TPC];
+    const float4* rp = hp + i * (HS / 4);
+#pragma unroll
+    for (int k4 = 0; k4 < HS / 4; ++k4) {
+      const float4 h = hc;
+      hc = (k4 + 1 < HS / 4) ? rp[k4 + 1] : hp[inext * (HS / 4)];
 #pragma unroll
       for (int c = 0; c < COLS; ++c) {
         acc[c][4 * k4 + 0] = fmaf(h.x, d[c], acc[c][4 * k4 + 0]);
@@ -213,12 +224,6 @@ __device__ __forceinline__ void layer_backward_weights(const float* __restrict__
         acc[c][4 * k4 + 2] = fmaf(h.z, d[c], acc[c][4 * k4 + 2]);
         acc[c][4 * k4 + 3] = fmaf(h.w, d[c], acc[c][4 * k4 + 3]);
       }
-    }
-    const float2 h = *reinterpret_cast<const float2*>(rp + HID - 2);
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) {
-      acc[c][HID - 2] = fmaf(h.x, d[c], acc[c][HID - 2]);
-      acc[c][HID - 1] = fmaf(h.y, d[c], acc[c][HID - 1]);
     }
   }
 #pragma unroll
@@ -244,8 +249,8 @@ __host__ __device__ inline int bnn_smem_floats(int batch, int n_in) {
   return x + 2 * yb + 4 * batch * HS + 64;   // X, Y, df, H1, H2, H3, E, scratch[64]
 }
 
-template <int COLS, int NC, bool WANT_GRAD>
-__global__ void __launch_bounds__(BnnShape<COLS, NC>::THREADS)
+template <int COLS, int NC, int ROWS, int MINB, bool WANT_GRAD>
+__global__ void __launch_bounds__(BnnShape<COLS, NC>::THREADS, MINB)
 bnn_nll_grad_kernel(BnnArgs a) {
   constexpr int TPC = BnnShape<COLS, NC>::TPC;
   extern __shared__ __align__(16) float smem[];
@@ -276,6 +281,10 @@ bnn_nll_grad_kernel(BnnArgs a) {
     const int64_t start = a.starts != nullptr ? a.starts[chain] : 0;
     for (int t = u; t < batch * n_in; t += TPC) sX[t] = __ldg(a.X + start * n_in + t);
     for (int t = u; t < batch; t += TPC) sY[t] = __ldg(a.y + start + t);
+    for (int t = u; t < 4 * batch; t += TPC) {     // zero padding columns of H1, H2, H3, E
+      H1[t * HS + HID] = 0.0f;
+      H1[t * HS + HID + 1] = 0.0f;
+    }
   }
   __syncthreads();
 
@@ -297,9 +306,9 @@ bnn_nll_grad_kernel(BnnArgs a) {
   }
   __syncthreads();
   // ---- P2, P3: layers 2 and 3 forward ----
-  if (active) sq += layer_forward<COLS, TPC>(th, L.oW2, L.ob2, H1, H2, batch, u);
+  if (active) sq += layer_forward<COLS, TPC, ROWS>(th, L.oW2, L.ob2, H1, H2, batch, u);
   __syncthreads();
-  if (active) sq += layer_forward<COLS, TPC>(th, L.oW3, L.ob3, H2, H3, batch, u);
+  if (active) sq += layer_forward<COLS, TPC, ROWS>(th, L.oW3, L.ob3, H2, H3, batch, u);
   __syncthreads();
 
   // ---- P4: head f[i] = H3[i,:] . W4 + b4 : per-thread partials, reduced through E ----
@@ -373,11 +382,11 @@ bnn_nll_grad_kernel(BnnArgs a) {
   }
   __syncthreads();
   // ---- layer 3 backward: dZ2 -> E (needs old W3 rows), then dW3 from H2 and dZ3 ----
-  if (active) layer_backward_data<COLS, TPC>(th, L.oW3, H3, H2, E, batch, u);
+  if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW3, H3, H2, E, batch, u);
   if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW3, L.ob3, H2, H3, batch, u, pscale);
   __syncthreads();
   // ---- layer 2 backward: dZ1 -> H3 (dZ3 is dead), then dW2 from H1 and dZ2 ----
-  if (active) layer_backward_data<COLS, TPC>(th, L.oW2, E, H1, H3, batch, u);
+  if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW2, E, H1, H3, batch, u);
   if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW2, L.ob2, H1, E, batch, u, pscale);
   __syncthreads();
   // ---- layer 1 backward: dW1 = X^T dZ1, db1 ----
@@ -421,8 +430,13 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
   float* H3 = H2 + PB * HS;
   float* E = H3 + PB * HS;
   const float* th = theta + net * L.D;
-  if (active)
+  if (active) {
     for (int t = u; t < batch * n_in; t += TPC) sX[t] = __ldg(X + p0 * n_in + t);
+    for (int t = u; t < 4 * PB; t += TPC) {
+      H1[t * HS + HID] = 0.0f;
+      H1[t * HS + HID + 1] = 0.0f;
+    }
+  }
   __syncthreads();
   if (active) {
 #pragma unroll
@@ -437,9 +451,9 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
     }
   }
   __syncthreads();
-  if (active) layer_forward<COLS, TPC>(th, L.oW2, L.ob2, H1, H2, batch, u);
+  if (active) layer_forward<COLS, TPC, 4>(th, L.oW2, L.ob2, H1, H2, batch, u);
   __syncthreads();
-  if (active) layer_forward<COLS, TPC>(th, L.oW3, L.ob3, H2, H3, batch, u);
+  if (active) layer_forward<COLS, TPC, 4>(th, L.oW3, L.ob3, H2, H3, batch, u);
   __syncthreads();
   if (active) {
     for (int i = 0; i < batch; ++i) {
@@ -461,27 +475,49 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
   }
 }
 
-// launch configuration shared by the entry points below
-constexpr int K4_COLS = 1;
+// ---- launch variants (COLS units per thread, NC chains per CTA, ROWS batch rows in
+// flight, min CTAs per SM); selected with sgmcmc_set_bnn_tuning, default chosen from the
+// sweep in profiles/ -------------------------------------------------------------------
+constexpr int K4_COLS = 1;      // K10 uses this shape
 constexpr int K4_NC = 5;
 
-static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
-  using Shape = BnnShape<K4_COLS, K4_NC>;
-  const size_t smem = (size_t)K4_NC * bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
+static int g_bnn_variant = 0;
+int bnn_variant_count() { return 6; }
+void set_bnn_variant(int v) { g_bnn_variant = v; }
+
+template <int COLS, int NC, int ROWS, int MINB>
+static int launch_variant(const BnnArgs& a, cudaStream_t st) {
+  using Shape = BnnShape<COLS, NC>;
+  const size_t smem = (size_t)NC * bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
   SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED,
              "minibatch of %d rows x %d inputs needs %zu B of shared memory per CTA (max 232448)",
              a.batch, a.L.n_in, smem);
-  const unsigned blocks = (unsigned)((a.n_chains + K4_NC - 1) / K4_NC);
+  const unsigned blocks = (unsigned)((a.n_chains + NC - 1) / NC);
   if (a.grad != nullptr) {
-    auto k = bnn_nll_grad_kernel<K4_COLS, K4_NC, true>;
+    auto k = bnn_nll_grad_kernel<COLS, NC, ROWS, MINB, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, Shape::THREADS, smem, st>>>(a);
   } else {
-    auto k = bnn_nll_grad_kernel<K4_COLS, K4_NC, false>;
+    auto k = bnn_nll_grad_kernel<COLS, NC, ROWS, MINB, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, Shape::THREADS, smem, st>>>(a);
   }
   return check_launch("bnn_nll_grad_kernel");
+}
+
+static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
+  // a large minibatch may not fit the default variant's shared memory: fall back to fewer
+  // chains per CTA
+  const size_t per_chain = bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
+  if (per_chain * 5 > 227 * 1024) return launch_variant<1, 1, 4, 1>(a, st);
+  switch (g_bnn_variant) {
+    case 1: return launch_variant<1, 4, 4, 3>(a, st);
+    case 2: return launch_variant<2, 10, 4, 1>(a, st);
+    case 3: return launch_variant<2, 5, 4, 2>(a, st);
+    case 4: return launch_variant<1, 5, 5, 2>(a, st);
+    case 5: return launch_variant<1, 2, 4, 6>(a, st);
+    default: return launch_variant<1, 5, 4, 2>(a, st);
+  }
 }
 
 static int make_bnn_args(BnnArgs& a, const float* theta, const float* X, const float* y,

@@ -56,4 +56,12 @@ int sgmcmc_set_update_tuning(int threads, int unroll) {
   return SGMCMC_OK;
 }
 
+int sgmcmc_set_bnn_tuning(int variant) {
+  if (variant < 0 || variant >= sgmcmc::bnn_variant_count())
+    return sgmcmc::set_error(SGMCMC_E_INVALID, "bnn variant must be in [0, %d) (got %d)",
+                             sgmcmc::bnn_variant_count(), variant);
+  sgmcmc::set_bnn_variant(variant);
+  return SGMCMC_OK;
+}
+
 }  // extern "C"

@@ -16,6 +16,8 @@ int check_launch(const char* what);
 void count_launch();
 int tuning_threads();
 int tuning_unroll();
+int bnn_variant_count();
+void set_bnn_variant(int v);
 
 #define SG_REQUIRE(cond, code, ...)                          \
   do {                                                       \

@@ -1,0 +1,177 @@
+"""Convergence diagnostics -- same entry points as
+pysgmcmc/diagnostics/sampler_diagnostics.py:47-194 (`effective_sample_sizes`,
+`gelman_rubin`), computed by GPU reductions (K8, csrc/moments.cu) plus one all-reduce of
+per-dimension chain sums when chains are sharded over several GPUs (K9).
+
+The reference delegates to pymc3 >= 3.1 (third-party, not vendored); the formulas are the
+ones its docstrings state (:76-82, :153-161) and pymc3 3.1 implements:
+
+    W = mean_j s_j^2,  B = n var_j(mean_j),  V_hat = W (n-1)/n + B/n,  R_hat = sqrt(V_hat / W)
+    n_eff = m n / (1 + 2 sum_{t=1}^{T} rho_t),  rho_t = 1 - V_t / (2 V_hat),
+    V_t = mean over chains and draws of (x_i - x_{i-t})^2, stop at the first t with
+    rho_{t-1} + rho_t < 0 (made even); floored and capped at m n.
+
+Everything that crosses GPUs is a SUM over chains, so ranks combine with
+``all_reduce(SUM)`` of ``[3, D]`` (+ ``[n_lags, D]``) float64 values and finalise
+redundantly.  Parity unpinned by the reference (see oracle/diagnostics.py).
+"""
+import numpy as np
+import torch
+
+from .. import _native
+
+__all__ = ("effective_sample_sizes", "gelman_rubin", "gelman_rubin_from_trace",
+           "effective_n_from_trace", "ChainSums")
+
+
+# ---------------------------------------------------------------------------------------
+# rank-local GPU reductions (K8)
+# ---------------------------------------------------------------------------------------
+def local_moment_sums(trace):
+    """trace ``[n, C, D]`` float32 CUDA -> float64 ``[3, D]``: sum_j mean_j, sum_j mean_j^2,
+    sum_j var_j(ddof=1) over the local chains."""
+    n, C, D = trace.shape
+    sums = torch.zeros((3, D), dtype=torch.float64, device=trace.device)
+    with torch.cuda.device(trace.device):
+        _native.call("sgmcmc_chain_moments_f32", _native.ptr(trace), _native.ptr(sums), n, C, D,
+                     _native.stream_ptr())
+    return sums
+
+
+def local_variogram_sums(trace, lag0, n_lags):
+    """float64 ``[n_lags, D]``: sum over local chains and draws of (x_i - x_{i-t})^2, t = lag0.."""
+    n, C, D = trace.shape
+    out = torch.zeros((n_lags, D), dtype=torch.float64, device=trace.device)
+    with torch.cuda.device(trace.device):
+        _native.call("sgmcmc_variogram_f32", _native.ptr(trace), _native.ptr(out), n, C, D, lag0, n_lags,
+                     _native.stream_ptr())
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# cross-rank combination (K9) and finalisation -- pure torch, runs on any device
+# ---------------------------------------------------------------------------------------
+def _all_reduce_sum(t, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class ChainSums(object):
+    """Per-dimension sums over ALL chains of the job (after the all-reduce)."""
+
+    def __init__(self, moment_sums, n_chains_local, n_draws, group=None):
+        packed = torch.cat([moment_sums.reshape(-1),
+                            torch.tensor([float(n_chains_local)], dtype=torch.float64,
+                                         device=moment_sums.device)])
+        packed = _all_reduce_sum(packed, group)
+        self.sums = packed[:-1].reshape(3, -1)
+        self.m = int(round(float(packed[-1])))
+        self.n = int(n_draws)
+        self.group = group
+
+    def v_hat_and_w(self):
+        m, n = self.m, self.n
+        mean_of_means = self.sums[0] / m
+        var_of_means = (self.sums[1] - m * mean_of_means ** 2) / (m - 1) if m > 1 else torch.zeros_like(self.sums[0])
+        B = n * var_of_means
+        W = self.sums[2] / m
+        return W * (n - 1) / n + B / n, W
+
+    def gelman_rubin(self):
+        v_hat, W = self.v_hat_and_w()
+        return torch.sqrt(v_hat / W)
+
+
+def effective_n_from_variograms(v_hat, m, n, variogram_block):
+    """pymc3-3.1 style ESS from V_hat and a callable ``variogram_block(lag0, n_lags) ->
+    [n_lags, D]`` of globally summed squared lag differences.  Lags are requested in blocks
+    until every dimension has hit its stopping rule."""
+    D = v_hat.shape[0]
+    v_hat = v_hat.detach().cpu().numpy()
+    rho_prev = np.ones(D)
+    rho_sum = np.zeros(D)                  # sum of rho[1 : t_stop - 1]
+    done = np.zeros(D, dtype=bool)
+    history = [np.ones(D)]                 # rho[0] = 1
+    t_stop = np.full(D, n)                 # value of t when the loop ends
+    t, block = 1, 16
+    while t < n and not done.all():
+        k = min(block, n - t)
+        vg = variogram_block(t, k).detach().cpu().numpy()
+        for b in range(k):
+            lag = t + b
+            rho = 1.0 - (vg[b] / (m * (n - lag))) / (2.0 * v_hat)
+            history.append(np.where(done, np.nan, rho))
+            newly = (~done) & ((rho_prev + rho) < 0)
+            t_stop[newly] = lag + 1        # loop exits with t = lag + 1
+            done |= newly
+            rho_prev = np.where(done, rho_prev, rho)
+        t += k
+    rho_all = np.stack(history)            # [t_max, D]
+    t_end = np.where(t_stop % 2 == 1, t_stop - 1, t_stop)
+    out = np.empty(D)
+    for d in range(D):
+        s = np.nansum(rho_all[1:max(1, t_end[d] - 1), d])
+        out[d] = min(m * n, np.floor(m * n / (1.0 + 2.0 * s)))
+    return out
+
+
+def gelman_rubin_from_trace(trace, group=None):
+    """R_hat per dimension for a device trace ``[n_draws, C_local, D]`` (all ranks together)."""
+    n, C, _ = trace.shape
+    return ChainSums(local_moment_sums(trace), C, n, group).gelman_rubin()
+
+
+def effective_n_from_trace(trace, group=None):
+    """ESS per dimension for a device trace ``[n_draws, C_local, D]`` (all ranks together)."""
+    n, C, _ = trace.shape
+    cs = ChainSums(local_moment_sums(trace), C, n, group)
+    v_hat, _ = cs.v_hat_and_w()
+    return effective_n_from_variograms(
+        v_hat, cs.m, n, lambda lag0, k: _all_reduce_sum(local_variogram_sums(trace, lag0, k), group))
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's entry points
+# ---------------------------------------------------------------------------------------
+def _chains_from_get_sampler(get_sampler, n_chains, samples_per_chain):
+    """`get_sampler(session)` is called once per chain like
+    pysgmcmc/diagnostics/sample_chains.py:367-382 does; each sampler advances on the device
+    and its `samples_per_chain` draws are stacked into one ``[n, m, D]`` trace.  A sampler
+    built with ``Session(n_chains=C)`` contributes C chains at once."""
+    from ..session import Session
+    traces, names, sizes = [], None, None
+    for _ in range(n_chains):
+        session = Session(output="torch")
+        sampler = get_sampler(session)
+        trace, _ = sampler.run(samples_per_chain)
+        traces.append(trace.to(torch.float32))
+        if names is None:
+            names = [getattr(p, "name", None) or "param_%d" % i for i, p in enumerate(sampler.params)]
+            sizes = list(sampler._sizes)
+    return torch.cat(traces, dim=1).contiguous(), names, sizes
+
+
+def _per_variable(values, names, sizes):
+    out, off = {}, 0
+    values = np.asarray(values)
+    for name, n in zip(names, sizes):
+        out[name] = values[off:off + n]
+        off += n
+    return out
+
+
+def effective_sample_sizes(get_sampler, n_chains=2, samples_per_chain=100):
+    """ESS of the sampler returned by `get_sampler` (sampler_diagnostics.py:47-115):
+    dict ``variable name -> array with one value per dimension``."""
+    trace, names, sizes = _chains_from_get_sampler(get_sampler, n_chains, samples_per_chain)
+    return _per_variable(effective_n_from_trace(trace), names, sizes)
+
+
+def gelman_rubin(get_sampler, n_chains=2, samples_per_chain=100):
+    """Potential scale reduction factors (sampler_diagnostics.py:118-194)."""
+    trace, names, sizes = _chains_from_get_sampler(get_sampler, n_chains, samples_per_chain)
+    if trace.shape[1] < 2:
+        raise ValueError("Gelman-Rubin diagnostic requires multiple chains of the same length.")
+    return _per_variable(gelman_rubin_from_trace(trace).cpu().numpy(), names, sizes)

@@ -275,3 +275,21 @@ def test_sgld_on_bnn_cost_uses_generic_update_kernel():
     for _ in range(6):
         sample, cost = next(s)
     assert torch.isfinite(cost).all() and cost.shape == (C,)
+
+
+def test_k4_launch_variants_agree():
+    """Every launch shape of K4 (sgmcmc_set_bnn_tuning) computes the same cost and gradient."""
+    C, N = 23, 400
+    X, y = sinc_data(N)
+    theta = obnn.init_theta(C, seed=5, dtype=np.float64) + 0.05 * np.random.RandomState(1).standard_normal((C, 5252))
+    starts = np.random.RandomState(2).randint(0, N - 19, size=C)
+    Xb, yb = obnn.gather_minibatch(X, y, starts, 20)
+    wc, wg, _ = obnn.nll_and_grad(theta, Xb, yb, n_examples=N)
+    try:
+        for v in range(6):
+            _native.call("sgmcmc_set_bnn_tuning", v)
+            cost, grad, _ = k4(theta, X, y, starts, 20, 20, N)
+            np.testing.assert_allclose(cost, wc, rtol=3e-6, err_msg="variant %d" % v)
+            assert_grad_close(grad, wg)
+    finally:
+        _native.call("sgmcmc_set_bnn_tuning", 0)
