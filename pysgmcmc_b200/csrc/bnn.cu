@@ -115,13 +115,14 @@ __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
     const int j = u + c * TPC;
+    const bool ok = j < HID;          // TPC * COLS may exceed 50 (one warp per chain: 64 slots)
 #pragma unroll
     for (int k = 0; k < HID; ++k) {
-      w[c][k] = __ldg(th + oW + k * HID + j);
+      w[c][k] = ok ? __ldg(th + oW + k * HID + j) : 0.0f;
       sq = fmaf(w[c][k], w[c][k], sq);
     }
     w[c][HID] = w[c][HID + 1] = 0.0f;
-    b[c] = __ldg(th + ob + j);
+    b[c] = ok ? __ldg(th + ob + j) : 0.0f;
     sq = fmaf(b[c], b[c], sq);
   }
   for (int i0 = 0; i0 < batch; i0 += ROWS) {
@@ -136,7 +137,8 @@ __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int
     for (int r = 0; r < ROWS; ++r)
       if (r < n_rows) {
 #pragma unroll
-        for (int c = 0; c < COLS; ++c) out[(i0 + r) * HS + u + c * TPC] = fast_tanh(acc[r][c]);
+        for (int c = 0; c < COLS; ++c)
+          if (u + c * TPC < HID) out[(i0 + r) * HS + u + c * TPC] = fast_tanh(acc[r][c]);
       }
   }
   return sq;
@@ -151,10 +153,11 @@ __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th
   float w[COLS][HS];
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
-    const float2* row = reinterpret_cast<const float2*>(th + oW + (u + c * TPC) * HID);
+    const bool ok = u + c * TPC < HID;
+    const float2* row = reinterpret_cast<const float2*>(th + oW + (ok ? u + c * TPC : 0) * HID);
 #pragma unroll
     for (int m = 0; m < HID / 2; ++m) {
-      const float2 v = __ldg(row + m);
+      const float2 v = ok ? __ldg(row + m) : make_float2(0.0f, 0.0f);
       w[c][2 * m] = v.x;
       w[c][2 * m + 1] = v.y;
     }
@@ -173,9 +176,11 @@ __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th
       if (r < n_rows) {
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
-          const int idx = (i0 + r) * HS + u + c * TPC;
-          const float h = h_prev[idx];
-          dz_prev[idx] = acc[r][c] * fmaf(-h, h, 1.0f);
+          if (u + c * TPC < HID) {
+            const int idx = (i0 + r) * HS + u + c * TPC;
+            const float h = h_prev[idx];
+            dz_prev[idx] = acc[r][c] * fmaf(-h, h, 1.0f);
+          }
         }
       }
   }
@@ -201,7 +206,7 @@ __device__ __forceinline__ void layer_backward_weights(const float* __restrict__
   float4 hc = hp[0];
   float dn[COLS];
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) dn[c] = dz[u + c * TPC];
+  for (int c = 0; c < COLS; ++c) dn[c] = (u + c * TPC < HID) ? dz[u + c * TPC] : 0.0f;
   for (int i = 0; i < batch; ++i) {
     float d[COLS];
 #pragma unroll
@@ -211,7 +216,7 @@ __device__ __forceinline__ void layer_backward_weights(const float* __restrict__
     }
     const int inext = i + 1 < batch ? i + 1 : i;
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) dn[c] = dz[inext * HS + u + c * TPC];
+    for (int c = 0; c < COLS; ++c) dn[c] = (u + c * TPC < HID) ? dz[inext * HS + u + c * TPC] : 0.0f;
     const float4* rp = hp + i * (HS / 4);
 #pragma unroll
     for (int k4 = 0; k4 < HS / 4; ++k4) {
@@ -229,18 +234,32 @@ __device__ __forceinline__ void layer_backward_weights(const float* __restrict__
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
     const int j = u + c * TPC;
+    if (j < HID) {
 #pragma unroll
-    for (int k = 0; k < HID; ++k)
-      gr[oW + k * HID + j] = fmaf(__ldg(th + oW + k * HID + j), pscale, acc[c][k]);
-    gr[ob + j] = fmaf(__ldg(th + ob + j), pscale, db[c]);
+      for (int k = 0; k < HID; ++k)
+        gr[oW + k * HID + j] = fmaf(__ldg(th + oW + k * HID + j), pscale, acc[c][k]);
+      gr[ob + j] = fmaf(__ldg(th + ob + j), pscale, db[c]);
+    }
   }
 }
 
-template <int COLS, int NC>
+// Launch shape: TPC threads cooperate on one chain, each owning COLS of the 50 hidden units
+// (unit j = u + c * TPC; slots with j >= 50 idle), NC chains per CTA.
+//   * TPC = 50 / COLS: every slot is a real unit, chains straddle warps, CTA-wide barriers;
+//   * TPC = 32, COLS = 2: ONE WARP PER CHAIN.  64 slots for 50 units (78 % of the FFMA
+//     lanes), but every shared-memory operand load is a pure warp broadcast (1 wavefront
+//     instead of ~2), all synchronisation is __syncwarp, and the warps of a CTA run their
+//     chains independently, which is what hides the shared-memory latency (profiles/).
+template <int COLS, int TPC, int NC>
 struct BnnShape {
-  static constexpr int TPC = HID / COLS;
   static constexpr int THREADS = ((NC * TPC + 31) / 32) * 32;
+  static constexpr bool WARP = TPC == 32;
 };
+
+template <bool WARP>
+__device__ __forceinline__ void chain_sync() {
+  if constexpr (WARP) __syncwarp(); else __syncthreads();
+}
 
 // shared memory per chain, in floats
 __host__ __device__ inline int bnn_smem_floats(int batch, int n_in) {
@@ -249,10 +268,10 @@ __host__ __device__ inline int bnn_smem_floats(int batch, int n_in) {
   return x + 2 * yb + 4 * batch * HS + 64;   // X, Y, df, H1, H2, H3, E, scratch[64]
 }
 
-template <int COLS, int NC, int ROWS, int MINB, bool WANT_GRAD>
-__global__ void __launch_bounds__(BnnShape<COLS, NC>::THREADS, MINB)
+template <int COLS, int TPC, int NC, int ROWS, int MINB, bool WANT_GRAD>
+__global__ void __launch_bounds__(BnnShape<COLS, TPC, NC>::THREADS, MINB)
 bnn_nll_grad_kernel(BnnArgs a) {
-  constexpr int TPC = BnnShape<COLS, NC>::TPC;
+  constexpr bool WARP = BnnShape<COLS, TPC, NC>::WARP;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   const int lc = tid / TPC;            // chain slot in this CTA
@@ -286,48 +305,51 @@ bnn_nll_grad_kernel(BnnArgs a) {
       H1[t * HS + HID + 1] = 0.0f;
     }
   }
-  __syncthreads();
+  chain_sync<WARP>();
 
   // ---- P1: layer 1 forward (n_in -> 50) ----
   if (active) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int j = u + c * TPC;
-      const float b = __ldg(th + L.ob1 + j);
-      sq = fmaf(b, b, sq);
-      for (int i = 0; i < batch; ++i) H1[i * HS + j] = b;
-      for (int m = 0; m < n_in; ++m) {
-        const float w = __ldg(th + L.oW1 + m * HID + j);
-        sq = fmaf(w, w, sq);
-        for (int i = 0; i < batch; ++i) H1[i * HS + j] = fmaf(sX[i * n_in + m], w, H1[i * HS + j]);
+      if (j < HID) {
+        const float b = __ldg(th + L.ob1 + j);
+        sq = fmaf(b, b, sq);
+        for (int i = 0; i < batch; ++i) H1[i * HS + j] = b;
+        for (int m = 0; m < n_in; ++m) {
+          const float w = __ldg(th + L.oW1 + m * HID + j);
+          sq = fmaf(w, w, sq);
+          for (int i = 0; i < batch; ++i) H1[i * HS + j] = fmaf(sX[i * n_in + m], w, H1[i * HS + j]);
+        }
+        for (int i = 0; i < batch; ++i) H1[i * HS + j] = fast_tanh(H1[i * HS + j]);
       }
-      for (int i = 0; i < batch; ++i) H1[i * HS + j] = fast_tanh(H1[i * HS + j]);
     }
   }
-  __syncthreads();
+  chain_sync<WARP>();
   // ---- P2, P3: layers 2 and 3 forward ----
   if (active) sq += layer_forward<COLS, TPC, ROWS>(th, L.oW2, L.ob2, H1, H2, batch, u);
-  __syncthreads();
+  chain_sync<WARP>();
   if (active) sq += layer_forward<COLS, TPC, ROWS>(th, L.oW3, L.ob3, H2, H3, batch, u);
-  __syncthreads();
+  chain_sync<WARP>();
 
   // ---- P4: head f[i] = H3[i,:] . W4 + b4 : per-thread partials, reduced through E ----
   float w4[COLS];
   if (active) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
-      w4[c] = __ldg(th + L.oW4 + u + c * TPC);
+      w4[c] = (u + c * TPC < HID) ? __ldg(th + L.oW4 + u + c * TPC) : 0.0f;
       sq = fmaf(w4[c], w4[c], sq);
     }
     for (int i = 0; i < batch; ++i) {
       float p = 0.0f;
 #pragma unroll
-      for (int c = 0; c < COLS; ++c) p = fmaf(H3[i * HS + u + c * TPC], w4[c], p);
+      for (int c = 0; c < COLS; ++c)
+        if (u + c * TPC < HID) p = fmaf(H3[i * HS + u + c * TPC], w4[c], p);
       E[i * HS + u] = p;
     }
     scr[u] = sq;
   }
-  __syncthreads();
+  chain_sync<WARP>();
   if (active) {
     const float b4 = __ldg(th + L.ob4), rho = __ldg(th + L.orho);
     const float e_rho = expf(rho);
@@ -340,7 +362,7 @@ bnn_nll_grad_kernel(BnnArgs a) {
       sY[i] = diff * diff;                                           // squared error (:370)
     }
   }
-  __syncthreads();
+  chain_sync<WARP>();
   if (active && u == 0) {
     // scalar tail of the cost (:372-388) and the rho / b4 gradients, one thread per chain
     const float b4 = __ldg(th + L.ob4), rho = __ldg(th + L.orho);
@@ -371,36 +393,40 @@ bnn_nll_grad_kernel(BnnArgs a) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int j = u + c * TPC;
-      float dw = 0.0f;
-      for (int i = 0; i < batch; ++i) {
-        const float h = H3[i * HS + j], df = sDf[i];
-        dw = fmaf(h, df, dw);
-        H3[i * HS + j] = (df * w4[c]) * fmaf(-h, h, 1.0f);
+      if (j < HID) {
+        float dw = 0.0f;
+        for (int i = 0; i < batch; ++i) {
+          const float h = H3[i * HS + j], df = sDf[i];
+          dw = fmaf(h, df, dw);
+          H3[i * HS + j] = (df * w4[c]) * fmaf(-h, h, 1.0f);
+        }
+        gr[L.oW4 + j] = fmaf(w4[c], pscale, dw);
       }
-      gr[L.oW4 + j] = fmaf(w4[c], pscale, dw);
     }
   }
-  __syncthreads();
+  chain_sync<WARP>();
   // ---- layer 3 backward: dZ2 -> E (needs old W3 rows), then dW3 from H2 and dZ3 ----
   if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW3, H3, H2, E, batch, u);
   if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW3, L.ob3, H2, H3, batch, u, pscale);
-  __syncthreads();
+  chain_sync<WARP>();
   // ---- layer 2 backward: dZ1 -> H3 (dZ3 is dead), then dW2 from H1 and dZ2 ----
   if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW2, E, H1, H3, batch, u);
   if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW2, L.ob2, H1, E, batch, u, pscale);
-  __syncthreads();
+  chain_sync<WARP>();
   // ---- layer 1 backward: dW1 = X^T dZ1, db1 ----
   if (active) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int j = u + c * TPC;
-      float db = 0.0f;
-      for (int i = 0; i < batch; ++i) db += H3[i * HS + j];
-      gr[L.ob1 + j] = fmaf(__ldg(th + L.ob1 + j), pscale, db);
-      for (int m = 0; m < n_in; ++m) {
-        float dw = 0.0f;
-        for (int i = 0; i < batch; ++i) dw = fmaf(sX[i * n_in + m], H3[i * HS + j], dw);
-        gr[L.oW1 + m * HID + j] = fmaf(__ldg(th + L.oW1 + m * HID + j), pscale, dw);
+      if (j < HID) {
+        float db = 0.0f;
+        for (int i = 0; i < batch; ++i) db += H3[i * HS + j];
+        gr[L.ob1 + j] = fmaf(__ldg(th + L.ob1 + j), pscale, db);
+        for (int m = 0; m < n_in; ++m) {
+          float dw = 0.0f;
+          for (int i = 0; i < batch; ++i) dw = fmaf(sX[i * n_in + m], H3[i * HS + j], dw);
+          gr[L.oW1 + m * HID + j] = fmaf(__ldg(th + L.oW1 + m * HID + j), pscale, dw);
+        }
       }
     }
   }
@@ -408,11 +434,10 @@ bnn_nll_grad_kernel(BnnArgs a) {
 
 // ---- K10: forward only, one "chain" = (stored network k, block of <= PB test points) ----
 constexpr int PB = 32;
-template <int COLS, int NC>
-__global__ void __launch_bounds__(BnnShape<COLS, NC>::THREADS)
+template <int COLS, int TPC, int NC>
+__global__ void __launch_bounds__(BnnShape<COLS, TPC, NC>::THREADS)
 bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X, float* __restrict__ out,
                    int64_t n_nets, int64_t n_points, BnnLayout L) {
-  constexpr int TPC = BnnShape<COLS, NC>::TPC;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   const int lc = tid / TPC, u = tid - lc * TPC;
@@ -482,23 +507,23 @@ constexpr int K4_COLS = 1;      // K10 uses this shape
 constexpr int K4_NC = 5;
 
 static int g_bnn_variant = 0;
-int bnn_variant_count() { return 6; }
+int bnn_variant_count() { return 10; }
 void set_bnn_variant(int v) { g_bnn_variant = v; }
 
-template <int COLS, int NC, int ROWS, int MINB>
+template <int COLS, int TPC, int NC, int ROWS, int MINB>
 static int launch_variant(const BnnArgs& a, cudaStream_t st) {
-  using Shape = BnnShape<COLS, NC>;
+  using Shape = BnnShape<COLS, TPC, NC>;
   const size_t smem = (size_t)NC * bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
   SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED,
              "minibatch of %d rows x %d inputs needs %zu B of shared memory per CTA (max 232448)",
              a.batch, a.L.n_in, smem);
   const unsigned blocks = (unsigned)((a.n_chains + NC - 1) / NC);
   if (a.grad != nullptr) {
-    auto k = bnn_nll_grad_kernel<COLS, NC, ROWS, MINB, true>;
+    auto k = bnn_nll_grad_kernel<COLS, TPC, NC, ROWS, MINB, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, Shape::THREADS, smem, st>>>(a);
   } else {
-    auto k = bnn_nll_grad_kernel<COLS, NC, ROWS, MINB, false>;
+    auto k = bnn_nll_grad_kernel<COLS, TPC, NC, ROWS, MINB, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, Shape::THREADS, smem, st>>>(a);
   }
@@ -506,17 +531,21 @@ static int launch_variant(const BnnArgs& a, cudaStream_t st) {
 }
 
 static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
-  // a large minibatch may not fit the default variant's shared memory: fall back to fewer
-  // chains per CTA
+  // a large minibatch may not fit the default variant's shared memory: fall back to one
+  // chain per CTA
   const size_t per_chain = bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
-  if (per_chain * 5 > 227 * 1024) return launch_variant<1, 1, 4, 1>(a, st);
+  if (per_chain * 5 > 227 * 1024) return launch_variant<1, 50, 1, 4, 1>(a, st);
   switch (g_bnn_variant) {
-    case 1: return launch_variant<1, 4, 4, 3>(a, st);
-    case 2: return launch_variant<2, 10, 4, 1>(a, st);
-    case 3: return launch_variant<2, 5, 4, 2>(a, st);
-    case 4: return launch_variant<1, 5, 5, 2>(a, st);
-    case 5: return launch_variant<1, 2, 4, 6>(a, st);
-    default: return launch_variant<1, 5, 4, 2>(a, st);
+    case 1: return launch_variant<1, 50, 4, 4, 3>(a, st);
+    case 2: return launch_variant<2, 25, 10, 4, 1>(a, st);
+    case 3: return launch_variant<2, 25, 5, 4, 2>(a, st);
+    case 4: return launch_variant<1, 50, 5, 5, 2>(a, st);
+    case 5: return launch_variant<1, 50, 2, 4, 6>(a, st);
+    case 6: return launch_variant<2, 32, 4, 4, 3>(a, st);    // one warp per chain, 4 chains / CTA
+    case 7: return launch_variant<2, 32, 2, 4, 6>(a, st);    // one warp per chain, 2 chains / CTA
+    case 8: return launch_variant<2, 32, 4, 5, 3>(a, st);    // ... 5 rows in flight
+    case 9: return launch_variant<2, 32, 1, 4, 12>(a, st);   // one warp per CTA
+    default: return launch_variant<1, 50, 5, 4, 2>(a, st);
   }
 }
 
@@ -617,10 +646,10 @@ extern "C" int sgmcmc_bnn_predict_f32(const float* theta, const float* X, float*
   SG_REQUIRE(theta && X && out, SGMCMC_E_INVALID, "bnn_predict: NULL pointer");
   SG_REQUIRE(n_in >= 1 && n_in <= 64, SGMCMC_E_UNSUPPORTED, "bnn: n_in must be in [1, 64] (got %d)", n_in);
   const BnnLayout L = make_layout(n_in);
-  using Shape = BnnShape<K4_COLS, K4_NC>;
+  using Shape = BnnShape<K4_COLS, HID / K4_COLS, K4_NC>;
   const size_t smem = (size_t)K4_NC * bnn_smem_floats(PB, n_in) * sizeof(float);
   SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED, "bnn_predict: n_in too large for shared memory");
-  auto k = bnn_predict_kernel<K4_COLS, K4_NC>;
+  auto k = bnn_predict_kernel<K4_COLS, HID / K4_COLS, K4_NC>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t items = n_nets * ((n_points + PB - 1) / PB);
   k<<<(unsigned)((items + K4_NC - 1) / K4_NC), Shape::THREADS, smem, (cudaStream_t)stream>>>(

@@ -8,6 +8,8 @@ from itertools import islice
 
 import numpy as np
 
+from ..tensor_utils import get_name
+
 
 class PYSGMCMCTrace(object):
     """A single chain of samples from a sampler (sample_chains.py:14-88)."""
@@ -48,8 +50,7 @@ class PYSGMCMCTrace(object):
         reference, `keep_every` is accepted but not applied, :166-169)."""
         samples = [sample for sample, _ in islice(sampler, n_samples)]
         if varnames is None:
-            varnames = [getattr(param, "name", None) or "param_%d" % i
-                        for i, param in enumerate(sampler.params)]
+            varnames = [get_name(param, "param_%d" % i) for i, param in enumerate(sampler.params)]
         return PYSGMCMCTrace(chain_id, samples, varnames)
 
     def __getitem__(self, index):

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from .. import _native
+from ..tensor_utils import get_name
 
 __all__ = ("effective_sample_sizes", "gelman_rubin", "gelman_rubin_from_trace",
            "effective_n_from_trace", "ChainSums")
@@ -148,7 +149,7 @@ def _chains_from_get_sampler(get_sampler, n_chains, samples_per_chain):
         trace, _ = sampler.run(samples_per_chain)
         traces.append(trace.to(torch.float32))
         if names is None:
-            names = [getattr(p, "name", None) or "param_%d" % i for i, p in enumerate(sampler.params)]
+            names = [get_name(p, "param_%d" % i) for i, p in enumerate(sampler.params)]
             sizes = list(sampler._sizes)
     return torch.cat(traces, dim=1).contiguous(), names, sizes
 

@@ -1,0 +1,270 @@
+"""BayesianNeuralNetwork -- the caller of the sampler hot path, same interface as
+pysgmcmc/models/bayesian_neural_network.py:146-630 (`train` / `predict`), running on the
+CUDA kernels: minibatch indices K7, cost + gradient K4, SGHMC update K1 (driven from C,
+K5) and the predictive forward pass K10.
+
+What is the same: constructor arguments and their validation, normalisation, the sampling
+schedule (burn-in, one network kept every `sample_steps` iterations after burn-in, stop at
+`n_nets`), the minibatch index stream (bit-exact with the reference's
+``generate_batches(seed=seed)``), the predictive mean / variance formulas.
+What differs: `session` is a :class:`pysgmcmc_b200.Session`; `dtype` is a torch dtype and
+defaults to float32; `get_net` other than `get_default_net` is not supported by the
+fused kernels (the network architecture is compiled in); weight initialisation uses a torch
+generator (TensorFlow's stream is not reproducible).
+"""
+import logging
+from collections import deque
+from time import time
+
+import numpy as np
+import torch
+
+from .. import _native
+from ..data_batches import DeviceBatchGenerator, generate_batches
+from ..placeholders import placeholder
+from ..sampling import Sampler
+from ..session import Session
+from ..stepsize_schedules import ConstantStepsizeSchedule
+from .base_model import (BaseModel, zero_mean_unit_var_normalization,
+                         zero_mean_unit_var_unnormalization)
+from .bnn_cost import (BayesianNeuralNetworkNLL, default_net_params, log_variance_prior_log_like,  # noqa: F401
+                       network_output, weight_prior_log_like)
+
+
+def get_default_net(inputs, params):
+    """The default architecture (bayesian_neural_network.py:28-69): three 50-unit tanh layers,
+    a linear head and a learned log-variance, as a function of explicit parameters."""
+    return network_output(params, inputs)
+
+
+class BayesianNeuralNetwork(object):
+    def __init__(self, session=None, sampling_method=Sampler.SGHMC,
+                 get_net=get_default_net,
+                 batch_generator=generate_batches,
+                 batch_size=20,
+                 stepsize_schedule=ConstantStepsizeSchedule(np.sqrt(1e-4)),
+                 n_nets=100, n_iters=50000,
+                 burn_in_steps=1000, sample_steps=100,
+                 normalize_input=True, normalize_output=True,
+                 seed=None, dtype=torch.float32, **sampler_kwargs):
+        # Sanitize inputs (bayesian_neural_network.py:238-268)
+        assert isinstance(n_nets, int)
+        assert isinstance(n_iters, int)
+        assert isinstance(burn_in_steps, int)
+        assert isinstance(sample_steps, int)
+        assert isinstance(batch_size, int)
+        assert isinstance(dtype, torch.dtype)
+
+        assert n_nets > 0
+        assert n_iters > 0
+        assert burn_in_steps >= 0
+        assert sample_steps > 0
+        assert batch_size > 0
+
+        assert callable(get_net)
+        assert callable(batch_generator)
+
+        assert hasattr(stepsize_schedule, "update")
+        assert hasattr(stepsize_schedule, "__next__")
+
+        if not Sampler.is_supported(sampling_method):
+            raise ValueError(
+                "'BayesianNeuralNetwork.__init__' received unsupported input "
+                "for parameter 'sampling_method'. Input was: {input}.\n"
+                "Supported sampling methods are enumerated in "
+                "'Sampler' enum type.".format(input=sampling_method)
+            )
+        if get_net is not get_default_net:
+            raise ValueError("the B200 engine compiles the default architecture (get_default_net) "
+                             "into its kernels; custom `get_net` callables are not supported")
+
+        self.sampling_method = sampling_method
+        self.stepsize_schedule = stepsize_schedule
+        self.get_net = get_net
+        self.batch_generator = batch_generator
+        self.normalize_input = normalize_input
+        self.normalize_output = normalize_output
+        self.n_nets = n_nets
+        self.n_iters = n_iters
+        self.batch_size = batch_size
+        self.sampler_kwargs = sampler_kwargs
+        self.burn_in_steps = burn_in_steps
+        self.sample_steps = sample_steps
+        self.samples = deque(maxlen=n_nets)
+        self.seed = seed
+        self.dtype = dtype
+        self.session = Session() if session is None else session
+        self.is_trained = False
+
+    # ------------------------------------------------------------------ train
+    @BaseModel._check_shapes_train
+    def train(self, X, y, *args, **kwargs):
+        """Sample `n_nets` networks from the posterior given X ``(N, D)``, y ``(N,)``
+        (bayesian_neural_network.py:391-533)."""
+        start_time = time()
+
+        self.X, self.y = X, y
+        if self.normalize_input:
+            self.X, self.x_mean, self.x_std = zero_mean_unit_var_normalization(self.X)
+        if self.normalize_output:
+            self.y, self.y_mean, self.y_std = zero_mean_unit_var_normalization(self.y)
+
+        n_datapoints, n_inputs = X.shape
+        device = self.session.device
+        single_chain = Session(device=device, n_chains=None, output="torch", stream=self.session.stream)
+
+        # minibatches: the reference's default generator is replaced by its on-device twin
+        # (same RandomState stream, data resident in HBM); any other generator is called like
+        # the reference calls it and feeds host minibatches through placeholders
+        if self.batch_generator is generate_batches:
+            seed = int(np.random.randint(1, 100000)) if self.seed is None else self.seed    # data_batches.py:101-102
+            batches = DeviceBatchGenerator(n_datapoints, self.batch_size, seeds=[seed], device=device)
+            self.nll = BayesianNeuralNetworkNLL(n_datapoints, self.batch_size, X=self.X, y=self.y,
+                                                starts_placeholder=batches.starts_placeholder,
+                                                device=device, dtype=self.dtype)
+        else:
+            self.X_Minibatch = placeholder(name="X_Minibatch")
+            self.Y_Minibatch = placeholder(name="Y_Minibatch")
+            batches = self.batch_generator(x=self.X, x_placeholder=self.X_Minibatch,
+                                           y=self.y, y_placeholder=self.Y_Minibatch,
+                                           batch_size=self.batch_size, seed=self.seed)
+            self.nll = BayesianNeuralNetworkNLL(n_datapoints, self.batch_size, n_in=n_inputs,
+                                                x_placeholder=self.X_Minibatch,
+                                                y_placeholder=self.Y_Minibatch,
+                                                device=device, dtype=self.dtype)
+
+        self.network_params = default_net_params(n_inputs, seed=self.seed, dtype=self.dtype, device=device)
+        self.samples.clear()
+
+        self.sampler_kwargs.update({
+            "params": self.network_params,
+            "cost_fun": self.nll,
+            "batch_generator": batches,
+            "session": single_chain,
+            "seed": self.seed,
+            "dtype": self.dtype,
+            "stepsize_schedule": self.stepsize_schedule,
+        })
+        if Sampler.is_burn_in_mcmc(self.sampling_method):
+            self.sampler_kwargs.update({
+                "scale_grad": n_datapoints,
+                "burn_in_steps": self.burn_in_steps,
+            })
+
+        self.sampler = Sampler.get_sampler(self.sampling_method, **self.sampler_kwargs)
+
+        logging.info("Starting sampling")
+
+        def log_full_training_error(iteration_index, is_sampling):
+            if not logging.getLogger().isEnabledFor(logging.INFO):
+                return
+            total_nll, total_mse = self._full_data_nll_mse()
+            seconds_elapsed = time() - start_time
+            if is_sampling:
+                logging.info("Iter {:8d} : NLL = {:.4e} MSE = {:.4e} "
+                             "Time = {:5.2f}".format(iteration_index, total_nll, total_mse, seconds_elapsed))
+            else:
+                logging.info("Iter {:8d} : NLL = {:.4e} MSE = {:.4e} "
+                             "Samples = {} Time = {:5.2f}".format(iteration_index, total_nll, total_mse,
+                                                                  len(self.samples), seconds_elapsed))
+
+        logging_intervals = {"burn-in": 512, "sampling": self.sample_steps}
+
+        # The reference inspects every iteration of islice(sampler, n_iters); only the
+        # iterations where it logs or keeps a sample matter, so the chain advances on the
+        # device from one such iteration to the next (bayesian_neural_network.py:510-531).
+        steps_done = 0
+        for iteration_index in range(self.n_iters):
+            burning_in = iteration_index <= self.burn_in_steps
+            log_burn = burning_in and iteration_index % logging_intervals["burn-in"] == 0
+            keep = not burning_in and iteration_index % logging_intervals["sampling"] == 0
+            if not (log_burn or keep):
+                continue
+            self.sampler.run(iteration_index + 1 - steps_done, keep_every=10 ** 9)
+            steps_done = iteration_index + 1
+            if log_burn:
+                log_full_training_error(iteration_index, is_sampling=False)
+            if keep:
+                log_full_training_error(iteration_index, is_sampling=True)
+                self.samples.append(self.sampler._theta[0].clone())
+                if len(self.samples) == self.n_nets:
+                    break
+        if steps_done < self.n_iters and len(self.samples) < self.n_nets:
+            self.sampler.run(self.n_iters - steps_done, keep_every=10 ** 9)
+
+        self.is_trained = True
+
+    def _full_data_nll_mse(self):
+        """NLL and MSE of the current parameters on the full training set (the reference's
+        `log_full_training_error`, :470-493; differentiable torch path, logging only)."""
+        saved = None
+        ph = getattr(self.nll, "starts_placeholder", None)
+        if ph is not None:
+            saved, ph.value = ph.value, None
+        try:
+            if self.nll.X is not None:
+                cost = self.nll([p.detach() for p in self.network_params])
+            else:
+                self.X_Minibatch.value, self.Y_Minibatch.value = self.X, self.y.reshape(-1, 1)
+                cost = self.nll([p.detach() for p in self.network_params])
+            return float(cost), float(self.nll.last_mse)
+        finally:
+            if ph is not None:
+                ph.value = saved
+
+    # ------------------------------------------------------------------ predict
+    def compute_network_output(self, params, input_data):
+        """Network output ``(N, 2)`` = (mean, log variance) for one parameter sample
+        (bayesian_neural_network.py:535-557); `params` is a flat ``[D]`` tensor or the list of
+        9 parameter arrays."""
+        device = self.session.device
+        if isinstance(params, (list, tuple)):
+            params = torch.cat([torch.as_tensor(np.asarray(p) if not isinstance(p, torch.Tensor) else p
+                                                ).reshape(-1) for p in params])
+        theta = params.to(device=device, dtype=torch.float32).reshape(1, -1).contiguous()
+        return self._forward(theta, input_data)[0]
+
+    def _forward(self, theta, input_data):
+        device = self.session.device
+        X = torch.as_tensor(np.asarray(input_data), dtype=torch.float32, device=device).contiguous()
+        n_nets, n_points = theta.shape[0], X.shape[0]
+        out = torch.empty((n_nets, n_points, 2), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _native.call("sgmcmc_bnn_predict_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(out),
+                         n_nets, X.shape[1], n_points, _native.stream_ptr(self.session.stream))
+        return out.cpu().numpy().astype(np.float64)
+
+    @BaseModel._check_shapes_predict
+    def predict(self, X_test, return_individual_predictions=False, *args, **kwargs):
+        """Predictive mean and variance at X_test ``(N, D)`` (bayesian_neural_network.py:560-630)."""
+        if not self.is_trained:
+            raise ValueError(
+                "Calling `bnn.predict()` on an untrained "
+                "Bayesian Neural Network 'bnn' is not supported! "
+                "Please call `bnn.train()` before calling `bnn.predict()`"
+            )
+
+        if self.normalize_input:
+            X_, _, _ = zero_mean_unit_var_normalization(X_test, self.x_mean, self.x_std)
+        else:
+            X_ = X_test
+
+        theta = torch.stack(list(self.samples)).to(torch.float32).contiguous()
+        out = self._forward(theta, X_)                      # [n_nets, N, 2]
+        f_out = out[:, :, 0]
+        theta_noise = np.exp(out[:, :, 1])
+
+        if return_individual_predictions:
+            if self.normalize_output:
+                f_out = zero_mean_unit_var_unnormalization(f_out, self.y_mean, self.y_std)
+                theta_noise *= self.y_std ** 2
+            return f_out, theta_noise
+
+        mean_prediction = np.mean(f_out, axis=0)
+        variance_prediction = np.mean((f_out - mean_prediction) ** 2, axis=0)
+
+        if self.normalize_output:
+            mean_prediction = zero_mean_unit_var_unnormalization(mean_prediction, self.y_mean, self.y_std)
+            variance_prediction *= self.y_std ** 2
+
+        return mean_prediction, variance_prediction

@@ -30,3 +30,26 @@ def safe_divide(x, y, small_constant=1e-16, name=None):
 def safe_sqrt(x, clip_value_min=0.0, clip_value_max=float("inf"), name=None):
     """``sqrt(clip(x, min, max))`` (tensor_utils.py:319-323)."""
     return torch.sqrt(torch.clamp(torch.as_tensor(x), min=clip_value_min, max=clip_value_max))
+
+
+# ---- variable names --------------------------------------------------------------------
+# tf.Variable objects carry a `name` the reference's diagnostics use as dictionary keys
+# (pysgmcmc/diagnostics/sample_chains.py:166-176).  torch tensors have no writable `name`,
+# so names live in a side table keyed by tensor identity.
+import weakref
+
+_NAMES = {}
+
+
+def set_name(tensor, name):
+    """Give `tensor` a variable name (returned by `get_name`, used by the diagnostics)."""
+    key = id(tensor)
+    _NAMES[key] = (weakref.ref(tensor, lambda _, key=key: _NAMES.pop(key, None)), str(name))
+    return tensor
+
+
+def get_name(tensor, default=None):
+    entry = _NAMES.get(id(tensor))
+    if entry is not None and entry[0]() is tensor:
+        return entry[1]
+    return default

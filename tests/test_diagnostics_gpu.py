@@ -13,6 +13,7 @@ from pysgmcmc_b200.diagnostics.objective_functions import gmm1_log_likelihood, t
 from pysgmcmc_b200.diagnostics.sampler_diagnostics import (effective_n_from_trace, gelman_rubin_from_trace,
                                                            local_moment_sums, local_variogram_sums)
 from pysgmcmc_b200.samplers import SGHMCSampler
+from pysgmcmc_b200.tensor_utils import set_name
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -57,8 +58,7 @@ def test_rhat_and_ess_match_oracle(phi):
 def test_reference_entry_points():
     """sampler_diagnostics.py:89-107,169-187: dict keyed by variable name, one value per dimension."""
     def get_sampler(session):
-        x = torch.tensor([1.0, 2.0], device=DEV)
-        x.name = "x:0"
+        x = set_name(torch.tensor([1.0, 2.0], device=DEV), "x:0")
         return SGHMCSampler(params=[x], cost_fun=lambda params: (params[0] ** 2).sum(), session=session,
                             burn_in_steps=10)
     ess = effective_sample_sizes(get_sampler)

@@ -102,5 +102,31 @@ if __name__ == "__main__":
         launches(sys.argv[2])
     elif mode == "rep":
         rep(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
-    else:
+    elif mode == "source":
         source(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 25)
+
+
+def opcodes(path, top=25):
+    """Dynamic instruction mix: warp-level executed instructions per SASS opcode."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True).stdout
+    hdr, cnt, smp = None, collections.Counter(), collections.Counter()
+    for r in csv.reader(io.StringIO(out)):
+        if r and r[0] == "Address":
+            hdr = r
+            continue
+        if hdr is None or len(r) != len(hdr) or not r[0].startswith("0x"):
+            continue
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+(\.[A-Z0-9_]+)?)", r[1])
+        op = m.group(2) if m else r[1][:12]
+        op = op.split(".")[0] if not op.startswith(("LDS", "LDG", "STG", "STS", "MUFU")) else op
+        cnt[op] += float(r[hdr.index("Instructions Executed")] or 0)
+        smp[op] += float(r[hdr.index("# Samples")] or 0)
+    tot, tots = sum(cnt.values()) or 1, sum(smp.values()) or 1
+    print("%-14s %14s %7s %9s" % ("opcode", "warp-inst", "share", "samples%"))
+    for op, c in cnt.most_common(top):
+        print("%-14s %14.0f %6.1f%% %8.1f%%" % (op, c, 100 * c / tot, 100 * smp[op] / tots))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "opcodes":
+    opcodes(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 25)
