@@ -11,7 +11,8 @@ Workload (BASELINE.json configs[3], one GPU's shard; weak scaling over GPUs):
   scale_grad = N; every chain has its own MT19937 minibatch stream and Philox noise
   substream.  A "step" is one sampler step of every chain: on-device minibatch start
   indices (K7), BNN cost + gradient (K4) and the fused SGHMC update (K1), all burn-in steps
-  (the 44 B/element variant of the update).
+  (the 44 B/element variant of the update); every 100th sample and cost is kept on the
+  device (the thinning of BayesianNeuralNetwork, sample_steps = 100).
 
 `value`   : chain-steps/s with everything resident in HBM (CUDA events, max over ranks).
 `e2e`     : the same metric through the C ABI with HOST buffers every step: minibatch start
@@ -237,13 +238,13 @@ def run_b200(args):
 
     # ---- device-resident throughput: `value` -------------------------------------------
     sampler, gen, nll = build()
-    sampler.run(W)
+    sampler.run(W, keep_every=max(W, 1))
     barrier()
     launches0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record()
-        sampler.run(K)
+        trace, costs = sampler.run(K, keep_every=SAMPLE_STEPS)   # thinned like BayesianNeuralNetwork
         e1.record()
         barrier()
     launches = _native.launch_count() - launches0
