@@ -4,24 +4,29 @@
 // K5: the host-side pipeline K4 -> K1 for `n_steps` steps of BNN-SGHMC,
 // K10: the forward pass over stored networks for the predictive.
 //
-// Work decomposition (K4).  A chain's step is 8 small GEMMs over a 20-row minibatch
-// (305 k FFMA).  A CTA owns NC chains; TPC = 50 / COLS threads cooperate on one chain and
-// thread u owns COLS of the 50 hidden units.  Every phase is "weights stationary in
-// registers": the thread loads its column (forward, dW) or row (dH) of the 50x50 kernel
-// straight from global memory into 50 registers per owned unit and streams the
-// activations of the minibatch from shared memory with 128-bit broadcast loads, four
-// batch rows in flight.  Activations (3 x B x 50) and one dZ buffer live in shared memory
-// (17 KB per chain); the gradient leaves in registers-to-global coalesced stores, so the
-// only HBM traffic is theta in and grad out (42 KB per chain-step).
-// The kernel is bound by the FP32 pipe and by shared-memory operand bandwidth, not by
-// HBM or tensor cores (DESIGN.md "K4").
+// Work decomposition (K4).  A chain's step is 6 small GEMMs over a 20-row minibatch plus
+// the 1-wide input / output layers (305 k FFMA).  A CTA owns NC chains; TPC threads
+// cooperate on one chain and thread u owns COLS of the 50 hidden units (unit j = u + c*TPC).
+// Every GEMM phase is "weights stationary in registers": the thread loads its column
+// (forward), row (backward-data) of the 50x50 kernel straight from global memory into 52
+// registers per owned unit and streams the activations of the minibatch from shared memory
+// with 128-bit warp-broadcast loads.  The activations H1, H2, H3 ([B x 52] each, rows padded
+// 50 -> 52 so every k-loop is 13 float4 steps) are the only shared memory (13 KB per chain);
+// backward overwrites them in place with dZ3, dZ2, dZ1.  The gradient leaves as coalesced
+// register-to-global stores, so HBM traffic is theta in and grad out (42 KB per chain-step).
+//
+// What bounds it (profiles/, DESIGN.md "K4"): on this SM a broadcast LDS.128 costs ~2.6
+// cycles that do NOT overlap FFMA issue (tools/micro/lds_bcast_bench.cu: time ~= FFMA/4 +
+// 2.6 * LDS.128), and each loaded activation word feeds only COLS FFMAs per thread.  COLS is
+// therefore the lever (fewer operand loads per FFMA), paid for with 52 registers per unit.
 #include "sampler_math.cuh"
 
 namespace sgmcmc {
 
 constexpr int HID = 50;      // hidden width of get_default_net (bayesian_neural_network.py:30-49)
 constexpr int HS = 52;       // row stride of the activation buffers: rows stay 16-byte aligned;
-                             // columns 50, 51 are zero padding so every k-loop is 13 float4 steps
+                             // columns 50, 51 are zero padding
+constexpr int K4S = HS / 4;  // float4 steps per k-loop
 
 struct BnnLayout {
   int n_in, D;
@@ -70,8 +75,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 
 // acc[r][c] += sum_k act[row r][k] * w[c][k]  for ROWS rows of a [B x HS] activation buffer.
-// The 128-bit broadcast loads of step k4+1 are issued before the FFMAs of step k4
-// (software pipelining: the shared-memory latency was the top stall in the ncu source view).
+// The 128-bit broadcast loads of step k4+1 are issued before the FFMAs of step k4.
 template <int COLS, int ROWS>
 __device__ __forceinline__ void dot_rows(const float* __restrict__ act, int i0, int n_rows,
                                          const float (&w)[COLS][HS], float (&acc)[ROWS][COLS]) {
@@ -83,8 +87,8 @@ __device__ __forceinline__ void dot_rows(const float* __restrict__ act, int i0, 
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) hc[r] = rp[r][0];
 #pragma unroll
-  for (int k4 = 0; k4 < HS / 4; ++k4) {
-    if (k4 + 1 < HS / 4) {
+  for (int k4 = 0; k4 < K4S; ++k4) {
+    if (k4 + 1 < K4S) {
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) hn[r] = rp[r][k4 + 1];
     }
@@ -97,7 +101,7 @@ __device__ __forceinline__ void dot_rows(const float* __restrict__ act, int i0, 
         acc[r][c] = fmaf(hc[r].z, w[c][4 * k4 + 2], acc[r][c]);
         acc[r][c] = fmaf(hc[r].w, w[c][4 * k4 + 3], acc[r][c]);
       }
-    if (k4 + 1 < HS / 4) {
+    if (k4 + 1 < K4S) {
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) hc[r] = hn[r];
     }
@@ -115,7 +119,7 @@ __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
     const int j = u + c * TPC;
-    const bool ok = j < HID;          // TPC * COLS may exceed 50 (one warp per chain: 64 slots)
+    const bool ok = j < HID;          // TPC * COLS may exceed 50 (idle unit slots)
 #pragma unroll
     for (int k = 0; k < HID; ++k) {
       w[c][k] = ok ? __ldg(th + oW + k * HID + j) : 0.0f;
@@ -144,12 +148,12 @@ __device__ __forceinline__ float layer_forward(const float* __restrict__ th, int
   return sq;
 }
 
-// dZ_prev[i][j] = (sum_m dZ[i][m] W[j][m]) * (1 - H_prev[i][j]^2), for the thread's units j
+// In place: h[i][j] <- (sum_m dz[i][m] W[j][m]) * (1 - h[i][j]^2)  for the thread's units j,
+// i.e. the activations of the layer below become its dZ.
 template <int COLS, int TPC, int ROWS>
 __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th, int oW,
-                                                    const float* __restrict__ dz,
-                                                    const float* __restrict__ h_prev,
-                                                    float* __restrict__ dz_prev, int batch, int u) {
+                                                    const float* __restrict__ dz, float* __restrict__ h,
+                                                    int batch, int u) {
   float w[COLS][HS];
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
@@ -178,8 +182,8 @@ __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th
         for (int c = 0; c < COLS; ++c) {
           if (u + c * TPC < HID) {
             const int idx = (i0 + r) * HS + u + c * TPC;
-            const float h = h_prev[idx];
-            dz_prev[idx] = acc[r][c] * fmaf(-h, h, 1.0f);
+            const float hv = h[idx];
+            h[idx] = acc[r][c] * fmaf(-hv, hv, 1.0f);
           }
         }
       }
@@ -187,69 +191,68 @@ __device__ __forceinline__ void layer_backward_data(const float* __restrict__ th
 }
 
 // dW[k][j] = sum_i H_prev[i][k] dZ[i][j], db[j] = sum_i dZ[i][j]  (+ weight-prior term),
-// written to grad for the thread's columns j.
-template <int COLS, int TPC>
+// written to grad for the thread's columns j.  The k range is walked in KPASS chunks so
+// that the COLS x chunk accumulators fit the register budget; every chunk streams only its
+// own part of the H_prev rows, so the operand traffic does not grow with KPASS.
+template <int COLS, int TPC, int KPASS>
 __device__ __forceinline__ void layer_backward_weights(const float* __restrict__ th,
                                                        float* __restrict__ gr, int oW, int ob,
                                                        const float* __restrict__ h_prev,
                                                        const float* __restrict__ dz, int batch, int u,
                                                        float pscale) {
-  float acc[COLS][HS], db[COLS];
-#pragma unroll
-  for (int c = 0; c < COLS; ++c) {
-    db[c] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < HS; ++k) acc[c][k] = 0.0f;
-  }
-  // flat (row, k4) walk with a one-step look-ahead on the broadcast loads
+  constexpr int CH = (K4S + KPASS - 1) / KPASS;       // float4 steps per chunk
   const float4* hp = reinterpret_cast<const float4*>(h_prev);
-  float4 hc = hp[0];
-  float dn[COLS];
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) dn[c] = (u + c * TPC < HID) ? dz[u + c * TPC] : 0.0f;
-  for (int i = 0; i < batch; ++i) {
-    float d[COLS];
+  for (int pass = 0; pass < KPASS; ++pass) {
+    const int k40 = pass * CH;
+    float acc[COLS][4 * CH], db[COLS];
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
-      d[c] = dn[c];
-      db[c] += d[c];
+      db[c] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4 * CH; ++k) acc[c][k] = 0.0f;
     }
-    const int inext = i + 1 < batch ? i + 1 : i;
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) dn[c] = (u + c * TPC < HID) ? dz[inext * HS + u + c * TPC] : 0.0f;
-    const float4* rp = hp + i * (HS / 4);
-#pragma unroll
-    for (int k4 = 0; k4 < HS / 4; ++k4) {
-      const float4 h = hc;
-      hc = (k4 + 1 < HS / 4) ? rp[k4 + 1] : hp[inext * (HS / 4)];
+    for (int i = 0; i < batch; ++i) {
+      float d[COLS];
 #pragma unroll
       for (int c = 0; c < COLS; ++c) {
-        acc[c][4 * k4 + 0] = fmaf(h.x, d[c], acc[c][4 * k4 + 0]);
-        acc[c][4 * k4 + 1] = fmaf(h.y, d[c], acc[c][4 * k4 + 1]);
-        acc[c][4 * k4 + 2] = fmaf(h.z, d[c], acc[c][4 * k4 + 2]);
-        acc[c][4 * k4 + 3] = fmaf(h.w, d[c], acc[c][4 * k4 + 3]);
+        d[c] = (u + c * TPC < HID) ? dz[i * HS + u + c * TPC] : 0.0f;
+        db[c] += d[c];
+      }
+      const float4* rp = hp + i * K4S + k40;
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        if (k40 + q < K4S) {
+          const float4 h = rp[q];
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) {
+            acc[c][4 * q + 0] = fmaf(h.x, d[c], acc[c][4 * q + 0]);
+            acc[c][4 * q + 1] = fmaf(h.y, d[c], acc[c][4 * q + 1]);
+            acc[c][4 * q + 2] = fmaf(h.z, d[c], acc[c][4 * q + 2]);
+            acc[c][4 * q + 3] = fmaf(h.w, d[c], acc[c][4 * q + 3]);
+          }
+        }
       }
     }
-  }
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) {
-    const int j = u + c * TPC;
-    if (j < HID) {
+    for (int c = 0; c < COLS; ++c) {
+      const int j = u + c * TPC;
+      if (j < HID) {
 #pragma unroll
-      for (int k = 0; k < HID; ++k)
-        gr[oW + k * HID + j] = fmaf(__ldg(th + oW + k * HID + j), pscale, acc[c][k]);
-      gr[ob + j] = fmaf(__ldg(th + ob + j), pscale, db[c]);
+        for (int kk = 0; kk < 4 * CH; ++kk) {
+          const int k = 4 * k40 + kk;
+          if (k < HID) gr[oW + k * HID + j] = fmaf(__ldg(th + oW + k * HID + j), pscale, acc[c][kk]);
+        }
+        if (pass == 0) gr[ob + j] = fmaf(__ldg(th + ob + j), pscale, db[c]);
+      }
     }
   }
 }
 
 // Launch shape: TPC threads cooperate on one chain, each owning COLS of the 50 hidden units
-// (unit j = u + c * TPC; slots with j >= 50 idle), NC chains per CTA.
-//   * TPC = 50 / COLS: every slot is a real unit, chains straddle warps, CTA-wide barriers;
-//   * TPC = 32, COLS = 2: ONE WARP PER CHAIN.  64 slots for 50 units (78 % of the FFMA
-//     lanes), but every shared-memory operand load is a pure warp broadcast (1 wavefront
-//     instead of ~2), all synchronisation is __syncwarp, and the warps of a CTA run their
-//     chains independently, which is what hides the shared-memory latency (profiles/).
+// (slots with j >= 50 idle), NC chains per CTA.  TPC == 32 is "one warp per chain"
+// (__syncwarp only, 64 slots for 50 units); otherwise chains straddle warps and the phases
+// are separated by CTA barriers.
 template <int COLS, int TPC, int NC>
 struct BnnShape {
   static constexpr int THREADS = ((NC * TPC + 31) / 32) * 32;
@@ -261,17 +264,18 @@ __device__ __forceinline__ void chain_sync() {
   if constexpr (WARP) __syncwarp(); else __syncthreads();
 }
 
-// shared memory per chain, in floats
+// shared memory per chain, in floats: X, Y, df, H1, H2, H3, scratch[128]
 __host__ __device__ inline int bnn_smem_floats(int batch, int n_in) {
   const int x = ((batch * n_in + 3) / 4) * 4;
   const int yb = ((batch + 3) / 4) * 4;
-  return x + 2 * yb + 4 * batch * HS + 64;   // X, Y, df, H1, H2, H3, E, scratch[64]
+  return x + 2 * yb + 3 * batch * HS + 128;
 }
 
-template <int COLS, int TPC, int NC, int ROWS, int MINB, bool WANT_GRAD>
+template <int COLS, int TPC, int NC, int ROWS, int KPASS, int MINB, bool WANT_GRAD>
 __global__ void __launch_bounds__(BnnShape<COLS, TPC, NC>::THREADS, MINB)
 bnn_nll_grad_kernel(BnnArgs a) {
   constexpr bool WARP = BnnShape<COLS, TPC, NC>::WARP;
+  static_assert(TPC <= 64, "scratch layout assumes at most 64 threads per chain");
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   const int lc = tid / TPC;            // chain slot in this CTA
@@ -288,8 +292,8 @@ bnn_nll_grad_kernel(BnnArgs a) {
   float* H1 = sDf + ((batch + 3) / 4) * 4;
   float* H2 = H1 + batch * HS;
   float* H3 = H2 + batch * HS;
-  float* E = H3 + batch * HS;
-  float* scr = E + batch * HS;         // [64]
+  float* sW4 = H3 + batch * HS;        // [64]: the head's weights
+  float* scr = sW4 + 64;               // [64]: per-thread partial sums
 
   const float* th = a.theta + (active ? chain : 0) * L.D;
   float* gr = (WANT_GRAD && a.grad != nullptr) ? a.grad + (active ? chain : 0) * L.D : nullptr;
@@ -300,10 +304,11 @@ bnn_nll_grad_kernel(BnnArgs a) {
     const int64_t start = a.starts != nullptr ? a.starts[chain] : 0;
     for (int t = u; t < batch * n_in; t += TPC) sX[t] = __ldg(a.X + start * n_in + t);
     for (int t = u; t < batch; t += TPC) sY[t] = __ldg(a.y + start + t);
-    for (int t = u; t < 4 * batch; t += TPC) {     // zero padding columns of H1, H2, H3, E
+    for (int t = u; t < 3 * batch; t += TPC) {     // zero padding columns of H1, H2, H3
       H1[t * HS + HID] = 0.0f;
       H1[t * HS + HID + 1] = 0.0f;
     }
+    for (int t = u; t < 64; t += TPC) sW4[t] = t < HID ? __ldg(th + L.oW4 + t) : 0.0f;
   }
   chain_sync<WARP>();
 
@@ -322,6 +327,8 @@ bnn_nll_grad_kernel(BnnArgs a) {
           for (int i = 0; i < batch; ++i) H1[i * HS + j] = fmaf(sX[i * n_in + m], w, H1[i * HS + j]);
         }
         for (int i = 0; i < batch; ++i) H1[i * HS + j] = fast_tanh(H1[i * HS + j]);
+        const float w4 = sW4[j];
+        sq = fmaf(w4, w4, sq);
       }
     }
   }
@@ -330,33 +337,22 @@ bnn_nll_grad_kernel(BnnArgs a) {
   if (active) sq += layer_forward<COLS, TPC, ROWS>(th, L.oW2, L.ob2, H1, H2, batch, u);
   chain_sync<WARP>();
   if (active) sq += layer_forward<COLS, TPC, ROWS>(th, L.oW3, L.ob3, H2, H3, batch, u);
+  if (active) scr[u] = sq;
   chain_sync<WARP>();
 
-  // ---- P4: head f[i] = H3[i,:] . W4 + b4 : per-thread partials, reduced through E ----
-  float w4[COLS];
-  if (active) {
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) {
-      w4[c] = (u + c * TPC < HID) ? __ldg(th + L.oW4 + u + c * TPC) : 0.0f;
-      sq = fmaf(w4[c], w4[c], sq);
-    }
-    for (int i = 0; i < batch; ++i) {
-      float p = 0.0f;
-#pragma unroll
-      for (int c = 0; c < COLS; ++c)
-        if (u + c * TPC < HID) p = fmaf(H3[i * HS + u + c * TPC], w4[c], p);
-      E[i * HS + u] = p;
-    }
-    scr[u] = sq;
-  }
-  chain_sync<WARP>();
+  // ---- P4: head f[i] = H3[i,:] . W4 + b4, one thread per batch row; loss pieces ----
   if (active) {
     const float b4 = __ldg(th + L.ob4), rho = __ldg(th + L.orho);
-    const float e_rho = expf(rho);
-    const float fvi = 1.0f / (e_rho + 1e-16f);                       // :368
+    const float fvi = 1.0f / (expf(rho) + 1e-16f);                   // :368
     for (int i = u; i < batch; i += TPC) {
+      const float4* hr = reinterpret_cast<const float4*>(H3 + i * HS);
+      const float4* wr = reinterpret_cast<const float4*>(sW4);
       float f = b4;
-      for (int t = 0; t < TPC; ++t) f += E[i * HS + t];
+#pragma unroll
+      for (int k4 = 0; k4 < K4S; ++k4) {
+        const float4 h = hr[k4], w = wr[k4];
+        f = fmaf(h.x, w.x, f); f = fmaf(h.y, w.y, f); f = fmaf(h.z, w.z, f); f = fmaf(h.w, w.w, f);
+      }
       const float diff = sY[i] - f;
       sDf[i] = -(diff * fvi) * a.inv_bs;                             // d cost / d f_i
       sY[i] = diff * diff;                                           // squared error (:370)
@@ -388,43 +384,45 @@ bnn_nll_grad_kernel(BnnArgs a) {
   if (gr == nullptr) return;           // cost only (uniform across the CTA)
 
   const float pscale = a.prior_den_inv * a.inv_n;
-  // ---- P5: layer 4 backward: dW4, dZ3 = (df W4^T) * (1 - H3^2) in place over H3 ----
+  // ---- P5: layer 4 backward: dW4, and dZ3 = (df W4^T) * (1 - H3^2) in place over H3 ----
   if (active) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int j = u + c * TPC;
       if (j < HID) {
+        const float w4 = sW4[j];
         float dw = 0.0f;
         for (int i = 0; i < batch; ++i) {
           const float h = H3[i * HS + j], df = sDf[i];
           dw = fmaf(h, df, dw);
-          H3[i * HS + j] = (df * w4[c]) * fmaf(-h, h, 1.0f);
+          H3[i * HS + j] = (df * w4) * fmaf(-h, h, 1.0f);
         }
-        gr[L.oW4 + j] = fmaf(w4[c], pscale, dw);
+        gr[L.oW4 + j] = fmaf(w4, pscale, dw);
       }
     }
   }
   chain_sync<WARP>();
-  // ---- layer 3 backward: dZ2 -> E (needs old W3 rows), then dW3 from H2 and dZ3 ----
-  if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW3, H3, H2, E, batch, u);
-  if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW3, L.ob3, H2, H3, batch, u, pscale);
+  // ---- layer 3: dW3 from H2 and dZ3, then H2 <- dZ2 (the rows of H2 must be dead first) ----
+  if (active) layer_backward_weights<COLS, TPC, KPASS>(th, gr, L.oW3, L.ob3, H2, H3, batch, u, pscale);
   chain_sync<WARP>();
-  // ---- layer 2 backward: dZ1 -> H3 (dZ3 is dead), then dW2 from H1 and dZ2 ----
-  if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW2, E, H1, H3, batch, u);
-  if (active) layer_backward_weights<COLS, TPC>(th, gr, L.oW2, L.ob2, H1, E, batch, u, pscale);
+  if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW3, H3, H2, batch, u);
   chain_sync<WARP>();
-  // ---- layer 1 backward: dW1 = X^T dZ1, db1 ----
+  // ---- layer 2: dW2 from H1 and dZ2, then H1 <- dZ1 ----
+  if (active) layer_backward_weights<COLS, TPC, KPASS>(th, gr, L.oW2, L.ob2, H1, H2, batch, u, pscale);
+  chain_sync<WARP>();
+  if (active) layer_backward_data<COLS, TPC, ROWS>(th, L.oW2, H2, H1, batch, u);
+  // ---- layer 1: dW1 = X^T dZ1, db1 (own column of dZ1 only: no barrier needed) ----
   if (active) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int j = u + c * TPC;
       if (j < HID) {
         float db = 0.0f;
-        for (int i = 0; i < batch; ++i) db += H3[i * HS + j];
+        for (int i = 0; i < batch; ++i) db += H1[i * HS + j];
         gr[L.ob1 + j] = fmaf(__ldg(th + L.ob1 + j), pscale, db);
         for (int m = 0; m < n_in; ++m) {
           float dw = 0.0f;
-          for (int i = 0; i < batch; ++i) dw = fmaf(sX[i * n_in + m], H3[i * HS + j], dw);
+          for (int i = 0; i < batch; ++i) dw = fmaf(sX[i * n_in + m], H1[i * HS + j], dw);
           gr[L.oW1 + m * HID + j] = fmaf(__ldg(th + L.oW1 + m * HID + j), pscale, dw);
         }
       }
@@ -453,25 +451,28 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
   float* H1 = sX + ((PB * n_in + 3) / 4) * 4 + 2 * PB;
   float* H2 = H1 + PB * HS;
   float* H3 = H2 + PB * HS;
-  float* E = H3 + PB * HS;
+  float* sW4 = H3 + PB * HS;
   const float* th = theta + net * L.D;
   if (active) {
     for (int t = u; t < batch * n_in; t += TPC) sX[t] = __ldg(X + p0 * n_in + t);
-    for (int t = u; t < 4 * PB; t += TPC) {
+    for (int t = u; t < 3 * PB; t += TPC) {
       H1[t * HS + HID] = 0.0f;
       H1[t * HS + HID + 1] = 0.0f;
     }
+    for (int t = u; t < 64; t += TPC) sW4[t] = t < HID ? __ldg(th + L.oW4 + t) : 0.0f;
   }
   __syncthreads();
   if (active) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int j = u + c * TPC;
-      const float b = __ldg(th + L.ob1 + j);
-      for (int i = 0; i < batch; ++i) {
-        float z = b;
-        for (int m = 0; m < n_in; ++m) z = fmaf(sX[i * n_in + m], __ldg(th + L.oW1 + m * HID + j), z);
-        H1[i * HS + j] = fast_tanh(z);
+      if (j < HID) {
+        const float b = __ldg(th + L.ob1 + j);
+        for (int i = 0; i < batch; ++i) {
+          float z = b;
+          for (int m = 0; m < n_in; ++m) z = fmaf(sX[i * n_in + m], __ldg(th + L.oW1 + m * HID + j), z);
+          H1[i * HS + j] = fast_tanh(z);
+        }
       }
     }
   }
@@ -481,36 +482,26 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
   if (active) layer_forward<COLS, TPC, 4>(th, L.oW3, L.ob3, H2, H3, batch, u);
   __syncthreads();
   if (active) {
-    for (int i = 0; i < batch; ++i) {
-      float p = 0.0f;
-#pragma unroll
-      for (int c = 0; c < COLS; ++c) p = fmaf(H3[i * HS + u + c * TPC], __ldg(th + L.oW4 + u + c * TPC), p);
-      E[i * HS + u] = p;
-    }
-  }
-  __syncthreads();
-  if (active) {
     const float b4 = __ldg(th + L.ob4), rho = __ldg(th + L.orho);
     for (int i = u; i < batch; i += TPC) {
       float f = b4;
-      for (int t = 0; t < TPC; ++t) f += E[i * HS + t];
+      for (int k = 0; k < HID; ++k) f = fmaf(H3[i * HS + k], sW4[k], f);
       out[(net * n_points + p0 + i) * 2 + 0] = f;
       out[(net * n_points + p0 + i) * 2 + 1] = rho;     // "ones_like(layer_4) * output_bias" (:63-67)
     }
   }
 }
 
-// ---- launch variants (COLS units per thread, NC chains per CTA, ROWS batch rows in
-// flight, min CTAs per SM); selected with sgmcmc_set_bnn_tuning, default chosen from the
-// sweep in profiles/ -------------------------------------------------------------------
-constexpr int K4_COLS = 1;      // K10 uses this shape
-constexpr int K4_NC = 5;
+// ---- launch shapes (COLS, TPC, NC chains per CTA, ROWS in flight, KPASS, min CTAs / SM),
+// selected with sgmcmc_set_bnn_tuning; the default is the fastest of the sweep recorded in
+// profiles/ ---------------------------------------------------------------------------
+constexpr int K10_COLS = 1, K10_TPC = 50, K10_NC = 5;
 
 static int g_bnn_variant = 0;
 int bnn_variant_count() { return 10; }
 void set_bnn_variant(int v) { g_bnn_variant = v; }
 
-template <int COLS, int TPC, int NC, int ROWS, int MINB>
+template <int COLS, int TPC, int NC, int ROWS, int KPASS, int MINB>
 static int launch_variant(const BnnArgs& a, cudaStream_t st) {
   using Shape = BnnShape<COLS, TPC, NC>;
   const size_t smem = (size_t)NC * bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
@@ -519,11 +510,11 @@ static int launch_variant(const BnnArgs& a, cudaStream_t st) {
              a.batch, a.L.n_in, smem);
   const unsigned blocks = (unsigned)((a.n_chains + NC - 1) / NC);
   if (a.grad != nullptr) {
-    auto k = bnn_nll_grad_kernel<COLS, TPC, NC, ROWS, MINB, true>;
+    auto k = bnn_nll_grad_kernel<COLS, TPC, NC, ROWS, KPASS, MINB, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, Shape::THREADS, smem, st>>>(a);
   } else {
-    auto k = bnn_nll_grad_kernel<COLS, TPC, NC, ROWS, MINB, false>;
+    auto k = bnn_nll_grad_kernel<COLS, TPC, NC, ROWS, KPASS, MINB, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, Shape::THREADS, smem, st>>>(a);
   }
@@ -531,21 +522,21 @@ static int launch_variant(const BnnArgs& a, cudaStream_t st) {
 }
 
 static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
-  // a large minibatch may not fit the default variant's shared memory: fall back to one
-  // chain per CTA
+  // a large minibatch may not fit the multi-chain shapes' shared memory: one chain per CTA
+  static const int nc_of_variant[10] = {5, 5, 8, 8, 5, 12, 8, 4, 4, 4};
   const size_t per_chain = bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
-  if (per_chain * 5 > 227 * 1024) return launch_variant<1, 50, 1, 4, 1>(a, st);
+  if (per_chain * nc_of_variant[g_bnn_variant] > 227 * 1024) return launch_variant<1, 50, 1, 4, 1, 1>(a, st);
   switch (g_bnn_variant) {
-    case 1: return launch_variant<1, 50, 4, 4, 3>(a, st);
-    case 2: return launch_variant<2, 25, 10, 4, 1>(a, st);
-    case 3: return launch_variant<2, 25, 5, 4, 2>(a, st);
-    case 4: return launch_variant<1, 50, 5, 5, 2>(a, st);
-    case 5: return launch_variant<1, 50, 2, 4, 6>(a, st);
-    case 6: return launch_variant<2, 32, 4, 4, 3>(a, st);    // one warp per chain, 4 chains / CTA
-    case 7: return launch_variant<2, 32, 2, 4, 6>(a, st);    // one warp per chain, 2 chains / CTA
-    case 8: return launch_variant<2, 32, 4, 5, 3>(a, st);    // ... 5 rows in flight
-    case 9: return launch_variant<2, 32, 1, 4, 12>(a, st);   // one warp per CTA
-    default: return launch_variant<1, 50, 5, 4, 2>(a, st);
+    case 1: return launch_variant<1, 50, 5, 4, 1, 3>(a, st);     // 1 unit / thread, 15 chains / SM
+    case 2: return launch_variant<2, 25, 8, 4, 2, 2>(a, st);     // 2 units / thread, 16 chains / SM
+    case 3: return launch_variant<2, 25, 8, 2, 2, 2>(a, st);     //   ... 2 rows in flight
+    case 4: return launch_variant<2, 25, 5, 4, 2, 3>(a, st);     //   ... 15 chains / SM in 3 CTAs
+    case 5: return launch_variant<3, 17, 12, 4, 3, 1>(a, st);    // 3 units / thread, 12 chains / SM
+    case 6: return launch_variant<3, 17, 8, 4, 3, 2>(a, st);     //   ... 16 chains / SM
+    case 7: return launch_variant<2, 32, 4, 4, 2, 3>(a, st);     // one warp per chain, 12 chains / SM
+    case 8: return launch_variant<2, 32, 4, 4, 2, 4>(a, st);     //   ... 16 chains / SM (<= 128 registers)
+    case 9: return launch_variant<1, 50, 4, 4, 1, 4>(a, st);     // 1 unit / thread, 16 chains / SM
+    default: return launch_variant<1, 50, 5, 4, 1, 2>(a, st);    // 1 unit / thread, 10 chains / SM
   }
 }
 
@@ -599,8 +590,7 @@ extern "C" int sgmcmc_bnn_nll_grad_f32(const float* theta, const float* X, const
 // synchronisation: per step K4 (cost + gradient at the old theta, minibatch
 // starts[s, :]) then K1 (fused SGHMC update), plus a device-to-device snapshot of
 // (theta, cost) every keep_every-th step.  The gradient goes through the caller's
-// `grad_scratch` [C, D]; a single-kernel variant that keeps it on chip is round-2 work
-// (DESIGN.md "K5").
+// `grad_scratch` [C, D].  Why this is two kernels and not one: DESIGN.md "K5".
 extern "C" int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float* v_hat,
                                         float* minv, const float* X, const float* y,
                                         const int32_t* starts, const float* z, float* trace,
@@ -646,13 +636,13 @@ extern "C" int sgmcmc_bnn_predict_f32(const float* theta, const float* X, float*
   SG_REQUIRE(theta && X && out, SGMCMC_E_INVALID, "bnn_predict: NULL pointer");
   SG_REQUIRE(n_in >= 1 && n_in <= 64, SGMCMC_E_UNSUPPORTED, "bnn: n_in must be in [1, 64] (got %d)", n_in);
   const BnnLayout L = make_layout(n_in);
-  using Shape = BnnShape<K4_COLS, HID / K4_COLS, K4_NC>;
-  const size_t smem = (size_t)K4_NC * bnn_smem_floats(PB, n_in) * sizeof(float);
+  using Shape = BnnShape<K10_COLS, K10_TPC, K10_NC>;
+  const size_t smem = (size_t)K10_NC * bnn_smem_floats(PB, n_in) * sizeof(float);
   SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED, "bnn_predict: n_in too large for shared memory");
-  auto k = bnn_predict_kernel<K4_COLS, HID / K4_COLS, K4_NC>;
+  auto k = bnn_predict_kernel<K10_COLS, K10_TPC, K10_NC>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t items = n_nets * ((n_points + PB - 1) / PB);
-  k<<<(unsigned)((items + K4_NC - 1) / K4_NC), Shape::THREADS, smem, (cudaStream_t)stream>>>(
+  k<<<(unsigned)((items + K10_NC - 1) / K10_NC), Shape::THREADS, smem, (cudaStream_t)stream>>>(
       theta, X, out, n_nets, n_points, L);
   return check_launch("bnn_predict_kernel");
 }
