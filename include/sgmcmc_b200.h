@@ -57,6 +57,11 @@ int sgmcmc_set_update_tuning(int threads, int unroll);
  * 0 is the default; the others exist for the sweeps recorded under profiles/. */
 int sgmcmc_set_bnn_tuning(int variant);
 
+/* Cap the grids of the update kernels (K1-K3) and of K4 to that many CTAs (persistent
+ * kernels that loop over their work; 0 = one CTA per unit of work, the default).  Used to
+ * leave SM resources free when two kernels are meant to run concurrently on two streams. */
+int sgmcmc_set_persistent_grids(int update_max_ctas, int bnn_max_ctas);
+
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t sgmcmc_launch_count(void);
 

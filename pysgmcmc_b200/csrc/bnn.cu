@@ -280,10 +280,15 @@ bnn_nll_grad_kernel(BnnArgs a) {
   const int tid = threadIdx.x;
   const int lc = tid / TPC;            // chain slot in this CTA
   const int u = tid - lc * TPC;        // unit group of this thread
-  const int64_t chain = (int64_t)blockIdx.x * NC + lc;
-  const bool active = lc < NC && chain < a.n_chains;
   const int batch = a.batch, n_in = a.L.n_in;
   const BnnLayout L = a.L;
+  // A CTA walks chain groups blockIdx.x, blockIdx.x + gridDim.x, ...: with gridDim.x ==
+  // number of groups this is one group per CTA; a smaller (persistent) grid leaves SM
+  // resources free for a concurrently running kernel (sgmcmc_set_bnn_tuning).
+  const int64_t n_groups = (a.n_chains + NC - 1) / NC;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  const int64_t chain = grp * NC + lc;
+  const bool active = lc < NC && chain < a.n_chains;
 
   const int per_chain = bnn_smem_floats(batch, n_in);
   float* sX = smem + (size_t)(lc < NC ? lc : 0) * per_chain;
@@ -381,7 +386,10 @@ bnn_nll_grad_kernel(BnnArgs a) {
       gr[L.ob4] = sdf + b4 * pscale;
     }
   }
-  if (gr == nullptr) return;           // cost only (uniform across the CTA)
+  if (gr == nullptr) {                 // cost only (uniform across the CTA)
+    chain_sync<WARP>();
+    continue;
+  }
 
   const float pscale = a.prior_den_inv * a.inv_n;
   // ---- P5: layer 4 backward: dW4, and dZ3 = (df W4^T) * (1 - H3^2) in place over H3 ----
@@ -427,6 +435,8 @@ bnn_nll_grad_kernel(BnnArgs a) {
         }
       }
     }
+  }
+  chain_sync<WARP>();                  // shared memory is reused by the next chain group
   }
 }
 
@@ -498,8 +508,10 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
 constexpr int K10_COLS = 1, K10_TPC = 50, K10_NC = 5;
 
 static int g_bnn_variant = 0;
+static int g_bnn_max_ctas = 0;          // 0: one CTA per chain group; > 0: persistent grid of that size
 int bnn_variant_count() { return 10; }
 void set_bnn_variant(int v) { g_bnn_variant = v; }
+void set_bnn_max_ctas(int n) { g_bnn_max_ctas = n; }
 
 template <int COLS, int TPC, int NC, int ROWS, int KPASS, int MINB>
 static int launch_variant(const BnnArgs& a, cudaStream_t st) {
@@ -508,7 +520,8 @@ static int launch_variant(const BnnArgs& a, cudaStream_t st) {
   SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED,
              "minibatch of %d rows x %d inputs needs %zu B of shared memory per CTA (max 232448)",
              a.batch, a.L.n_in, smem);
-  const unsigned blocks = (unsigned)((a.n_chains + NC - 1) / NC);
+  unsigned blocks = (unsigned)((a.n_chains + NC - 1) / NC);
+  if (g_bnn_max_ctas > 0 && blocks > (unsigned)g_bnn_max_ctas) blocks = (unsigned)g_bnn_max_ctas;
   if (a.grad != nullptr) {
     auto k = bnn_nll_grad_kernel<COLS, TPC, NC, ROWS, KPASS, MINB, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

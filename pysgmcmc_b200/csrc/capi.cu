@@ -11,6 +11,7 @@ static thread_local char g_error[512] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_threads{256};
 static std::atomic<int> g_unroll{1};
+static std::atomic<int> g_update_max_ctas{0};
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -31,6 +32,7 @@ int check_launch(const char* what) {
 
 int tuning_threads() { return g_threads.load(std::memory_order_relaxed); }
 int tuning_unroll() { return g_unroll.load(std::memory_order_relaxed); }
+int tuning_update_max_ctas() { return g_update_max_ctas.load(std::memory_order_relaxed); }
 
 }  // namespace sgmcmc
 
@@ -53,6 +55,14 @@ int sgmcmc_set_update_tuning(int threads, int unroll) {
       return sgmcmc::set_error(SGMCMC_E_INVALID, "unroll must be 1 or 2 (got %d)", unroll);
     sgmcmc::g_unroll.store(unroll);
   }
+  return SGMCMC_OK;
+}
+
+int sgmcmc_set_persistent_grids(int update_max_ctas, int bnn_max_ctas) {
+  if (update_max_ctas < 0 || bnn_max_ctas < 0)
+    return sgmcmc::set_error(SGMCMC_E_INVALID, "grid caps must be >= 0");
+  sgmcmc::g_update_max_ctas.store(update_max_ctas);
+  sgmcmc::set_bnn_max_ctas(bnn_max_ctas);
   return SGMCMC_OK;
 }
 

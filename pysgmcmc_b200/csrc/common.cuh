@@ -18,6 +18,8 @@ int tuning_threads();
 int tuning_unroll();
 int bnn_variant_count();
 void set_bnn_variant(int v);
+void set_bnn_max_ctas(int n);
+int tuning_update_max_ctas();
 
 #define SG_REQUIRE(cond, code, ...)                          \
   do {                                                       \

@@ -79,7 +79,11 @@ __global__ void sghmc_update_kernel(T* __restrict__ theta, T* __restrict__ v, T*
                                     const T* __restrict__ grad, const T* __restrict__ z, int64_t n,
                                     SghmcScalars<T> s, NoiseArgs na) {
   const int64_t n_groups = (n + 3) >> 2;
-  const int64_t base = (int64_t)blockIdx.x * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
+  // grid-stride over the groups: with the default launch the loop runs once; a capped
+  // (persistent) grid walks the array in chunks of gridDim.x * blockDim.x * UNROLL groups
+  const int64_t chunk = (int64_t)gridDim.x * blockDim.x * UNROLL;
+  for (int64_t base = (int64_t)blockIdx.x * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
+       base - threadIdx.x < n_groups; base += chunk) {
   Pack<T> th[UNROLL], vv[UNROLL], gr[UNROLL], ta[UNROLL], gg[UNROLL], vh[UNROLL], mi[UNROLL], zz[UNROLL];
   int valid[UNROLL];
 #pragma unroll
@@ -126,6 +130,7 @@ __global__ void sghmc_update_kernel(T* __restrict__ theta, T* __restrict__ v, T*
       }
     }
   }
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -137,7 +142,11 @@ __global__ void sgld_update_kernel(T* __restrict__ theta, T* __restrict__ tau, T
                                    const T* __restrict__ grad, const T* __restrict__ z, int64_t n,
                                    SgldScalars<T> s, NoiseArgs na) {
   const int64_t n_groups = (n + 3) >> 2;
-  const int64_t base = (int64_t)blockIdx.x * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
+  // grid-stride over the groups: with the default launch the loop runs once; a capped
+  // (persistent) grid walks the array in chunks of gridDim.x * blockDim.x * UNROLL groups
+  const int64_t chunk = (int64_t)gridDim.x * blockDim.x * UNROLL;
+  for (int64_t base = (int64_t)blockIdx.x * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
+       base - threadIdx.x < n_groups; base += chunk) {
   Pack<T> th[UNROLL], gr[UNROLL], ta[UNROLL], gg[UNROLL], vh[UNROLL], mi[UNROLL], zz[UNROLL];
   int valid[UNROLL];
 #pragma unroll
@@ -182,6 +191,7 @@ __global__ void sgld_update_kernel(T* __restrict__ theta, T* __restrict__ tau, T
       }
     }
   }
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -192,7 +202,11 @@ __global__ void rsghmc_update_kernel(T* __restrict__ theta, T* __restrict__ p,
                                      const T* __restrict__ grad, const T* __restrict__ z, int64_t n,
                                      RsghmcScalars<T> s, NoiseArgs na) {
   const int64_t n_groups = (n + 3) >> 2;
-  const int64_t base = (int64_t)blockIdx.x * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
+  // grid-stride over the groups: with the default launch the loop runs once; a capped
+  // (persistent) grid walks the array in chunks of gridDim.x * blockDim.x * UNROLL groups
+  const int64_t chunk = (int64_t)gridDim.x * blockDim.x * UNROLL;
+  for (int64_t base = (int64_t)blockIdx.x * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
+       base - threadIdx.x < n_groups; base += chunk) {
   Pack<T> th[UNROLL], pp[UNROLL], gr[UNROLL], zz[UNROLL];
   int valid[UNROLL];
 #pragma unroll
@@ -216,6 +230,7 @@ __global__ void rsghmc_update_kernel(T* __restrict__ theta, T* __restrict__ p,
       store_pack<T, ALIGNED>(theta, gi, valid[u], th[u]);
       store_pack<T, ALIGNED>(p, gi, valid[u], pp[u]);
     }
+  }
   }
 }
 
@@ -248,6 +263,8 @@ static inline LaunchShape launch_shape(int64_t n) {
   const int64_t n_groups = (n + 3) / 4;
   const int64_t per_block = (int64_t)ls.threads * ls.unroll;
   ls.blocks = (unsigned)((n_groups + per_block - 1) / per_block);
+  const int cap = tuning_update_max_ctas();
+  if (cap > 0 && ls.blocks > (unsigned)cap) ls.blocks = (unsigned)cap;
   return ls;
 }
 
