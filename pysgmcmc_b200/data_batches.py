@@ -129,6 +129,18 @@ class DeviceBatchGenerator(object):
                          _native.stream_ptr())
         return out
 
+    def state_dict(self):
+        """MT19937 streams plus the not yet consumed part of the current block."""
+        rest = None if self._buf is None else self._buf[self._pos:].clone()
+        return {"state": self.state.clone(), "pending": rest}
+
+    def load_state_dict(self, state):
+        self.state.copy_(state["state"])
+        self._buf = state["pending"]
+        self._pos = 0
+        if self._buf is not None and self._buf.shape[0] == 0:
+            self._buf = None
+
     def __iter__(self):
         return self
 

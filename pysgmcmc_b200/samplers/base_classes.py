@@ -270,6 +270,39 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
 
         return params, cost
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything needed to continue this chain bit-identically: the flat state arrays,
+        the iteration counter (= Philox step), the noise seed and, for on-device minibatch
+        generators, the MT19937 streams.  (The reference keeps its state in TF session
+        variables and has no checkpointing)"""
+        state = {
+            "theta": self._theta.clone(),
+            "n_iterations": self.n_iterations,
+            "noise_seed": self._noise_seed,
+            "epsilon": self.epsilon.value,
+        }
+        if self._STATE_NAMES:
+            state["state"] = self._state.clone()
+            state["state_names"] = tuple(self._STATE_NAMES)
+        gen = self.batch_generator
+        if gen is not None and hasattr(gen, "state_dict"):
+            state["batch_generator"] = gen.state_dict()
+        return state
+
+    def load_state_dict(self, state):
+        assert tuple(state["theta"].shape) == tuple(self._theta.shape), "layout mismatch"
+        self._theta.copy_(state["theta"])
+        if self._STATE_NAMES:
+            assert tuple(state["state_names"]) == tuple(self._STATE_NAMES)
+            self._state.copy_(state["state"])
+        self.n_iterations = int(state["n_iterations"])
+        self._noise_seed = int(state["noise_seed"])
+        self.epsilon.value = state["epsilon"]
+        gen = self.batch_generator
+        if "batch_generator" in state and gen is not None and hasattr(gen, "load_state_dict"):
+            gen.load_state_dict(state["batch_generator"])
+
     # ------------------------------------------------------------------ device-resident runs
     def _can_run_fused(self):
         return (self._native_target is not None and self.batch_generator is None

@@ -296,3 +296,30 @@ def test_k4_launch_variants_agree():
             assert_grad_close(grad, wg)
     finally:
         _native.call("sgmcmc_set_bnn_tuning", 0)
+
+
+def test_checkpoint_resume_is_bit_identical():
+    """state_dict / load_state_dict: a resumed BNN-SGHMC run continues the same chain (state,
+    Philox step counter and MT19937 minibatch streams are all restored)."""
+    C, N = 6, 300
+    X, y = sinc_data(N)
+
+    def build():
+        gen = DeviceBatchGenerator(N, 20, n_chains=C, seed=5, device=DEV, block=8)
+        nll = BayesianNeuralNetworkNLL(N, 20, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+        return SGHMCSampler(params=default_net_params(1, n_chains=C, seed=3, device=DEV), cost_fun=nll,
+                            batch_generator=gen, burn_in_steps=12, scale_grad=float(N), seed=7,
+                            session=Session(device=DEV, n_chains=C, output="torch"))
+    a = build()
+    for _ in range(9):
+        next(a)                                   # leaves a partially consumed index block
+    ckpt = a.state_dict()
+    for _ in range(11):
+        next(a)
+    b = build()
+    b.load_state_dict(ckpt)
+    assert b.n_iterations == 9 and b.is_burning_in
+    for _ in range(11):
+        next(b)
+    assert torch.equal(a._theta, b._theta) and torch.equal(a._state, b._state)
+    assert a.n_iterations == b.n_iterations == 20
