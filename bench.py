@@ -110,12 +110,14 @@ def run_reference(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    n_chains = 64 * cores
-    steps = max(1, min(args.steps, 20))
-    warmup = max(1, min(args.warmup, 2))
+    # Exactly K timed steps; each step advances a BOUNDED sample of the workload's chains,
+    # sized (at ~2500 chain-steps/s per core for this NumPy port) so K steps take <= ~2 min.
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 5))
+    chains_per_core = max(1, min(64, int(120.0 * 2500.0 / steps)))
+    n_chains = chains_per_core * cores
     value, dt = cpu_chain_steps_per_s(n_chains, steps, warmup, cores)
-    sample = ("%d chains x %d steps of the same BNN-SGHMC workload (NumPy oracle port, %d processes); "
-              "reference TF 1.x is not installable on this image" % (n_chains, steps, cores))
+    sample = ("%d of the workload's chains x %d steps of the same BNN-SGHMC step (NumPy oracle port, %d "
+              "processes); reference TF 1.x is not installable on this image" % (n_chains, steps, cores))
     line = {
         "impl": "reference", "metric": "chain-steps/s (BNN SGHMC)", "value": value, "unit": "chain-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
