@@ -31,12 +31,27 @@ chain_moments_kernel(const float* __restrict__ trace, double* __restrict__ sums,
     for (int64_t j = c0 + threadIdx.y; j < c1; j += MT_DY) {
       const float* p = trace + j * n_dims + d;
       const double x0 = (double)p[0];
-      double s1 = 0.0, s2 = 0.0;
-      for (int64_t i = 1; i < n_draws; ++i) {
-        const double x = (double)p[i * stride] - x0;
-        s1 += x;
-        s2 += x * x;
+      // four independent accumulator pairs keep four strided loads in flight per thread
+      double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+      int64_t i = 1;
+      for (; i + 3 < n_draws; i += 4) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = __ldcs(p + (i + q) * stride);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double x = (double)v[q] - x0;
+          a1[q] += x;
+          a2[q] += x * x;
+        }
       }
+      for (; i < n_draws; ++i) {
+        const double x = (double)p[i * stride] - x0;
+        a1[0] += x;
+        a2[0] += x * x;
+      }
+      const double s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      const double s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
       const double n = (double)n_draws;
       const double mean = x0 + s1 / n;
       const double var = n_draws > 1 ? (s2 - s1 * s1 / n) / (n - 1.0) : 0.0;
