@@ -62,6 +62,10 @@ int sgmcmc_set_bnn_tuning(int variant);
  * leave SM resources free when two kernels are meant to run concurrently on two streams. */
 int sgmcmc_set_persistent_grids(int update_max_ctas, int bnn_max_ctas);
 
+/* Chains per chunk inside sgmcmc_bnn_sghmc_run_f32: K4 and K1 run back to back on one chunk
+ * at a time so that the chunk's gradient stays in L2 (0 = all chains in one chunk). */
+int sgmcmc_set_bnn_chunk(int64_t chains);
+
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t sgmcmc_launch_count(void);
 

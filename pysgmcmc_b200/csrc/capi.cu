@@ -66,6 +66,12 @@ int sgmcmc_set_persistent_grids(int update_max_ctas, int bnn_max_ctas) {
   return SGMCMC_OK;
 }
 
+int sgmcmc_set_bnn_chunk(int64_t chains) {
+  if (chains < 0) return sgmcmc::set_error(SGMCMC_E_INVALID, "chunk must be >= 0");
+  sgmcmc::set_bnn_chunk(chains);
+  return SGMCMC_OK;
+}
+
 int sgmcmc_set_bnn_tuning(int variant) {
   if (variant < 0 || variant >= sgmcmc::bnn_variant_count())
     return sgmcmc::set_error(SGMCMC_E_INVALID, "bnn variant must be in [0, %d) (got %d)",

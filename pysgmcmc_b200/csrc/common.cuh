@@ -19,6 +19,7 @@ int tuning_unroll();
 int bnn_variant_count();
 void set_bnn_variant(int v);
 void set_bnn_max_ctas(int n);
+void set_bnn_chunk(int64_t c);
 int tuning_update_max_ctas();
 
 #define SG_REQUIRE(cond, code, ...)                          \
