@@ -109,6 +109,7 @@ def effective_n_from_variograms(v_hat, m, n, variogram_block):
             done |= newly
             rho_prev = np.where(done, rho_prev, rho)
         t += k
+        block = min(2 * block, 1024)       # slowly mixing chains need thousands of lags
     rho_all = np.stack(history)            # [t_max, D]
     t_end = np.where(t_stop % 2 == 1, t_stop - 1, t_stop)
     out = np.empty(D)

@@ -3,6 +3,8 @@
 Run in the BUILD container (needs /root/reference for part 1):
     python tests/golden/make_golden.py
 
+0. relativistic_ess_published.json -- REFERENCE DATA: the published ESS-vs-stepsize table
+   (see make_published_ess).
 1. bnn_priors.npz  -- REFERENCE DATA: the reference's own golden vectors
    (pysgmcmc/tests/data/bayesian_neural_network_priors/{weights_inputs,weights,
    log_variance}.npy, asserted bit-exactly in
@@ -110,8 +112,29 @@ def make_bnn():
                         cost=cost, grad=grad, mse=mse)
 
 
+def make_published_ess():
+    """REFERENCE DATA: the only numbers the reference publishes for this path -- mean ESS of
+    Relativistic SGHMC vs stepsize (docs/source/notebooks/data/effective_sample_sizes/
+    Relativistic_SGHMC.json, produced by docs/source/experiments/compute_ess.py:177-253:
+    20 segments x 10 000 kept draws, keep_every = 10, 5 repeats).  Repacked as
+    {target: [[stepsize, mean over repeats, min, max], ...]} sorted by stepsize."""
+    import json
+    src = "/root/reference/docs/source/notebooks/data/effective_sample_sizes/Relativistic_SGHMC.json"
+    data = json.load(open(src))
+    out = {}
+    for target, table in data.items():
+        rows = []
+        for eps, reps in table.items():
+            vals = np.array(reps, dtype=np.float64).ravel()
+            rows.append([float(eps), float(vals.mean()), float(vals.min()), float(vals.max())])
+        out[target] = sorted(rows)
+    with open(os.path.join(HERE, "relativistic_ess_published.json"), "w") as f:
+        json.dump(out, f)
+
+
 if __name__ == "__main__":
     make_priors()
+    make_published_ess()
     make_trajectories()
     make_bnn()
     for f in sorted(os.listdir(HERE)):
