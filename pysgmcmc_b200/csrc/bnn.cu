@@ -74,6 +74,14 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
+__device__ __forceinline__ bool aligned_to_dev(const void* p, size_t a) {
+  return (reinterpret_cast<uintptr_t>(p) % a) == 0;
+}
+
+}  // namespace sgmcmc
+#include "bnn_mma.cuh"
+namespace sgmcmc {
+
 // acc[r][c] += sum_k act[row r][k] * w[c][k]  for ROWS rows of a [B x HS] activation buffer.
 // The 128-bit broadcast loads of step k4+1 are issued before the FFMAs of step k4.
 template <int COLS, int ROWS>
@@ -511,7 +519,7 @@ static int g_bnn_variant = 0;
 static int g_bnn_max_ctas = 0;          // 0: one CTA per chain group; > 0: persistent grid of that size
 static int64_t g_bnn_chunk = 0;         // chains per K4+K1 chunk inside sgmcmc_bnn_sghmc_run_f32 (0: all)
 void set_bnn_chunk(int64_t c) { g_bnn_chunk = c; }
-int bnn_variant_count() { return 10; }
+int bnn_variant_count() { return 11; }
 void set_bnn_variant(int v) { g_bnn_variant = v; }
 void set_bnn_max_ctas(int n) { g_bnn_max_ctas = n; }
 
@@ -536,12 +544,44 @@ static int launch_variant(const BnnArgs& a, cudaStream_t st) {
   return check_launch("bnn_nll_grad_kernel");
 }
 
+// K4 on the tensor pipe (bnn_mma.cuh): one CTA of ceil(batch / 16) warps per chain.
+template <int NB8>
+static int launch_mma(const BnnArgs& a, cudaStream_t st) {
+  constexpr int NTHR = 32 * ((NB8 + 1) / 2);
+  const size_t smem = (size_t)bnn_mma_smem_floats(a.batch, a.L.n_in, a.L.D) * sizeof(float);
+  SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED, "bnn (mma): %zu B of shared memory per CTA", smem);
+  unsigned blocks = (unsigned)a.n_chains;
+  if (g_bnn_max_ctas > 0 && blocks > (unsigned)g_bnn_max_ctas) blocks = (unsigned)g_bnn_max_ctas;
+  if (a.grad != nullptr) {
+    auto k = bnn_mma_kernel<NB8, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    k<<<blocks, NTHR, smem, st>>>(a);
+  } else {
+    auto k = bnn_mma_kernel<NB8, false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    k<<<blocks, NTHR, smem, st>>>(a);
+  }
+  return check_launch("bnn_mma_kernel");
+}
+
+static int launch_mma_batch(const BnnArgs& a, cudaStream_t st) {
+  switch ((a.batch + 7) / 8) {
+    case 1: return launch_mma<1>(a, st);
+    case 2: return launch_mma<2>(a, st);
+    case 3: return launch_mma<3>(a, st);
+    default: return launch_mma<4>(a, st);
+  }
+}
+
 static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
-  // a large minibatch may not fit the multi-chain shapes' shared memory: one chain per CTA
+  if (g_bnn_variant >= 10 && a.batch <= 32) return launch_mma_batch(a, st);
   static const int nc_of_variant[10] = {5, 5, 8, 8, 5, 12, 8, 4, 4, 4};
+  const int variant = g_bnn_variant < 10 ? g_bnn_variant : 0;
   const size_t per_chain = bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);
-  if (per_chain * nc_of_variant[g_bnn_variant] > 227 * 1024) return launch_variant<1, 50, 1, 4, 1, 1>(a, st);
-  switch (g_bnn_variant) {
+  if (per_chain * nc_of_variant[variant] > 227 * 1024) return launch_variant<1, 50, 1, 4, 1, 1>(a, st);
+  switch (variant) {
     case 1: return launch_variant<1, 50, 5, 4, 1, 3>(a, st);     // 1 unit / thread, 15 chains / SM
     case 2: return launch_variant<2, 25, 8, 4, 2, 2>(a, st);     // 2 units / thread, 16 chains / SM
     case 3: return launch_variant<2, 25, 8, 2, 2, 2>(a, st);     //   ... 2 rows in flight

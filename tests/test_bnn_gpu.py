@@ -289,7 +289,7 @@ def test_k4_launch_variants_agree():
     Xb, yb = obnn.gather_minibatch(X, y, starts, 20)
     wc, wg, _ = obnn.nll_and_grad(theta, Xb, yb, n_examples=N)
     try:
-        for v in range(10):
+        for v in range(11):
             _native.call("sgmcmc_set_bnn_tuning", v)
             cost, grad, _ = k4(theta, X, y, starts, 20, 20, N)
             np.testing.assert_allclose(cost, wc, rtol=3e-6, err_msg="variant %d" % v)
