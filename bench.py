@@ -42,6 +42,7 @@ SAMPLE_STEPS = 100                      # thinning of BayesianNeuralNetwork (def
 FLOP_PER_CHAIN_STEP_K4 = 2 * 305000.0   # fwd 102 k + bwd 203 k FFMA
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12    # 74.4: 148 SMs x 128 lanes x 2 x max clock
 BYTES_PER_ELEM_K1_BURN_IN = 44
+MMA_SYNC_TF32_PEAK_TFLOPS = 277.0       # tools/micro/mma_tf32_bench.cu (legacy mma.sync path of sm_100a)
 
 
 def synthetic_sinc(n=N_EXAMPLES, seed=1):
@@ -61,6 +62,15 @@ def measured_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two kernels of the step at
+    the headline shape, from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------------------
@@ -279,15 +289,26 @@ def run_b200(args):
         peak, which = measured_peaks()
         k1_gbs = BYTES_PER_ELEM_K1_BURN_IN * C * D / (kernels["k1_sghmc_update_ms"] * 1e6)
         k4_tf = FLOP_PER_CHAIN_STEP_K4 * C / (kernels["k4_bnn_nll_grad_ms"] * 1e9)
+        traffic = ncu_traffic()
         r_k1 = {"kernel": "sghmc_update_kernel (K1, burn-in)", "bound": "hbm", "achieved": k1_gbs,
                 "peak": peak, "peak_source": which, "unit": "GB/s", "frac": k1_gbs / peak,
-                "frac_of_nominal_8TBps": k1_gbs / 8000.0, "traffic": None,
+                "frac_of_nominal_8TBps": k1_gbs / 8000.0,
+                "traffic": traffic.get("k1_burn_in_bytes_per_launch") if C == 8192 else None,
+                "traffic_source": traffic.get("source") if C == 8192 else None,
                 "algorithmic_bytes_per_launch": BYTES_PER_ELEM_K1_BURN_IN * C * D,
                 "ms_per_launch": kernels["k1_sghmc_update_ms"]}
-        r_k4 = {"kernel": "bnn_nll_grad_kernel (K4)", "bound": "fp32", "achieved": k4_tf,
-                "peak": FP32_PEAK_TFLOPS, "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 x 1.965 GHz",
-                "unit": "TFLOP/s", "frac": k4_tf / FP32_PEAK_TFLOPS, "traffic": None,
+        r_k4 = {"kernel": "bnn_mma_kernel (K4: 3xTF32 mma.sync cost + gradient)", "bound": "fp32",
+                "achieved": k4_tf, "peak": FP32_PEAK_TFLOPS,
+                "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 x 1.965 GHz (the pipe the reference's "
+                               "fp32 arithmetic is defined on; the kernel runs its GEMMs as 3 TF32 tensor-pipe "
+                               "products per fp32 product)",
+                "unit": "TFLOP/s", "frac": k4_tf / FP32_PEAK_TFLOPS,
+                "tensor_pipe": {"executed_TFLOPs": 3 * k4_tf, "peak_mma_sync_tf32": MMA_SYNC_TF32_PEAK_TFLOPS,
+                                "frac": 3 * k4_tf / MMA_SYNC_TF32_PEAK_TFLOPS,
+                                "peak_source": "measured: tools/micro/mma_tf32_bench.cu on this pool's B200"},
+                "traffic": traffic.get("k4_bytes_per_launch") if C == 8192 else None,
                 "algorithmic_flops_per_launch": FLOP_PER_CHAIN_STEP_K4 * C,
+                "algorithmic_bytes_per_launch": 2 * 4 * C * D,
                 "ms_per_launch": kernels["k4_bnn_nll_grad_ms"]}
         dominant_is_k4 = kernels["k4_bnn_nll_grad_ms"] >= kernels["k1_sghmc_update_ms"]
         roofline = dict(r_k4 if dominant_is_k4 else r_k1)

@@ -53,8 +53,10 @@ const char* sgmcmc_last_error(void);
  * Measured on B200 (profiles/): 256 x 1 is fastest; more groups per thread cost occupancy. */
 int sgmcmc_set_update_tuning(int threads, int unroll);
 
-/* Launch shape of the BNN kernel K4 (units per thread, chains per CTA, rows in flight):
- * 0 is the default; the others exist for the sweeps recorded under profiles/. */
+/* Implementation of the BNN kernel K4: 10 (the default) is the tensor-pipe kernel
+ * (3xTF32 mma.sync, csrc/bnn_mma.cuh; minibatches of up to 32 rows, larger ones fall back to
+ * 0); 0-9 are launch shapes of the FFMA kernel (units per thread, chains per CTA, rows in
+ * flight) kept for the sweeps recorded under profiles/. */
 int sgmcmc_set_bnn_tuning(int variant);
 
 /* Cap the grids of the update kernels (K1-K3) and of K4 to that many CTAs (persistent
@@ -65,6 +67,15 @@ int sgmcmc_set_persistent_grids(int update_max_ctas, int bnn_max_ctas);
 /* Chains per chunk inside sgmcmc_bnn_sghmc_run_f32: K4 and K1 run back to back on one chunk
  * at a time so that the chunk's gradient stays in L2 (0 = all chains in one chunk). */
 int sgmcmc_set_bnn_chunk(int64_t chains);
+
+/* sgmcmc_bnn_sghmc_run_f32 as ONE kernel per step (cost + gradient + SGHMC update of a chain
+ * in one CTA, the gradient never leaves shared memory; csrc/bnn_fused.cu): bit-identical to
+ * K4 then K1, 40 instead of 52 B of HBM traffic per element-step and no grad_scratch, but
+ * slower at large chain counts (too few warps per SM for the update's instruction stream,
+ * DESIGN.md "K5"), so on = 0 (K4 then K1) is the default.  on = 1 selects the fused kernel,
+ * on = 3 the fused kernel without the TMA L2 prefetch of the state rows.  max_ctas > 0 caps
+ * its grid (persistent CTAs looping over chains). */
+int sgmcmc_set_bnn_fused(int on, int max_ctas);
 
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t sgmcmc_launch_count(void);

@@ -19,66 +19,7 @@
 // cycles that do NOT overlap FFMA issue (tools/micro/lds_bcast_bench.cu: time ~= FFMA/4 +
 // 2.6 * LDS.128), and each loaded activation word feeds only COLS FFMAs per thread.  COLS is
 // therefore the lever (fewer operand loads per FFMA), paid for with 52 registers per unit.
-#include "sampler_math.cuh"
-
-namespace sgmcmc {
-
-constexpr int HID = 50;      // hidden width of get_default_net (bayesian_neural_network.py:30-49)
-constexpr int HS = 52;       // row stride of the activation buffers: rows stay 16-byte aligned;
-                             // columns 50, 51 are zero padding
-constexpr int K4S = HS / 4;  // float4 steps per k-loop
-
-struct BnnLayout {
-  int n_in, D;
-  int oW1, ob1, oW2, ob2, oW3, ob3, oW4, ob4, orho;
-};
-
-static BnnLayout make_layout(int n_in) {
-  BnnLayout L;
-  L.n_in = n_in;
-  int o = 0;
-  L.oW1 = o; o += n_in * HID;
-  L.ob1 = o; o += HID;
-  L.oW2 = o; o += HID * HID;
-  L.ob2 = o; o += HID;
-  L.oW3 = o; o += HID * HID;
-  L.ob3 = o; o += HID;
-  L.oW4 = o; o += HID;
-  L.ob4 = o; o += 1;
-  L.orho = o; o += 1;
-  L.D = o;
-  return L;
-}
-
-struct BnnArgs {
-  const float* theta;     // [C, D]
-  const float* X;         // [N, n_in]
-  const float* y;         // [N]
-  const int32_t* starts;  // [C] (NULL: every chain starts at row 0)
-  float* cost;            // [C]
-  float* grad;            // [C, D] or NULL
-  float* mse;             // [C] or NULL
-  int64_t n_chains;
-  int batch;              // rows actually in the minibatch
-  float inv_bs;           // 1 / configured batch size          (:377)
-  float inv_n;            // 1 / n_examples                     (:380)
-  float prior_den_inv;    // 1 / (D + 3e-16)   safe_divide in weight_prior_log_like (:141)
-  BnnLayout L;
-};
-
-// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx + rcp.approx): |error| ~ 2e-7,
-// saturates correctly at +-1.  3000 activations per chain-step make the libm tanhf
-// (~25 instructions) a third of the kernel; this is 6.
-__device__ __forceinline__ float fast_tanh(float x) {
-  const float e = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, e + 1.0f);
-}
-
-__device__ __forceinline__ bool aligned_to_dev(const void* p, size_t a) {
-  return (reinterpret_cast<uintptr_t>(p) % a) == 0;
-}
-
-}  // namespace sgmcmc
+#include "bnn_common.cuh"
 #include "bnn_mma.cuh"
 namespace sgmcmc {
 
@@ -515,7 +456,7 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
 // profiles/ ---------------------------------------------------------------------------
 constexpr int K10_COLS = 1, K10_TPC = 50, K10_NC = 5;
 
-static int g_bnn_variant = 0;
+static int g_bnn_variant = 10;        // 10: tensor-pipe kernel (bnn_mma.cuh); 0-9: FFMA launch shapes
 static int g_bnn_max_ctas = 0;          // 0: one CTA per chain group; > 0: persistent grid of that size
 static int64_t g_bnn_chunk = 0;         // chains per K4+K1 chunk inside sgmcmc_bnn_sghmc_run_f32 (0: all)
 void set_bnn_chunk(int64_t c) { g_bnn_chunk = c; }
@@ -657,7 +598,7 @@ extern "C" int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, floa
                                         uint64_t step0, uint64_t chain_offset, void* stream) {
   SG_REQUIRE(n_steps >= 0 && n_burn_in >= 0 && keep_every >= 1, SGMCMC_E_INVALID,
              "bnn_sghmc_run: n_steps, n_burn_in must be >= 0 and keep_every >= 1");
-  SG_REQUIRE(grad_scratch && cost_scratch, SGMCMC_E_INVALID, "bnn_sghmc_run: scratch buffers must not be NULL");
+  SG_REQUIRE(cost_scratch, SGMCMC_E_INVALID, "bnn_sghmc_run: cost_scratch must not be NULL");
   SG_REQUIRE(v && tau && g && v_hat && minv, SGMCMC_E_INVALID, "bnn_sghmc_run: state arrays must not be NULL");
   BnnArgs a;
   if (int rc = make_bnn_args(a, theta, X, y, starts, cost_scratch, grad_scratch, nullptr, n_chains, n_in,
@@ -673,9 +614,30 @@ extern "C" int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, floa
   // next chunk overwrites the dirty gradient lines before they are written back, so the
   // gradient never costs HBM bandwidth (52 -> 40 B per element-step).
   const int64_t chunk = g_bnn_chunk > 0 ? g_bnn_chunk : n_chains;
+  FusedStepArgs f;
+  f.theta = theta; f.v = v; f.tau = tau; f.g = g; f.v_hat = v_hat; f.minv = minv;
+  f.z = z;
+  f.s = make_sghmc_scalars<float>(epsilon, mdecay, scale_grad);
+  f.burn_in = 1; f.store_minv = 0;
+  SG_REQUIRE(scale_grad > 0, SGMCMC_E_INVALID, "bnn_sghmc_run: scale_grad must be > 0");
+  // one kernel per step (bnn_fused.cu) whenever the shape allows it; else K4 then K1
+  const bool fused = bnn_fused_enabled() && g_bnn_chunk == 0 && bnn_fused_supported(a, f);
+  SG_REQUIRE(fused || grad_scratch, SGMCMC_E_INVALID, "bnn_sghmc_run: grad_scratch must not be NULL");
   for (int64_t s = 0; s < n_steps; ++s) {
     const int burn_in = adapt_forever || s < n_burn_in;
     const int store_minv = burn_in && (s == n_burn_in - 1 || (adapt_forever && s == n_steps - 1));
+    if (fused) {
+      BnnArgs ac = a;
+      ac.starts = starts != nullptr ? starts + s * n_chains : nullptr;
+      f.z = z != nullptr ? z + s * n : nullptr;
+      f.na = NoiseArgs{seed, step0 + (uint64_t)s, chain_offset * (uint64_t)D / 4};
+      f.burn_in = burn_in; f.store_minv = store_minv;
+      if (int rc = launch_bnn_sghmc_fused(ac, f, st)) return rc;
+      if ((s + 1) % keep_every == 0)
+        if (int rc = snapshot(trace, cost_trace, (s + 1) / keep_every - 1, theta, cost_scratch, n_chains, D, st))
+          return rc;
+      continue;
+    }
     for (int64_t c0 = 0; c0 < n_chains; c0 += chunk) {
       const int64_t nc = n_chains - c0 < chunk ? n_chains - c0 : chunk;
       BnnArgs ac = a;

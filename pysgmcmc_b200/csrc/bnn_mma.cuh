@@ -32,6 +32,8 @@
 //    fused K5 kernel, feeds the SGHMC update without touching HBM.
 #pragma once
 
+#include "bnn_common.cuh"
+
 namespace sgmcmc {
 
 constexpr int AS = 56;   // row stride of the activation buffers: 50 units, the 1-column, 5 zeros
@@ -39,12 +41,22 @@ constexpr int NT8 = 7;   // 8-wide tiles covering those 56 columns
 
 // x = hi + lo with hi = x truncated to TF32 -- which is what the tensor core does to a raw
 // fp32 operand (it reads the top 19 bits), so hi costs no instruction -- and lo the exact fp32
-// remainder (2 instructions).  |lo| < 2^-10 |x| with the sign of x; the hardware truncates lo
-// to 11 bits too.  Per product the dropped pieces (lo*lo and the truncated tails of the two
-// lo's) are each <= 2^-20 relative and have the SIGN OF THE PRODUCT, so a dot product comes out
-// scaled by (1 - ~6e-7) plus fp32-rounding-sized noise: no amplification under cancellation.
+// remainder (2 instructions).  |lo| < 2^-10 |x|; the hardware truncates lo to 11 bits too.
+// Measured on the B200 against the float64 oracle: gradient error 4e-8 rms / 1e-6 max of
+// max|g| per chain (the FFMA kernel: 1e-8 / 4e-7).  SGMCMC_TF32_ROUND_SPLIT=1 rounds hi instead
+// (one more integer add per split, unbiased lo): an emulation of 51-term dot products shows
+// 3.7x less split error, but on the device the total error does not move (it is dominated by
+// the tensor core's own fp32 accumulation) while K4 slows from 0.218 to 0.223 ms, so the
+// truncating split is the default.
+#ifndef SGMCMC_TF32_ROUND_SPLIT
+#define SGMCMC_TF32_ROUND_SPLIT 0
+#endif
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+#if SGMCMC_TF32_ROUND_SPLIT
+  hi = __float_as_uint(x) + 0x1000u;
+#else
   hi = __float_as_uint(x);
+#endif
   lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
 }
 
@@ -270,8 +282,10 @@ __device__ __forceinline__ BnnMmaSmem bnn_mma_carve(float* base, int batch, int 
 // The cost and (WANT_GRAD) the gradient of ONE chain, by the NW = ceil(NB8 / 2) warps of a
 // CTA.  On return (after a chain barrier) s.R holds the gradient in the parameter layout
 // (theta is gone) and thread 0 has the cost and the sum of squared errors.
-// `th` is the chain's parameter row in global memory (staged here into R).
-template <int NB8, bool WANT_GRAD>
+// `th` is the chain's parameter row in global memory (staged here into R).  COHERENT: the
+// calling kernel also WRITES theta (K5), so the row is read with ld.global.cg (L2, where the
+// update phase re-reads it) instead of the read-only path.
+template <int NB8, bool WANT_GRAD, bool COHERENT = false>
 __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __restrict__ th,
                                               const int32_t* __restrict__ start_ptr, const BnnMmaSmem& s,
                                               float& cost_out, float& sse_out) {
@@ -295,7 +309,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int q = q0 + u * NTHR + tid;
-        v[u] = q < n4 ? __ldg(src + q) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        v[u] = q < n4 ? (COHERENT ? __ldcg(src + q) : __ldg(src + q)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -308,7 +322,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
   } else {
 #pragma unroll 4
     for (int q = tid; q < D; q += NTHR) {
-      const float v = __ldg(th + q);
+      const float v = COHERENT ? __ldcg(th + q) : __ldg(th + q);
       R[q] = v;
       sq = fmaf(v, v, sq);
     }
@@ -507,6 +521,10 @@ __global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), NB8 > 2 ? 6 : 8) bnn_mma
   for (int64_t chain = blockIdx.x; chain < a.n_chains; chain += gridDim.x) {
     const float* th = a.theta + chain * D;
     float cost = 0.0f, sse = 0.0f;
+    // persistent grid: pull the next chain's parameter row towards L2 while this one computes
+    if (tid == 0 && chain + gridDim.x < a.n_chains && (D & 3) == 0 && aligned_to_dev(a.theta, 16))
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(th + (int64_t)gridDim.x * D), "r"(D * 4)
+                   : "memory");
     bnn_chain_mma<NB8, WANT_GRAD>(a, th, a.starts != nullptr ? a.starts + chain : nullptr, s, cost, sse);
     if (tid == 0) {
       a.cost[chain] = cost;

@@ -3,7 +3,7 @@
 #include <atomic>
 #include <stdarg.h>
 
-#include "common.cuh"
+#include "bnn_common.cuh"
 
 namespace sgmcmc {
 
@@ -69,6 +69,14 @@ int sgmcmc_set_persistent_grids(int update_max_ctas, int bnn_max_ctas) {
 int sgmcmc_set_bnn_chunk(int64_t chains) {
   if (chains < 0) return sgmcmc::set_error(SGMCMC_E_INVALID, "chunk must be >= 0");
   sgmcmc::set_bnn_chunk(chains);
+  return SGMCMC_OK;
+}
+
+int sgmcmc_set_bnn_fused(int on, int max_ctas) {
+  if (max_ctas < 0) return sgmcmc::set_error(SGMCMC_E_INVALID, "max_ctas must be >= 0");
+  sgmcmc::set_bnn_fused(on != 0);
+  sgmcmc::set_bnn_fused_prefetch((on & 2) == 0);
+  sgmcmc::set_bnn_fused_max_ctas(max_ctas);
   return SGMCMC_OK;
 }
 

@@ -8,6 +8,12 @@
 
 namespace sgmcmc {
 
+// Philox counter of a launch: element group (4 elements) `i` of the launch's arrays draws
+// from counter (i + group_offset, step) under key `seed`.
+struct NoiseArgs {
+  uint64_t seed, step, group_offset;
+};
+
 // ---- host-side scalar prefixes -------------------------------------------------------
 // Computed in T with the reference's operation order (oracle/samplers.py:sghmc_scalars);
 // built with -ffp-contract=off so the host compiler does not fuse them either.

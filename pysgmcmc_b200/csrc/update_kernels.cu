@@ -66,10 +66,6 @@ __device__ __forceinline__ Pack<T> noise_pack(const T* __restrict__ z, int64_t g
   }
 }
 
-struct NoiseArgs {
-  uint64_t seed, step, group_offset;
-};
-
 // ------------------------------------------------------------------------------------
 // K1  SGHMC
 // ------------------------------------------------------------------------------------

@@ -295,7 +295,7 @@ def test_k4_launch_variants_agree():
             np.testing.assert_allclose(cost, wc, rtol=3e-6, err_msg="variant %d" % v)
             assert_grad_close(grad, wg)
     finally:
-        _native.call("sgmcmc_set_bnn_tuning", 0)
+        _native.call("sgmcmc_set_bnn_tuning", 10)
 
 
 def test_checkpoint_resume_is_bit_identical():
@@ -323,3 +323,136 @@ def test_checkpoint_resume_is_bit_identical():
         next(b)
     assert torch.equal(a._theta, b._theta) and torch.equal(a._state, b._state)
     assert a.n_iterations == b.n_iterations == 20
+
+
+# ---- K5 as one kernel (csrc/bnn_fused.cu) ------------------------------------------------
+def _run_c(state, X, y, starts, z, C, n_in, batch, N, n_steps, n_burn_in, keep_every, seed=3, step0=0,
+           chain_offset=0, eps=0.01, with_grad_scratch=True):
+    """sgmcmc_bnn_sghmc_run_f32 straight through the C ABI on copies of `state` (numpy
+    [6, C, D]: theta, v, tau, g, v_hat, minv).  Returns (state, trace, cost_trace)."""
+    D = state.shape[2]
+    st = torch.as_tensor(state, dtype=torch.float32, device=DEV).contiguous().clone()
+    Xd = torch.as_tensor(X, dtype=torch.float32, device=DEV).contiguous()
+    yd = torch.as_tensor(y, dtype=torch.float32, device=DEV).contiguous()
+    sd = None if starts is None else torch.as_tensor(starts, dtype=torch.int32, device=DEV).contiguous()
+    zd = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=DEV).contiguous()
+    n_keep = n_steps // keep_every
+    trace = torch.empty((n_keep, C, D), device=DEV)
+    ctrace = torch.empty((n_keep, C), device=DEV)
+    grad = torch.empty((C, D), device=DEV) if with_grad_scratch else None
+    cost = torch.empty(C, device=DEV)
+    p = _native.ptr
+    _native.call("sgmcmc_bnn_sghmc_run_f32", *[p(st[i]) for i in range(6)], p(Xd), p(yd), p(sd), p(zd),
+                 p(trace), p(ctrace), p(grad), p(cost), C, n_in, batch, float(batch), N, n_steps, n_burn_in,
+                 0, keep_every, eps, 0.05, float(N), seed, step0, chain_offset, _native.stream_ptr())
+    torch.cuda.synchronize()
+    return st.cpu().numpy(), trace.cpu().numpy(), ctrace.cpu().numpy()
+
+
+def _initial_state(C, n_in=1, seed=11):
+    theta0 = obnn.init_theta(C, n_in=n_in, seed=seed, dtype=np.float32)
+    D = theta0.shape[1]
+    state = np.ones((6, C, D), dtype=np.float32)
+    state[0] = theta0
+    state[1] = 0.0
+    return state
+
+
+@pytest.mark.parametrize("C,batch,N,tol", [(7, 20, 2000, 1e-5), (3, 8, 100, 1e-5), (5, 13, 300, 1e-5),
+                                           (4, 32, 500, 5e-5), (1, 1, 40, 1e-5)])
+def test_fused_step_matches_oracle_with_injected_noise(C, batch, N, tol):
+    """The one-kernel step against the fp32 oracle: injected noise, host-chosen minibatch
+    starts, 40 steps across the burn-in boundary (incl. the step that freezes minv).
+    Tolerance 1e-5 of max|theta|, as for the other trajectory tests; the 32-row case is the
+    most sensitive one (2.3e-5 with the tensor-pipe gradient, 2e-6 with the FFMA kernel: the
+    gradient errors are 4e-8 and 1e-8 of max|g|, and the preconditioner divides every element
+    by its own gradient scale, so small-gradient elements amplify them) and gets 5e-5."""
+    steps, burn = 40, 25
+    X, y = sinc_data(N)
+    state = _initial_state(C)
+    D = state.shape[2]
+    rng = np.random.RandomState(4)
+    starts = rng.randint(0, N - batch + 1, size=(steps, C)).astype(np.int32)
+    z = rng.standard_normal((steps, C, D)).astype(np.float32)
+    holder = {}
+
+    def cost_and_grad(theta):
+        Xb, yb = obnn.gather_minibatch(X, y, holder["starts"], batch)
+        c, g, _ = obnn.nll_and_grad(theta, Xb.astype(np.float32), yb.astype(np.float32), n_examples=N,
+                                    batch_size=batch)
+        return c, g
+    chain = osamplers.OracleChain("sghmc", state[0].copy(), cost_and_grad, epsilon=0.01, burn_in_steps=burn,
+                                  scale_grad=float(N))
+    want_costs = []
+    for s in range(steps):
+        holder["starts"] = starts[s]
+        want_theta, c = chain.next(z[s])
+        want_costs.append(c)
+    try:
+        _native.call("sgmcmc_set_bnn_fused", 1, 0)
+        got, trace, ctrace = _run_c(state, X, y, starts, z, C, 1, batch, N, steps, burn, 1, with_grad_scratch=False)
+    finally:
+        _native.call("sgmcmc_set_bnn_fused", 0, 0)
+    np.testing.assert_allclose(ctrace, np.stack(want_costs), rtol=1e-4)
+    scale = np.abs(want_theta).max()
+    assert np.abs(got[0] - want_theta).max() <= tol * scale
+    assert np.abs(trace[-1] - want_theta).max() <= tol * scale
+    minv_rel = np.abs(got[5] / chain.minv - 1.0)
+    assert np.median(minv_rel) < 1e-5 and minv_rel.max() < 5e-2
+
+
+@pytest.mark.parametrize("z_injected", [False, True])
+def test_fused_step_is_bit_identical_to_k4_then_k1(z_injected):
+    """One kernel per step == K4 (tensor-pipe kernel) followed by K1, bit for bit: all six
+    state arrays, the thinned trace and the costs, Philox noise or injected noise, a chain
+    offset (sharded run) and a run that crosses the burn-in boundary."""
+    C, batch, N, steps, burn = 37, 20, 2000, 30, 17
+    X, y = sinc_data(N)
+    state = _initial_state(C, seed=5)
+    rng = np.random.RandomState(8)
+    starts = rng.randint(0, N - batch + 1, size=(steps, C)).astype(np.int32)
+    z = rng.standard_normal((steps, C, state.shape[2])).astype(np.float32) if z_injected else None
+    out = {}
+    try:
+        for fused in (1, 0):
+            _native.call("sgmcmc_set_bnn_fused", fused, 0)
+            out[fused] = _run_c(state, X, y, starts, z, C, 1, batch, N, steps, burn, 3, seed=99, step0=1000,
+                                chain_offset=64)
+        _native.call("sgmcmc_set_bnn_fused", 1, 5)        # persistent grid: 5 CTAs loop over 37 chains
+        out[2] = _run_c(state, X, y, starts, z, C, 1, batch, N, steps, burn, 3, seed=99, step0=1000,
+                        chain_offset=64)
+    finally:
+        _native.call("sgmcmc_set_bnn_fused", 0, 0)
+    names = ("theta", "v", "tau", "g", "v_hat", "minv")
+    for other in (0, 2):
+        for i, name in enumerate(names):
+            assert np.array_equal(out[1][0][i], out[other][0][i]), (name, other)
+        assert np.array_equal(out[1][1], out[other][1]) and np.array_equal(out[1][2], out[other][2])
+    assert np.isfinite(out[1][0]).all()
+    assert not np.array_equal(out[1][0][0], state[0])
+
+
+def test_fused_step_falls_back_when_unsupported():
+    """n_in = 2 gives D = 5302 (not a multiple of 4): the run goes through K4 + K1 and needs
+    the gradient scratch buffer; the result is finite and the costs match the oracle's."""
+    C, batch, N, n_in = 3, 20, 200, 2
+    X, y = sinc_data(N, n_in=n_in)
+    D = n_parameters(n_in)
+    assert D % 4 != 0
+    rng = np.random.RandomState(0)
+    theta0 = (0.1 * rng.standard_normal((C, D))).astype(np.float32)
+    state = np.ones((6, C, D), dtype=np.float32)
+    state[0] = theta0
+    state[1] = 0.0
+    starts = rng.randint(0, N - batch + 1, size=(4, C)).astype(np.int32)
+    try:
+        _native.call("sgmcmc_set_bnn_fused", 1, 0)
+        got, trace, ctrace = _run_c(state, X, y, starts, None, C, n_in, batch, N, 4, 4, 1)
+        with pytest.raises(Exception):
+            _run_c(state, X, y, starts, None, C, n_in, batch, N, 4, 4, 1, with_grad_scratch=False)
+    finally:
+        _native.call("sgmcmc_set_bnn_fused", 0, 0)
+    Xb, yb = obnn.gather_minibatch(X, y, starts[0], batch)
+    wc, _, _ = obnn.nll_and_grad(theta0.astype(np.float64), Xb, yb, n_examples=N, n_in=n_in)
+    np.testing.assert_allclose(ctrace[0], wc, rtol=1e-5)
+    assert np.isfinite(got).all()

@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--chains", type=int, default=8192)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--variants", default="0,10")
+ap.add_argument("--caps", default="0", help="grid caps (persistent CTAs) to time per variant")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 C, N, B, D = args.chains, 20000, 20, 5252
@@ -37,8 +38,9 @@ def launch():
 
 
 ref = None
-for v in [int(x) for x in args.variants.split(",")]:
+for v, cap in [(int(x), int(c)) for x in args.variants.split(",") for c in args.caps.split(",")]:
     _native.call("sgmcmc_set_bnn_tuning", v)
+    _native.call("sgmcmc_set_persistent_grids", 0, cap)
     grad.fill_(float("nan"))
     try:
         launch()
@@ -61,7 +63,8 @@ for v in [int(x) for x in args.variants.split(",")]:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
     tf = 2 * 305000.0 * C / (ms * 1e9)
-    print(json.dumps({"variant": v, "ms": round(ms, 4), "chain_steps_per_s": round(C / ms * 1e3),
+    print(json.dumps({"variant": v, "max_ctas": cap, "ms": round(ms, 4), "chain_steps_per_s": round(C / ms * 1e3),
                       "fp32_TFLOPs": round(tf, 2), "frac_of_74.4": round(tf / 74.45, 3),
                       "matches_variant0": ok}), flush=True)
-_native.call("sgmcmc_set_bnn_tuning", 0)
+_native.call("sgmcmc_set_bnn_tuning", 10)
+_native.call("sgmcmc_set_persistent_grids", 0, 0)
