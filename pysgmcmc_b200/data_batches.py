@@ -118,12 +118,54 @@ class DeviceBatchGenerator(object):
             _native.call("sgmcmc_mt19937_seed", _native.ptr(self.state), _native.ptr(self.seeds),
                          self.n_chains, _native.stream_ptr())
 
+    def _side_stream(self):
+        """A high-priority stream for K7: the index kernel is latency bound and tiny (one
+        thread per chain), so its CTAs slot in next to the compute kernels of the main stream."""
+        if getattr(self, "_side", None) is None:
+            with torch.cuda.device(self.device):
+                self._side = torch.cuda.Stream(device=self.device, priority=-1)
+                # the streams were seeded on the current stream
+                self._side.wait_stream(torch.cuda.current_stream(self.device))
+        return self._side
+
+    def next_block_async(self, n_steps):
+        """Start the generation of the next `n_steps` steps on the generator's side stream.
+        Returns ``(starts, event)``: the consumer's stream must wait for `event` before it
+        reads `starts` (int32 ``[n_steps, C]``) and call ``starts.record_stream(consumer)``.
+        Blocks are generated in call order."""
+        assert self._buf is None or self._pos == self._buf.shape[0], \
+            "next_block cannot be mixed with a partially consumed next() block"
+        side = self._side_stream()
+        with torch.cuda.device(self.device):
+            if not getattr(self, "_side_owns_state", False):
+                # everything queued so far on the current stream (seeding, load_state_dict,
+                # earlier next_block calls) happens before the side stream touches the state
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                self._side_owns_state = True
+            # the block belongs to the SIDE stream's allocator pool: memory freed on the main
+            # stream may still be read by kernels queued there, and K7 runs ahead of them
+            with torch.cuda.stream(side):
+                out = torch.empty((n_steps, self.n_chains), dtype=torch.int32, device=self.device)
+            _native.call("sgmcmc_mt19937_starts", _native.ptr(self.state), _native.ptr(out),
+                         self.n_chains, n_steps, self.n_examples - self.batch_size,
+                         _native.stream_ptr(side))
+            event = torch.cuda.Event()
+            event.record(side)
+        return out, event
+
+    def _reclaim_state(self):
+        """Make the current stream the owner of the MT19937 state again."""
+        if getattr(self, "_side_owns_state", False):
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side_owns_state = False
+
     def next_block(self, n_steps):
         """Start indices of the next `n_steps` steps: int32 ``[n_steps, C]``."""
         assert self._buf is None or self._pos == self._buf.shape[0], \
             "next_block cannot be mixed with a partially consumed next() block"
-        out = torch.empty((n_steps, self.n_chains), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
+            self._reclaim_state()
+            out = torch.empty((n_steps, self.n_chains), dtype=torch.int32, device=self.device)
             _native.call("sgmcmc_mt19937_starts", _native.ptr(self.state), _native.ptr(out),
                          self.n_chains, n_steps, self.n_examples - self.batch_size,
                          _native.stream_ptr())
@@ -131,10 +173,14 @@ class DeviceBatchGenerator(object):
 
     def state_dict(self):
         """MT19937 streams plus the not yet consumed part of the current block."""
+        with torch.cuda.device(self.device):
+            self._reclaim_state()
         rest = None if self._buf is None else self._buf[self._pos:].clone()
         return {"state": self.state.clone(), "pending": rest}
 
     def load_state_dict(self, state):
+        with torch.cuda.device(self.device):
+            self._reclaim_state()
         self.state.copy_(state["state"])
         self._buf = state["pending"]
         self._pos = 0

@@ -94,19 +94,50 @@ class SGHMCSampler(BurnInMCMCSampler):
         n_burn_in = min(n_steps, self._burn_in_remaining())
         if self._native_target is not None:
             self._target_run(n_steps, n_burn_in, keep_every, None, trace, costs, epsilon)
+            self.n_iterations += n_steps
         else:
-            cf = self.cost_fun
-            starts = None if self.batch_generator is None else self.batch_generator.next_block(n_steps)
-            batch = cf.actual_batch if starts is not None else min(cf.X.shape[0], 256)
-            if self._grad is None:
-                self._grad = torch.empty_like(self._theta)
-            cost_scratch = torch.empty(self.n_chains, dtype=self.dtype, device=self.device)
+            self._bnn_run(n_steps, n_burn_in, keep_every, trace, costs, epsilon)
+
+    #: steps per K5 call when the minibatch indices come from the device generator: K7 for
+    #: the next chunk runs on a side stream while the main stream samples the current one
+    RUN_CHUNK = 128
+
+    def _bnn_run(self, n_steps, n_burn_in, keep_every, trace, costs, epsilon):
+        """K5 (csrc/bnn.cu: sgmcmc_bnn_sghmc_run_f32) in chunks of whole thinning periods, with
+        the on-device minibatch indices (K7) of chunk i+1 generated concurrently with chunk i."""
+        cf, gen = self.cost_fun, self.batch_generator
+        batch = cf.actual_batch if gen is not None else min(cf.X.shape[0], 256)
+        if self._grad is None:
+            self._grad = torch.empty_like(self._theta)
+        cost_scratch = torch.empty(self.n_chains, dtype=self.dtype, device=self.device)
+        if gen is None or n_steps <= self.RUN_CHUNK:
+            chunk = n_steps
+        elif n_steps < keep_every:
+            chunk = self.RUN_CHUNK
+        else:
+            chunk = keep_every * max(1, self.RUN_CHUNK // keep_every)
+        main = self.session.stream if self.session.stream is not None else torch.cuda.current_stream(self.device)
+        C, D = self.n_chains, self.n_params_per_chain
+        pending = None if gen is None else gen.next_block_async(min(chunk, n_steps))
+        done = 0
+        while done < n_steps:
+            n = min(chunk, n_steps - done)
+            starts = None
+            if gen is not None:
+                starts, ready = pending
+                pending = gen.next_block_async(min(chunk, n_steps - done - n)) if done + n < n_steps else None
+                main.wait_event(ready)
+                starts.record_stream(main)
+            k0 = done // keep_every                       # chunks start on a thinning boundary
+            tr = trace[k0:] if trace is not None and k0 < trace.shape[0] else None
+            co = costs[k0:] if costs is not None and k0 < costs.shape[0] else None
             _native.call("sgmcmc_bnn_sghmc_run_f32", *[_native.ptr(a) for a in self._arrays()],
                          _native.ptr(cf.X), _native.ptr(cf.y), _native.ptr(starts), None,
-                         _native.ptr(trace), _native.ptr(costs), _native.ptr(self._grad),
-                         _native.ptr(cost_scratch), self.n_chains, cf.n_in, batch, float(cf.batch_size),
-                         cf.n_examples, n_steps, n_burn_in, int(self.burn_in_steps == 0), keep_every,
-                         epsilon, self.mdecay, self.scale_grad, self._noise_seed, self.n_iterations,
-                         self.session.chain_offset, self._stream())
-            self.cost = cost_scratch
-        self.n_iterations += n_steps
+                         _native.ptr(tr), _native.ptr(co), _native.ptr(self._grad),
+                         _native.ptr(cost_scratch), C, cf.n_in, batch, float(cf.batch_size),
+                         cf.n_examples, n, min(n, max(0, n_burn_in - done)), int(self.burn_in_steps == 0),
+                         keep_every, epsilon, self.mdecay, self.scale_grad, self._noise_seed,
+                         self.n_iterations, self.session.chain_offset, self._stream())
+            self.n_iterations += n
+            done += n
+        self.cost = cost_scratch

@@ -243,6 +243,39 @@ def test_bnn_sghmc_run_equals_per_step_and_oracle():
     assert torch.isfinite(a._theta).all()
 
 
+@pytest.mark.parametrize("keep_every,run_chunk", [(5, 16), (7, 16), (100, 16), (1, 8)])
+def test_bnn_sghmc_chunked_run_with_side_stream_indices(keep_every, run_chunk, monkeypatch):
+    """run() splits long runs into chunks of whole thinning periods and generates the
+    minibatch indices of the next chunk on a side stream (K7 || K4 + K1): same states, trace
+    and costs as one step at a time, across the burn-in boundary, incl. a trailing partial
+    thinning period and a second run() that continues the streams."""
+    monkeypatch.setattr(SGHMCSampler, "RUN_CHUNK", run_chunk)
+    C, N, batch, steps, burn = 9, 2000, 20, 60, 25
+    X, y = sinc_data(N)
+
+    def build():
+        gen = DeviceBatchGenerator(N, batch, n_chains=C, seed=5, device=DEV, block=16)
+        nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+        params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+        return SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen, burn_in_steps=burn,
+                            scale_grad=float(N), seed=77,
+                            session=Session(device=DEV, n_chains=C, output="torch"))
+    a, b = build(), build()
+    trace, costs = a.run(steps, keep_every=keep_every)
+    trace2, costs2 = a.run(20, keep_every=keep_every)
+    assert a.n_iterations == steps + 20 and trace.shape[0] == steps // keep_every
+    for s in range(steps + 20):
+        sample, cost = next(b)
+        tr, co, local = (trace, costs, s) if s < steps else (trace2, costs2, s - steps)
+        if (local + 1) % keep_every == 0:
+            k = (local + 1) // keep_every - 1
+            assert torch.equal(tr[k], b._theta), "trace at step %d" % s
+            assert torch.equal(co[k], cost), "cost at step %d" % s
+    for name in ("v", "tau", "g", "v_hat", "minv"):
+        assert torch.equal(a._state_array(name), b._state_array(name)), name
+    assert torch.equal(a._theta, b._theta)
+
+
 def test_reference_style_host_batches_single_chain():
     """Reference wiring: generate_batches feeding placeholders, one chain, numpy outputs."""
     from pysgmcmc_b200.data_batches import generate_batches
