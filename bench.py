@@ -382,51 +382,38 @@ def per_kernel_times(sampler, gen, nll, torch, _native, n=30):
 
 
 def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks):
-    """K steps through sgmcmc_bnn_sghmc_run_f32 with host buffers: per step the minibatch
-    start indices are copied from pinned host memory, the per-chain cost is copied back to
-    pinned host memory and the host waits for it (what `sample, cost = next(sampler)`
-    means); every SAMPLE_STEPS-th step the whole sample [C, D] is copied back as well."""
+    """K steps through the public host-facing iterator `SGHMCSampler.iter_host`: per step the
+    minibatch start indices are copied from pinned host memory, K4 + K1 run through the C ABI
+    (sgmcmc_bnn_sghmc_run_f32) and the per-chain cost is copied back to pinned host memory,
+    where the host receives it (what `sample, cost = next(sampler)` means); every
+    SAMPLE_STEPS-th step the whole sample [C, D] is copied back as well.  The iterator keeps
+    up to 8 steps queued ahead and runs the copies on their own streams, so the device does not
+    idle while the host handles a result or a sample crosses PCIe."""
     K_e = min(K, 300)
     rng = np.random.RandomState(7)
     host_starts = torch.from_numpy(
         rng.randint(0, N_EXAMPLES - BATCH + 1, size=(W + K_e, C)).astype(np.int32)).pin_memory()
-    host_cost = torch.empty(C, dtype=torch.float32).pin_memory()
-    host_sample = torch.empty((C, D), dtype=torch.float32).pin_memory()
-    dev_starts = torch.empty(C, dtype=torch.int32, device=dev)
-    grad = sampler._grad if sampler._grad is not None else torch.empty_like(sampler._theta)
-    cost = torch.empty(C, device=dev)
-    p = _native.ptr
-    arrs = sampler._arrays()
-    st = _native.stream_ptr()
-
-    def step(s):
-        dev_starts.copy_(host_starts[s], non_blocking=True)
-        _native.call("sgmcmc_bnn_sghmc_run_f32", *[p(a) for a in arrs], p(nll.X), p(nll.y), p(dev_starts),
-                     None, None, None, p(grad), p(cost), C, N_IN, BATCH, float(BATCH), N_EXAMPLES,
-                     1, 1, 1, 1, EPS, MDECAY, float(N_EXAMPLES), 1, sampler.n_iterations,
-                     sampler.session.chain_offset, st)
-        host_cost.copy_(cost, non_blocking=True)
-        if (s + 1) % SAMPLE_STEPS == 0:
-            host_sample.copy_(sampler._theta, non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the caller holds (sample, cost) now
-        sampler.n_iterations += 1
-    for s in range(W):
-        step(s)
+    checksum = 0.0
+    for _ in sampler.iter_host(host_starts[:W], sample_every=SAMPLE_STEPS):
+        pass
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s in range(W, W + K_e):
-        step(s)
+    n_samples = 0
+    for sample, cost in sampler.iter_host(host_starts[W:], sample_every=SAMPLE_STEPS, lookahead=8):
+        checksum += float(cost[0])                       # the host reads every step's result
+        n_samples += sample is not None
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
-    n_samples = sum(1 for s in range(W, W + K_e) if (s + 1) % SAMPLE_STEPS == 0)
+    assert np.isfinite(checksum)
     return {"value": C * world * K_e / (ms / 1e3), "unit": "chain-steps/s", "steps": K_e,
             "ms_per_step": ms / K_e, "wall_ms_per_step": wall_ms / K_e,
             "h2d_bytes_per_step": C * 4, "d2h_bytes_per_step": C * 4 + n_samples * C * D * 4 / K_e,
-            "api": "sgmcmc_bnn_sghmc_run_f32 (C ABI), one call per step, pinned host buffers, host sync per step"}
+            "api": "SGHMCSampler.iter_host -> sgmcmc_bnn_sghmc_run_f32 (C ABI), one call per step, pinned host "
+                   "buffers, host receives every step's cost, up to 8 steps queued ahead"}
 
 
 def main():

@@ -141,3 +141,103 @@ class SGHMCSampler(BurnInMCMCSampler):
             self.n_iterations += n
             done += n
         self.cost = cost_scratch
+
+    # ---- next(sampler) with HOST minibatches, pipelined ---------------------------------
+    def iter_host(self, host_starts, sample_every=None, lookahead=4):
+        """Generator over ``(sample, cost)`` like ``next(sampler)``, for the BNN cost with the
+        dataset resident on the device and the minibatch choice made on the HOST: row s of
+        `host_starts` (pinned int32 ``[n_steps, C]``) holds the start index of every chain's
+        minibatch of step s (``x[start:start+B]``, data_batches.py:120-123).
+
+        Every step copies its row host->device, runs K4 + K1 and copies the per-chain cost
+        back into pinned host memory; every `sample_every`-th step the whole sample ``[C, D]``
+        comes back as well (``None`` otherwise) -- the thinning of
+        ``BayesianNeuralNetwork.train`` (bayesian_neural_network.py:510-531).  Unlike a plain
+        ``next()`` loop the device never waits for the host: up to `lookahead` further steps
+        are already queued when ``(sample_s, cost_s)`` is yielded, the copies run on their own
+        streams (one per direction) and the sample is snapshotted device-to-device before it
+        travels, so the result is the same as the synchronous loop, bit for bit.
+
+        The yielded arrays are views of pinned buffers that are re-used `lookahead + 1`
+        (cost) / one (sample) yields later: copy what must be kept.
+        """
+        assert self._bnn_run_ok() and self._native_target is None, "iter_host needs the native BNN cost"
+        assert host_starts.dtype == torch.int32 and host_starts.dim() == 2 and host_starts.shape[1] == self.n_chains
+        assert lookahead >= 0
+        cf, C, D, dev = self.cost_fun, self.n_chains, self.n_params_per_chain, self.device
+        n_steps, nbuf = host_starts.shape[0], lookahead + 1
+        p = _native.ptr
+        main = self.session.stream if self.session.stream is not None else torch.cuda.current_stream(dev)
+        if getattr(self, "_io_streams", None) is None:
+            self._io_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = self._io_streams                # host->device and device->host copies
+        if self._grad is None:
+            self._grad = torch.empty_like(self._theta)
+        d_starts = torch.empty((nbuf, C), dtype=torch.int32, device=dev)
+        d_cost = torch.empty((nbuf, C), dtype=self.dtype, device=dev)
+        d_stage = torch.empty((C, D), dtype=self.dtype, device=dev) if sample_every else None
+        for t in (d_starts, d_cost) + ((d_stage,) if sample_every else ()):
+            t.record_stream(s_in)
+            t.record_stream(s_out)
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        h_cost = torch.empty((nbuf, C), dtype=self.dtype).pin_memory()
+        h_sample = torch.empty((C, D), dtype=self.dtype).pin_memory() if sample_every else None
+        step_done = [None] * nbuf         # the kernels of the step that last used buffer b are done
+        out_done = [None] * nbuf          # ... and its results are in host memory
+        sample_done = None
+        epsilon = float(next(self.stepsize_schedule))
+        wants_sample = [False] * nbuf
+
+        def enqueue(s):
+            nonlocal sample_done
+            b = s % nbuf
+            if step_done[b] is not None:
+                s_in.wait_event(step_done[b])         # d_starts[b] is no longer read
+            with torch.cuda.stream(s_in):
+                d_starts[b].copy_(host_starts[s], non_blocking=True)
+            h2d = torch.cuda.Event()
+            h2d.record(s_in)
+            main.wait_event(h2d)
+            if out_done[b] is not None:
+                main.wait_event(out_done[b])          # d_cost[b] has left the device
+            # burn-in steps left INCLUDING this one, capped at 2: the kernel writes `minv` back
+            # only on the last burn-in step (n_burn_in == 1), where it is frozen
+            n_burn_in = min(2, max(0, self.burn_in_steps - self.n_iterations))
+            with torch.cuda.device(dev):
+                _native.call("sgmcmc_bnn_sghmc_run_f32", *[p(a) for a in self._arrays()], p(cf.X), p(cf.y),
+                             p(d_starts[b]), None, None, None, p(self._grad), p(d_cost[b]), C, cf.n_in,
+                             cf.actual_batch, float(cf.batch_size), cf.n_examples, 1, n_burn_in,
+                             int(self.burn_in_steps == 0), 1, epsilon, self.mdecay, self.scale_grad,
+                             self._noise_seed, self.n_iterations, self.session.chain_offset,
+                             _native.stream_ptr(main))
+            self.n_iterations += 1
+            wants_sample[b] = bool(sample_every) and (s + 1) % sample_every == 0
+            if wants_sample[b]:
+                if sample_done is not None:
+                    main.wait_event(sample_done)      # the previous sample has left the staging buffer
+                with torch.cuda.stream(main):
+                    d_stage.copy_(self._theta, non_blocking=True)
+            step_done[b] = torch.cuda.Event()
+            step_done[b].record(main)
+            s_out.wait_event(step_done[b])
+            with torch.cuda.stream(s_out):
+                h_cost[b].copy_(d_cost[b], non_blocking=True)
+                if wants_sample[b]:
+                    h_sample.copy_(d_stage, non_blocking=True)
+                    sample_done = torch.cuda.Event()
+                    sample_done.record(s_out)
+            out_done[b] = torch.cuda.Event()
+            out_done[b].record(s_out)
+
+        queued = 0
+        for s in range(n_steps):
+            while queued < n_steps and queued <= s + lookahead:
+                enqueue(queued)
+                queued += 1
+            b = s % nbuf
+            out_done[b].synchronize()                 # (sample_s, cost_s) are in host memory now
+            self.cost = d_cost[b]
+            yield (h_sample.numpy() if wants_sample[b] else None), h_cost[b].numpy()
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)

@@ -276,6 +276,41 @@ def test_bnn_sghmc_chunked_run_with_side_stream_indices(keep_every, run_chunk, m
     assert torch.equal(a._theta, b._theta)
 
 
+@pytest.mark.parametrize("lookahead", [0, 1, 3])
+def test_iter_host_pipelined_equals_synchronous_steps(lookahead):
+    """sampler.iter_host (host minibatch indices in, cost and thinned samples out, copies and
+    the next step overlapped) == the same steps through next(sampler) with the indices fed one
+    row at a time; crosses the burn-in boundary."""
+    C, N, batch, steps, burn, every = 6, 2000, 20, 40, 17, 8
+    X, y = sinc_data(N)
+    rng = np.random.RandomState(3)
+    host_starts = torch.from_numpy(rng.randint(0, N - batch + 1, size=(steps, C)).astype(np.int32)).pin_memory()
+
+    def build():
+        ph = DeviceBatchGenerator(N, batch, n_chains=C, seed=5, device=DEV).starts_placeholder
+        nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=ph, device=DEV)
+        params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+        s = SGHMCSampler(params=params, cost_fun=nll, burn_in_steps=burn, scale_grad=float(N), seed=21,
+                         session=Session(device=DEV, n_chains=C, output="torch"))
+        return s, ph
+    a, _ = build()
+    b, ph = build()
+    got = [(None if smp is None else smp.copy(), cost.copy())
+           for smp, cost in a.iter_host(host_starts, sample_every=every, lookahead=lookahead)]
+    assert len(got) == steps and a.n_iterations == steps
+    for s in range(steps):
+        ph.value = host_starts[s].to(DEV)     # (a feed_dict would be dropped after burn-in, :454)
+        sample, cost = next(b)
+        assert np.array_equal(got[s][1], cost.cpu().numpy()), "cost at step %d" % s
+        if (s + 1) % every == 0:
+            assert np.array_equal(got[s][0], b._theta.cpu().numpy()), "sample at step %d" % s
+        else:
+            assert got[s][0] is None
+    for name in ("v", "tau", "g", "v_hat", "minv"):
+        assert torch.equal(a._state_array(name), b._state_array(name)), name
+    assert torch.equal(a._theta, b._theta) and not a.is_burning_in
+
+
 def test_reference_style_host_batches_single_chain():
     """Reference wiring: generate_batches feeding placeholders, one chain, numpy outputs."""
     from pysgmcmc_b200.data_batches import generate_batches
