@@ -138,7 +138,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(chains_per_gpu, n_gpus):
@@ -345,7 +345,7 @@ def run_b200(args):
         "sampling_phase": sampling_phase,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def per_kernel_times(sampler, gen, nll, torch, _native, n=30):
@@ -394,7 +394,7 @@ def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_o
     host_starts = torch.from_numpy(
         rng.randint(0, N_EXAMPLES - BATCH + 1, size=(W + K_e, C)).astype(np.int32)).pin_memory()
     checksum = 0.0
-    for _ in sampler.iter_host(host_starts[:W], sample_every=SAMPLE_STEPS):
+    for _ in sampler.iter_host(host_starts[:W], sample_every=SAMPLE_STEPS, lookahead=8):
         pass
     barrier()
     t0 = time.perf_counter()
@@ -416,7 +416,27 @@ def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_o
                    "buffers, host receives every step's cost, up to 8 steps queued ahead"}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 from here on
+    (NCCL prints its version banner there) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -192,6 +192,32 @@ int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float
                              float epsilon, float mdecay, float scale_grad,
                              uint64_t seed, uint64_t step0, uint64_t chain_offset, void* stream);
 
+/* ---- K5 with HOST buffers: the pipelined `sample, cost = next(sampler)` of the BNN path
+ * (samplers/base_classes.py:258-310,408-456; csrc/host_pipeline.cu).  Every `step` copies
+ * that step's minibatch start indices from pinned host memory (host_starts [C]), runs
+ * K4 + K1 on `stream`, copies the per-chain cost to pinned host memory (host_cost [C]) and,
+ * if host_sample != NULL, the new sample theta [C, D] too (through a device-side snapshot,
+ * so later steps do not wait for PCIe).  `step` never blocks the host; `wait(ticket)` blocks
+ * until the results of that step are in host memory.  Up to `depth` steps may be in flight:
+ * a ticket can be waited for until `depth` further steps were enqueued, and its host buffers
+ * must stay untouched until then.  burn_in_left = burn-in steps left including this one
+ * (0 = sampling phase; minv is written back only on the last burn-in step).  The handle owns
+ * the copy streams, events and device-side slot buffers. */
+typedef struct sgmcmc_bnn_host_pipeline sgmcmc_bnn_host_pipeline;
+int sgmcmc_bnn_host_pipeline_create(sgmcmc_bnn_host_pipeline** out, int64_t n_chains, int n_in,
+                                    int depth, int with_samples);
+int sgmcmc_bnn_host_pipeline_destroy(sgmcmc_bnn_host_pipeline* p);
+int sgmcmc_bnn_host_pipeline_step(sgmcmc_bnn_host_pipeline* p,
+                                  float* theta, float* v, float* tau, float* g, float* v_hat, float* minv,
+                                  const float* X, const float* y,
+                                  const int32_t* host_starts, float* host_cost, float* host_sample,
+                                  float* grad_scratch, int n_in, int batch, float batch_size_cfg,
+                                  int64_t n_examples, int burn_in_left, int adapt_forever,
+                                  float epsilon, float mdecay, float scale_grad,
+                                  uint64_t seed, uint64_t step, uint64_t chain_offset, void* stream,
+                                  int64_t* ticket);
+int sgmcmc_bnn_host_pipeline_wait(sgmcmc_bnn_host_pipeline* p, int64_t ticket);
+
 /* ---- K10: BNN predictive, replaces bayesian_neural_network.py:535-557 -------------
  * out[k, i, 0] = f(x_i; theta_k), out[k, i, 1] = rho_k  for n_nets stored samples. */
 int sgmcmc_bnn_predict_f32(const float* theta, const float* X, float* out,

@@ -156,88 +156,82 @@ class SGHMCSampler(BurnInMCMCSampler):
         ``next()`` loop the device never waits for the host: up to `lookahead` further steps
         are already queued when ``(sample_s, cost_s)`` is yielded, the copies run on their own
         streams (one per direction) and the sample is snapshotted device-to-device before it
-        travels, so the result is the same as the synchronous loop, bit for bit.
+        travels, so the result is the same as the synchronous loop, bit for bit.  The pipeline
+        itself is native (csrc/host_pipeline.cu: two ctypes calls per step).
 
         The yielded arrays are views of pinned buffers that are re-used `lookahead + 1`
         (cost) / one (sample) yields later: copy what must be kept.
         """
         assert self._bnn_run_ok() and self._native_target is None, "iter_host needs the native BNN cost"
         assert host_starts.dtype == torch.int32 and host_starts.dim() == 2 and host_starts.shape[1] == self.n_chains
-        assert lookahead >= 0
+        assert host_starts.is_pinned() and host_starts.is_contiguous(), "host_starts must be pinned host memory"
+        assert 0 <= lookahead < 64
         cf, C, D, dev = self.cost_fun, self.n_chains, self.n_params_per_chain, self.device
-        n_steps, nbuf = host_starts.shape[0], lookahead + 1
-        p = _native.ptr
-        main = self.session.stream if self.session.stream is not None else torch.cuda.current_stream(dev)
-        if getattr(self, "_io_streams", None) is None:
-            self._io_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-        s_in, s_out = self._io_streams                # host->device and device->host copies
+        n_steps, depth = host_starts.shape[0], lookahead + 1
         if self._grad is None:
             self._grad = torch.empty_like(self._theta)
-        d_starts = torch.empty((nbuf, C), dtype=torch.int32, device=dev)
-        d_cost = torch.empty((nbuf, C), dtype=self.dtype, device=dev)
-        d_stage = torch.empty((C, D), dtype=self.dtype, device=dev) if sample_every else None
-        for t in (d_starts, d_cost) + ((d_stage,) if sample_every else ()):
-            t.record_stream(s_in)
-            t.record_stream(s_out)
-        s_in.wait_stream(main)
-        s_out.wait_stream(main)
-        h_cost = torch.empty((nbuf, C), dtype=self.dtype).pin_memory()
-        h_sample = torch.empty((C, D), dtype=self.dtype).pin_memory() if sample_every else None
-        step_done = [None] * nbuf         # the kernels of the step that last used buffer b are done
-        out_done = [None] * nbuf          # ... and its results are in host memory
-        sample_done = None
+        handle, h_cost, h_sample = self._host_pipeline(depth, bool(sample_every))
         epsilon = float(next(self.stepsize_schedule))
-        wants_sample = [False] * nbuf
+        arrays = [_native.ptr(a) for a in self._arrays()]
+        X, y, grad = _native.ptr(cf.X), _native.ptr(cf.y), _native.ptr(self._grad)
+        starts0, row_bytes = host_starts.data_ptr(), C * 4
+        cost0 = h_cost.data_ptr()
+        sample_ptr = h_sample.data_ptr() if sample_every else None
+        stream = self._stream()
+        ticket = ctypes.c_int64()
+        wants_sample = [False] * depth
+        first = None
 
         def enqueue(s):
-            nonlocal sample_done
-            b = s % nbuf
-            if step_done[b] is not None:
-                s_in.wait_event(step_done[b])         # d_starts[b] is no longer read
-            with torch.cuda.stream(s_in):
-                d_starts[b].copy_(host_starts[s], non_blocking=True)
-            h2d = torch.cuda.Event()
-            h2d.record(s_in)
-            main.wait_event(h2d)
-            if out_done[b] is not None:
-                main.wait_event(out_done[b])          # d_cost[b] has left the device
-            # burn-in steps left INCLUDING this one, capped at 2: the kernel writes `minv` back
-            # only on the last burn-in step (n_burn_in == 1), where it is frozen
-            n_burn_in = min(2, max(0, self.burn_in_steps - self.n_iterations))
-            with torch.cuda.device(dev):
-                _native.call("sgmcmc_bnn_sghmc_run_f32", *[p(a) for a in self._arrays()], p(cf.X), p(cf.y),
-                             p(d_starts[b]), None, None, None, p(self._grad), p(d_cost[b]), C, cf.n_in,
-                             cf.actual_batch, float(cf.batch_size), cf.n_examples, 1, n_burn_in,
-                             int(self.burn_in_steps == 0), 1, epsilon, self.mdecay, self.scale_grad,
-                             self._noise_seed, self.n_iterations, self.session.chain_offset,
-                             _native.stream_ptr(main))
-            self.n_iterations += 1
+            nonlocal first
+            b = s % depth
             wants_sample[b] = bool(sample_every) and (s + 1) % sample_every == 0
-            if wants_sample[b]:
-                if sample_done is not None:
-                    main.wait_event(sample_done)      # the previous sample has left the staging buffer
-                with torch.cuda.stream(main):
-                    d_stage.copy_(self._theta, non_blocking=True)
-            step_done[b] = torch.cuda.Event()
-            step_done[b].record(main)
-            s_out.wait_event(step_done[b])
-            with torch.cuda.stream(s_out):
-                h_cost[b].copy_(d_cost[b], non_blocking=True)
-                if wants_sample[b]:
-                    h_sample.copy_(d_stage, non_blocking=True)
-                    sample_done = torch.cuda.Event()
-                    sample_done.record(s_out)
-            out_done[b] = torch.cuda.Event()
-            out_done[b].record(s_out)
+            _native.call("sgmcmc_bnn_host_pipeline_step", handle, *arrays, X, y, starts0 + s * row_bytes,
+                         cost0 + b * row_bytes, sample_ptr if wants_sample[b] else None, grad, cf.n_in,
+                         cf.actual_batch, float(cf.batch_size), cf.n_examples,
+                         min(2, max(0, self.burn_in_steps - self.n_iterations)),
+                         int(self.burn_in_steps == 0), epsilon, self.mdecay, self.scale_grad,
+                         self._noise_seed, self.n_iterations, self.session.chain_offset, stream,
+                         ctypes.byref(ticket))
+            if first is None:
+                first = ticket.value                  # tickets count over the life of the handle
+            self.n_iterations += 1
 
         queued = 0
-        for s in range(n_steps):
-            while queued < n_steps and queued <= s + lookahead:
-                enqueue(queued)
-                queued += 1
-            b = s % nbuf
-            out_done[b].synchronize()                 # (sample_s, cost_s) are in host memory now
-            self.cost = d_cost[b]
-            yield (h_sample.numpy() if wants_sample[b] else None), h_cost[b].numpy()
-        main.wait_stream(s_in)
-        main.wait_stream(s_out)
+        with torch.cuda.device(dev):
+            for s in range(n_steps):
+                while queued < n_steps and queued <= s + lookahead:
+                    enqueue(queued)
+                    queued += 1
+                _native.call("sgmcmc_bnn_host_pipeline_wait", handle, first + s)   # step s is in host memory
+                b = s % depth
+                yield (h_sample.numpy() if wants_sample[b] else None), h_cost[b].numpy()
+
+    def _host_pipeline(self, depth, with_samples):
+        """The native stepper of `iter_host` and its pinned result buffers, kept between calls
+        (pinning [C, D] floats costs tens of milliseconds)."""
+        cached = getattr(self, "_host_pipe", None)
+        if cached is not None and cached[0] == (depth, with_samples):
+            return cached[1:]
+        self.close_host_pipeline()
+        C, D = self.n_chains, self.n_params_per_chain
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.call("sgmcmc_bnn_host_pipeline_create", ctypes.byref(handle), C, self.cost_fun.n_in, depth,
+                         int(with_samples))
+        h_cost = torch.empty((depth, C), dtype=self.dtype).pin_memory()
+        h_sample = torch.empty((C, D), dtype=self.dtype).pin_memory() if with_samples else None
+        self._host_pipe = ((depth, with_samples), handle, h_cost, h_sample)
+        return handle, h_cost, h_sample
+
+    def close_host_pipeline(self):
+        cached = getattr(self, "_host_pipe", None)
+        if cached is not None:
+            self._host_pipe = None
+            _native.call("sgmcmc_bnn_host_pipeline_destroy", cached[1])
+
+    def __del__(self):
+        try:
+            self.close_host_pipeline()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
