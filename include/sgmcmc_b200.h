@@ -59,6 +59,11 @@ int sgmcmc_set_update_tuning(int threads, int unroll);
  * flight) kept for the sweeps recorded under profiles/. */
 int sgmcmc_set_bnn_tuning(int variant);
 
+/* K1 walks its arrays from the end (the first CTAs take the last elements): after K4, which
+ * walks the chains in ascending order, the tail of theta and of the gradient is still in L2
+ * (and K1 then ends where the next K4 begins).  On by default; results do not depend on it. */
+int sgmcmc_set_update_reverse(int on);
+
 /* Cap the grids of the update kernels (K1-K3) and of K4 to that many CTAs (persistent
  * kernels that loop over their work; 0 = one CTA per unit of work, the default).  Used to
  * leave SM resources free when two kernels are meant to run concurrently on two streams. */
@@ -67,6 +72,13 @@ int sgmcmc_set_persistent_grids(int update_max_ctas, int bnn_max_ctas);
 /* Chains per chunk inside sgmcmc_bnn_sghmc_run_f32: K4 and K1 run back to back on one chunk
  * at a time so that the chunk's gradient stays in L2 (0 = all chains in one chunk). */
 int sgmcmc_set_bnn_chunk(int64_t chains);
+
+/* Two-stream pipeline inside sgmcmc_bnn_sghmc_run_f32: the chains are walked in chunks of
+ * `chunk_chains`; K4 of a chunk runs on the caller's stream while K1 of the previous chunk
+ * runs on a stream owned by the library, the gradient going through a ring of `ring` (default
+ * 2) chunk-sized slots of grad_scratch.  Results are bit-identical to the sequential order.
+ * chunk_chains = 0 switches it off. */
+int sgmcmc_set_bnn_pipeline(int64_t chunk_chains, int ring);
 
 /* sgmcmc_bnn_sghmc_run_f32 as ONE kernel per step (cost + gradient + SGHMC update of a chain
  * in one CTA, the gradient never leaves shared memory; csrc/bnn_fused.cu): bit-identical to

@@ -33,6 +33,8 @@ SIGNATURES = {
     "sgmcmc_set_bnn_tuning": [c_int],
     "sgmcmc_set_persistent_grids": [c_int, c_int],
     "sgmcmc_set_bnn_chunk": [c_int64],
+    "sgmcmc_set_bnn_pipeline": [c_int64, c_int],
+    "sgmcmc_set_update_reverse": [c_int],
     "sgmcmc_set_bnn_fused": [c_int, c_int],
     "sgmcmc_launch_count": [],
     "sgmcmc_sghmc_step_f32": [_P] * 8 + [c_int64, c_float, c_float, c_float, c_int, c_int,

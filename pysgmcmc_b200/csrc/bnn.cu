@@ -536,6 +536,53 @@ static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
   }
 }
 
+// ---- two-stream pipeline of K5 (sgmcmc_set_bnn_pipeline) --------------------------------
+// K4 of chunk j+1 (stream of the caller) runs WHILE K1 of chunk j (library-owned stream)
+// streams that chunk's state: the SMs host CTAs of both kernels at once (both ask for the
+// maximum shared-memory carveout, otherwise an SM would have to drain to switch), K1 fills the
+// partial waves of K4 and vice versa, and a chunk's theta and gradient are still in L2 when
+// K1 reads them.  The gradient goes through a ring of `ring` chunk-sized slots of grad_scratch,
+// so its dirty lines are overwritten in L2 instead of being written back.
+static int64_t g_pipe_chunk = 0;        // chains per chunk (0: pipeline off)
+static int g_pipe_ring = 2;
+void set_bnn_pipeline(int64_t chunk, int ring) { g_pipe_chunk = chunk; g_pipe_ring = ring; }
+
+constexpr int PIPE_MAX_RING = 8;
+struct PipeResources {
+  int device = -1;
+  cudaStream_t s_upd = nullptr;
+  cudaEvent_t k4_done[PIPE_MAX_RING], slot_free[PIPE_MAX_RING], begin = nullptr, snap = nullptr;
+};
+static PipeResources g_pipe[16];
+
+static int get_pipe(PipeResources** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 16) return set_error(SGMCMC_E_CUDA, "bnn pipeline: cudaGetDevice failed");
+  PipeResources& r = g_pipe[dev];
+  if (r.device != dev) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = greatest priority (numerically lowest)
+    e = cudaStreamCreateWithPriority(&r.s_upd, cudaStreamNonBlocking, hi);
+    for (int i = 0; i < PIPE_MAX_RING && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&r.k4_done[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.slot_free[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.begin, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.snap, cudaEventDisableTiming);
+    if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "bnn pipeline: %s", cudaGetErrorString(e));
+    r.device = dev;
+  }
+  *out = &r;
+  return SGMCMC_OK;
+}
+
+#define SG_CUDA_RC(call)                                                                     \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) return set_error(SGMCMC_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
 static int make_bnn_args(BnnArgs& a, const float* theta, const float* X, const float* y,
                          const int32_t* starts, float* cost, float* grad, float* mse, int64_t n_chains,
                          int n_in, int batch, float batch_size_cfg, int64_t n_examples) {
@@ -623,6 +670,60 @@ extern "C" int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, floa
   // one kernel per step (bnn_fused.cu) whenever the shape allows it; else K4 then K1
   const bool fused = bnn_fused_enabled() && g_bnn_chunk == 0 && bnn_fused_supported(a, f);
   SG_REQUIRE(fused || grad_scratch, SGMCMC_E_INVALID, "bnn_sghmc_run: grad_scratch must not be NULL");
+  if (!fused && g_pipe_chunk > 0 && g_pipe_chunk < n_chains && z == nullptr) {
+    // ---- pipelined: K4 chunks on `st`, K1 chunks on the library's update stream -----------
+    PipeResources* P = nullptr;
+    if (int rc = get_pipe(&P)) return rc;
+    const int64_t pc = g_pipe_chunk;
+    int ring = g_pipe_ring < 1 ? 1 : (g_pipe_ring > PIPE_MAX_RING ? PIPE_MAX_RING : g_pipe_ring);
+    const int64_t n_chunks = (n_chains + pc - 1) / pc;
+    if (ring > n_chains / pc) ring = (int)(n_chains / pc);      // the ring lives inside grad_scratch [C, D]
+    SG_REQUIRE((pc * D) % 4 == 0, SGMCMC_E_INVALID, "bnn pipeline: chunk * D must be a multiple of 4");
+    SG_CUDA_RC(cudaEventRecord(P->begin, st));
+    SG_CUDA_RC(cudaStreamWaitEvent(P->s_upd, P->begin, 0));          // everything queued before this call
+    int64_t j = 0;                                                   // global chunk counter
+    for (int64_t s = 0; s < n_steps; ++s) {
+      const int burn_in = adapt_forever || s < n_burn_in;
+      const int store_minv = burn_in && (s == n_burn_in - 1 || (adapt_forever && s == n_steps - 1));
+      for (int64_t c0 = 0; c0 < n_chains; c0 += pc, ++j) {
+        const int64_t nc = n_chains - c0 < pc ? n_chains - c0 : pc;
+        const int slot = (int)(j % ring);
+        float* gslot = grad_scratch + (int64_t)slot * pc * D;
+        // K1 of chunk j - ring has read this slot; it comes after K1 of this chunk's previous
+        // step on the in-order update stream, so theta of the chunk is up to date as well
+        if (j >= ring) SG_CUDA_RC(cudaStreamWaitEvent(st, P->slot_free[slot], 0));
+        BnnArgs ac = a;
+        ac.theta = theta + c0 * D;
+        ac.cost = cost_scratch + c0;
+        ac.grad = gslot;
+        ac.n_chains = nc;
+        ac.starts = starts != nullptr ? starts + s * n_chains + c0 : nullptr;
+        if (int rc = launch_nll_grad(ac, st)) return rc;
+        SG_CUDA_RC(cudaEventRecord(P->k4_done[slot], st));
+        SG_CUDA_RC(cudaStreamWaitEvent(P->s_upd, P->k4_done[slot], 0));
+        const int64_t o = c0 * D;
+        if (int rc = sgmcmc_sghmc_step_f32(theta + o, v + o, tau + o, g + o, v_hat + o, minv + o, gslot, nullptr,
+                                           nc * D, epsilon, mdecay, scale_grad, burn_in, store_minv, seed,
+                                           step0 + (uint64_t)s, (chain_offset + (uint64_t)c0) * (uint64_t)D,
+                                           (void*)P->s_upd))
+          return rc;
+        SG_CUDA_RC(cudaEventRecord(P->slot_free[slot], P->s_upd));
+      }
+      if ((s + 1) % keep_every == 0) {
+        // the sample and the costs of this step, after its last K1 and before the next K4
+        // overwrites the costs
+        if (int rc = snapshot(trace, cost_trace, (s + 1) / keep_every - 1, theta, cost_scratch, n_chains, D,
+                              P->s_upd))
+          return rc;
+        SG_CUDA_RC(cudaEventRecord(P->snap, P->s_upd));
+        SG_CUDA_RC(cudaStreamWaitEvent(st, P->snap, 0));
+      }
+    }
+    // the caller's stream continues after the last update
+    SG_CUDA_RC(cudaEventRecord(P->snap, P->s_upd));
+    SG_CUDA_RC(cudaStreamWaitEvent(st, P->snap, 0));
+    return SGMCMC_OK;
+  }
   for (int64_t s = 0; s < n_steps; ++s) {
     const int burn_in = adapt_forever || s < n_burn_in;
     const int store_minv = burn_in && (s == n_burn_in - 1 || (adapt_forever && s == n_steps - 1));

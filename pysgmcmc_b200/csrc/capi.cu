@@ -12,6 +12,8 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_threads{256};
 static std::atomic<int> g_unroll{1};
 static std::atomic<int> g_update_max_ctas{0};
+static std::atomic<int> g_update_carveout{-1};
+static std::atomic<int> g_update_reverse{1};   // measured: -2 % (burn-in) / -3 % (sampling) per BNN step
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -33,6 +35,8 @@ int check_launch(const char* what) {
 int tuning_threads() { return g_threads.load(std::memory_order_relaxed); }
 int tuning_unroll() { return g_unroll.load(std::memory_order_relaxed); }
 int tuning_update_max_ctas() { return g_update_max_ctas.load(std::memory_order_relaxed); }
+int tuning_update_carveout() { return g_update_carveout.load(std::memory_order_relaxed); }
+int tuning_update_reverse() { return g_update_reverse.load(std::memory_order_relaxed); }
 
 }  // namespace sgmcmc
 
@@ -55,6 +59,19 @@ int sgmcmc_set_update_tuning(int threads, int unroll) {
       return sgmcmc::set_error(SGMCMC_E_INVALID, "unroll must be 1 or 2 (got %d)", unroll);
     sgmcmc::g_unroll.store(unroll);
   }
+  return SGMCMC_OK;
+}
+
+int sgmcmc_set_bnn_pipeline(int64_t chunk_chains, int ring) {
+  if (chunk_chains < 0 || ring < 0) return sgmcmc::set_error(SGMCMC_E_INVALID, "pipeline: chunk and ring must be >= 0");
+  sgmcmc::set_bnn_pipeline(chunk_chains, ring == 0 ? 2 : ring);
+  // K1 must ask for the same shared-memory carveout as K4, or the two never share an SM
+  sgmcmc::g_update_carveout.store(chunk_chains > 0 ? 100 : -1);
+  return SGMCMC_OK;
+}
+
+int sgmcmc_set_update_reverse(int on) {
+  sgmcmc::g_update_reverse.store(on & 3);   // bit 0: reverse walk, bit 1: theta stored with normal L2 priority
   return SGMCMC_OK;
 }
 

@@ -20,7 +20,10 @@ int bnn_variant_count();
 void set_bnn_variant(int v);
 void set_bnn_max_ctas(int n);
 void set_bnn_chunk(int64_t c);
+void set_bnn_pipeline(int64_t chunk, int ring);
+int tuning_update_carveout();
 int tuning_update_max_ctas();
+int tuning_update_reverse();
 
 #define SG_REQUIRE(cond, code, ...)                          \
   do {                                                       \

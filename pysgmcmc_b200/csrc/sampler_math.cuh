@@ -12,6 +12,7 @@ namespace sgmcmc {
 // from counter (i + group_offset, step) under key `seed`.
 struct NoiseArgs {
   uint64_t seed, step, group_offset;
+  int reverse = 0;   // K1: walk the array from its end (L2 reuse after K4, see bnn.cu)
 };
 
 // ---- host-side scalar prefixes -------------------------------------------------------

@@ -36,10 +36,13 @@ __device__ __forceinline__ Pack<T> load_pack(const T* __restrict__ p, int64_t gr
 }
 
 template <typename T, bool ALIGNED>
-__device__ __forceinline__ void store_pack(T* __restrict__ p, int64_t group, int valid, const Pack<T>& r) {
+__device__ __forceinline__ void store_pack(T* __restrict__ p, int64_t group, int valid, const Pack<T>& r,
+                                           bool keep = false) {
   if (ALIGNED && valid == 4) {
     if constexpr (sizeof(T) == 4) {
-      st_stream(reinterpret_cast<float4*>(p) + group, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+      // keep: write-back with normal L2 priority (the next kernel reads this array first)
+      if (keep) reinterpret_cast<float4*>(p)[group] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+      else st_stream(reinterpret_cast<float4*>(p) + group, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
     } else {
       st_stream(reinterpret_cast<double2*>(p) + 2 * group, make_double2(r.v[0], r.v[1]));
       st_stream(reinterpret_cast<double2*>(p) + 2 * group + 1, make_double2(r.v[2], r.v[3]));
@@ -78,7 +81,10 @@ __global__ void sghmc_update_kernel(T* __restrict__ theta, T* __restrict__ v, T*
   // grid-stride over the groups: with the default launch the loop runs once; a capped
   // (persistent) grid walks the array in chunks of gridDim.x * blockDim.x * UNROLL groups
   const int64_t chunk = (int64_t)gridDim.x * blockDim.x * UNROLL;
-  for (int64_t base = (int64_t)blockIdx.x * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
+  // na.reverse: the CTAs scheduled first take the END of the array -- what the kernel that ran
+  // before (K4, ascending over chains) touched last and is therefore still in L2
+  const unsigned bid = (na.reverse & 1) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+  for (int64_t base = (int64_t)bid * ((int64_t)blockDim.x * UNROLL) + threadIdx.x;
        base - threadIdx.x < n_groups; base += chunk) {
   Pack<T> th[UNROLL], vv[UNROLL], gr[UNROLL], ta[UNROLL], gg[UNROLL], vh[UNROLL], mi[UNROLL], zz[UNROLL];
   int valid[UNROLL];
@@ -116,7 +122,7 @@ __global__ void sghmc_update_kernel(T* __restrict__ theta, T* __restrict__ v, T*
         }
         sghmc_apply(th[u].v[i], vv[u].v[i], minv_t, gr[u].v[i], zz[u].v[i], s);
       }
-      store_pack<T, ALIGNED>(theta, gi, valid[u], th[u]);
+      store_pack<T, ALIGNED>(theta, gi, valid[u], th[u], (na.reverse & 2) != 0);
       store_pack<T, ALIGNED>(v, gi, valid[u], vv[u]);
       if constexpr (BURN_IN) {
         store_pack<T, ALIGNED>(tau, gi, valid[u], ta[u]);
@@ -302,24 +308,28 @@ static int sghmc_step(T* theta, T* v, T* tau, T* g, T* v_hat, T* minv, const T* 
     aligned = aligned && aligned_to(p, 16);
   }
   const SghmcScalars<T> s = make_sghmc_scalars<T>(epsilon, mdecay, scale_grad);
-  const NoiseArgs na{seed, step, elem_offset / 4};
+  NoiseArgs na{seed, step, elem_offset / 4};
+  na.reverse = tuning_update_reverse();
   const LaunchShape ls = launch_shape<T>(n);
   cudaStream_t st = (cudaStream_t)stream;
   const bool ext_z = z != nullptr;
+  const int carve = tuning_update_carveout();   // 100: share SMs with K4 (two-stream pipeline); -1: default
+#define SG_LAUNCH_K1(BI, SM)                                                                          \
+  {                                                                                                   \
+    auto k = sghmc_update_kernel<T, BI, SM, EZ, AL, U>;                                               \
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);                   \
+    k<<<ls.blocks, ls.threads, 0, st>>>(theta, v, tau, g, v_hat, minv, grad, z, n, s, na);            \
+  }
   SG_DISPATCH_UNROLL(ls.unroll,
     SG_DISPATCH_BOOL(aligned, AL,
       SG_DISPATCH_BOOL(ext_z, EZ,
         if (burn_in) {
-          if (store_minv)
-            sghmc_update_kernel<T, true, true, EZ, AL, U><<<ls.blocks, ls.threads, 0, st>>>(
-                theta, v, tau, g, v_hat, minv, grad, z, n, s, na);
-          else
-            sghmc_update_kernel<T, true, false, EZ, AL, U><<<ls.blocks, ls.threads, 0, st>>>(
-                theta, v, tau, g, v_hat, minv, grad, z, n, s, na);
+          if (store_minv) SG_LAUNCH_K1(true, true)
+          else SG_LAUNCH_K1(true, false)
         } else {
-          sghmc_update_kernel<T, false, false, EZ, AL, U><<<ls.blocks, ls.threads, 0, st>>>(
-              theta, v, tau, g, v_hat, minv, grad, z, n, s, na);
+          SG_LAUNCH_K1(false, false)
         })))
+#undef SG_LAUNCH_K1
   return check_launch("sghmc_update_kernel");
 }
 

@@ -500,6 +500,30 @@ def test_fused_step_is_bit_identical_to_k4_then_k1(z_injected):
     assert not np.array_equal(out[1][0][0], state[0])
 
 
+@pytest.mark.parametrize("chunk,ring", [(8, 2), (8, 3), (5, 2), (36, 2), (1, 8)])
+def test_two_stream_pipeline_is_bit_identical(chunk, ring):
+    """K4 of chunk j+1 overlapped with K1 of chunk j on a second stream (gradient through a
+    ring of chunk-sized slots) == the sequential K4 then K1 over all chains: states, thinned
+    trace and costs, Philox noise, a chain offset, crossing the burn-in boundary, partial last
+    chunk; and the caller's stream sees the final state without further synchronisation."""
+    C, batch, N, steps, burn = 37, 20, 2000, 30, 17
+    X, y = sinc_data(N)
+    state = _initial_state(C, seed=5)
+    starts = np.random.RandomState(8).randint(0, N - batch + 1, size=(steps, C)).astype(np.int32)
+    out = {}
+    try:
+        for mode in (0, 1):
+            _native.call("sgmcmc_set_bnn_pipeline", chunk if mode else 0, ring)
+            out[mode] = _run_c(state, X, y, starts, None, C, 1, batch, N, steps, burn, 3, seed=99, step0=1000,
+                               chain_offset=64)
+    finally:
+        _native.call("sgmcmc_set_bnn_pipeline", 0, 0)
+    for i, name in enumerate(("theta", "v", "tau", "g", "v_hat", "minv")):
+        assert np.array_equal(out[0][0][i], out[1][0][i]), name
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert np.isfinite(out[1][0]).all() and not np.array_equal(out[1][0][0], state[0])
+
+
 def test_fused_step_falls_back_when_unsupported():
     """n_in = 2 gives D = 5302 (not a multiple of 4): the run goes through K4 + K1 and needs
     the gradient scratch buffer; the result is finite and the costs match the oracle's."""

@@ -272,9 +272,12 @@ def test_tuning_knobs_do_not_change_results():
     grad = rng.standard_normal(n).astype(np.float32)
     ref = None
     try:
-        for threads in (128, 256, 512):
-            for unroll in (1, 2):
+        for threads, unroll, reverse, cap in [(th, un, rv, 0) for th in (128, 256, 512) for un in (1, 2)
+                                              for rv in (1, 0)] + [(256, 1, 1, 37), (256, 1, 0, 37)]:
+            if True:
                 _native.call("sgmcmc_set_update_tuning", threads, unroll)
+                _native.call("sgmcmc_set_update_reverse", reverse)     # walk order of K1 (L2 reuse)
+                _native.call("sgmcmc_set_persistent_grids", cap, 0)    # capped grid looping over the array
                 t = {k: dev(v) for k, v in st.items()}
                 call_sghmc(t, dev(grad), None, 0.01, 0.05, 1.0, True, True, torch.float32, seed=3, step=1)
                 torch.cuda.synchronize()
@@ -282,9 +285,11 @@ def test_tuning_knobs_do_not_change_results():
                     ref = t
                 else:
                     for k in t:
-                        assert torch.equal(t[k], ref[k]), (threads, unroll, k)
+                        assert torch.equal(t[k], ref[k]), (threads, unroll, reverse, cap, k)
     finally:
         _native.call("sgmcmc_set_update_tuning", 256, 1)
+        _native.call("sgmcmc_set_update_reverse", 1)
+        _native.call("sgmcmc_set_persistent_grids", 0, 0)
 
 
 # ------------------------------------------------------------------------------------
