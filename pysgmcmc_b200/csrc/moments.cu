@@ -101,6 +101,130 @@ variogram_kernel(const float* __restrict__ trace, double* __restrict__ out, int6
   }
 }
 
+
+// ---- vectorised paths ----------------------------------------------------------------------
+// The scalar kernels above touch 128 B per (chain, draw) and warp, and consecutive draws of a
+// chain are n_chains * D * 4 bytes apart: every request opens its own DRAM page (measured
+// 1.3-1.5 TB/s).  Here a thread owns 4 (moments) or 2 (variogram) consecutive dimensions, a CTA
+// reads 4 KB / 1 KB contiguous per (chain, draw) row, and every thread keeps 8-16 independent
+// 128- / 64-bit loads in flight.
+constexpr int MV_THREADS = 256;
+constexpr int MV_CHAINS = 32;            // chains per CTA
+constexpr int MV_UNROLL = 8;
+
+__global__ void __launch_bounds__(MV_THREADS, 2)
+chain_moments_vec_kernel(const float4* __restrict__ trace4, double* __restrict__ sums, int64_t n_draws,
+                         int64_t n_chains, int64_t d4) {
+  const int64_t q = (int64_t)blockIdx.x * MV_THREADS + threadIdx.x;
+  if (q >= d4) return;
+  const int64_t c0 = (int64_t)blockIdx.y * MV_CHAINS;
+  const int64_t c1 = min(c0 + MV_CHAINS, n_chains);
+  const int64_t stride = n_chains * d4;
+  const double n = (double)n_draws;
+  double s_mean[4] = {0.0, 0.0, 0.0, 0.0}, s_mean2[4] = {0.0, 0.0, 0.0, 0.0}, s_var[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t j = c0; j < c1; ++j) {
+    const float4* p = trace4 + j * d4 + q;
+    const float4 f0 = __ldcs(p);
+    const double x0[4] = {(double)f0.x, (double)f0.y, (double)f0.z, (double)f0.w};
+    double a1[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    double a2[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    for (int64_t i = 1; i < n_draws; i += MV_UNROLL) {
+      float4 v[MV_UNROLL];
+#pragma unroll
+      for (int u = 0; u < MV_UNROLL; ++u)      // past the end: the first draw again, which adds exactly 0
+        v[u] = i + u < n_draws ? __ldcs(p + (i + u) * stride) : f0;
+#pragma unroll
+      for (int u = 0; u < MV_UNROLL; ++u) {
+        const double x[4] = {(double)v[u].x - x0[0], (double)v[u].y - x0[1], (double)v[u].z - x0[2],
+                             (double)v[u].w - x0[3]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a1[u & 1][k] += x[k];
+          a2[u & 1][k] = fma(x[k], x[k], a2[u & 1][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double s1 = a1[0][k] + a1[1][k], s2 = a2[0][k] + a2[1][k];
+      const double mean = x0[k] + s1 / n;
+      const double var = n_draws > 1 ? (s2 - s1 * s1 / n) / (n - 1.0) : 0.0;
+      s_mean[k] += mean;
+      s_mean2[k] = fma(mean, mean, s_mean2[k]);
+      s_var[k] += var;
+    }
+  }
+  const int64_t D = 4 * d4, d = 4 * q;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    atomicAdd(sums + d + k, s_mean[k]);
+    atomicAdd(sums + D + d + k, s_mean2[k]);
+    atomicAdd(sums + 2 * D + d + k, s_var[k]);
+  }
+}
+
+// Lags 1 .. VW in ONE pass: a thread owns 2 dimensions and keeps the last VW draws of its
+// chain in a register ring (as doubles, converted once), so every trace element is read once
+// and costs one subtraction and one FMA per lag.  For many lags this kernel is bound by the
+// FP64 pipe (2 * VW instructions per element), not by HBM.
+constexpr int VW = 16;
+constexpr int VW_THREADS = 128;
+constexpr int VW_CHAINS = 64;
+
+template <bool FIRST>
+__device__ __forceinline__ void variogram_block(const float2 (&v)[VW], int64_t base, int64_t n_draws,
+                                                double (&ring)[VW][2], double (&acc)[VW][2]) {
+#pragma unroll
+  for (int k = 0; k < VW; ++k) {
+    if (base + k < n_draws) {
+      const double x[2] = {(double)v[k].x, (double)v[k].y};
+#pragma unroll
+      for (int t = 1; t <= VW; ++t) {
+        if (!FIRST || k >= t) {                  // (FIRST: draw k has no predecessor at lag t > k)
+          const int r = (k - t) & (VW - 1);
+          const double d0 = x[0] - ring[r][0], d1 = x[1] - ring[r][1];
+          acc[t - 1][0] = fma(d0, d0, acc[t - 1][0]);
+          acc[t - 1][1] = fma(d1, d1, acc[t - 1][1]);
+        }
+      }
+      ring[k][0] = x[0];
+      ring[k][1] = x[1];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(VW_THREADS, 2)
+variogram_window_kernel(const float2* __restrict__ trace2, double* __restrict__ out, int64_t n_draws,
+                        int64_t n_chains, int64_t d2, int n_lags) {
+  const int64_t q = (int64_t)blockIdx.x * VW_THREADS + threadIdx.x;
+  if (q >= d2) return;
+  const int64_t c0 = (int64_t)blockIdx.y * VW_CHAINS;
+  const int64_t c1 = min(c0 + VW_CHAINS, n_chains);
+  const int64_t stride = n_chains * d2;
+  double acc[VW][2];
+#pragma unroll
+  for (int t = 0; t < VW; ++t) acc[t][0] = acc[t][1] = 0.0;
+  for (int64_t j = c0; j < c1; ++j) {
+    const float2* p = trace2 + j * d2 + q;
+    double ring[VW][2];
+    for (int64_t base = 0; base < n_draws; base += VW) {
+      float2 v[VW];
+#pragma unroll
+      for (int k = 0; k < VW; ++k)
+        v[k] = base + k < n_draws ? __ldcs(p + (base + k) * stride) : make_float2(0.0f, 0.0f);
+      if (base == 0) variogram_block<true>(v, base, n_draws, ring, acc);
+      else variogram_block<false>(v, base, n_draws, ring, acc);
+    }
+  }
+  const int64_t D = 2 * d2, d = 2 * q;
+#pragma unroll
+  for (int t = 0; t < VW; ++t)
+    if (t < n_lags) {
+      atomicAdd(out + (int64_t)t * D + d, acc[t][0]);
+      atomicAdd(out + (int64_t)t * D + d + 1, acc[t][1]);
+    }
+}
+
 }  // namespace sgmcmc
 
 using namespace sgmcmc;
@@ -118,6 +242,13 @@ extern "C" int sgmcmc_chain_moments_f32(const float* trace, double* sums, int64_
                                         int64_t n_dims, void* stream) {
   if (int rc = check_trace_args(trace, sums, n_draws, n_chains, n_dims)) return rc;
   if (n_draws == 0 || n_chains == 0 || n_dims == 0) return SGMCMC_OK;
+  if (n_dims % 4 == 0 && aligned_to(trace, 16) && (n_chains + MV_CHAINS - 1) / MV_CHAINS <= 65535) {
+    const int64_t d4 = n_dims / 4;
+    const dim3 grid((unsigned)((d4 + MV_THREADS - 1) / MV_THREADS), (unsigned)((n_chains + MV_CHAINS - 1) / MV_CHAINS));
+    chain_moments_vec_kernel<<<grid, MV_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(trace), sums, n_draws, n_chains, d4);
+    return check_launch("chain_moments_vec_kernel");
+  }
   const dim3 block(MT_DX, MT_DY);
   const dim3 grid((unsigned)((n_dims + MT_DX - 1) / MT_DX),
                   (unsigned)((n_chains + CHAINS_PER_BLOCK - 1) / CHAINS_PER_BLOCK));
@@ -131,6 +262,15 @@ extern "C" int sgmcmc_variogram_f32(const float* trace, double* variogram, int64
   if (int rc = check_trace_args(trace, variogram, n_draws, n_chains, n_dims)) return rc;
   SG_REQUIRE(lag0 >= 1 && n_lags >= 0 && n_lags <= 65535, SGMCMC_E_INVALID, "lag0 must be >= 1, n_lags in [0, 65535]");
   if (n_draws == 0 || n_chains == 0 || n_dims == 0 || n_lags == 0) return SGMCMC_OK;
+  if (lag0 == 1 && n_lags <= VW && n_dims % 2 == 0 && aligned_to(trace, 8) &&
+      (n_chains + VW_CHAINS - 1) / VW_CHAINS <= 65535) {
+    // the first block of lags (what well-mixed chains need): one pass over the trace
+    const int64_t d2 = n_dims / 2;
+    const dim3 grid((unsigned)((d2 + VW_THREADS - 1) / VW_THREADS), (unsigned)((n_chains + VW_CHAINS - 1) / VW_CHAINS));
+    variogram_window_kernel<<<grid, VW_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(trace), variogram, n_draws, n_chains, d2, (int)n_lags);
+    return check_launch("variogram_window_kernel");
+  }
   const dim3 block(MT_DX, MT_DY);
   const dim3 grid((unsigned)((n_dims + MT_DX - 1) / MT_DX),
                   (unsigned)((n_chains + CHAINS_PER_BLOCK - 1) / CHAINS_PER_BLOCK), (unsigned)n_lags);

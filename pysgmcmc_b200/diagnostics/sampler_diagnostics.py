@@ -112,11 +112,11 @@ def effective_n_from_variograms(v_hat, m, n, variogram_block):
         block = min(2 * block, 1024)       # slowly mixing chains need thousands of lags
     rho_all = np.stack(history)            # [t_max, D]
     t_end = np.where(t_stop % 2 == 1, t_stop - 1, t_stop)
-    out = np.empty(D)
-    for d in range(D):
-        s = np.nansum(rho_all[1:max(1, t_end[d] - 1), d])
-        out[d] = min(m * n, np.floor(m * n / (1.0 + 2.0 * s)))
-    return out
+    # sum of rho[1 : t_end - 1] per dimension, all dimensions at once
+    lag = np.arange(rho_all.shape[0])[:, None]
+    inside = (lag >= 1) & (lag < np.maximum(1, t_end - 1)[None, :])
+    s = np.nansum(np.where(inside, rho_all, 0.0), axis=0)
+    return np.minimum(m * n, np.floor(m * n / (1.0 + 2.0 * s)))
 
 
 def gelman_rubin_from_trace(trace, group=None):

@@ -38,10 +38,15 @@ def timed(fn, iters=5):
 ms = timed(lambda: local_moment_sums(trace))
 print(json.dumps({"kernel": "chain_moments_kernel", "trace_GB": round(gb, 2), "ms": round(ms, 3),
                   "GBps": round(gb / ms * 1e3, 1)}))
-lags = 4
+lags = 16
 ms = timed(lambda: local_variogram_sums(trace, 1, lags))
-print(json.dumps({"kernel": "variogram_kernel", "lags": lags, "ms": round(ms, 3),
-                  "GBps_algorithmic": round(2 * lags * gb / ms * 1e3, 1)}))
+elems = trace.numel()
+print(json.dumps({"kernel": "variogram_window_kernel (lags 1..16 in one pass)", "lags": lags, "ms": round(ms, 3),
+                  "ms_per_lag": round(ms / lags, 3), "trace_GBps": round(gb / ms * 1e3, 1),
+                  "fp64_TFLOPs": round(3.0 * lags * elems / ms / 1e9, 2)}))
+ms = timed(lambda: local_variogram_sums(trace, 17, 4), iters=2)
+print(json.dumps({"kernel": "variogram_kernel (general lags, scalar)", "lags": 4, "ms": round(ms, 3),
+                  "ms_per_lag": round(ms / 4, 3)}))
 t0 = time.perf_counter()
 rhat = gelman_rubin_from_trace(trace)
 ess = effective_n_from_trace(trace)
