@@ -245,6 +245,12 @@ int sgmcmc_chain_moments_f32(const float* trace, double* sums, int64_t n_draws, 
                              int64_t n_dims, void* stream);
 int sgmcmc_variogram_f32(const float* trace, double* variogram, int64_t n_draws, int64_t n_chains,
                          int64_t n_dims, int64_t lag0, int64_t n_lags, void* stream);
+/* The same sums for the n_sel dimensions listed in `dims` (device int64 [n_sel]) only:
+ * variogram is double [n_lags, n_sel].  Used for the few dimensions whose ESS stopping rule has
+ * not fired after the first block of lags. */
+int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double* variogram,
+                                int64_t n_draws, int64_t n_chains, int64_t n_dims, int64_t n_sel,
+                                int64_t lag0, int64_t n_lags, void* stream);
 
 #ifdef __cplusplus
 }

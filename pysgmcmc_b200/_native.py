@@ -64,6 +64,7 @@ SIGNATURES = {
     "sgmcmc_bnn_predict_f32": [_P, _P, _P, c_int64, c_int, c_int64, _P],
     "sgmcmc_chain_moments_f32": [_P, _P, c_int64, c_int64, c_int64, _P],
     "sgmcmc_variogram_f32": [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
+    "sgmcmc_variogram_select_f32": [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
 }
 _RESTYPES = {"sgmcmc_last_error": c_char_p, "sgmcmc_launch_count": c_int64}
 

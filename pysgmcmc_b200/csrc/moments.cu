@@ -225,6 +225,47 @@ variogram_window_kernel(const float2* __restrict__ trace2, double* __restrict__ 
     }
 }
 
+
+// Variogram sums of a FEW selected dimensions (the ones whose ESS stopping rule has not fired
+// after the first block of lags): thread = chain, CTA = (selected dimension, 256 chains, lag).
+constexpr int VS_THREADS = 256;
+__global__ void __launch_bounds__(VS_THREADS)
+variogram_select_kernel(const float* __restrict__ trace, const int64_t* __restrict__ dims, double* __restrict__ out,
+                        int64_t n_draws, int64_t n_chains, int64_t n_dims, int64_t n_sel, int64_t lag0) {
+  __shared__ double red[VS_THREADS / 32];
+  const int64_t d = dims[blockIdx.x];
+  const int64_t j = (int64_t)blockIdx.y * VS_THREADS + threadIdx.x;
+  const int64_t t = lag0 + blockIdx.z;
+  double acc = 0.0;
+  if (j < n_chains && t < n_draws) {
+    const int64_t stride = n_chains * n_dims;
+    const float* p = trace + j * n_dims + d;
+    double a[2] = {0.0, 0.0};
+    int64_t i = t;
+    for (; i + 1 < n_draws; i += 2) {
+      const double d0 = (double)p[i * stride] - (double)p[(i - t) * stride];
+      const double d1 = (double)p[(i + 1) * stride] - (double)p[(i + 1 - t) * stride];
+      a[0] = fma(d0, d0, a[0]);
+      a[1] = fma(d1, d1, a[1]);
+    }
+    if (i < n_draws) {
+      const double d0 = (double)p[i * stride] - (double)p[(i - t) * stride];
+      a[0] = fma(d0, d0, a[0]);
+    }
+    acc = a[0] + a[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < VS_THREADS / 32; ++w) s += red[w];
+    atomicAdd(out + (int64_t)blockIdx.z * n_sel + blockIdx.x, s);
+  }
+}
+
 }  // namespace sgmcmc
 
 using namespace sgmcmc;
@@ -276,4 +317,21 @@ extern "C" int sgmcmc_variogram_f32(const float* trace, double* variogram, int64
                   (unsigned)((n_chains + CHAINS_PER_BLOCK - 1) / CHAINS_PER_BLOCK), (unsigned)n_lags);
   variogram_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(trace, variogram, n_draws, n_chains, n_dims, lag0);
   return check_launch("variogram_kernel");
+}
+
+// Like sgmcmc_variogram_f32 for the `n_sel` dimensions listed in `dims` (device, int64) only:
+// `variogram` is [n_lags, n_sel], ACCUMULATED into.
+extern "C" int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double* variogram,
+                                           int64_t n_draws, int64_t n_chains, int64_t n_dims, int64_t n_sel,
+                                           int64_t lag0, int64_t n_lags, void* stream) {
+  if (int rc = check_trace_args(trace, variogram, n_draws, n_chains, n_dims)) return rc;
+  SG_REQUIRE(lag0 >= 1 && n_lags >= 0 && n_lags <= 65535 && n_sel >= 0, SGMCMC_E_INVALID,
+             "lag0 must be >= 1, n_lags in [0, 65535], n_sel >= 0");
+  SG_REQUIRE((n_chains + VS_THREADS - 1) / VS_THREADS <= 65535, SGMCMC_E_INVALID, "too many chains");
+  if (n_draws == 0 || n_chains == 0 || n_dims == 0 || n_lags == 0 || n_sel == 0) return SGMCMC_OK;
+  SG_REQUIRE(dims != nullptr, SGMCMC_E_INVALID, "dims must not be NULL");
+  const dim3 grid((unsigned)n_sel, (unsigned)((n_chains + VS_THREADS - 1) / VS_THREADS), (unsigned)n_lags);
+  variogram_select_kernel<<<grid, VS_THREADS, 0, (cudaStream_t)stream>>>(trace, dims, variogram, n_draws, n_chains,
+                                                                         n_dims, n_sel, lag0);
+  return check_launch("variogram_select_kernel");
 }

@@ -49,6 +49,17 @@ def local_variogram_sums(trace, lag0, n_lags):
     return out
 
 
+def local_variogram_select_sums(trace, dims, lag0, n_lags):
+    """float64 ``[n_lags, len(dims)]``: the same sums for the listed dimensions only."""
+    n, C, D = trace.shape
+    idx = torch.as_tensor(np.asarray(dims, dtype=np.int64), device=trace.device)
+    out = torch.zeros((n_lags, idx.numel()), dtype=torch.float64, device=trace.device)
+    with torch.cuda.device(trace.device):
+        _native.call("sgmcmc_variogram_select_f32", _native.ptr(trace), _native.ptr(idx), _native.ptr(out),
+                     n, C, D, idx.numel(), lag0, n_lags, _native.stream_ptr())
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 # cross-rank combination (K9) and finalisation -- pure torch, runs on any device
 # ---------------------------------------------------------------------------------------
@@ -85,10 +96,12 @@ class ChainSums(object):
         return torch.sqrt(v_hat / W)
 
 
-def effective_n_from_variograms(v_hat, m, n, variogram_block):
+def effective_n_from_variograms(v_hat, m, n, variogram_block, select_block=None):
     """pymc3-3.1 style ESS from V_hat and a callable ``variogram_block(lag0, n_lags) ->
     [n_lags, D]`` of globally summed squared lag differences.  Lags are requested in blocks
-    until every dimension has hit its stopping rule."""
+    until every dimension has hit its stopping rule; once fewer than a quarter of the
+    dimensions are still open, ``select_block(lag0, n_lags, dims) -> [n_lags, len(dims)]``
+    (if given) is asked for those dimensions only."""
     D = v_hat.shape[0]
     v_hat = v_hat.detach().cpu().numpy()
     rho_prev = np.ones(D)
@@ -99,7 +112,12 @@ def effective_n_from_variograms(v_hat, m, n, variogram_block):
     t, block = 1, 16
     while t < n and not done.all():
         k = min(block, n - t)
-        vg = variogram_block(t, k).detach().cpu().numpy()
+        active = np.flatnonzero(~done)
+        if select_block is not None and t > 1 and 4 * active.size <= D:
+            vg = np.full((k, D), np.nan)
+            vg[:, active] = select_block(t, k, active).detach().cpu().numpy()
+        else:
+            vg = variogram_block(t, k).detach().cpu().numpy()
         for b in range(k):
             lag = t + b
             rho = 1.0 - (vg[b] / (m * (n - lag))) / (2.0 * v_hat)
@@ -131,7 +149,8 @@ def effective_n_from_trace(trace, group=None):
     cs = ChainSums(local_moment_sums(trace), C, n, group)
     v_hat, _ = cs.v_hat_and_w()
     return effective_n_from_variograms(
-        v_hat, cs.m, n, lambda lag0, k: _all_reduce_sum(local_variogram_sums(trace, lag0, k), group))
+        v_hat, cs.m, n, lambda lag0, k: _all_reduce_sum(local_variogram_sums(trace, lag0, k), group),
+        lambda lag0, k, dims: _all_reduce_sum(local_variogram_select_sums(trace, dims, lag0, k), group))
 
 
 # ---------------------------------------------------------------------------------------

@@ -48,6 +48,20 @@ def test_moment_and_variogram_sums(m, n, D):
         np.testing.assert_allclose(vg[b], want, rtol=1e-10)
 
 
+def test_variogram_of_selected_dimensions():
+    """sgmcmc_variogram_select_f32 (a few dimensions, any lags) == the columns of the full sums."""
+    from pysgmcmc_b200.diagnostics.sampler_diagnostics import local_variogram_select_sums
+    m, n, D = 300, 45, 70
+    x = ar1(m, n, D, 0.8, seed=4)
+    trace = torch.as_tensor(np.ascontiguousarray(x.transpose(1, 0, 2)), device=DEV)
+    dims = np.array([69, 0, 13, 14])
+    got = local_variogram_select_sums(trace, dims, 17, 40).cpu().numpy()      # lags 17 .. 56 (>= n: zero)
+    for b in range(40):
+        t = 17 + b
+        want = odiag.variogram(x, t)[dims] * (m * (n - t)) if t < n else np.zeros(4)
+        np.testing.assert_allclose(got[b], want, rtol=1e-10, atol=1e-12)
+
+
 @pytest.mark.parametrize("phi", [0.0, 0.5, 0.95])
 def test_rhat_and_ess_match_oracle(phi):
     m, n, D = 16, 400, 6
