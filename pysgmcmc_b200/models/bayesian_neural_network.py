@@ -7,7 +7,9 @@ What is the same: constructor arguments and their validation, normalisation, the
 schedule (burn-in, one network kept every `sample_steps` iterations after burn-in, stop at
 `n_nets`), the minibatch index stream (bit-exact with the reference's
 ``generate_batches(seed=seed)``), the predictive mean / variance formulas.
-What differs: `session` is a :class:`pysgmcmc_b200.Session`; `dtype` is a torch dtype and
+What differs: `session` is a :class:`pysgmcmc_b200.Session` (with ``Session(n_chains=C)`` C
+independent chains sample in parallel and each kept iteration yields C networks); `dtype` is a
+torch dtype and
 defaults to float32; `get_net` other than `get_default_net` is not supported by the
 fused kernels (the network architecture is compiled in); weight initialisation uses a torch
 generator (TensorFlow's stream is not reproducible).
@@ -111,18 +113,27 @@ class BayesianNeuralNetwork(object):
 
         n_datapoints, n_inputs = X.shape
         device = self.session.device
-        single_chain = Session(device=device, n_chains=None, output="torch", stream=self.session.stream)
+        # Session(n_chains=C): C independent chains sample the same posterior in one set of
+        # kernel launches and every kept iteration contributes C networks (an extension; the
+        # reference is one chain per model, which is what n_chains=None gives)
+        n_chains = self.session.n_chains
+        chain_session = Session(device=device, n_chains=n_chains, output="torch", stream=self.session.stream,
+                                chain_offset=self.session.chain_offset)
 
         # minibatches: the reference's default generator is replaced by its on-device twin
         # (same RandomState stream, data resident in HBM); any other generator is called like
         # the reference calls it and feeds host minibatches through placeholders
         if self.batch_generator is generate_batches:
             seed = int(np.random.randint(1, 100000)) if self.seed is None else self.seed    # data_batches.py:101-102
-            batches = DeviceBatchGenerator(n_datapoints, self.batch_size, seeds=[seed], device=device)
+            seeds = [seed] if n_chains is None else [(seed + j) % 2 ** 32 for j in range(n_chains)]
+            batches = DeviceBatchGenerator(n_datapoints, self.batch_size, seeds=seeds, device=device)
             self.nll = BayesianNeuralNetworkNLL(n_datapoints, self.batch_size, X=self.X, y=self.y,
                                                 starts_placeholder=batches.starts_placeholder,
                                                 device=device, dtype=self.dtype)
         else:
+            if n_chains is not None:
+                raise ValueError("Session(n_chains=C) needs the default `generate_batches` (per-chain "
+                                 "minibatch streams are generated on the device)")
             self.X_Minibatch = placeholder(name="X_Minibatch")
             self.Y_Minibatch = placeholder(name="Y_Minibatch")
             batches = self.batch_generator(x=self.X, x_placeholder=self.X_Minibatch,
@@ -133,14 +144,15 @@ class BayesianNeuralNetwork(object):
                                                 y_placeholder=self.Y_Minibatch,
                                                 device=device, dtype=self.dtype)
 
-        self.network_params = default_net_params(n_inputs, seed=self.seed, dtype=self.dtype, device=device)
+        self.network_params = default_net_params(n_inputs, n_chains=n_chains, seed=self.seed, dtype=self.dtype,
+                                                 device=device)
         self.samples.clear()
 
         self.sampler_kwargs.update({
             "params": self.network_params,
             "cost_fun": self.nll,
             "batch_generator": batches,
-            "session": single_chain,
+            "session": chain_session,
             "seed": self.seed,
             "dtype": self.dtype,
             "stepsize_schedule": self.stepsize_schedule,
@@ -186,8 +198,9 @@ class BayesianNeuralNetwork(object):
                 log_full_training_error(iteration_index, is_sampling=False)
             if keep:
                 log_full_training_error(iteration_index, is_sampling=True)
-                self.samples.append(self.sampler._theta[0].clone())
-                if len(self.samples) == self.n_nets:
+                for row in self.sampler._theta.clone():           # one network per chain
+                    self.samples.append(row)
+                if len(self.samples) >= self.n_nets:
                     break
         if steps_done < self.n_iters and len(self.samples) < self.n_nets:
             self.sampler.run(self.n_iters - steps_done, keep_every=10 ** 9)
@@ -207,7 +220,8 @@ class BayesianNeuralNetwork(object):
             else:
                 self.X_Minibatch.value, self.Y_Minibatch.value = self.X, self.y.reshape(-1, 1)
                 cost = self.nll([p.detach() for p in self.network_params])
-            return float(cost), float(self.nll.last_mse)
+            # (averaged over the chains when there are several)
+            return float(torch.as_tensor(cost).float().mean()), float(torch.as_tensor(self.nll.last_mse).float().mean())
         finally:
             if ph is not None:
                 ph.value = saved

@@ -96,3 +96,29 @@ def test_device_and_host_generators_give_the_same_chain():
     b.train(x_train, y_train)
     sa, sb = torch.stack(list(a.samples)), torch.stack(list(b.samples))
     assert torch.allclose(sa, sb, rtol=1e-6, atol=1e-7)
+
+
+def test_multi_chain_training_pools_networks_from_all_chains():
+    """Session(n_chains=C): C chains with their own minibatch and noise streams train at once;
+    every kept iteration contributes one network per chain (an extension of the reference's
+    one-chain model), and the pooled predictive passes the reference's accuracy criterion."""
+    x_train, y_train, X_test = sinc_problem(1)
+    y_test = sinc(X_test)
+    C = 8
+    bnn = BayesianNeuralNetwork(session=Session(device=DEV, n_chains=C), burn_in_steps=1000, n_nets=40,
+                                sample_steps=100, seed=1)
+    bnn.train(x_train, y_train)
+    assert bnn.is_trained and len(bnn.samples) == 40
+    assert bnn.sampler.n_chains == C and bnn.sampler.n_iterations == 1501       # kept iterations 1100 .. 1500
+    nets = torch.stack(list(bnn.samples))
+    assert len({float(v) for v in nets[:C, 7]}) == C, "the chains are independent"
+    mean, var = bnn.predict(X_test)
+    assert np.allclose(np.mean((y_test - mean) ** 2), 0.0, atol=1e-01)
+    # same seed -> same pool of networks
+    bnn2 = BayesianNeuralNetwork(session=Session(device=DEV, n_chains=C), burn_in_steps=1000, n_nets=40,
+                                 sample_steps=100, seed=1)
+    bnn2.train(x_train, y_train)
+    assert all(torch.equal(a, b) for a, b in zip(bnn.samples, bnn2.samples))
+    with pytest.raises(ValueError):
+        BayesianNeuralNetwork(session=Session(device=DEV, n_chains=C), batch_generator=lambda **kw: iter(()),
+                              n_nets=2).train(x_train, y_train)
