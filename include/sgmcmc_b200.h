@@ -252,6 +252,35 @@ int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double*
                                 int64_t n_draws, int64_t n_chains, int64_t n_dims, int64_t n_sel,
                                 int64_t lag0, int64_t n_lags, void* stream);
 
+/* ---- Stein variational gradient descent (K11-K14) -------------------------------------
+ * Replaces pysgmcmc/samplers/svgd.py:81-182 and the helpers it calls,
+ * pysgmcmc/tensor_utils.py:160-208 (median), :326-419 (pdist), :422-577 (squareform).
+ * The particles are the chain layout: float [n_particles, n_dims] row-major.
+ *
+ * sgmcmc_median_f32: out[0] = median of `values` (middle value, or the mean of the two
+ * middle values of an even count; tensor_utils.py:194-208).  Exact (radix select), any
+ * finite floats.  scratch: 4096 bytes of device memory, 8-byte aligned.
+ *
+ * sgmcmc_svgd_kernel_matrix_f32 (svgd.py:150-160): kernel_matrix [n, n] =
+ * exp(-P / h^2 / 2) with P[i,j] = (||x_i - x_j||)^2 and h = sqrt(0.5 * median(P) /
+ * log(n + 1)); kernel_sum [n] = its row sums; bandwidth [4] = {median(P), h, h^2, 0}.
+ * Everything stays on the device.  n_particles <= 46340.
+ *
+ * sgmcmc_svgd_update_f32 (svgd.py:125-148,162-167): with grad[i] = d cost(x_i) / d x_i,
+ *   phi   = (K @ grad + (-(K @ X) + X * kernel_sum[:, None]) / h^2) / n
+ *   hist  = alpha * hist + one_minus_alpha * phi^2
+ *   X    -= epsilon * phi / (fudge_factor + sqrt(hist))
+ * historical_grad and particles are updated in place (particles through
+ * particles_scratch [n, D], because every output row reads all of X). */
+int sgmcmc_median_f32(const float* values, int64_t n_values, float* out, void* scratch, void* stream);
+int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kernel_matrix, float* kernel_sum,
+                                  float* bandwidth, void* scratch, int64_t n_particles, int64_t n_dims,
+                                  void* stream);
+int sgmcmc_svgd_update_f32(float* particles, const float* grad, float* historical_grad,
+                           const float* kernel_matrix, const float* kernel_sum, const float* bandwidth,
+                           float* particles_scratch, int64_t n_particles, int64_t n_dims, float epsilon,
+                           float alpha, float one_minus_alpha, float fudge_factor, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

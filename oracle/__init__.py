@@ -28,4 +28,4 @@ Parity status (see DESIGN.md "Oracle"):
 Every function cites the reference file:line it follows.
 """
 
-from . import tensor_utils, samplers, targets, bnn, mt19937, philox, diagnostics  # noqa: F401
+from . import tensor_utils, samplers, targets, bnn, mt19937, philox, diagnostics, svgd  # noqa: F401

@@ -1,5 +1,5 @@
 """Sampler enumeration and factory -- same interface and error texts as
-pysgmcmc/sampling.py:5-273 (SVGD is outside the scope of this engine).
+pysgmcmc/sampling.py:5-273.
 """
 import inspect
 from enum import Enum
@@ -11,6 +11,7 @@ class Sampler(Enum):
     SGHMC = "SGHMC"
     RelativisticSGHMC = "RelativisticSGHMC"
     SGLD = "SGLD"
+    SVGD = "SVGD"
 
     @staticmethod
     def is_burn_in_mcmc(sampling_method):
@@ -107,6 +108,7 @@ def _sampler_class(sampling_method):
         Sampler.SGHMC: samplers.SGHMCSampler,
         Sampler.SGLD: samplers.SGLDSampler,
         Sampler.RelativisticSGHMC: samplers.RelativisticSGHMCSampler,
+        Sampler.SVGD: samplers.SVGDSampler,
     }
     if sampling_method not in table:
         raise ValueError("Sampling method {} is not supported by this engine; choose one of "

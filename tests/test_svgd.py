@@ -1,0 +1,366 @@
+"""Stein variational gradient descent: oracle pins on CPU, kernels
+K11-K14 and the `SVGDSampler` class against the oracle on the GPU.
+
+What pins the oracle (reference's own tests): `pdist` / `squareform` are asserted equal to
+scipy's (pysgmcmc/tests/test_tensor_utils.py:46-86) and `median` has doctest values
+(pysgmcmc/tensor_utils.py:180-192).  SVGD trajectories are unpinned by the reference;
+oracle/svgd.py restates svgd.py:81-182 line by line.
+
+Tolerances (float32): the median is selected exactly, so given the same distance matrix it
+is bit-exact; distances, the kernel matrix and the Stein direction are sums evaluated in a
+different order than NumPy's, compared at rtol 1e-5 (north_star part 1) with an absolute
+floor of 1e-6 x the scale of the quantity.
+"""
+import numpy as np
+import pytest
+import torch
+from scipy.spatial.distance import pdist as pdist_scipy, squareform as squareform_scipy
+
+from oracle import svgd as osvgd, targets as otargets
+from pysgmcmc_b200 import tensor_utils
+from pysgmcmc_b200.sampling import Sampler
+
+DEV = "cuda:0"
+
+
+# ----------------------------------------------------------------------------- CPU: oracle pins
+def test_oracle_pdist_and_squareform_equal_scipy():
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        x = rng.rand(rng.randint(2, 20), rng.randint(1, 10))
+        assert np.allclose(osvgd.pdist(x), pdist_scipy(x, metric="euclidean"))
+        assert np.allclose(osvgd.squareform(osvgd.pdist(x)), squareform_scipy(pdist_scipy(x)))
+    # the doctest input of tensor_utils.py:356-366
+    x = np.array([[0.77228064, 0.09543156], [0.3918973, 0.96806584], [0.66008144, 0.22163063]])
+    assert np.allclose(osvgd.pdist(x), pdist_scipy(x))
+    assert osvgd.squareform(np.zeros(0)).shape == (1, 1)
+    with pytest.raises(ValueError):
+        osvgd.squareform(np.zeros(4))
+    with pytest.raises(ValueError):
+        osvgd.pdist(rng.rand(2, 2, 1))
+    with pytest.raises(NotImplementedError):
+        osvgd.pdist(x, metric="lengthy_metric")
+
+
+def test_oracle_median_doctests():
+    assert osvgd.median(np.array([1., 3., 5.])) == 3.0              # tensor_utils.py:180-184
+    assert osvgd.median(np.array([1., 3., 5., 7.])) == 4.0          # :189-192
+    rng = np.random.RandomState(1)
+    for n in (1, 2, 9, 100, 101):
+        x = rng.randn(n).astype(np.float32)
+        assert osvgd.median(x) == np.float32(np.median(x))
+
+
+def test_oracle_svgd_step_matches_an_independent_float64_formula():
+    rng = np.random.RandomState(2)
+    X = rng.randn(6, 3)
+    G = rng.randn(6, 3)
+    state = osvgd.svgd_init(X)
+    osvgd.svgd_step(state, G, epsilon=0.1)
+    P = squareform_scipy(pdist_scipy(X)) ** 2
+    h2 = 0.5 * np.median(P) / np.log(7.0)
+    K = np.exp(-P / h2 / 2)
+    phi = (K @ G + (-K @ X + X * K.sum(1, keepdims=True)) / h2) / 6
+    hist = 0.1 * phi ** 2
+    assert np.allclose(state["historical_grad"], hist, rtol=1e-12)
+    assert np.allclose(state["theta"], X - 0.1 * phi / (1e-6 + np.sqrt(hist)), rtol=1e-12)
+
+
+def test_host_pdist_squareform_median_follow_the_reference():
+    rng = np.random.RandomState(3)
+    x = rng.rand(7, 3)
+    t = torch.tensor(x)
+    assert np.allclose(tensor_utils.pdist(t).numpy(), pdist_scipy(x))
+    assert np.allclose(tensor_utils.squareform(tensor_utils.pdist(t)).numpy(), squareform_scipy(pdist_scipy(x)))
+    assert tensor_utils.squareform(torch.zeros(0)).shape == (1, 1)
+    with pytest.raises(NotImplementedError):
+        tensor_utils.squareform(torch.zeros(4, 4))
+    with pytest.raises(ValueError):
+        tensor_utils.squareform(torch.zeros(4))
+    with pytest.raises(ValueError):
+        tensor_utils.pdist(torch.zeros(2, 2, 1))
+    with pytest.raises(NotImplementedError):
+        tensor_utils.pdist(t, metric="lengthy_metric")
+    assert float(tensor_utils.median(torch.tensor([1., 3., 5.], dtype=torch.float64))) == 3.0
+    assert float(tensor_utils.median(torch.tensor([1., 3., 5., 7.], dtype=torch.float64))) == 4.0
+
+
+def test_factory_knows_svgd_and_checks_its_arguments():
+    assert Sampler.SVGD.value == "SVGD"
+    assert not Sampler.is_supported(Sampler.SVGD)            # sampling.py:64: BNN supports SGHMC/SGLD only
+    assert not Sampler.is_burn_in_mcmc(Sampler.SVGD)
+    with pytest.raises(ValueError) as err:
+        Sampler.get_sampler(Sampler.SVGD, particles=[], cost_fun=None, mdecay=0.1)
+    assert "'SVGDSampler' does not take any parameter with name 'mdecay'" in str(err.value)
+    assert "-particles\n-cost_fun\n-batch_generator\n-stepsize_schedule\n-alpha\n-fudge_factor" in str(err.value)
+    with pytest.raises(ValueError) as err:
+        Sampler.get_sampler(Sampler.SVGD, cost_fun=None)
+    assert "particles was not overwritten" in str(err.value)
+
+
+# ----------------------------------------------------------------------------- GPU: kernels
+def _native():
+    from pysgmcmc_b200 import _native
+    return _native
+
+
+def _kernel_matrix(X):
+    nat = _native()
+    n, D = X.shape
+    K = torch.empty((n, n), dtype=torch.float32, device=DEV)
+    ksum = torch.empty(n, dtype=torch.float32, device=DEV)
+    bw = torch.zeros(4, dtype=torch.float32, device=DEV)
+    scratch = torch.zeros(512, dtype=torch.int64, device=DEV)
+    nat.call("sgmcmc_svgd_kernel_matrix_f32", nat.ptr(X), nat.ptr(K), nat.ptr(ksum), nat.ptr(bw),
+             nat.ptr(scratch), n, D, nat.stream_ptr())
+    return K, ksum, bw
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 256, 257, 4096, 65537, 1000003])
+def test_k12_median_is_exact(n):
+    rng = np.random.RandomState(n)
+    x = (rng.randn(n) * 10 ** rng.uniform(-3, 3, size=n)).astype(np.float32)
+    if n > 100:
+        x[rng.randint(0, n, size=n // 3)] = 0.0                 # ties, like the zero diagonal
+        x[rng.randint(0, n, size=n // 5)] = x[0]
+    got = tensor_utils.median(torch.tensor(x, device=DEV))
+    assert got.dtype == torch.float32
+    assert float(got) == float(osvgd.median(x))
+
+
+@pytest.mark.gpu
+def test_k12_median_of_special_values():
+    for values in ([0.0, 0.0, 0.0, 0.0], [-1.0, -2.0, -3.0], [-0.0, 0.0], [3e38, -3e38, 1e-45, -1e-45],
+                   [np.inf, 1.0, 2.0], [5.0]):
+        x = np.array(values, dtype=np.float32)
+        got = float(tensor_utils.median(torch.tensor(x, device=DEV)))
+        assert got == float(osvgd.median(x)), values
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,D", [(2, 2), (10, 2), (7, 3), (64, 16), (65, 17), (100, 50), (130, 5252), (300, 8)])
+def test_k11_k13_kernel_matrix_matches_the_oracle(n, D):
+    rng = np.random.RandomState(n * 1000 + D)
+    X = (rng.randn(n, D) * rng.uniform(0.5, 2.0)).astype(np.float32)
+    K, ksum, bw = _kernel_matrix(torch.tensor(X, device=DEV))
+    K, ksum, bw = K.cpu().numpy(), ksum.cpu().numpy(), bw.cpu().numpy()
+    K_ref, _, h_ref = osvgd.svgd_kernel(X.astype(np.float64))
+    P_ref = squareform_scipy(pdist_scipy(X.astype(np.float64))) ** 2
+    assert np.array_equal(K, K.T), "K11 must mirror its tiles bit for bit (K14 reads rows as columns)"
+    assert np.all(np.diag(K) == 1.0)
+    assert np.isclose(bw[0], np.median(P_ref), rtol=1e-5)
+    assert np.isclose(bw[1], h_ref, rtol=1e-5)
+    assert np.isclose(bw[2], h_ref ** 2, rtol=1e-5)
+    # exp amplifies a relative error of its argument by |argument| (<= ~20 where K matters)
+    assert np.allclose(K, K_ref, rtol=2e-4, atol=1e-7)
+    assert np.allclose(ksum, K_ref.sum(1), rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_k12_bandwidth_is_the_exact_median_of_the_device_distances():
+    """Given K11's own float32 distances the bandwidth follows svgd.py:155-157 bit for bit."""
+    rng = np.random.RandomState(5)
+    for n, D in ((9, 2), (10, 2), (64, 5), (101, 7)):
+        X = torch.tensor(rng.randn(n, D).astype(np.float32), device=DEV)
+        K, _, bw = _kernel_matrix(X)
+        d = X[:, None, :] - X[None, :, :]
+        bw = bw.cpu().numpy()
+        # recover P from K is lossy; recompute P the way K11 does is not available on the host,
+        # so check the chain median -> h -> h^2 instead
+        med = np.float32(bw[0])
+        h = np.sqrt(np.float32(0.5) * med / np.log(np.float32(n) + np.float32(1.0)))
+        assert abs(float(bw[1]) - float(h)) <= 1.2e-7 * float(h)
+        assert float(bw[2]) == float(np.float32(bw[1]) * np.float32(bw[1]))
+        P64 = (d.double() ** 2).sum(-1).cpu().numpy()
+        assert np.isclose(med, np.median(P64), rtol=1e-5)
+
+
+def _svgd_update(X, G, hist, eps=0.1, alpha=0.9, fudge=1e-6):
+    nat = _native()
+    n, D = X.shape
+    K, ksum, bw = _kernel_matrix(X)
+    scratch = torch.empty_like(X)
+    nat.call("sgmcmc_svgd_update_f32", nat.ptr(X), nat.ptr(G), nat.ptr(hist), nat.ptr(K), nat.ptr(ksum),
+             nat.ptr(bw), nat.ptr(scratch), n, D, eps, alpha, 1. - alpha, fudge, nat.stream_ptr())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,D", [(2, 2), (10, 2), (7, 3), (16, 4), (128, 64), (129, 65), (200, 52), (132, 5252),
+                                 (1024, 8)])
+def test_k14_single_step_matches_the_oracle(n, D):
+    rng = np.random.RandomState(n + 7 * D)
+    X = rng.randn(n, D).astype(np.float32)
+    G = rng.randn(n, D).astype(np.float32)
+    H = (rng.rand(n, D) * 0.1).astype(np.float32)
+    state = dict(theta=X.astype(np.float64), historical_grad=H.astype(np.float64))
+    osvgd.svgd_step(state, G.astype(np.float64), 0.1)
+    Xd, Gd, Hd = (torch.tensor(a, device=DEV) for a in (X, G, H))
+    _svgd_update(Xd, Gd, Hd)
+    scale = np.abs(X).max()
+    assert np.allclose(Hd.cpu().numpy(), state["historical_grad"], rtol=2e-4, atol=1e-9)
+    assert np.allclose(Xd.cpu().numpy(), state["theta"], rtol=1e-5, atol=1e-5 * scale)
+    assert torch.equal(Gd.cpu(), torch.tensor(G))
+
+
+@pytest.mark.gpu
+def test_k14_vector_and_scalar_code_paths_agree():
+    """n % 4 == 0 and D % 4 == 0 takes the 128-bit path; a misaligned view of the same data
+    takes the scalar path.  Same arithmetic, same order: bit-identical."""
+    rng = np.random.RandomState(11)
+    n, D = 64, 24
+    X, G = rng.randn(n, D).astype(np.float32), rng.randn(n, D).astype(np.float32)
+    outs = []
+    for shift in (0, 1):
+        bufs = []
+        for a in (X, G, np.zeros_like(X)):
+            raw = torch.zeros(n * D + 4, dtype=torch.float32, device=DEV)
+            view = raw[shift:shift + n * D].view(n, D)
+            view.copy_(torch.tensor(a))
+            bufs.append(view)
+        _svgd_update(*bufs)
+        outs.append((bufs[0].cpu().clone(), bufs[2].cpu().clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+# ----------------------------------------------------------------------------- GPU: sampler class
+def _banana_cost(x):
+    return 0.5 * (0.01 * x[0] ** 2 + (x[1] + 0.1 * x[0] ** 2 - 10) ** 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_particles", [10, 64])
+def test_svgd_sampler_trajectory_matches_the_oracle(n_particles):
+    """The notebook's configuration (docs/source/notebooks/SVGD.ipynb: banana, 10 particles,
+    N(0,1) starts, default stepsize 0.1) against the float64 oracle, rtol 1e-5 of the particle
+    scale for 50 steps.  Not longer on purpose: once the particles settle, the AdaGrad-normalised
+    direction phi / sqrt(hist) turns sign-like around phi = 0 and ANY rounding difference is
+    amplified -- the float32 and float64 oracles themselves separate by 1e-4 at step 65 and by
+    O(1) at step 100 (measured), so later steps say nothing about the implementation."""
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.samplers import SVGDSampler
+    rng = np.random.RandomState(4)
+    X0 = rng.randn(n_particles, 2).astype(np.float32)
+    particles = [torch.tensor(x, device=DEV) for x in X0]
+    sampler = SVGDSampler(particles=particles, cost_fun=_banana_cost, session=Session(device=DEV, output="numpy"))
+    ref64 = osvgd.OracleSVGD(X0.astype(np.float64), otargets.banana_cost_and_grad)
+    n_steps = 50
+    for step in range(n_steps):
+        sample, cost = next(sampler)
+        t64, c64 = next(ref64)
+        assert isinstance(sample, list) and len(sample) == n_particles and sample[0].shape == (2,)
+        assert cost.shape == (n_particles,)
+        got = np.stack(sample)
+        assert np.abs(got - t64).max() <= 1e-5 * np.abs(t64).max(), step
+        assert np.allclose(cost, c64, rtol=1e-4, atol=1e-4), step
+    # long run: the particle cloud stays on the banana (mean cost of the oracle's cloud: ~0.25)
+    for step in range(450):
+        sample, cost = next(sampler)
+    got = np.stack(sample)
+    assert np.isfinite(got).all() and 0.0 <= cost.mean() < 2.0
+    n_steps += 450
+    assert sampler.n_iterations == n_steps
+    # the user's tensors are live views of the state (tf.Variable behaviour)
+    assert np.array_equal(np.stack([p.cpu().numpy() for p in particles]), got)
+
+
+@pytest.mark.gpu
+def test_svgd_sampler_interface_and_errors():
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.samplers import SVGDSampler
+    mk = lambda shape: [torch.zeros(shape, device=DEV) + i for i in range(4)]
+    with pytest.raises(ValueError):
+        SVGDSampler(particles=mk((2, 1)), cost_fun=_banana_cost)          # stacked particles must be 2-d
+    with pytest.raises(AssertionError):
+        SVGDSampler(particles=mk((2,)), cost_fun=_banana_cost, alpha="0.9")
+    with pytest.raises(AssertionError):
+        SVGDSampler(particles=mk((2,)), cost_fun=None)
+    sampler = Sampler.get_sampler(Sampler.SVGD, particles=mk((2,)), cost_fun=_banana_cost,
+                                  session=Session(device=DEV, output="torch"))
+    assert sampler.cost_fun.__name__ == "_banana_cost"
+    assert float(sampler.epsilon.value) == 0.1 and sampler.alpha == 0.9 and sampler.fudge_factor == 1e-6
+    assert iter(sampler) is sampler
+    sample, cost = next(sampler)
+    assert len(sample) == 4 and sample[0].is_cuda and cost.shape == (4,)
+    K, kgrad = sampler.svgd_kernel()
+    K_ref, kgrad_ref, h_ref = osvgd.svgd_kernel(sampler.particles.cpu().numpy().astype(np.float64))
+    assert np.allclose(K.cpu().numpy(), K_ref, rtol=1e-4)
+    assert np.allclose(kgrad.cpu().numpy(), kgrad_ref, rtol=1e-3, atol=1e-5)
+    assert np.isclose(float(sampler.bandwidth), h_ref, rtol=1e-5)
+    # run() == repeated next(); checkpoint round trip continues bit-identically
+    state = sampler.state_dict()
+    trace, costs = sampler.run(6, keep_every=2)
+    assert trace.shape == (3, 4, 2) and costs.shape == (3, 4)
+    sampler.load_state_dict(state)
+    for k in range(6):
+        sample, _ = next(sampler)
+        if k % 2 == 1:
+            assert torch.equal(torch.stack(sample), trace[k // 2])
+
+
+@pytest.mark.gpu
+def test_svgd_python_loop_and_vmap_costs_agree():
+    """A cost function torch.vmap cannot trace (data-dependent Python branch) falls back to
+    one call per particle; both give the same trajectory."""
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.samplers import SVGDSampler
+
+    def branching_cost(x):
+        if float(x[0]) > 1e30:          # .item() inside vmap raises -> per-particle loop
+            return x.sum()
+        return _banana_cost(x)
+
+    rng = np.random.RandomState(8)
+    X0 = rng.randn(12, 2).astype(np.float32)
+    runs = []
+    for fun in (_banana_cost, branching_cost):
+        s = SVGDSampler([torch.tensor(x, device=DEV) for x in X0], fun, session=Session(device=DEV, output="torch"))
+        for _ in range(20):
+            sample, _ = next(s)
+        runs.append(torch.stack(sample).cpu().numpy())
+    assert np.allclose(runs[0], runs[1], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_svgd_on_the_bnn_cost_kernel():
+    """The reference's svgd.py:7-10 wishes for SVGD over BNN weights; here a particle is one
+    flat network (the chain layout), its cost and gradient come from K4."""
+    from oracle import bnn as obnn
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.models.bnn_cost import BayesianNeuralNetworkNLL, default_net_params, n_parameters
+    from pysgmcmc_b200.samplers import SVGDSampler
+    rng = np.random.RandomState(9)
+    N, n = 20, 24
+    Xd = rng.rand(N, 1).astype(np.float32)
+    yd = np.sinc(Xd * 10 - 5).sum(1).astype(np.float32)
+    D = n_parameters(1)
+    params = default_net_params(1, n_chains=n, seed=3, device=DEV)
+    flat = torch.cat([p.reshape(n, -1) for p in params], dim=1)
+    assert flat.shape == (n, D)
+    nll = BayesianNeuralNetworkNLL(N, batch_size=20, X=Xd, y=yd, device=DEV)
+    particles = [flat[i].clone() for i in range(n)]
+    sampler = SVGDSampler(particles, nll, session=Session(device=DEV, output="torch"))
+    X0 = flat.cpu().numpy()
+
+    def cost_and_grad(theta):
+        C = theta.shape[0]
+        cost, grad, _ = obnn.nll_and_grad(theta, np.repeat(Xd[None].astype(np.float64), C, axis=0),
+                                          np.repeat(yd[None].astype(np.float64), C, axis=0),
+                                          n_examples=N, batch_size=20)
+        return cost, grad
+
+    ref = osvgd.OracleSVGD(X0.astype(np.float64), cost_and_grad, epsilon=0.1)
+    for step in range(5):
+        sample, cost = next(sampler)
+        t64, c64 = next(ref)
+        assert np.allclose(cost.cpu().numpy(), c64, rtol=2e-5), step
+        # the AdaGrad history is a smooth function of the Stein direction: tight everywhere
+        assert np.allclose(sampler.historical_grad.cpu().numpy(), ref.state["historical_grad"],
+                           rtol=1e-3, atol=1e-12), step
+        # the update phi / (1e-6 + sqrt(hist)) is NOT smooth where |phi| < ~1e-5 on the first steps
+        # (hist starts at 0, svgd.py:117-120): d x / d phi reaches eps / fudge = 1e5 there, so a few
+        # of the 126 048 coordinates may move by up to ~1e-4 for a 1e-9 difference in phi
+        err = np.abs(torch.stack(sample).cpu().numpy() - t64)
+        tight = err <= 2e-5 + 1e-5 * np.abs(t64)
+        assert tight.mean() > 0.998, (step, tight.mean())
+        assert err.max() < 5e-3, (step, err.max())
