@@ -1,0 +1,101 @@
+"""Per-kernel times of one SVGD step (K11-K14, csrc/svgd.cu) and of the whole
+`next(sampler)` with the BNN cost kernel K4 supplying the gradients.
+    python tools/bench_svgd.py [--quick]
+Rooflines: K14 is FP32-pipe bound, 4 n^2 D flop (two products sharing the K operand) against
+74.4 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz); K11 is 3 n^2 D / 2 flop-equivalents on the
+same pipe (subtract + FMA per term, upper triangle only); K12/K13 are latency / L2 bound.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pysgmcmc_b200 import _native  # noqa: E402
+
+dev = torch.device("cuda:0")
+FP32_PEAK = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    quick = "--quick" in sys.argv
+    shapes = [(10, 2), (1024, 2), (256, 5252), (1024, 5252), (2048, 5252), (4096, 5252), (4096, 64), (8192, 1024)]
+    if quick:
+        shapes = [(10, 2), (1024, 5252)]
+    for n, D in shapes:
+        g = torch.Generator(device=dev).manual_seed(1)
+        X = torch.randn((n, D), device=dev, generator=g)
+        G = torch.randn((n, D), device=dev, generator=g)
+        H = torch.zeros((n, D), device=dev)
+        K = torch.empty((n, n), device=dev)
+        ksum = torch.empty(n, device=dev)
+        bw = torch.zeros(4, device=dev)
+        scratch = torch.zeros(512, dtype=torch.int64, device=dev)
+        Xs = torch.empty_like(X)
+        X0 = X.clone()
+        s = _native.stream_ptr()
+
+        def kernel_matrix():
+            _native.call("sgmcmc_svgd_kernel_matrix_f32", _native.ptr(X), _native.ptr(K), _native.ptr(ksum),
+                         _native.ptr(bw), _native.ptr(scratch), n, D, s)
+
+        def median_only():
+            _native.call("sgmcmc_median_f32", _native.ptr(K), n * n, _native.ptr(bw), _native.ptr(scratch), s)
+
+        def update():
+            # eps = 0 keeps the particles where they are, so every repetition does the same work
+            _native.call("sgmcmc_svgd_update_f32", _native.ptr(X), _native.ptr(G), _native.ptr(H), _native.ptr(K),
+                         _native.ptr(ksum), _native.ptr(bw), _native.ptr(Xs), n, D, 0.0, 0.9, 0.1, 1e-6, s)
+
+        reps = 5 if n * n * D > 5e10 else 20
+        ms_km = timed(kernel_matrix, reps)
+        ms_med = timed(median_only, reps)
+        kernel_matrix()
+        ms_up = timed(update, reps)
+        assert torch.equal(X, X0)
+        flop_up = 4.0 * n * n * D
+        flop_sq = 1.5 * n * n * D
+        print(json.dumps({
+            "n_particles": n, "n_dims": D,
+            "k11_k12_k13_kernel_matrix_ms": round(ms_km, 4), "k12_median_ms": round(ms_med, 4),
+            "k11_sqdist_TFLOPs_equiv": round(flop_sq / max(ms_km - ms_med, 1e-6) / 1e9, 2),
+            "k14_update_ms": round(ms_up, 4), "k14_TFLOPs": round(flop_up / ms_up / 1e9, 2),
+            "k14_frac_of_fp32_peak": round(flop_up / ms_up / 1e9 / FP32_PEAK, 3),
+            "svgd_step_ms": round(ms_km + ms_up, 4),
+            "particle_updates_per_s": round(n / (ms_km + ms_up) * 1e3)}), flush=True)
+
+    # whole next(sampler) on the BNN posterior: one particle = one 1-50-50-50-1 network
+    if not quick:
+        from pysgmcmc_b200 import Session
+        from pysgmcmc_b200.models.bnn_cost import BayesianNeuralNetworkNLL, default_net_params
+        from pysgmcmc_b200.samplers import SVGDSampler
+        rng = np.random.RandomState(1)
+        Xd = rng.rand(20, 1).astype(np.float32)
+        yd = np.sinc(Xd * 10 - 5).sum(1).astype(np.float32)
+        for n in (256, 1024, 2048):
+            flat = torch.cat([p.reshape(n, -1) for p in default_net_params(1, n_chains=n, seed=1, device=dev)], dim=1)
+            nll = BayesianNeuralNetworkNLL(20, batch_size=20, X=Xd, y=yd, device=dev)
+            sampler = SVGDSampler([flat[i].clone() for i in range(n)], nll, session=Session(device=dev, output="torch"))
+            ms = timed(sampler._step_on_device, 10)
+            print(json.dumps({"workload": "BNN-SVGD next(sampler) on device (K4 + K11-K14)", "n_particles": n,
+                              "n_dims": flat.shape[1], "ms_per_step": round(ms, 4),
+                              "particle_steps_per_s": round(n / ms * 1e3)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
