@@ -272,6 +272,11 @@ int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double*
  *   X    -= epsilon * phi / (fudge_factor + sqrt(hist))
  * historical_grad and particles are updated in place (particles through
  * particles_scratch [n, D], because every output row reads all of X). */
+/* Implementation of the update GEMM (K14): 0 = automatic (default), 1 = FP32 FFMA kernel,
+ * 2 = tcgen05 tensor-core kernel (3xTF32 products accumulated in TMEM, csrc/svgd_umma.cu)
+ * whenever the shape is eligible (n_particles % 4 == 0, n_dims % 4 == 0, 16-byte aligned
+ * pointers); otherwise the FFMA kernel runs. */
+int sgmcmc_set_svgd_tuning(int impl);
 int sgmcmc_median_f32(const float* values, int64_t n_values, float* out, void* scratch, void* stream);
 int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kernel_matrix, float* kernel_sum,
                                   float* bandwidth, void* scratch, int64_t n_particles, int64_t n_dims,

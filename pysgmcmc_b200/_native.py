@@ -65,6 +65,7 @@ SIGNATURES = {
     "sgmcmc_chain_moments_f32": [_P, _P, c_int64, c_int64, c_int64, _P],
     "sgmcmc_variogram_f32": [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
     "sgmcmc_variogram_select_f32": [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
+    "sgmcmc_set_svgd_tuning": [c_int],
     "sgmcmc_median_f32": [_P, c_int64, _P, _P, _P],
     "sgmcmc_svgd_kernel_matrix_f32": [_P] * 5 + [c_int64, c_int64, _P],
     "sgmcmc_svgd_update_f32": [_P] * 7 + [c_int64, c_int64, c_float, c_float, c_float, c_float, _P],

@@ -14,6 +14,8 @@
 // bound for any n beyond a few dozen particles.  It runs the products in FP32 FFMA
 // (the reference's float32 matmul; TF32 inputs would cost 1e-3 relative in the Stein
 // direction, beyond the 1e-5 trajectory tolerance).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace sgmcmc {
@@ -415,6 +417,13 @@ svgd_update_kernel(const float* __restrict__ K, const float* __restrict__ X, con
   }
 }
 
+// csrc/svgd_umma.cu: the same update on the tcgen05 tensor cores (3xTF32, TMEM accumulators)
+int launch_svgd_update_umma(const float* K, const float* X, const float* G, const float* ksum, const float* bw,
+                            float* hist, float* Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
+                            float fudge, cudaStream_t stream);
+
+static std::atomic<int> g_svgd_impl{0};      // 0 = auto, 1 = FFMA kernel, 2 = tcgen05 kernel wherever it is eligible
+
 static int check_svgd_sizes(int64_t n, int64_t D) {
   SG_REQUIRE(n >= 0 && D >= 0, SGMCMC_E_INVALID, "svgd: n_particles and n_dims must be >= 0");
   SG_REQUIRE(n <= 46340, SGMCMC_E_UNSUPPORTED, "svgd: at most 46340 particles (n^2 must fit 31 bits), got %lld", (long long)n);
@@ -425,6 +434,12 @@ static int check_svgd_sizes(int64_t n, int64_t D) {
 }  // namespace sgmcmc
 
 using namespace sgmcmc;
+
+extern "C" int sgmcmc_set_svgd_tuning(int impl) {
+  SG_REQUIRE(impl >= 0 && impl <= 2, SGMCMC_E_INVALID, "svgd impl must be 0 (auto), 1 (FFMA) or 2 (tcgen05), got %d", impl);
+  g_svgd_impl.store(impl);
+  return SGMCMC_OK;
+}
 
 extern "C" int sgmcmc_median_f32(const float* values, int64_t n_values, float* out, void* scratch, void* stream) {
   SG_REQUIRE(n_values >= 1, SGMCMC_E_INVALID, "median: needs at least one value");
@@ -471,7 +486,16 @@ extern "C" int sgmcmc_svgd_update_f32(float* particles, const float* grad, float
   const bool vec = (n % 4 == 0) && (D % 4 == 0) && aligned_to(particles, 16) && aligned_to(grad, 16) &&
                    aligned_to(historical_grad, 16) && aligned_to(kernel_matrix, 16) &&
                    aligned_to(particles_scratch, 16);
-  if (vec)
+  const int impl = g_svgd_impl.load(std::memory_order_relaxed);
+  const bool umma_ok = vec && aligned_to(kernel_sum, 4);
+  // auto: the tensor-core kernel needs enough rows to fill its 128-row tile and enough columns to amortise
+  // its prologue; measured crossover in profiles/r01_svgd_k14_tcgen05.jsonl
+  const bool use_umma = impl == 2 ? umma_ok : (impl == 0 && umma_ok && n >= 128 && D >= 128);
+  if (use_umma) {
+    if (int rc = launch_svgd_update_umma(kernel_matrix, particles, grad, kernel_sum, bandwidth, historical_grad,
+                                         particles_scratch, n, D, epsilon, alpha, one_minus_alpha, fudge_factor, s))
+      return rc;
+  } else if (vec)
     svgd_update_kernel<true><<<grid, 256, 0, s>>>(kernel_matrix, particles, grad, kernel_sum, bandwidth,
                                                   historical_grad, particles_scratch, n, D, epsilon, alpha,
                                                   one_minus_alpha, fudge_factor);
@@ -479,7 +503,8 @@ extern "C" int sgmcmc_svgd_update_f32(float* particles, const float* grad, float
     svgd_update_kernel<false><<<grid, 256, 0, s>>>(kernel_matrix, particles, grad, kernel_sum, bandwidth,
                                                    historical_grad, particles_scratch, n, D, epsilon, alpha,
                                                    one_minus_alpha, fudge_factor);
-  if (int rc = check_launch("svgd_update_kernel")) return rc;
+  if (!use_umma)
+    if (int rc = check_launch("svgd_update_kernel")) return rc;
   const cudaError_t e = cudaMemcpyAsync(particles, particles_scratch, sizeof(float) * (size_t)n * (size_t)D,
                                         cudaMemcpyDeviceToDevice, s);
   if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd: cudaMemcpyAsync: %s", cudaGetErrorString(e));

@@ -176,19 +176,29 @@ def test_k12_bandwidth_is_the_exact_median_of_the_device_distances():
         assert np.isclose(med, np.median(P64), rtol=1e-5)
 
 
-def _svgd_update(X, G, hist, eps=0.1, alpha=0.9, fudge=1e-6):
+def _svgd_update(X, G, hist, eps=0.1, alpha=0.9, fudge=1e-6, impl=0):
+    """impl: 0 = automatic choice, 1 = FFMA kernel, 2 = tcgen05 kernel (sgmcmc_set_svgd_tuning)."""
     nat = _native()
     n, D = X.shape
     K, ksum, bw = _kernel_matrix(X)
     scratch = torch.empty_like(X)
-    nat.call("sgmcmc_svgd_update_f32", nat.ptr(X), nat.ptr(G), nat.ptr(hist), nat.ptr(K), nat.ptr(ksum),
-             nat.ptr(bw), nat.ptr(scratch), n, D, eps, alpha, 1. - alpha, fudge, nat.stream_ptr())
+    nat.call("sgmcmc_set_svgd_tuning", impl)
+    try:
+        nat.call("sgmcmc_svgd_update_f32", nat.ptr(X), nat.ptr(G), nat.ptr(hist), nat.ptr(K), nat.ptr(ksum),
+                 nat.ptr(bw), nat.ptr(scratch), n, D, eps, alpha, 1. - alpha, fudge, nat.stream_ptr())
+        torch.cuda.synchronize()
+    finally:
+        nat.call("sgmcmc_set_svgd_tuning", 0)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("n,D", [(2, 2), (10, 2), (7, 3), (16, 4), (128, 64), (129, 65), (200, 52), (132, 5252),
-                                 (1024, 8)])
-def test_k14_single_step_matches_the_oracle(n, D):
+                                 (1024, 8), (4, 4), (36, 20), (128, 128), (256, 384), (1000, 260), (1024, 1024)])
+def test_k14_single_step_matches_the_oracle(n, D, impl):
+    """Both implementations of K14 (FFMA and tcgen05 3xTF32) against the float64 oracle; shapes
+    the tensor-core kernel is not eligible for (n or D not a multiple of 4) run the FFMA kernel
+    under either setting."""
     rng = np.random.RandomState(n + 7 * D)
     X = rng.randn(n, D).astype(np.float32)
     G = rng.randn(n, D).astype(np.float32)
@@ -196,7 +206,7 @@ def test_k14_single_step_matches_the_oracle(n, D):
     state = dict(theta=X.astype(np.float64), historical_grad=H.astype(np.float64))
     osvgd.svgd_step(state, G.astype(np.float64), 0.1)
     Xd, Gd, Hd = (torch.tensor(a, device=DEV) for a in (X, G, H))
-    _svgd_update(Xd, Gd, Hd)
+    _svgd_update(Xd, Gd, Hd, impl=impl)
     scale = np.abs(X).max()
     assert np.allclose(Hd.cpu().numpy(), state["historical_grad"], rtol=2e-4, atol=1e-9)
     assert np.allclose(Xd.cpu().numpy(), state["theta"], rtol=1e-5, atol=1e-5 * scale)
@@ -221,6 +231,26 @@ def test_k14_vector_and_scalar_code_paths_agree():
         _svgd_update(*bufs)
         outs.append((bufs[0].cpu().clone(), bufs[2].cpu().clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,D", [(128, 128), (512, 640), (2048, 5252)])
+def test_k14_tensor_core_and_ffma_kernels_agree(n, D):
+    """3xTF32 on tcgen05 against plain FP32 FFMA on the same inputs: the Stein direction agrees to
+    fp32 rounding level (the split drops only the lo*lo term, 2^-22 relative per product)."""
+    g = torch.Generator(device=DEV).manual_seed(n + D)
+    X = torch.randn((n, D), device=DEV, generator=g)
+    G = torch.randn((n, D), device=DEV, generator=g)
+    out = {}
+    for impl in (1, 2):
+        Xi, Hi = X.clone(), torch.full((n, D), 0.05, device=DEV)
+        _svgd_update(Xi, G, Hi, impl=impl)
+        out[impl] = (Xi, Hi)
+    dx = (out[1][0] - out[2][0]).abs().max().item()
+    dh = ((out[1][1] - out[2][1]).abs() / out[1][1].abs()).max().item()
+    assert dx <= 2e-6 * X.abs().max().item(), dx
+    assert dh <= 2e-5, dh
+    assert not torch.equal(out[1][0], X), "the update must have moved the particles"
 
 
 # ----------------------------------------------------------------------------- GPU: sampler class
