@@ -264,7 +264,11 @@ int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double*
  * sgmcmc_svgd_kernel_matrix_f32 (svgd.py:150-160): kernel_matrix [n, n] =
  * exp(-P / h^2 / 2) with P[i,j] = (||x_i - x_j||)^2 and h = sqrt(0.5 * median(P) /
  * log(n + 1)); kernel_sum [n] = its row sums; bandwidth [4] = {median(P), h, h^2, 0}.
- * Everything stays on the device.  n_particles <= 46340.
+ * Everything stays on the device.  n_particles <= 46340.  scratch: 4096 + 4 * (n_particles +
+ * n_dims) bytes of device memory, 16-byte aligned.  kernel_matrix comes out symmetric bit for
+ * bit (sgmcmc_svgd_update_f32 reads its rows as columns).  Large aligned shapes compute the
+ * distances from the Gram matrix of the centred particles on the tcgen05 tensor cores
+ * (3xTF32, csrc/svgd_sqdist_umma.cu), the others subtract before squaring on the FP32 pipe.
  *
  * sgmcmc_svgd_update_f32 (svgd.py:125-148,162-167): with grad[i] = d cost(x_i) / d x_i,
  *   phi   = (K @ grad + (-(K @ X) + X * kernel_sum[:, None]) / h^2) / n
@@ -272,10 +276,12 @@ int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double*
  *   X    -= epsilon * phi / (fudge_factor + sqrt(hist))
  * historical_grad and particles are updated in place (particles through
  * particles_scratch [n, D], because every output row reads all of X). */
-/* Implementation of the update GEMM (K14): 0 = automatic (default), 1 = FP32 FFMA kernel,
- * 2 = tcgen05 tensor-core kernel (3xTF32 products accumulated in TMEM, csrc/svgd_umma.cu)
- * whenever the shape is eligible (n_particles % 4 == 0, n_dims % 4 == 0, 16-byte aligned
- * pointers); otherwise the FFMA kernel runs. */
+/* Implementation of the distance kernel (K11) and of the update GEMM (K14): 0 = automatic
+ * (default: tensor cores for n_particles >= 256 / 128 and n_dims >= 128), 1 = FP32 FFMA
+ * kernels, 2 = tcgen05 tensor-core kernels (3xTF32 products accumulated in TMEM,
+ * csrc/svgd_umma.cu, csrc/svgd_sqdist_umma.cu) whenever the shape is eligible (n_dims % 4 == 0,
+ * for K14 also n_particles % 4 == 0, 16-byte aligned pointers), otherwise the FFMA kernels run;
+ * 23 / 24 = 2 with 3 / 4 producer register buffers in K14 (sweeps). */
 int sgmcmc_set_svgd_tuning(int impl);
 int sgmcmc_median_f32(const float* values, int64_t n_values, float* out, void* scratch, void* stream);
 int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kernel_matrix, float* kernel_sum,

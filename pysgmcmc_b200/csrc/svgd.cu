@@ -420,9 +420,14 @@ svgd_update_kernel(const float* __restrict__ K, const float* __restrict__ X, con
 // csrc/svgd_umma.cu: the same update on the tcgen05 tensor cores (3xTF32, TMEM accumulators)
 int launch_svgd_update_umma(const float* K, const float* X, const float* G, const float* ksum, const float* bw,
                             float* hist, float* Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
-                            float fudge, cudaStream_t stream);
+                            float fudge, int prefetch, cudaStream_t stream);
 
-static std::atomic<int> g_svgd_impl{0};      // 0 = auto, 1 = FFMA kernel, 2 = tcgen05 kernel wherever it is eligible
+// 0 = auto, 1 = FFMA kernel, 2 = tcgen05 kernel wherever it is eligible; 22/23/24 = tcgen05 with 2/3/4
+// producer register buffers (sweeps)
+static std::atomic<int> g_svgd_impl{0};
+
+// csrc/svgd_sqdist_umma.cu: K11 through the Gram matrix of the centred particles on the tensor cores
+int launch_svgd_sqdist_umma(const float* X, float* P, float* work, int n, int D, cudaStream_t stream);
 
 static int check_svgd_sizes(int64_t n, int64_t D) {
   SG_REQUIRE(n >= 0 && D >= 0, SGMCMC_E_INVALID, "svgd: n_particles and n_dims must be >= 0");
@@ -436,7 +441,8 @@ static int check_svgd_sizes(int64_t n, int64_t D) {
 using namespace sgmcmc;
 
 extern "C" int sgmcmc_set_svgd_tuning(int impl) {
-  SG_REQUIRE(impl >= 0 && impl <= 2, SGMCMC_E_INVALID, "svgd impl must be 0 (auto), 1 (FFMA) or 2 (tcgen05), got %d", impl);
+  SG_REQUIRE((impl >= 0 && impl <= 2) || (impl >= 22 && impl <= 24), SGMCMC_E_INVALID,  /* 22 == 2 */
+             "svgd impl must be 0 (auto), 1 (FFMA), 2 (tcgen05) or 22-24 (tcgen05, 2-4 producer buffers), got %d", impl);
   g_svgd_impl.store(impl);
   return SGMCMC_OK;
 }
@@ -460,9 +466,17 @@ extern "C" int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kern
              SGMCMC_E_ALIGN, "svgd: misaligned pointer");
   cudaStream_t s = (cudaStream_t)stream;
   const int n = (int)n_particles, D = (int)n_dims;
-  const unsigned nt = (unsigned)((n + SD_T - 1) / SD_T);
-  svgd_sqdist_kernel<<<dim3(nt, nt), 256, 0, s>>>(particles, kernel_matrix, n, D);
-  if (int rc = check_launch("svgd_sqdist_kernel")) return rc;
+  const int impl = g_svgd_impl.load(std::memory_order_relaxed);
+  const bool umma_ok = (D % 4 == 0) && aligned_to(particles, 16) && aligned_to(scratch, 16);
+  const bool use_umma = impl >= 2 ? umma_ok : (impl == 0 && umma_ok && n >= 256 && D >= 128);
+  if (use_umma) {
+    float* work = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + 4096);
+    if (int rc = launch_svgd_sqdist_umma(particles, kernel_matrix, work, n, D, s)) return rc;
+  } else {
+    const unsigned nt = (unsigned)((n + SD_T - 1) / SD_T);
+    svgd_sqdist_kernel<<<dim3(nt, nt), 256, 0, s>>>(particles, kernel_matrix, n, D);
+    if (int rc = check_launch("svgd_sqdist_kernel")) return rc;
+  }
   if (int rc = launch_select(kernel_matrix, n_particles * n_particles, bandwidth, scratch, (float)n, s)) return rc;
   svgd_kernel_matrix_kernel<<<n, 256, 0, s>>>(kernel_matrix, kernel_sum, bandwidth, n);
   return check_launch("svgd_kernel_matrix_kernel");
@@ -489,11 +503,12 @@ extern "C" int sgmcmc_svgd_update_f32(float* particles, const float* grad, float
   const int impl = g_svgd_impl.load(std::memory_order_relaxed);
   const bool umma_ok = vec && aligned_to(kernel_sum, 4);
   // auto: the tensor-core kernel needs enough rows to fill its 128-row tile and enough columns to amortise
-  // its prologue; measured crossover in profiles/r01_svgd_k14_tcgen05.jsonl
-  const bool use_umma = impl == 2 ? umma_ok : (impl == 0 && umma_ok && n >= 128 && D >= 128);
+  // its prologue; measured crossover in profiles/r01_svgd_tcgen05.jsonl
+  const bool use_umma = impl >= 2 ? umma_ok : (impl == 0 && umma_ok && n >= 128 && D >= 128);
   if (use_umma) {
     if (int rc = launch_svgd_update_umma(kernel_matrix, particles, grad, kernel_sum, bandwidth, historical_grad,
-                                         particles_scratch, n, D, epsilon, alpha, one_minus_alpha, fudge_factor, s))
+                                         particles_scratch, n, D, epsilon, alpha, one_minus_alpha, fudge_factor,
+                                         impl >= 20 ? impl - 20 : 0, s))
       return rc;
   } else if (vec)
     svgd_update_kernel<true><<<grid, 256, 0, s>>>(kernel_matrix, particles, grad, kernel_sum, bandwidth,

@@ -40,6 +40,7 @@ struct UmRegs {
   float4 a0, a1, g0, x0, g1, x1;
 };
 
+template <int PF>     // register buffers of the producers: global loads run PF - 1 blocks ahead of the split
 __global__ void __launch_bounds__(UM_THREADS, 1)
 svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X, const float* __restrict__ G,
                         const float* __restrict__ ksum, const float* __restrict__ bw, float* __restrict__ hist,
@@ -146,14 +147,18 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
       umma::mbar_arrive(umma::smem_u32(&full_bar[s]));
     };
 
-    UmRegs r0, r1;
-    load(r0, 0);
-    for (int kb = 0; kb < nkb; kb += 2) {
-      if (kb + 1 < nkb) load(r1, kb + 1);
-      produce(r0, kb);
-      if (kb + 1 < nkb) {
-        if (kb + 2 < nkb) load(r0, kb + 2);
-        produce(r1, kb + 1);
+    UmRegs r[PF];
+#pragma unroll
+    for (int p = 0; p < PF - 1; ++p)
+      if (p < nkb) load(r[p], p);
+    for (int kb0 = 0; kb0 < nkb; kb0 += PF) {
+#pragma unroll
+      for (int p = 0; p < PF; ++p) {
+        const int kb = kb0 + p;
+        if (kb < nkb) {
+          if (kb + PF - 1 < nkb) load(r[(p + PF - 1) % PF], kb + PF - 1);
+          produce(r[p], kb);
+        }
       }
     }
 
@@ -230,21 +235,35 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
 
 // Launch helper used by sgmcmc_svgd_update_f32 (svgd.cu).  Requirements (checked by the caller):
 // n % 4 == 0, D % 4 == 0, all pointers 16-byte aligned.
-int launch_svgd_update_umma(const float* K, const float* X, const float* G, const float* ksum, const float* bw,
-                            float* hist, float* Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
-                            float fudge, cudaStream_t stream) {
+template <int PF>
+static int launch_umma_pf(const float* K, const float* X, const float* G, const float* ksum, const float* bw,
+                          float* hist, float* Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
+                          float fudge, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    const cudaError_t e = cudaFuncSetAttribute(svgd_update_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)UM_SMEM);
+    const cudaError_t e = cudaFuncSetAttribute(svgd_update_umma_kernel<PF>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM);
     if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd_update_umma_kernel: %s", cudaGetErrorString(e));
     configured = true;
   }
   const dim3 grid((unsigned)((D + UM_BN - 1) / UM_BN), (unsigned)((n + UM_BM - 1) / UM_BM));
   SG_REQUIRE(grid.y <= 65535, SGMCMC_E_UNSUPPORTED, "svgd: too many particles");
-  svgd_update_umma_kernel<<<grid, UM_THREADS, UM_SMEM, stream>>>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha,
-                                                                  one_minus_alpha, fudge);
+  svgd_update_umma_kernel<PF><<<grid, UM_THREADS, UM_SMEM, stream>>>(K, X, G, ksum, bw, hist, Xout, n, D, eps,
+                                                                      alpha, one_minus_alpha, fudge);
   return check_launch("svgd_update_umma_kernel");
+}
+
+// prefetch: register buffers of the producers (2..4); 0 = the default
+int launch_svgd_update_umma(const float* K, const float* X, const float* G, const float* ksum, const float* bw,
+                            float* hist, float* Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
+                            float fudge, int prefetch, cudaStream_t stream) {
+  // measured (profiles/r01_svgd_k14_prefetch_sweep.jsonl): 2, 3 and 4 buffers run within 2 % of each other -- the
+  // kernel is bound by the LSU data pipe (global loads + staging stores), not by load latency -- so 2 is the default
+  switch (prefetch) {
+    case 3: return launch_umma_pf<3>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+    case 4: return launch_umma_pf<4>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+    default: return launch_umma_pf<2>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+  }
 }
 
 }  // namespace sgmcmc

@@ -73,7 +73,8 @@ class SVGDSampler(MCMCSampler):
         self._kernel_matrix = torch.empty((n, n), dtype=torch.float32, device=dev)
         self._kernel_sum = torch.empty((n,), dtype=torch.float32, device=dev)
         self._bandwidth = torch.zeros((4,), dtype=torch.float32, device=dev)
-        self._select_scratch = torch.zeros((512,), dtype=torch.int64, device=dev)     # 4096 bytes
+        # 4096 bytes for the median select + (n + D) floats for the centred-Gram distance kernel
+        self._select_scratch = torch.zeros((512 + (n + D + 1) // 2,), dtype=torch.int64, device=dev)
         self._particles_scratch = torch.empty((n, D), dtype=torch.float32, device=dev)
         self._grad = torch.empty((n, D), dtype=torch.float32, device=dev)
         self._vmap_ok = None

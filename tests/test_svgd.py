@@ -104,15 +104,20 @@ def _native():
     return _native
 
 
-def _kernel_matrix(X):
+def _kernel_matrix(X, impl=0):
     nat = _native()
     n, D = X.shape
     K = torch.empty((n, n), dtype=torch.float32, device=DEV)
     ksum = torch.empty(n, dtype=torch.float32, device=DEV)
     bw = torch.zeros(4, dtype=torch.float32, device=DEV)
-    scratch = torch.zeros(512, dtype=torch.int64, device=DEV)
-    nat.call("sgmcmc_svgd_kernel_matrix_f32", nat.ptr(X), nat.ptr(K), nat.ptr(ksum), nat.ptr(bw),
-             nat.ptr(scratch), n, D, nat.stream_ptr())
+    scratch = torch.zeros(512 + (n + D + 1) // 2, dtype=torch.int64, device=DEV)
+    nat.call("sgmcmc_set_svgd_tuning", impl)
+    try:
+        nat.call("sgmcmc_svgd_kernel_matrix_f32", nat.ptr(X), nat.ptr(K), nat.ptr(ksum), nat.ptr(bw),
+                 nat.ptr(scratch), n, D, nat.stream_ptr())
+        torch.cuda.synchronize()
+    finally:
+        nat.call("sgmcmc_set_svgd_tuning", 0)
     return K, ksum, bw
 
 
@@ -139,11 +144,16 @@ def test_k12_median_of_special_values():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,D", [(2, 2), (10, 2), (7, 3), (64, 16), (65, 17), (100, 50), (130, 5252), (300, 8)])
-def test_k11_k13_kernel_matrix_matches_the_oracle(n, D):
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("n,D", [(2, 2), (10, 2), (7, 3), (64, 16), (65, 17), (100, 50), (130, 5252), (300, 8),
+                                 (128, 256), (257, 132), (513, 64), (1000, 1028)])
+def test_k11_k13_kernel_matrix_matches_the_oracle(n, D, impl):
+    """Both implementations of K11 (difference-then-square on the FP32 pipe; centred Gram matrix as
+    3xTF32 on tcgen05) against the float64 oracle, with the particle cloud far from the origin
+    (offset 5: what the centring is for).  Shapes with D % 4 != 0 run the FFMA kernel either way."""
     rng = np.random.RandomState(n * 1000 + D)
-    X = (rng.randn(n, D) * rng.uniform(0.5, 2.0)).astype(np.float32)
-    K, ksum, bw = _kernel_matrix(torch.tensor(X, device=DEV))
+    X = (5.0 + rng.randn(n, D) * rng.uniform(0.5, 2.0)).astype(np.float32)
+    K, ksum, bw = _kernel_matrix(torch.tensor(X, device=DEV), impl=impl)
     K, ksum, bw = K.cpu().numpy(), ksum.cpu().numpy(), bw.cpu().numpy()
     K_ref, _, h_ref = osvgd.svgd_kernel(X.astype(np.float64))
     P_ref = squareform_scipy(pdist_scipy(X.astype(np.float64))) ** 2
@@ -180,7 +190,7 @@ def _svgd_update(X, G, hist, eps=0.1, alpha=0.9, fudge=1e-6, impl=0):
     """impl: 0 = automatic choice, 1 = FFMA kernel, 2 = tcgen05 kernel (sgmcmc_set_svgd_tuning)."""
     nat = _native()
     n, D = X.shape
-    K, ksum, bw = _kernel_matrix(X)
+    K, ksum, bw = _kernel_matrix(X, impl=1)
     scratch = torch.empty_like(X)
     nat.call("sgmcmc_set_svgd_tuning", impl)
     try:
@@ -390,9 +400,10 @@ def test_svgd_on_the_bnn_cost_kernel():
         assert np.isclose(hist, hist_ref, rtol=1e-3, atol=1e-6 * hist_ref.max()).mean() > 0.998, step
         assert np.allclose(hist, hist_ref, rtol=0.05, atol=1e-4 * hist_ref.max()), step
         # the update phi / (1e-6 + sqrt(hist)) is NOT smooth where |phi| < ~1e-5 on the first steps
-        # (hist starts at 0, svgd.py:117-120): d x / d phi reaches eps / fudge = 1e5 there, so a few
-        # of the 126 048 coordinates may move by up to ~1e-4 for a 1e-9 difference in phi
+        # (hist starts at 0, svgd.py:117-120): there the step is eps * phi / (1e-6 + 0.316 |phi|), which
+        # swings between -0.316 and +0.316 across phi = 0, so the handful of the 126 048 coordinates
+        # whose phi is within rounding of zero may land anywhere in that range; all others must be tight
         err = np.abs(torch.stack(sample).cpu().numpy() - t64)
         tight = err <= 2e-5 + 1e-5 * np.abs(t64)
         assert tight.mean() > 0.998, (step, tight.mean())
-        assert err.max() < 5e-3, (step, err.max())
+        assert np.median(err) < 1e-6 and err.max() < 0.7, (step, np.median(err), err.max())

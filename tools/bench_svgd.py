@@ -32,7 +32,38 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def k14_sweep():
+    """K14 only: FFMA, tcgen05 with 2/3/4 producer register buffers.  `--k14-sweep [n D]`"""
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    shapes = [(int(args[0]), int(args[1]))] if len(args) >= 2 else [(1024, 5252), (4096, 5252), (8192, 1024)]
+    for n, D in shapes:
+        g = torch.Generator(device=dev).manual_seed(1)
+        X = torch.randn((n, D), device=dev, generator=g)
+        G = torch.randn((n, D), device=dev, generator=g)
+        H = torch.zeros((n, D), device=dev)
+        K = torch.rand((n, n), device=dev, generator=g)
+        K = ((K + K.t()) * 0.5).contiguous()
+        ksum = K.sum(1).contiguous()
+        bw = torch.tensor([1.0, 1.0, 1.0, 0.0], device=dev)
+        Xs = torch.empty_like(X)
+        s = _native.stream_ptr()
+
+        def update():
+            _native.call("sgmcmc_svgd_update_f32", _native.ptr(X), _native.ptr(G), _native.ptr(H), _native.ptr(K),
+                         _native.ptr(ksum), _native.ptr(bw), _native.ptr(Xs), n, D, 0.0, 0.9, 0.1, 1e-6, s)
+        row = {"n_particles": n, "n_dims": D}
+        for impl in (1, 22, 23, 24):
+            _native.call("sgmcmc_set_svgd_tuning", impl)
+            ms = timed(update, 5 if n * n * D > 5e10 else 20)
+            _native.call("sgmcmc_set_svgd_tuning", 0)
+            row["impl_%d_ms" % impl] = round(ms, 4)
+            row["impl_%d_TFLOPs" % impl] = round(4.0 * n * n * D / ms / 1e9, 1)
+        print(json.dumps(row), flush=True)
+
+
 def main():
+    if "--k14-sweep" in sys.argv:
+        return k14_sweep()
     quick = "--quick" in sys.argv
     shapes = [(10, 2), (1024, 2), (128, 128), (256, 5252), (1024, 5252), (2048, 5252), (4096, 5252), (4096, 64),
               (8192, 1024)]
@@ -46,7 +77,7 @@ def main():
         K = torch.empty((n, n), device=dev)
         ksum = torch.empty(n, device=dev)
         bw = torch.zeros(4, device=dev)
-        scratch = torch.zeros(512, dtype=torch.int64, device=dev)
+        scratch = torch.zeros(512 + (n + D + 1) // 2, dtype=torch.int64, device=dev)
         Xs = torch.empty_like(X)
         X0 = X.clone()
         s = _native.stream_ptr()
@@ -64,13 +95,17 @@ def main():
                          _native.ptr(ksum), _native.ptr(bw), _native.ptr(Xs), n, D, 0.0, 0.9, 0.1, 1e-6, s)
 
         reps = 5 if n * n * D > 5e10 else 20
+        _native.call("sgmcmc_set_svgd_tuning", 1)
+        ms_km_ffma = timed(kernel_matrix, reps)
+        _native.call("sgmcmc_set_svgd_tuning", 0)
         ms_km = timed(kernel_matrix, reps)
         ms_med = timed(median_only, reps)
         kernel_matrix()
         flop_up = 4.0 * n * n * D
         flop_sq = 1.5 * n * n * D
         row = {"n_particles": n, "n_dims": D,
-               "k11_k12_k13_kernel_matrix_ms": round(ms_km, 4), "k12_median_ms": round(ms_med, 4),
+               "k11_k12_k13_kernel_matrix_ms": round(ms_km, 4), "k11_k12_k13_ffma_ms": round(ms_km_ffma, 4),
+               "k12_median_ms": round(ms_med, 4),
                "k11_sqdist_TFLOPs_equiv": round(flop_sq / max(ms_km - ms_med, 1e-6) / 1e9, 2)}
         best = None
         for impl, tag in ((1, "ffma"), (2, "tcgen05")):
