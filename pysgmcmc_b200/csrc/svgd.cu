@@ -205,8 +205,72 @@ __global__ void svgd_select_pick_kernel(SelectState* st, int shift, int last, fl
   }
 }
 
+// Small inputs (up to SELECT_SMALL_MAX values, i.e. 362 particles): all four passes in ONE CTA with the
+// histograms in shared memory -- one launch instead of nine; the result is the same exact selection.
+constexpr int64_t SELECT_SMALL_MAX = 131072;
+
+__global__ void __launch_bounds__(1024)
+svgd_select_small_kernel(const uint32_t* __restrict__ values, int n_values, float* out, float n_particles) {
+  __shared__ uint32_t h[2][256];
+  __shared__ uint32_t prefix[2];
+  __shared__ uint32_t rank[2];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    rank[1] = (uint32_t)(n_values / 2);
+    rank[0] = (n_values % 2 == 1) ? (uint32_t)(n_values / 2) : (uint32_t)(n_values / 2 - 1);
+    prefix[0] = prefix[1] = 0;
+  }
+  const int n_round = (n_values + 31) / 32 * 32;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) h[0][tid] = h[1][tid] = 0;
+    __syncthreads();
+    const uint32_t p0 = prefix[0], p1 = prefix[1];
+    const uint32_t mask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
+    const bool same = (p0 == p1);
+    for (int i = tid; i < n_round; i += 1024) {
+      const bool in = i < n_values;
+      const uint32_t key = in ? float_key(values[i]) : 0u;
+      const uint32_t bin = (key >> shift) & 255u;
+      warp_aggregated_inc(h[0], bin, in && (key & mask) == p0);
+      if (!same) warp_aggregated_inc(h[1], bin, in && (key & mask) == p1);
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const uint32_t* hh = same ? h[0] : h[tid];
+      const uint32_t r = rank[tid];
+      uint32_t cum = 0, bin = 255;
+      for (uint32_t b = 0; b < 256; ++b) {
+        const uint32_t c = hh[b];
+        if (r < cum + c) { bin = b; break; }
+        cum += c;
+      }
+      prefix[tid] |= bin << shift;
+      rank[tid] = r - cum;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float lo = __uint_as_float(key_float(prefix[0]));
+    const float hi = __uint_as_float(key_float(prefix[1]));
+    const float med = (prefix[0] == prefix[1]) ? lo : __fdiv_rn(__fadd_rn(hi, lo), 2.0f);
+    out[0] = med;
+    if (n_particles > 0.0f) {
+      const float hb = __fsqrt_rn(__fdiv_rn(__fmul_rn(0.5f, med), logf(__fadd_rn(n_particles, 1.0f))));
+      out[1] = hb;
+      out[2] = __fmul_rn(hb, hb);
+      out[3] = 0.0f;
+    }
+  }
+}
+
 static int launch_select(const float* values, int64_t n_values, float* out, void* scratch, float n_particles,
                          cudaStream_t stream) {
+  if (n_values <= SELECT_SMALL_MAX) {
+    svgd_select_small_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const uint32_t*>(values), (int)n_values, out,
+                                                     n_particles);
+    return check_launch("svgd_select_small_kernel");
+  }
   SelectState* st = reinterpret_cast<SelectState*>(scratch);
   svgd_select_init_kernel<<<1, 256, 0, stream>>>(st, (unsigned long long)n_values);
   if (int rc = check_launch("svgd_select_init_kernel")) return rc;

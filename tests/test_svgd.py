@@ -391,16 +391,21 @@ def test_svgd_on_the_bnn_cost_kernel():
 
     ref = osvgd.OracleSVGD(X0.astype(np.float64), cost_and_grad, epsilon=0.1)
     for step in range(5):
+        if step > 0:
+            # teacher forcing: every step starts from the oracle's state, because the handful of
+            # coordinates described below would otherwise feed O(0.1) differences into later steps
+            sampler.particles.copy_(torch.tensor(ref.state["theta"], dtype=torch.float32))
+            sampler.historical_grad.copy_(torch.tensor(ref.state["historical_grad"], dtype=torch.float32))
         sample, cost = next(sampler)
         t64, c64 = next(ref)
         assert np.allclose(cost.cpu().numpy(), c64, rtol=2e-5), step
-        # the AdaGrad history is a smooth function of the Stein direction: tight everywhere
-        hist, hist_ref = sampler.historical_grad.cpu().numpy(), ref.state["historical_grad"]
+        # the AdaGrad history is a smooth function of the Stein direction: tight (almost) everywhere
         # (K4's gradient carries ~1e-6 * max|g| absolute error, so small phi are relatively coarser)
+        hist, hist_ref = sampler.historical_grad.cpu().numpy(), ref.state["historical_grad"]
         assert np.isclose(hist, hist_ref, rtol=1e-3, atol=1e-6 * hist_ref.max()).mean() > 0.998, step
         assert np.allclose(hist, hist_ref, rtol=0.05, atol=1e-4 * hist_ref.max()), step
-        # the update phi / (1e-6 + sqrt(hist)) is NOT smooth where |phi| < ~1e-5 on the first steps
-        # (hist starts at 0, svgd.py:117-120): there the step is eps * phi / (1e-6 + 0.316 |phi|), which
+        # the update phi / (1e-6 + sqrt(hist)) is NOT smooth where |phi| < ~1e-5 while hist is ~0
+        # (it starts at 0, svgd.py:117-120): there the step is eps * phi / (1e-6 + 0.316 |phi|), which
         # swings between -0.316 and +0.316 across phi = 0, so the handful of the 126 048 coordinates
         # whose phi is within rounding of zero may land anywhere in that range; all others must be tight
         err = np.abs(torch.stack(sample).cpu().numpy() - t64)
