@@ -12,40 +12,52 @@
 // 128-bit loads, split them and write hi and lo straight into the no-swizzle canonical layouts
 // the MMA descriptors describe (csrc/umma.cuh; conventions pinned by tools/micro/umma_probe.cu).
 //
-// CTA = 128 particles (rows i) x 128 dimensions (d); UMMA tile M = 128, N = 256: columns
-// 0..127 of the accumulator are KG, 128..255 are KX, so K is read once for both products.
-// Contraction over the particles j in blocks of 16, a 4-stage shared-memory ring:
+// CTA = MT x 128 particles (rows i) x 128 dimensions (d); UMMA tile M = 128, N = 256: columns
+// 0..127 of an accumulator are KG, 128..255 are KX, so K is read once for both products.  MT = 2
+// row tiles per CTA share one B tile and fill all 512 TMEM columns: twice the tensor work for
+// 1.33x the operand staging, which is what bounds the kernel (151-165 against 109-125 TFLOP/s).
+// Contraction over the particles j in blocks of 16, a 4-stage (MT = 2: 3-stage) shared-memory ring:
 //   warps 0-7  producers: global -> registers (one block ahead) -> split -> shared; then epilogue
 //   warp  8    one lane issues 6 tcgen05.mma per block (2 k-steps x 3 products), tcgen05.commit
 //              releases the stage / publishes the accumulator through mbarriers
 // Shared memory per stage: A hi+lo 2 x 8 KB (K-major, 8-row groups 128 B apart), B hi+lo
 // 2 x 18 KB (K-major, 8-row groups padded to 144 B so that the scalar transposing stores of a
-// warp -- 4 k x 8 d-quads per instruction -- hit 32 distinct banks).  TMEM: 256 of 512 columns.
+// warp -- 4 k x 8 d-quads per instruction -- hit 32 distinct banks).  TMEM: 256 columns per row tile.
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace sgmcmc {
 
-constexpr int UM_BM = 128, UM_BN = 128, UM_BK = 16, UM_STAGES = 4;
+constexpr int UM_BM = 128, UM_BN = 128, UM_BK = 16;
 constexpr int UM_PRODUCERS = 256, UM_THREADS = UM_PRODUCERS + 32;
 constexpr uint32_t UM_A_SBO = 128, UM_A_LBO = 16 * UM_A_SBO;          // 128 rows = 16 groups
 constexpr uint32_t UM_B_SBO = 144, UM_B_LBO = 32 * UM_B_SBO;          // 256 rows = 32 groups
 constexpr uint32_t UM_A_PART = UM_A_LBO * (UM_BK / 4);                // hi (or lo) of A: 8192
 constexpr uint32_t UM_B_PART = UM_B_LBO * (UM_BK / 4);                // hi (or lo) of B: 18432
-constexpr uint32_t UM_STAGE = 2 * UM_A_PART + 2 * UM_B_PART;          // 53248
-constexpr uint32_t UM_SMEM = UM_STAGES * UM_STAGE;                    // 212992
 constexpr uint32_t UM_X_ROWS_OFF = 16 * UM_B_SBO;                     // B rows 128..255 (the X half)
-
-struct UmRegs {
-  float4 a0, a1, g0, x0, g1, x1;
+// MT = row tiles (of 128 particles) per CTA sharing one B tile: MT = 2 fills all 512 TMEM columns and does
+// twice the tensor work for 1.33x the staging work (the kernel is bound by the staging)
+template <int MT> struct UmCfg {
+  static constexpr int STAGES = MT == 1 ? 4 : 3;
+  static constexpr uint32_t STAGE = 2 * MT * UM_A_PART + 2 * UM_B_PART;   // 53248 / 69632
+  static constexpr uint32_t SMEM = STAGES * STAGE;                         // 212992 / 208896
+  static constexpr int TMEM_COLS = 256 * MT;
 };
 
-template <int PF>     // register buffers of the producers: global loads run PF - 1 blocks ahead of the split
+template <int MT>
+struct UmRegs {
+  float4 a[MT][2], g0, x0, g1, x1;
+};
+
+template <int PF, int MT>     // PF: register buffers of the producers (global loads run PF - 1 blocks ahead)
 __global__ void __launch_bounds__(UM_THREADS, 1)
 svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X, const float* __restrict__ G,
                         const float* __restrict__ ksum, const float* __restrict__ bw, float* __restrict__ hist,
                         float* __restrict__ Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
                         float fudge) {
+  constexpr int UM_STAGES = UmCfg<MT>::STAGES;
+  constexpr uint32_t UM_STAGE = UmCfg<MT>::STAGE;
+  constexpr uint32_t UM_A_ALL = MT * UM_A_PART;      // all hi (or all lo) A tiles of a stage
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[UM_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[UM_STAGES];
@@ -53,7 +65,7 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int d0 = blockIdx.x * UM_BN, i0 = blockIdx.y * UM_BM;
+  const int d0 = blockIdx.x * UM_BN, i0 = blockIdx.y * (UM_BM * MT);
   const int nkb = (n + UM_BK - 1) / UM_BK;
   const uint32_t smem_base = umma::smem_u32(smem);
 
@@ -66,7 +78,7 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
     umma::mbar_init(umma::smem_u32(&accum_bar), 1);
     umma::mbar_init_fence();
   }
-  if (warp == UM_PRODUCERS / 32) umma::tmem_alloc<256>(umma::smem_u32(&tmem_slot));
+  if (warp == UM_PRODUCERS / 32) umma::tmem_alloc<UmCfg<MT>::TMEM_COLS>(umma::smem_u32(&tmem_slot));
   umma::fence_before_thread_sync();
   __syncthreads();
   umma::fence_after_thread_sync();
@@ -76,8 +88,13 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
     // ------------------------------------------------------------------ producers
     // A: thread -> (row am, 8 consecutive j): one 32-byte sector of K per thread and block
     const int am = tid & 127, akh = tid >> 7;
-    const bool a_row_in = (i0 + am) < n;
-    const float* a_ptr = K + (int64_t)(i0 + am) * n + akh * 8;
+    bool a_row_in[MT];
+    const float* a_ptr[MT];
+#pragma unroll
+    for (int t = 0; t < MT; ++t) {
+      a_row_in[t] = (i0 + t * UM_BM + am) < n;
+      a_ptr[t] = K + (int64_t)(i0 + t * UM_BM + am) * n + akh * 8;
+    }
     const uint32_t a_off = (uint32_t)(akh * 2) * UM_A_LBO + (uint32_t)am * 16;
     // B: lane -> (k within a quad kr, d-quad dql); a warp-load reads 4 rows x 128 contiguous bytes
     const int kr = lane & 3, dql = lane >> 2;
@@ -97,11 +114,14 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
     }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    auto load = [&](UmRegs& r, int kb) {
+    auto load = [&](UmRegs<MT>& r, int kb) {
       const int j0 = kb * UM_BK;
       const int ja = j0 + akh * 8;
-      r.a0 = (a_row_in && ja < n) ? __ldg(reinterpret_cast<const float4*>(a_ptr + j0)) : zero4;
-      r.a1 = (a_row_in && ja + 4 < n) ? __ldg(reinterpret_cast<const float4*>(a_ptr + j0 + 4)) : zero4;
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        r.a[t][0] = (a_row_in[t] && ja < n) ? __ldg(reinterpret_cast<const float4*>(a_ptr[t] + j0)) : zero4;
+        r.a[t][1] = (a_row_in[t] && ja + 4 < n) ? __ldg(reinterpret_cast<const float4*>(a_ptr[t] + j0 + 4)) : zero4;
+      }
       const bool in0 = b_col_in[0] && (j0 + bk[0]) < n, in1 = b_col_in[1] && (j0 + bk[1]) < n;
       const int64_t o0 = (int64_t)j0 * D + b_goff[0], o1 = (int64_t)j0 * D + b_goff[1];
       r.g0 = in0 ? __ldg(reinterpret_cast<const float4*>(G + o0)) : zero4;
@@ -126,19 +146,23 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
       pl[0] = lo.x; pl[4] = lo.y; pl[8] = lo.z; pl[12] = lo.w;
     };
 
-    auto produce = [&](const UmRegs& r, int kb) {
+    auto produce = [&](const UmRegs<MT>& r, int kb) {
       const int s = kb % UM_STAGES;
       const uint32_t parity = ((uint32_t)(kb / UM_STAGES) & 1u) ^ 1u;
       umma::mbar_wait(umma::smem_u32(&empty_bar[s]), parity);
       uint8_t* stage = smem + (uint32_t)s * UM_STAGE;
       float4 hi, lo;
-      split4(r.a0, hi, lo);
-      *reinterpret_cast<float4*>(stage + a_off) = hi;
-      *reinterpret_cast<float4*>(stage + UM_A_PART + a_off) = lo;
-      split4(r.a1, hi, lo);
-      *reinterpret_cast<float4*>(stage + a_off + UM_A_LBO) = hi;
-      *reinterpret_cast<float4*>(stage + UM_A_PART + a_off + UM_A_LBO) = lo;
-      uint8_t* b_hi = stage + 2 * UM_A_PART;
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        uint8_t* a_hi = stage + (uint32_t)t * UM_A_PART + a_off;
+        split4(r.a[t][0], hi, lo);
+        *reinterpret_cast<float4*>(a_hi) = hi;
+        *reinterpret_cast<float4*>(a_hi + UM_A_ALL) = lo;
+        split4(r.a[t][1], hi, lo);
+        *reinterpret_cast<float4*>(a_hi + UM_A_LBO) = hi;
+        *reinterpret_cast<float4*>(a_hi + UM_A_ALL + UM_A_LBO) = lo;
+      }
+      uint8_t* b_hi = stage + 2 * UM_A_ALL;
       store_b(b_hi, b_off[0], r.g0);
       store_b(b_hi, b_off[0] + UM_X_ROWS_OFF, r.x0);
       store_b(b_hi, b_off[1], r.g1);
@@ -147,7 +171,7 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
       umma::mbar_arrive(umma::smem_u32(&full_bar[s]));
     };
 
-    UmRegs r[PF];
+    UmRegs<MT> r[PF];
 #pragma unroll
     for (int p = 0; p < PF - 1; ++p)
       if (p < nkb) load(r[p], p);
@@ -166,13 +190,14 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
     umma::mbar_wait(umma::smem_u32(&accum_bar), 0);
     umma::fence_after_thread_sync();
     const int q = warp & 3, hcol = warp >> 2;
-    const int i = i0 + 32 * q + lane;
-    const bool row_in = i < n;
-    const float ks = row_in ? ksum[i] : 0.0f;
     const float h2 = bw[2], nf = (float)n;
-    const uint32_t trow = taddr + ((uint32_t)(32 * q) << 16);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int tc = 0; tc < MT * 4; ++tc) {
+      const int t = tc >> 2, c = tc & 3;
+      const int i = i0 + t * UM_BM + 32 * q + lane;
+      const bool row_in = i < n;
+      const float ks = row_in ? ksum[i] : 0.0f;
+      const uint32_t trow = taddr + ((uint32_t)(32 * q) << 16) + (uint32_t)(t * 2 * UM_BN);
       const int col = 64 * hcol + 16 * c;
       float accg[16], accx[16];
       umma::tmem_ld16(trow + (uint32_t)col, accg);
@@ -210,13 +235,17 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
         const uint32_t stage = smem_base + (uint32_t)s * UM_STAGE;
 #pragma unroll
         for (int ks = 0; ks < UM_BK / 8; ++ks) {
-          const uint32_t a_hi = stage + (uint32_t)ks * 2 * UM_A_LBO, a_lo = a_hi + UM_A_PART;
-          const uint32_t b_hi = stage + 2 * UM_A_PART + (uint32_t)ks * 2 * UM_B_LBO, b_lo = b_hi + UM_B_PART;
-          const uint64_t da_hi = umma::smem_desc(a_hi, UM_A_LBO, UM_A_SBO), da_lo = umma::smem_desc(a_lo, UM_A_LBO, UM_A_SBO);
+          const uint32_t b_hi = stage + 2 * UM_A_ALL + (uint32_t)ks * 2 * UM_B_LBO, b_lo = b_hi + UM_B_PART;
           const uint64_t db_hi = umma::smem_desc(b_hi, UM_B_LBO, UM_B_SBO), db_lo = umma::smem_desc(b_lo, UM_B_LBO, UM_B_SBO);
-          umma::mma_tf32(taddr, da_lo, db_hi, idesc, (kb | ks) != 0);      // small terms first
-          umma::mma_tf32(taddr, da_hi, db_lo, idesc, 1);
-          umma::mma_tf32(taddr, da_hi, db_hi, idesc, 1);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            const uint32_t a_hi = stage + (uint32_t)t * UM_A_PART + (uint32_t)ks * 2 * UM_A_LBO, a_lo = a_hi + UM_A_ALL;
+            const uint64_t da_hi = umma::smem_desc(a_hi, UM_A_LBO, UM_A_SBO), da_lo = umma::smem_desc(a_lo, UM_A_LBO, UM_A_SBO);
+            const uint32_t td = taddr + (uint32_t)(t * 2 * UM_BN);
+            umma::mma_tf32(td, da_lo, db_hi, idesc, (kb | ks) != 0);      // small terms first
+            umma::mma_tf32(td, da_hi, db_lo, idesc, 1);
+            umma::mma_tf32(td, da_hi, db_hi, idesc, 1);
+          }
         }
         umma::commit(umma::smem_u32(&empty_bar[s]));                      // stage free once these MMAs retire
         if (kb == nkb - 1) umma::commit(umma::smem_u32(&accum_bar));      // accumulator complete
@@ -229,27 +258,27 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
   __syncthreads();
   if (warp == UM_PRODUCERS / 32) {
     umma::fence_after_thread_sync();
-    umma::tmem_dealloc<256>(taddr);
+    umma::tmem_dealloc<UmCfg<MT>::TMEM_COLS>(taddr);
   }
 }
 
 // Launch helper used by sgmcmc_svgd_update_f32 (svgd.cu).  Requirements (checked by the caller):
 // n % 4 == 0, D % 4 == 0, all pointers 16-byte aligned.
-template <int PF>
+template <int PF, int MT>
 static int launch_umma_pf(const float* K, const float* X, const float* G, const float* ksum, const float* bw,
                           float* hist, float* Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
                           float fudge, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    const cudaError_t e = cudaFuncSetAttribute(svgd_update_umma_kernel<PF>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM);
+    const cudaError_t e = cudaFuncSetAttribute(svgd_update_umma_kernel<PF, MT>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmCfg<MT>::SMEM);
     if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd_update_umma_kernel: %s", cudaGetErrorString(e));
     configured = true;
   }
-  const dim3 grid((unsigned)((D + UM_BN - 1) / UM_BN), (unsigned)((n + UM_BM - 1) / UM_BM));
+  const dim3 grid((unsigned)((D + UM_BN - 1) / UM_BN), (unsigned)((n + UM_BM * MT - 1) / (UM_BM * MT)));
   SG_REQUIRE(grid.y <= 65535, SGMCMC_E_UNSUPPORTED, "svgd: too many particles");
-  svgd_update_umma_kernel<PF><<<grid, UM_THREADS, UM_SMEM, stream>>>(K, X, G, ksum, bw, hist, Xout, n, D, eps,
-                                                                      alpha, one_minus_alpha, fudge);
+  svgd_update_umma_kernel<PF, MT><<<grid, UM_THREADS, UmCfg<MT>::SMEM, stream>>>(
+      K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge);
   return check_launch("svgd_update_umma_kernel");
 }
 
@@ -259,10 +288,27 @@ int launch_svgd_update_umma(const float* K, const float* X, const float* G, cons
                             float fudge, int prefetch, cudaStream_t stream) {
   // measured (profiles/r01_svgd_k14_prefetch_sweep.jsonl): 2, 3 and 4 buffers run within 2 % of each other -- the
   // kernel is bound by the LSU data pipe (global loads + staging stores), not by load latency -- so 2 is the default
+  // variant 3: one 128-row tile per CTA, 3 buffers; 4: one tile, 2 buffers (the round-1 first version);
+  // default: two row tiles per CTA (all 512 TMEM columns) whenever there are more than 128 particles
   switch (prefetch) {
-    case 3: return launch_umma_pf<3>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
-    case 4: return launch_umma_pf<4>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
-    default: return launch_umma_pf<2>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+    case 3: return launch_umma_pf<3, 1>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+    case 4: return launch_umma_pf<2, 1>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+    default: {
+      // one CTA per SM (shared memory), so time ~ waves x work per CTA; a two-tile CTA costs ~1.45-1.55x a
+      // one-tile CTA (measured: profiles/r01_svgd_k14_prefetch_sweep.jsonl, 1024 / 4096 / 8192 particles)
+      static int n_sm = 0;
+      if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+      }
+      const long long cols = (D + UM_BN - 1) / UM_BN;
+      const long long c1 = cols * ((n + UM_BM - 1) / UM_BM), c2 = cols * ((n + 2 * UM_BM - 1) / (2 * UM_BM));
+      const double cost1 = (double)((c1 + n_sm - 1) / n_sm), cost2 = 1.55 * (double)((c2 + n_sm - 1) / n_sm);
+      if (n > UM_BM && cost2 < cost1)
+        return launch_umma_pf<2, 2>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+      return launch_umma_pf<2, 1>(K, X, G, ksum, bw, hist, Xout, n, D, eps, alpha, one_minus_alpha, fudge, stream);
+    }
   }
 }
 

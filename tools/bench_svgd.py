@@ -52,7 +52,7 @@ def k14_sweep():
             _native.call("sgmcmc_svgd_update_f32", _native.ptr(X), _native.ptr(G), _native.ptr(H), _native.ptr(K),
                          _native.ptr(ksum), _native.ptr(bw), _native.ptr(Xs), n, D, 0.0, 0.9, 0.1, 1e-6, s)
         row = {"n_particles": n, "n_dims": D}
-        for impl in (1, 22, 23, 24):
+        for impl in (1, 2, 23, 24):
             _native.call("sgmcmc_set_svgd_tuning", impl)
             ms = timed(update, 5 if n * n * D > 5e10 else 20)
             _native.call("sgmcmc_set_svgd_tuning", 0)
