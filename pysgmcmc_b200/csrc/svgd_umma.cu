@@ -20,9 +20,11 @@
 //   warps 0-7  producers: global -> registers (one block ahead) -> split -> shared; then epilogue
 //   warp  8    one lane issues 6 tcgen05.mma per block (2 k-steps x 3 products), tcgen05.commit
 //              releases the stage / publishes the accumulator through mbarriers
-// Shared memory per stage: A hi+lo 2 x 8 KB (K-major, 8-row groups 128 B apart), B hi+lo
-// 2 x 18 KB (K-major, 8-row groups padded to 144 B so that the scalar transposing stores of a
-// warp -- 4 k x 8 d-quads per instruction -- hit 32 distinct banks).  TMEM: 256 columns per row tile.
+// Shared memory per stage: A hi+lo 2 x 9 KB per row tile, B hi+lo 2 x 18 KB, both K-major with the
+// 8-row groups padded to 144 B so that the scalar transposing stores of a warp -- 4 k x 8 column
+// quads per instruction -- hit 32 distinct banks (A is read as rows of the symmetric K, so its global
+// loads are as coalesced as B's: the first version gathered one row of K per lane and spent a third
+// of the LSU data-pipe wavefronts on that).  TMEM: 256 columns per row tile.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -30,17 +32,17 @@ namespace sgmcmc {
 
 constexpr int UM_BM = 128, UM_BN = 128, UM_BK = 16;
 constexpr int UM_PRODUCERS = 256, UM_THREADS = UM_PRODUCERS + 32;
-constexpr uint32_t UM_A_SBO = 128, UM_A_LBO = 16 * UM_A_SBO;          // 128 rows = 16 groups
+constexpr uint32_t UM_A_SBO = 144, UM_A_LBO = 16 * UM_A_SBO;          // 128 rows = 16 groups (padded like B)
 constexpr uint32_t UM_B_SBO = 144, UM_B_LBO = 32 * UM_B_SBO;          // 256 rows = 32 groups
-constexpr uint32_t UM_A_PART = UM_A_LBO * (UM_BK / 4);                // hi (or lo) of A: 8192
+constexpr uint32_t UM_A_PART = UM_A_LBO * (UM_BK / 4);                // hi (or lo) of A: 9216
 constexpr uint32_t UM_B_PART = UM_B_LBO * (UM_BK / 4);                // hi (or lo) of B: 18432
 constexpr uint32_t UM_X_ROWS_OFF = 16 * UM_B_SBO;                     // B rows 128..255 (the X half)
 // MT = row tiles (of 128 particles) per CTA sharing one B tile: MT = 2 fills all 512 TMEM columns and does
 // twice the tensor work for 1.33x the staging work (the kernel is bound by the staging)
 template <int MT> struct UmCfg {
   static constexpr int STAGES = MT == 1 ? 4 : 3;
-  static constexpr uint32_t STAGE = 2 * MT * UM_A_PART + 2 * UM_B_PART;   // 53248 / 69632
-  static constexpr uint32_t SMEM = STAGES * STAGE;                         // 212992 / 208896
+  static constexpr uint32_t STAGE = 2 * MT * UM_A_PART + 2 * UM_B_PART;   // 55296 / 73728
+  static constexpr uint32_t SMEM = STAGES * STAGE;                         // 221184 / 221184
   static constexpr int TMEM_COLS = 256 * MT;
 };
 
@@ -86,22 +88,18 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
 
   if (warp < UM_PRODUCERS / 32) {
     // ------------------------------------------------------------------ producers
-    // A: thread -> (row am, 8 consecutive j): one 32-byte sector of K per thread and block
-    const int am = tid & 127, akh = tid >> 7;
-    bool a_row_in[MT];
-    const float* a_ptr[MT];
-#pragma unroll
-    for (int t = 0; t < MT; ++t) {
-      a_row_in[t] = (i0 + t * UM_BM + am) < n;
-      a_ptr[t] = K + (int64_t)(i0 + t * UM_BM + am) * n + akh * 8;
-    }
-    const uint32_t a_off = (uint32_t)(akh * 2) * UM_A_LBO + (uint32_t)am * 16;
-    // B: lane -> (k within a quad kr, d-quad dql); a warp-load reads 4 rows x 128 contiguous bytes
+    // Both operands are read along their contiguous index with the contraction index j as the row:
+    // B[j, d] = G / X rows, A[i, j] = K[j, i] (K is symmetric bit for bit, see K11).
+    // lane -> (k within a quad kr, quad of columns dql); a warp-load reads 4 rows x 128 contiguous bytes,
+    // the matching warp-store writes 4 k x 32 columns as 32-bit words into 32 distinct banks.
     const int kr = lane & 3, dql = lane >> 2;
     int bk[2];
     bool b_col_in[2];
     int64_t b_goff[2];
     uint32_t b_off[2];
+    bool a_col_in[MT][2];
+    int64_t a_goff[MT][2];
+    uint32_t a_off[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int tau = 2 * warp + e, kq = tau & 3, dq = 8 * (tau >> 2) + dql;
@@ -111,18 +109,26 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
       b_goff[e] = (int64_t)bk[e] * D + d;
       b_off[e] = (uint32_t)(dq >> 1) * UM_B_SBO + (uint32_t)(4 * (dq & 1)) * 16 + (uint32_t)kq * UM_B_LBO +
                  (uint32_t)kr * 4;
+      a_off[e] = (uint32_t)(dq >> 1) * UM_A_SBO + (uint32_t)(4 * (dq & 1)) * 16 + (uint32_t)kq * UM_A_LBO +
+                 (uint32_t)kr * 4;
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        const int i = i0 + t * UM_BM + 4 * dq;
+        a_col_in[t][e] = i < n;
+        a_goff[t][e] = (int64_t)bk[e] * n + i;
+      }
     }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto load = [&](UmRegs<MT>& r, int kb) {
       const int j0 = kb * UM_BK;
-      const int ja = j0 + akh * 8;
+      const bool k_in0 = (j0 + bk[0]) < n, k_in1 = (j0 + bk[1]) < n;
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
-        r.a[t][0] = (a_row_in[t] && ja < n) ? __ldg(reinterpret_cast<const float4*>(a_ptr[t] + j0)) : zero4;
-        r.a[t][1] = (a_row_in[t] && ja + 4 < n) ? __ldg(reinterpret_cast<const float4*>(a_ptr[t] + j0 + 4)) : zero4;
+        r.a[t][0] = (k_in0 && a_col_in[t][0]) ? __ldg(reinterpret_cast<const float4*>(K + (int64_t)j0 * n + a_goff[t][0])) : zero4;
+        r.a[t][1] = (k_in1 && a_col_in[t][1]) ? __ldg(reinterpret_cast<const float4*>(K + (int64_t)j0 * n + a_goff[t][1])) : zero4;
       }
-      const bool in0 = b_col_in[0] && (j0 + bk[0]) < n, in1 = b_col_in[1] && (j0 + bk[1]) < n;
+      const bool in0 = b_col_in[0] && k_in0, in1 = b_col_in[1] && k_in1;
       const int64_t o0 = (int64_t)j0 * D + b_goff[0], o1 = (int64_t)j0 * D + b_goff[1];
       r.g0 = in0 ? __ldg(reinterpret_cast<const float4*>(G + o0)) : zero4;
       r.x0 = in0 ? __ldg(reinterpret_cast<const float4*>(X + o0)) : zero4;
@@ -137,11 +143,11 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
       umma::split_tf32(v.w, hi.w, lo.w);
     };
 
-    auto store_b = [&](uint8_t* b_hi, uint32_t off, const float4& v) {
+    auto store_b = [&](uint8_t* b_hi, uint32_t off, const float4& v, uint32_t lo_off) {
       float4 hi, lo;
       split4(v, hi, lo);
       float* ph = reinterpret_cast<float*>(b_hi + off);
-      float* pl = reinterpret_cast<float*>(b_hi + UM_B_PART + off);
+      float* pl = reinterpret_cast<float*>(b_hi + lo_off + off);
       ph[0] = hi.x; ph[4] = hi.y; ph[8] = hi.z; ph[12] = hi.w;      // consecutive d = consecutive rows, 16 B apart
       pl[0] = lo.x; pl[4] = lo.y; pl[8] = lo.z; pl[12] = lo.w;
     };
@@ -151,22 +157,16 @@ svgd_update_umma_kernel(const float* __restrict__ K, const float* __restrict__ X
       const uint32_t parity = ((uint32_t)(kb / UM_STAGES) & 1u) ^ 1u;
       umma::mbar_wait(umma::smem_u32(&empty_bar[s]), parity);
       uint8_t* stage = smem + (uint32_t)s * UM_STAGE;
-      float4 hi, lo;
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
-        uint8_t* a_hi = stage + (uint32_t)t * UM_A_PART + a_off;
-        split4(r.a[t][0], hi, lo);
-        *reinterpret_cast<float4*>(a_hi) = hi;
-        *reinterpret_cast<float4*>(a_hi + UM_A_ALL) = lo;
-        split4(r.a[t][1], hi, lo);
-        *reinterpret_cast<float4*>(a_hi + UM_A_LBO) = hi;
-        *reinterpret_cast<float4*>(a_hi + UM_A_ALL + UM_A_LBO) = lo;
+        store_b(stage + (uint32_t)t * UM_A_PART, a_off[0], r.a[t][0], UM_A_ALL);
+        store_b(stage + (uint32_t)t * UM_A_PART, a_off[1], r.a[t][1], UM_A_ALL);
       }
       uint8_t* b_hi = stage + 2 * UM_A_ALL;
-      store_b(b_hi, b_off[0], r.g0);
-      store_b(b_hi, b_off[0] + UM_X_ROWS_OFF, r.x0);
-      store_b(b_hi, b_off[1], r.g1);
-      store_b(b_hi, b_off[1] + UM_X_ROWS_OFF, r.x1);
+      store_b(b_hi, b_off[0], r.g0, UM_B_PART);
+      store_b(b_hi, b_off[0] + UM_X_ROWS_OFF, r.x0, UM_B_PART);
+      store_b(b_hi, b_off[1], r.g1, UM_B_PART);
+      store_b(b_hi, b_off[1] + UM_X_ROWS_OFF, r.x1, UM_B_PART);
       umma::fence_proxy_async_smem();
       umma::mbar_arrive(umma::smem_u32(&full_bar[s]));
     };
