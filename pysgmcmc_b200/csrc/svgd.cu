@@ -566,9 +566,11 @@ extern "C" int sgmcmc_svgd_update_f32(float* particles, const float* grad, float
                    aligned_to(particles_scratch, 16);
   const int impl = g_svgd_impl.load(std::memory_order_relaxed);
   const bool umma_ok = vec && aligned_to(kernel_sum, 4);
-  // auto: the tensor-core kernel needs enough rows to fill its 128-row tile and enough columns to amortise
-  // its prologue; measured crossover in profiles/r01_svgd_tcgen05.jsonl
-  const bool use_umma = impl >= 2 ? umma_ok : (impl == 0 && umma_ok && n >= 128 && D >= 128);
+  // auto: the tensor-core kernel needs enough rows to fill its 128-row tile and enough work to amortise its
+  // prologue; measured (profiles/r01_svgd_tcgen05.jsonl): 128 x 128 FFMA 0.029 vs 0.032 ms, 256 x 5252 0.070 vs
+  // 0.044 ms, 4096 x 64 0.50 vs 0.23 ms
+  const bool use_umma = impl >= 2 ? umma_ok
+                                  : (impl == 0 && umma_ok && n >= 128 && D >= 64 && (int64_t)n * D >= 65536);
   if (use_umma) {
     if (int rc = launch_svgd_update_umma(kernel_matrix, particles, grad, kernel_sum, bandwidth, historical_grad,
                                          particles_scratch, n, D, epsilon, alpha, one_minus_alpha, fudge_factor,
