@@ -264,8 +264,11 @@ int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double*
  * sgmcmc_svgd_kernel_matrix_f32 (svgd.py:150-160): kernel_matrix [n, n] =
  * exp(-P / h^2 / 2) with P[i,j] = (||x_i - x_j||)^2 and h = sqrt(0.5 * median(P) /
  * log(n + 1)); kernel_sum [n] = its row sums; bandwidth [4] = {median(P), h, h^2, 0}.
- * Everything stays on the device.  n_particles <= 46340.  scratch: 4096 + 4 * (n_particles +
- * n_dims) bytes of device memory, 16-byte aligned.  kernel_matrix comes out symmetric bit for
+ * Everything stays on the device.  n_particles <= 46340.  scratch: device memory, 16-byte
+ * aligned, `scratch_bytes` long: 4096 bytes always; 4096 + 4 * (n_particles + n_dims + 3) bytes
+ * to be eligible for the tensor-core distance kernel; sgmcmc_svgd_scratch_bytes() returns the size
+ * with which that kernel may also slice the contraction over the dimensions when the particle
+ * count alone gives too few tiles to fill the SMs.  kernel_matrix comes out symmetric bit for
  * bit (sgmcmc_svgd_update_f32 reads its rows as columns).  Large aligned shapes compute the
  * distances from the Gram matrix of the centred particles on the tcgen05 tensor cores
  * (3xTF32, csrc/svgd_sqdist_umma.cu), the others subtract before squaring on the FP32 pipe.
@@ -284,9 +287,10 @@ int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double*
  * 23 / 24 = 2 with 3 / 4 producer register buffers in K14 (sweeps). */
 int sgmcmc_set_svgd_tuning(int impl);
 int sgmcmc_median_f32(const float* values, int64_t n_values, float* out, void* scratch, void* stream);
+int64_t sgmcmc_svgd_scratch_bytes(int64_t n_particles, int64_t n_dims);
 int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kernel_matrix, float* kernel_sum,
-                                  float* bandwidth, void* scratch, int64_t n_particles, int64_t n_dims,
-                                  void* stream);
+                                  float* bandwidth, void* scratch, int64_t scratch_bytes,
+                                  int64_t n_particles, int64_t n_dims, void* stream);
 int sgmcmc_svgd_update_f32(float* particles, const float* grad, float* historical_grad,
                            const float* kernel_matrix, const float* kernel_sum, const float* bandwidth,
                            float* particles_scratch, int64_t n_particles, int64_t n_dims, float epsilon,

@@ -67,10 +67,11 @@ SIGNATURES = {
     "sgmcmc_variogram_select_f32": [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
     "sgmcmc_set_svgd_tuning": [c_int],
     "sgmcmc_median_f32": [_P, c_int64, _P, _P, _P],
-    "sgmcmc_svgd_kernel_matrix_f32": [_P] * 5 + [c_int64, c_int64, _P],
+    "sgmcmc_svgd_scratch_bytes": [c_int64, c_int64],
+    "sgmcmc_svgd_kernel_matrix_f32": [_P] * 5 + [c_int64, c_int64, c_int64, _P],
     "sgmcmc_svgd_update_f32": [_P] * 7 + [c_int64, c_int64, c_float, c_float, c_float, c_float, _P],
 }
-_RESTYPES = {"sgmcmc_last_error": c_char_p, "sgmcmc_launch_count": c_int64}
+_RESTYPES = {"sgmcmc_last_error": c_char_p, "sgmcmc_launch_count": c_int64, "sgmcmc_svgd_scratch_bytes": c_int64}
 
 _lib = None
 
@@ -101,6 +102,15 @@ def call(name, *args):
         msg = lib.sgmcmc_last_error()
         raise NativeError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else "?"))
     return rc
+
+
+def svgd_scratch(n_particles, n_dims, device):
+    """Scratch buffer for sgmcmc_svgd_kernel_matrix_f32 (int64 elements so that it is 16-byte aligned)."""
+    import torch
+    nbytes = int(load().sgmcmc_svgd_scratch_bytes(n_particles, n_dims))
+    if nbytes < 0:
+        raise NativeError("sgmcmc_svgd_scratch_bytes: unsupported size %d x %d" % (n_particles, n_dims))
+    return torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
 
 
 def launch_count():

@@ -131,6 +131,8 @@ __global__ void svgd_select_init_kernel(SelectState* st, unsigned long long n_va
   }
 }
 
+constexpr int SELECT_UNROLL = 8;
+
 __device__ __forceinline__ void warp_aggregated_inc(uint32_t* hist, uint32_t bin, bool active) {
   // one shared-memory atomic per distinct bin of the warp (distances cluster in few bins)
   const unsigned live = __ballot_sync(0xFFFFFFFFu, active);
@@ -151,12 +153,22 @@ svgd_select_hist_kernel(const uint32_t* __restrict__ values, int64_t n_values, i
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   // all lanes of a warp run the same number of iterations (warp-synchronous helpers below)
   const int64_t n_round = (n_values + 31) / 32 * 32;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    const bool in = i < n_values;
-    const uint32_t key = in ? float_key(values[i]) : 0u;
-    const uint32_t bin = (key >> shift) & 255u;
-    warp_aggregated_inc(h[0], bin, in && (key & mask) == p0);
-    if (!same) warp_aggregated_inc(h[1], bin, in && (key & mask) == p1);
+  // SELECT_UNROLL independent loads in flight per thread: the passes are bound by load latency otherwise
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride * SELECT_UNROLL) {
+    uint32_t key[SELECT_UNROLL];
+    bool in[SELECT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SELECT_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      in[u] = i < n_values;
+      key[u] = in[u] ? float_key(values[i]) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < SELECT_UNROLL; ++u) {
+      const uint32_t bin = (key[u] >> shift) & 255u;
+      warp_aggregated_inc(h[0], bin, in[u] && (key[u] & mask) == p0);
+      if (!same) warp_aggregated_inc(h[1], bin, in[u] && (key[u] & mask) == p1);
+    }
   }
   __syncthreads();
   if (h[0][threadIdx.x]) atomicAdd(&st->hist[0][threadIdx.x], h[0][threadIdx.x]);
@@ -228,12 +240,21 @@ svgd_select_small_kernel(const uint32_t* __restrict__ values, int n_values, floa
     const uint32_t p0 = prefix[0], p1 = prefix[1];
     const uint32_t mask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
     const bool same = (p0 == p1);
-    for (int i = tid; i < n_round; i += 1024) {
-      const bool in = i < n_values;
-      const uint32_t key = in ? float_key(values[i]) : 0u;
-      const uint32_t bin = (key >> shift) & 255u;
-      warp_aggregated_inc(h[0], bin, in && (key & mask) == p0);
-      if (!same) warp_aggregated_inc(h[1], bin, in && (key & mask) == p1);
+    for (int i0 = tid; i0 < n_round; i0 += 1024 * SELECT_UNROLL) {
+      uint32_t key[SELECT_UNROLL];
+      bool in[SELECT_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SELECT_UNROLL; ++u) {
+        const int i = i0 + u * 1024;
+        in[u] = i < n_values;
+        key[u] = in[u] ? float_key(values[i]) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < SELECT_UNROLL; ++u) {
+        const uint32_t bin = (key[u] >> shift) & 255u;
+        warp_aggregated_inc(h[0], bin, in[u] && (key[u] & mask) == p0);
+        if (!same) warp_aggregated_inc(h[1], bin, in[u] && (key[u] & mask) == p1);
+      }
     }
     __syncthreads();
     if (tid < 2) {
@@ -274,7 +295,7 @@ static int launch_select(const float* values, int64_t n_values, float* out, void
   SelectState* st = reinterpret_cast<SelectState*>(scratch);
   svgd_select_init_kernel<<<1, 256, 0, stream>>>(st, (unsigned long long)n_values);
   if (int rc = check_launch("svgd_select_init_kernel")) return rc;
-  const int64_t want = (n_values + 256 * 8 - 1) / (256 * 8);
+  const int64_t want = (n_values + 256 * SELECT_UNROLL - 1) / (256 * SELECT_UNROLL);
   const int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
@@ -491,7 +512,10 @@ int launch_svgd_update_umma(const float* K, const float* X, const float* G, cons
 static std::atomic<int> g_svgd_impl{0};
 
 // csrc/svgd_sqdist_umma.cu: K11 through the Gram matrix of the centred particles on the tensor cores
-int launch_svgd_sqdist_umma(const float* X, float* P, float* work, int n, int D, cudaStream_t stream);
+int launch_svgd_sqdist_umma(const float* X, float* P, float* work, int64_t work_floats, int n, int D,
+                            cudaStream_t stream);
+int64_t svgd_sqdist_work_floats(int n, int D, int n_slices);
+int svgd_sqdist_best_slices(int n, int D);
 
 static int check_svgd_sizes(int64_t n, int64_t D) {
   SG_REQUIRE(n >= 0 && D >= 0, SGMCMC_E_INVALID, "svgd: n_particles and n_dims must be >= 0");
@@ -519,23 +543,32 @@ extern "C" int sgmcmc_median_f32(const float* values, int64_t n_values, float* o
   return launch_select(values, n_values, out, scratch, 0.0f, (cudaStream_t)stream);
 }
 
+extern "C" int64_t sgmcmc_svgd_scratch_bytes(int64_t n_particles, int64_t n_dims) {
+  if (n_particles < 0 || n_dims < 0 || n_particles > 46340 || n_dims > ((int64_t)1 << 30)) return -1;
+  const int n = (int)n_particles, D = (int)n_dims;
+  return 4096 + 4 * svgd_sqdist_work_floats(n, D, (n >= 1 && D >= 1) ? svgd_sqdist_best_slices(n, D) : 1);
+}
+
 extern "C" int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kernel_matrix, float* kernel_sum,
-                                             float* bandwidth, void* scratch, int64_t n_particles, int64_t n_dims,
-                                             void* stream) {
+                                             float* bandwidth, void* scratch, int64_t scratch_bytes,
+                                             int64_t n_particles, int64_t n_dims, void* stream) {
   if (int rc = check_svgd_sizes(n_particles, n_dims)) return rc;
   SG_REQUIRE(n_particles >= 1 && n_dims >= 1, SGMCMC_E_INVALID, "svgd: needs at least one particle and one dimension");
   SG_REQUIRE(particles && kernel_matrix && kernel_sum && bandwidth && scratch, SGMCMC_E_INVALID, "svgd: NULL pointer");
+  SG_REQUIRE(scratch_bytes >= 4096, SGMCMC_E_INVALID, "svgd: scratch must hold at least 4096 bytes");
   SG_REQUIRE(aligned_to(particles, 4) && aligned_to(kernel_matrix, 4) && aligned_to(kernel_sum, 4) &&
                  aligned_to(bandwidth, 4) && aligned_to(scratch, 8),
              SGMCMC_E_ALIGN, "svgd: misaligned pointer");
   cudaStream_t s = (cudaStream_t)stream;
   const int n = (int)n_particles, D = (int)n_dims;
   const int impl = g_svgd_impl.load(std::memory_order_relaxed);
-  const bool umma_ok = (D % 4 == 0) && aligned_to(particles, 16) && aligned_to(scratch, 16);
+  const int64_t work_floats = (scratch_bytes - 4096) / 4;
+  const bool umma_ok = (D % 4 == 0) && aligned_to(particles, 16) && aligned_to(scratch, 16) &&
+                       work_floats >= svgd_sqdist_work_floats(n, D, 1);
   const bool use_umma = impl >= 2 ? umma_ok : (impl == 0 && umma_ok && n >= 256 && D >= 128);
   if (use_umma) {
     float* work = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + 4096);
-    if (int rc = launch_svgd_sqdist_umma(particles, kernel_matrix, work, n, D, s)) return rc;
+    if (int rc = launch_svgd_sqdist_umma(particles, kernel_matrix, work, work_floats, n, D, s)) return rc;
   } else {
     const unsigned nt = (unsigned)((n + SD_T - 1) / SD_T);
     svgd_sqdist_kernel<<<dim3(nt, nt), 256, 0, s>>>(particles, kernel_matrix, n, D);

@@ -80,7 +80,7 @@ svgd_row_norm_kernel(const float* __restrict__ X, const float* __restrict__ mean
 
 __global__ void __launch_bounds__(SQ_THREADS, 1)
 svgd_sqdist_umma_kernel(const float* __restrict__ X, const float* __restrict__ mean, const float* __restrict__ norms,
-                        float* __restrict__ P, int n, int D) {
+                        float* __restrict__ P, float* __restrict__ partial, int n, int D, int n_slices) {
   const int i0 = blockIdx.y * SQ_BM, j0 = blockIdx.x * SQ_BN;
   if (j0 + SQ_BN - 1 < i0) return;                   // tile entirely below the diagonal (uniform exit)
 
@@ -91,7 +91,11 @@ svgd_sqdist_umma_kernel(const float* __restrict__ X, const float* __restrict__ m
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkb = (D + SQ_BK - 1) / SQ_BK;
+  // blockIdx.z = slice of the contraction (n_slices > 1 when there are too few tiles to fill the SMs): the
+  // slice's partial Gram tile goes to `partial`, svgd_sqdist_finalize_kernel adds the slices in a fixed order
+  const int nkb_all = (D + SQ_BK - 1) / SQ_BK, kb_per = (nkb_all + n_slices - 1) / n_slices;
+  const int kb_begin = (int)blockIdx.z * kb_per;
+  const int nkb = min(kb_per, nkb_all - kb_begin);
   const uint32_t smem_base = umma::smem_u32(smem);
 
   if (tid == 0) {
@@ -133,7 +137,8 @@ svgd_sqdist_umma_kernel(const float* __restrict__ X, const float* __restrict__ m
       float4 v[SQ_GROUPS];
       float4 m;
     };
-    auto load = [&](Regs& q, int kb) {
+    auto load = [&](Regs& q, int kb_local) {
+      const int kb = kb_begin + kb_local;
       const int d = kb * SQ_BK + 4 * dq;
       const bool din = d < D;
       q.m = din ? __ldg(reinterpret_cast<const float4*>(mean + d)) : zero4;
@@ -189,6 +194,13 @@ svgd_sqdist_umma_kernel(const float* __restrict__ X, const float* __restrict__ m
       umma::tmem_ld16(trow + (uint32_t)col, acc);
       const int jb = j0 + col;
       if (jb + 15 < i0 + 32 * qd || jb >= n) continue;      // warp-uniform: chunk entirely below the diagonal / out of range
+      if (n_slices > 1) {
+        const int64_t tile = (int64_t)blockIdx.z * gridDim.x * gridDim.y + (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        float4* dst = reinterpret_cast<float4*>(partial + (tile * SQ_BM + 32 * qd + lane) * SQ_BN + col);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dst[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+        continue;
+      }
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int j = jb + e;
@@ -239,8 +251,60 @@ svgd_sqdist_umma_kernel(const float* __restrict__ X, const float* __restrict__ m
   }
 }
 
-// Requirements (checked by the caller): D % 4 == 0, X 16-byte aligned; work = float[D + n], 16-byte aligned.
-int launch_svgd_sqdist_umma(const float* X, float* P, float* work, int n, int D, cudaStream_t stream) {
+// Sum of the slices' partial Gram tiles (fixed order) -> distances, same write pattern as the fused epilogue.
+// grid (tiles_x, padded rows), 256 threads = the 256 columns of a tile.
+__global__ void __launch_bounds__(SQ_BN)
+svgd_sqdist_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ norms, float* __restrict__ P,
+                            int n, int n_slices, int tiles_y) {
+  const int i = blockIdx.y, ty = i / SQ_BM, r = i % SQ_BM;
+  const int j0 = blockIdx.x * SQ_BN, j = j0 + threadIdx.x;
+  if (j0 + SQ_BN - 1 < ty * SQ_BM || i >= n || j >= n || j < i) return;
+  if (j == i) {
+    P[(int64_t)i * n + i] = 0.0f;
+    return;
+  }
+  const int64_t tiles = (int64_t)gridDim.x * tiles_y, tile = (int64_t)ty * gridDim.x + blockIdx.x;
+  float dot = 0.0f;
+  for (int s = 0; s < n_slices; ++s) dot = __fadd_rn(dot, partial[((s * tiles + tile) * SQ_BM + r) * SQ_BN + threadIdx.x]);
+  const float p = fmaxf(__fadd_rn(__fadd_rn(norms[i], norms[j]), __fmul_rn(-2.0f, dot)), 0.0f);
+  P[(int64_t)i * n + j] = p;
+  P[(int64_t)j * n + i] = p;
+}
+
+static int sqdist_slices(int n, int D, int n_sm) {
+  const int tx = (n + SQ_BN - 1) / SQ_BN, ty = (n + SQ_BM - 1) / SQ_BM;
+  int upper = 0;
+  for (int y = 0; y < ty; ++y)
+    for (int x = 0; x < tx; ++x) upper += (x * SQ_BN + SQ_BN - 1 >= y * SQ_BM);
+  const int nkb = (D + SQ_BK - 1) / SQ_BK;
+  int s = n_sm / (upper > 0 ? upper : 1);
+  s = s < 1 ? 1 : (s > 8 ? 8 : s);
+  if (s > nkb / 8) s = nkb / 8 > 0 ? nkb / 8 : 1;          // at least 8 blocks of 16 dimensions per slice
+  const int per = (nkb + s - 1) / s;
+  return (nkb + per - 1) / per;                             // no empty slice
+}
+
+// floats of scratch after the 4096-byte select state: mean[D] + norms[n] (+ padding) + the slices' partial tiles
+int64_t svgd_sqdist_work_floats(int n, int D, int n_slices) {
+  const int64_t head = ((int64_t)D + n + 3) / 4 * 4;
+  const int64_t tiles = (int64_t)((n + SQ_BN - 1) / SQ_BN) * ((n + SQ_BM - 1) / SQ_BM);
+  return head + (n_slices > 1 ? (int64_t)n_slices * tiles * SQ_BM * SQ_BN : 0);
+}
+
+int svgd_sqdist_best_slices(int n, int D) {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  return sqdist_slices(n, D, n_sm);
+}
+
+// Requirements (checked by the caller): D % 4 == 0, X 16-byte aligned; work = float[work_floats], 16-byte
+// aligned; the contraction is sliced only as far as `work_floats` allows.
+int launch_svgd_sqdist_umma(const float* X, float* P, float* work, int64_t work_floats, int n, int D,
+                            cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     const cudaError_t e = cudaFuncSetAttribute(svgd_sqdist_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -248,15 +312,31 @@ int launch_svgd_sqdist_umma(const float* X, float* P, float* work, int n, int D,
     if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd_sqdist_umma_kernel: %s", cudaGetErrorString(e));
     configured = true;
   }
+  int n_slices = svgd_sqdist_best_slices(n, D);
+  while (n_slices > 1 && svgd_sqdist_work_floats(n, D, n_slices) > work_floats) --n_slices;
+  if (n_slices > 1) {   // re-balance so that no slice is empty
+    const int nkb = (D + SQ_BK - 1) / SQ_BK, per = (nkb + n_slices - 1) / n_slices;
+    n_slices = (nkb + per - 1) / per;
+  }
+  SG_REQUIRE(svgd_sqdist_work_floats(n, D, 1) <= work_floats, SGMCMC_E_INVALID,
+             "svgd: scratch too small (%lld floats after the select state, need %lld)", (long long)work_floats,
+             (long long)svgd_sqdist_work_floats(n, D, 1));
   float* mean = work;
   float* norms = work + D;
+  float* partial = work + ((int64_t)D + n + 3) / 4 * 4;
   svgd_col_mean_kernel<<<(D + 31) / 32, 256, 0, stream>>>(X, mean, n, D);
   if (int rc = check_launch("svgd_col_mean_kernel")) return rc;
   svgd_row_norm_kernel<<<n, 256, 0, stream>>>(X, mean, norms, D);
   if (int rc = check_launch("svgd_row_norm_kernel")) return rc;
-  const dim3 grid((unsigned)((n + SQ_BN - 1) / SQ_BN), (unsigned)((n + SQ_BM - 1) / SQ_BM));
-  svgd_sqdist_umma_kernel<<<grid, SQ_THREADS, SQ_SMEM, stream>>>(X, mean, norms, P, n, D);
-  return check_launch("svgd_sqdist_umma_kernel");
+  const dim3 grid((unsigned)((n + SQ_BN - 1) / SQ_BN), (unsigned)((n + SQ_BM - 1) / SQ_BM), (unsigned)n_slices);
+  svgd_sqdist_umma_kernel<<<grid, SQ_THREADS, SQ_SMEM, stream>>>(X, mean, norms, P, partial, n, D, n_slices);
+  if (int rc = check_launch("svgd_sqdist_umma_kernel")) return rc;
+  if (n_slices > 1) {
+    const dim3 fgrid(grid.x, grid.y * SQ_BM);
+    svgd_sqdist_finalize_kernel<<<fgrid, SQ_BN, 0, stream>>>(partial, norms, P, n, n_slices, (int)grid.y);
+    return check_launch("svgd_sqdist_finalize_kernel");
+  }
+  return SGMCMC_OK;
 }
 
 }  // namespace sgmcmc

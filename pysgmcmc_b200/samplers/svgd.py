@@ -73,8 +73,9 @@ class SVGDSampler(MCMCSampler):
         self._kernel_matrix = torch.empty((n, n), dtype=torch.float32, device=dev)
         self._kernel_sum = torch.empty((n,), dtype=torch.float32, device=dev)
         self._bandwidth = torch.zeros((4,), dtype=torch.float32, device=dev)
-        # 4096 bytes for the median select + (n + D) floats for the centred-Gram distance kernel
-        self._select_scratch = torch.zeros((512 + (n + D + 1) // 2,), dtype=torch.int64, device=dev)
+        # median select state + work space of the centred-Gram distance kernel
+        with torch.cuda.device(dev):
+            self._select_scratch = _native.svgd_scratch(n, D, dev)
         self._particles_scratch = torch.empty((n, D), dtype=torch.float32, device=dev)
         self._grad = torch.empty((n, D), dtype=torch.float32, device=dev)
         self._vmap_ok = None
@@ -112,7 +113,7 @@ class SVGDSampler(MCMCSampler):
         _native.call("sgmcmc_svgd_kernel_matrix_f32", _native.ptr(self.particles),
                      _native.ptr(self._kernel_matrix), _native.ptr(self._kernel_sum),
                      _native.ptr(self._bandwidth), _native.ptr(self._select_scratch),
-                     self.n_particles, self.n_dims, self._stream())
+                     self._select_scratch.numel() * 8, self.n_particles, self.n_dims, self._stream())
 
     def svgd_kernel(self, particles=None):
         """RBF kernel matrix of the current particles and its summed gradients

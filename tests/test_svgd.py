@@ -104,17 +104,18 @@ def _native():
     return _native
 
 
-def _kernel_matrix(X, impl=0):
+def _kernel_matrix(X, impl=0, full_scratch=True):
     nat = _native()
     n, D = X.shape
     K = torch.empty((n, n), dtype=torch.float32, device=DEV)
     ksum = torch.empty(n, dtype=torch.float32, device=DEV)
     bw = torch.zeros(4, dtype=torch.float32, device=DEV)
-    scratch = torch.zeros(512 + (n + D + 1) // 2, dtype=torch.int64, device=DEV)
+    scratch = nat.svgd_scratch(n, D, DEV) if full_scratch else \
+        torch.zeros(512 + (n + D + 4) // 2, dtype=torch.int64, device=DEV)
     nat.call("sgmcmc_set_svgd_tuning", impl)
     try:
         nat.call("sgmcmc_svgd_kernel_matrix_f32", nat.ptr(X), nat.ptr(K), nat.ptr(ksum), nat.ptr(bw),
-                 nat.ptr(scratch), n, D, nat.stream_ptr())
+                 nat.ptr(scratch), scratch.numel() * 8, n, D, nat.stream_ptr())
         torch.cuda.synchronize()
     finally:
         nat.call("sgmcmc_set_svgd_tuning", 0)
@@ -261,6 +262,28 @@ def test_k14_tensor_core_and_ffma_kernels_agree(n, D):
     assert dx <= 2e-6 * X.abs().max().item(), dx
     assert dh <= 2e-5, dh
     assert not torch.equal(out[1][0], X), "the update must have moved the particles"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,D", [(256, 5252), (520, 2048), (1024, 1024)])
+def test_k11_sliced_contraction_matches_the_unsliced_kernel(n, D):
+    """With the scratch of sgmcmc_svgd_scratch_bytes the tensor-core distance kernel slices the
+    contraction over the dimensions (few tiles, many SMs) and adds the slices in a fixed order; with
+    the minimal scratch it runs unsliced.  Same products, different grouping of the fp32 sums."""
+    rng = np.random.RandomState(n + D)
+    X = torch.tensor((3.0 + rng.randn(n, D)).astype(np.float32), device=DEV)
+    nat = _native()
+    assert nat.load().sgmcmc_svgd_scratch_bytes(n, D) > 4096 + 4 * (n + D + 3), "expected a sliced configuration"
+    K1, s1, b1 = _kernel_matrix(X, impl=2, full_scratch=False)
+    K2, s2, b2 = _kernel_matrix(X, impl=2, full_scratch=True)
+    K3, _, _ = _kernel_matrix(X, impl=2, full_scratch=True)
+    assert torch.equal(K2, K3), "the sliced sum is deterministic"
+    assert torch.equal(K2, K2.t()) and bool((torch.diagonal(K2) == 1).all())
+    assert torch.allclose(K1, K2, rtol=5e-5, atol=1e-7)
+    assert torch.allclose(b1, b2, rtol=1e-6)
+    K_ref, _, h_ref = osvgd.svgd_kernel(X.cpu().numpy().astype(np.float64))
+    assert np.allclose(K2.cpu().numpy(), K_ref, rtol=2e-4, atol=1e-7)
+    assert np.isclose(float(b2[1]), h_ref, rtol=1e-5)
 
 
 # ----------------------------------------------------------------------------- GPU: sampler class

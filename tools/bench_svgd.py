@@ -77,14 +77,14 @@ def main():
         K = torch.empty((n, n), device=dev)
         ksum = torch.empty(n, device=dev)
         bw = torch.zeros(4, device=dev)
-        scratch = torch.zeros(512 + (n + D + 1) // 2, dtype=torch.int64, device=dev)
+        scratch = _native.svgd_scratch(n, D, dev)
         Xs = torch.empty_like(X)
         X0 = X.clone()
         s = _native.stream_ptr()
 
         def kernel_matrix():
             _native.call("sgmcmc_svgd_kernel_matrix_f32", _native.ptr(X), _native.ptr(K), _native.ptr(ksum),
-                         _native.ptr(bw), _native.ptr(scratch), n, D, s)
+                         _native.ptr(bw), _native.ptr(scratch), scratch.numel() * 8, n, D, s)
 
         def median_only():
             _native.call("sgmcmc_median_f32", _native.ptr(K), n * n, _native.ptr(bw), _native.ptr(scratch), s)

@@ -19,13 +19,13 @@ for impl in (1, 2):
         K = torch.empty((n, n), device=dev)
         ksum = torch.empty(n, device=dev)
         bw = torch.zeros(4, device=dev)
-        scratch = torch.zeros(512 + (n + D + 1) // 2, dtype=torch.int64, device=dev)
+        scratch = _native.svgd_scratch(n, D, dev)
         Xs = torch.empty_like(X)
         s = _native.stream_ptr()
         _native.call("sgmcmc_set_svgd_tuning", impl)
         for _ in range(2):
             _native.call("sgmcmc_svgd_kernel_matrix_f32", _native.ptr(X), _native.ptr(K), _native.ptr(ksum),
-                         _native.ptr(bw), _native.ptr(scratch), n, D, s)
+                         _native.ptr(bw), _native.ptr(scratch), scratch.numel() * 8, n, D, s)
             _native.call("sgmcmc_svgd_update_f32", _native.ptr(X), _native.ptr(G), _native.ptr(H), _native.ptr(K),
                          _native.ptr(ksum), _native.ptr(bw), _native.ptr(Xs), n, D, 0.1, 0.9, 0.1, 1e-6, s)
         torch.cuda.synchronize()
