@@ -133,12 +133,23 @@ __global__ void svgd_select_init_kernel(SelectState* st, unsigned long long n_va
 
 constexpr int SELECT_UNROLL = 8;
 
-__device__ __forceinline__ void warp_aggregated_inc(uint32_t* hist, uint32_t bin, bool active) {
-  // one shared-memory atomic per distinct bin of the warp (distances cluster in few bins)
-  const unsigned live = __ballot_sync(0xFFFFFFFFu, active);
-  if (!active) return;
-  const unsigned peers = __match_any_sync(live, bin);
-  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+// Histogram increment for one element per lane.  The leading digit of distances clusters in two or three bins
+// per warp, so pass 0 peels the distinct bins off with shuffle + ballot (one shared atomic per distinct bin);
+// the later digits are spread out and go straight to shared-memory atomics.
+__device__ __forceinline__ void warp_aggregated_inc(uint32_t* hist, uint32_t bin, bool active, bool clustered) {
+  if (!clustered) {
+    if (active) atomicAdd(&hist[bin], 1u);
+    return;
+  }
+  unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
+  const int lane = (int)(threadIdx.x & 31);
+  while (remaining) {                                   // warp-uniform loop
+    const int leader = __ffs(remaining) - 1;
+    const uint32_t b = __shfl_sync(0xFFFFFFFFu, bin, leader);
+    const unsigned same_bin = __ballot_sync(0xFFFFFFFFu, active && bin == b);
+    if (lane == leader) atomicAdd(&hist[b], (uint32_t)__popc(same_bin));
+    remaining &= ~same_bin;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -166,8 +177,8 @@ svgd_select_hist_kernel(const uint32_t* __restrict__ values, int64_t n_values, i
 #pragma unroll
     for (int u = 0; u < SELECT_UNROLL; ++u) {
       const uint32_t bin = (key[u] >> shift) & 255u;
-      warp_aggregated_inc(h[0], bin, in[u] && (key[u] & mask) == p0);
-      if (!same) warp_aggregated_inc(h[1], bin, in[u] && (key[u] & mask) == p1);
+      warp_aggregated_inc(h[0], bin, in[u] && (key[u] & mask) == p0, shift == 24);
+      if (!same) warp_aggregated_inc(h[1], bin, in[u] && (key[u] & mask) == p1, shift == 24);
     }
   }
   __syncthreads();
@@ -252,8 +263,8 @@ svgd_select_small_kernel(const uint32_t* __restrict__ values, int n_values, floa
 #pragma unroll
       for (int u = 0; u < SELECT_UNROLL; ++u) {
         const uint32_t bin = (key[u] >> shift) & 255u;
-        warp_aggregated_inc(h[0], bin, in[u] && (key[u] & mask) == p0);
-        if (!same) warp_aggregated_inc(h[1], bin, in[u] && (key[u] & mask) == p1);
+        warp_aggregated_inc(h[0], bin, in[u] && (key[u] & mask) == p0, shift == 24);
+        if (!same) warp_aggregated_inc(h[1], bin, in[u] && (key[u] & mask) == p1, shift == 24);
       }
     }
     __syncthreads();
@@ -296,7 +307,9 @@ static int launch_select(const float* values, int64_t n_values, float* out, void
   svgd_select_init_kernel<<<1, 256, 0, stream>>>(st, (unsigned long long)n_values);
   if (int rc = check_launch("svgd_select_init_kernel")) return rc;
   const int64_t want = (n_values + 256 * SELECT_UNROLL - 1) / (256 * SELECT_UNROLL);
-  const int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  // every CTA ends with up to 512 global atomics onto the same 512 counters: keep the CTAs few (2 per SM);
+  // 8 loads in flight per thread still cover the latency
+  const int grid = (int)(want < 1 ? 1 : (want > 148 * 2 ? 148 * 2 : want));
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     svgd_select_hist_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(values), n_values, shift, st);
