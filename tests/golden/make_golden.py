@@ -17,6 +17,11 @@ Run in the BUILD container (needs /root/reference for part 1):
    pin the oracle against silent edits and give the CUDA tests a second,
    file-based comparison point.  Noise is NOT stored: it is
    ``RandomState(seed).standard_normal`` (a frozen legacy stream).
+3. svgd.npz -- ORACLE DATA (float64): the reference has no SVGD test or golden either
+   (only docs/source/notebooks/SVGD.ipynb's plot); the notebook's configuration
+   (banana, 10 particles, N(0, 1) starts, stepsize 0.1) and a 64-particle one, first
+   50 steps (later steps are chaotic, see tests/test_svgd.py), plus kernel matrix and
+   bandwidth of the start.
 """
 import os
 import sys
@@ -26,7 +31,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
-from oracle import bnn, samplers, targets  # noqa: E402
+from oracle import bnn, samplers, svgd, targets  # noqa: E402
 
 REF = "/root/reference/pysgmcmc/tests/data/bayesian_neural_network_priors"
 CHECKPOINTS = (1, 2, 10, 100, 500, 1000)
@@ -112,6 +117,33 @@ def make_bnn():
                         cost=cost, grad=grad, mse=mse)
 
 
+SVGD_CASES = (("banana_10", 10, 4), ("banana_64", 64, 5))
+SVGD_CHECKPOINTS = (1, 2, 5, 10, 20, 50)
+
+
+def svgd_case(n_particles, seed, n_steps=50):
+    X0 = np.random.RandomState(seed).standard_normal((n_particles, 2))
+    K, kgrad, h = svgd.svgd_kernel(X0)
+    ref = svgd.OracleSVGD(X0, targets.banana_cost_and_grad)
+    thetas, costs = [], []
+    for step in range(1, n_steps + 1):
+        theta, cost = next(ref)
+        costs.append(cost)
+        if step in SVGD_CHECKPOINTS:
+            thetas.append(theta)
+    return dict(theta0=X0, kernel_matrix=K, kernel_gradients=kgrad, bandwidth=np.float64(h),
+                theta=np.stack(thetas), cost=np.stack(costs),
+                historical_grad=ref.state["historical_grad"])
+
+
+def make_svgd():
+    out = {}
+    for name, n, seed in SVGD_CASES:
+        for k, v in svgd_case(n, seed).items():
+            out["%s/%s" % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, "svgd.npz"), **out)
+
+
 def make_published_ess():
     """REFERENCE DATA: the only numbers the reference publishes for this path -- mean ESS of
     Relativistic SGHMC vs stepsize (docs/source/notebooks/data/effective_sample_sizes/
@@ -137,5 +169,6 @@ if __name__ == "__main__":
     make_published_ess()
     make_trajectories()
     make_bnn()
+    make_svgd()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -22,7 +22,8 @@ def test_header_declares_the_hot_path():
     names = declared_functions()
     for required in ("sgmcmc_sghmc_step_f32", "sgmcmc_sgld_step_f32", "sgmcmc_rsghmc_step_f32",
                      "sgmcmc_bnn_nll_grad_f32", "sgmcmc_bnn_sghmc_run_f32", "sgmcmc_mt19937_starts",
-                     "sgmcmc_target_chains_run_f32", "sgmcmc_chain_moments_f32"):
+                     "sgmcmc_target_chains_run_f32", "sgmcmc_chain_moments_f32",
+                     "sgmcmc_svgd_kernel_matrix_f32", "sgmcmc_svgd_update_f32", "sgmcmc_median_f32"):
         assert required in names
 
 
@@ -52,6 +53,15 @@ def test_version_and_error_reporting_without_gpu():
     assert lib.sgmcmc_sghmc_step_f32(None, None, None, None, None, None, None, None, 16,
                                      0.01, 0.05, 1.0, 1, 0, 0, 0, 2, None) == -1   # elem_offset % 4
     assert lib.sgmcmc_mt19937_starts(None, None, 4, 4, 10, None) == -1
+    assert lib.sgmcmc_svgd_kernel_matrix_f32(None, None, None, None, None, 4096, 4, 2, None) == -1
+    assert lib.sgmcmc_svgd_update_f32(None, None, None, None, None, None, None, 4, 2, 0.1, 0.9, 0.1, 1e-6, None) == -1
+    assert lib.sgmcmc_median_f32(None, 0, None, None, None) == -1
+    assert lib.sgmcmc_set_svgd_tuning(7) == -1 and lib.sgmcmc_set_svgd_tuning(0) == 0
+    # the scratch size is host arithmetic: select state + mean/norms (+ slices of partial Gram tiles)
+    assert lib.sgmcmc_svgd_scratch_bytes(10, 2) == 4096 + 4 * 12
+    assert lib.sgmcmc_svgd_scratch_bytes(4096, 5252) == 4096 + 4 * (4096 + 5252)
+    assert lib.sgmcmc_svgd_scratch_bytes(1024, 5252) > 4096 + 4 * (1024 + 5252)
+    assert lib.sgmcmc_svgd_scratch_bytes(50000, 2) == -1
 
 
 def test_no_product_module_imports_the_oracle():

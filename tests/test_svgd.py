@@ -66,6 +66,22 @@ def test_oracle_svgd_step_matches_an_independent_float64_formula():
     assert np.allclose(state["theta"], X - 0.1 * phi / (1e-6 + np.sqrt(hist)), rtol=1e-12)
 
 
+def test_oracle_reproduces_the_svgd_golden_file():
+    """tests/golden/svgd.npz (made by tests/golden/make_golden.py from the oracle) pins the
+    restatement against silent edits; the GPU tests below read the same file."""
+    import importlib.util
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(golden, "svgd.npz"))
+    for name, n, seed in mg.SVGD_CASES:
+        res = mg.svgd_case(n, seed)
+        for key, value in res.items():
+            assert np.allclose(value, g[name + "/" + key], rtol=1e-9, atol=1e-12), (name, key)
+
+
 def test_host_pdist_squareform_median_follow_the_reference():
     rng = np.random.RandomState(3)
     x = rng.rand(7, 3)
@@ -325,6 +341,33 @@ def test_svgd_sampler_trajectory_matches_the_oracle(n_particles):
     assert sampler.n_iterations == n_steps
     # the user's tensors are live views of the state (tf.Variable behaviour)
     assert np.array_equal(np.stack([p.cpu().numpy() for p in particles]), got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["banana_10", "banana_64"])
+def test_svgd_sampler_against_the_golden_file(name):
+    """File-based comparison point (tests/golden/svgd.npz): kernel matrix, bandwidth and kernel
+    gradients of the start, particles at steps 1, 2, 5, 10, 20, 50, every cost."""
+    import os
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.samplers import SVGDSampler
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "svgd.npz"))
+    X0 = g[name + "/theta0"].astype(np.float32)
+    sampler = SVGDSampler([torch.tensor(x, device=DEV) for x in X0], _banana_cost,
+                          session=Session(device=DEV, output="numpy"))
+    K, kgrad = sampler.svgd_kernel()
+    assert np.allclose(K.cpu().numpy(), g[name + "/kernel_matrix"], rtol=1e-4, atol=1e-7)
+    assert np.allclose(kgrad.cpu().numpy(), g[name + "/kernel_gradients"], rtol=1e-3, atol=1e-5)
+    assert np.isclose(float(sampler.bandwidth), float(g[name + "/bandwidth"]), rtol=1e-5)
+    checkpoints, k = (1, 2, 5, 10, 20, 50), 0
+    for step in range(1, 51):
+        sample, cost = next(sampler)
+        assert np.allclose(cost, g[name + "/cost"][step - 1], rtol=1e-4, atol=1e-4), step
+        if step in checkpoints:
+            want = g[name + "/theta"][k]
+            assert np.abs(np.stack(sample) - want).max() <= 1e-5 * np.abs(want).max(), step
+            k += 1
+    assert np.allclose(sampler.historical_grad.cpu().numpy(), g[name + "/historical_grad"], rtol=1e-3, atol=1e-9)
 
 
 @pytest.mark.gpu
