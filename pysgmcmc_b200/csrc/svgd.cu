@@ -4,16 +4,19 @@
 //
 // The particles ARE the engine's chain layout: X[n particles, D] fp32 row-major.  Unlike
 // the other samplers the update couples all particles, so one step is
-//   K11  svgd_sqdist_kernel        P[i,j] = (||x_i - x_j||)^2           FP32 pipe, n^2 D / 2
-//   K12  svgd_select_*             median of the n^2 entries of P       radix select, 4 passes over P (L2)
+//   K11  squared distances         P[i,j] = (||x_i - x_j||)^2           n^2 D / 2 MAC
+//   K12  svgd_select_*             median of the n^2 entries of P       exact radix select, 4 passes (L2)
 //   K13  svgd_kernel_matrix_kernel K = exp(-P / h^2 / 2), row sums      n^2 exp, in place
-//   K14  svgd_update_kernel        [K G | K X] (one GEMM, K read once) + Stein direction
-//                                  + AdaGrad history + particle update in the epilogue
+//   K14  Stein direction           [K G | K X] (one GEMM, K read once) + AdaGrad history + update in
+//                                  the epilogue                          4 n^2 D flop
 // all enqueued on the caller's stream with no host round trip (the bandwidth h stays on the
-// device).  K14 is the hot kernel: 4 n^2 D flop against (n^2 + 5 n D) * 4 bytes, i.e. compute
-// bound for any n beyond a few dozen particles.  It runs the products in FP32 FFMA
-// (the reference's float32 matmul; TF32 inputs would cost 1e-3 relative in the Stein
-// direction, beyond the 1e-5 trajectory tolerance).
+// device).  K11 and K14 exist twice:
+//   * here, on the FP32 pipe (FFMA; K11 subtracts before squaring like pdist): small or unaligned
+//     shapes, and the second implementation the tests compare against;
+//   * in svgd_sqdist_umma.cu / svgd_umma.cu on the tcgen05 tensor cores as 3xTF32 with TMEM
+//     accumulators (fp32 accuracy; plain TF32 would cost 1e-3 relative in the Stein direction,
+//     beyond the 1e-5 trajectory tolerance): 2.5-4x faster from a few hundred particles on.
+// This file also holds the C entry points and the choice between the two.
 #include <atomic>
 
 #include "common.cuh"
@@ -307,9 +310,9 @@ static int launch_select(const float* values, int64_t n_values, float* out, void
   svgd_select_init_kernel<<<1, 256, 0, stream>>>(st, (unsigned long long)n_values);
   if (int rc = check_launch("svgd_select_init_kernel")) return rc;
   const int64_t want = (n_values + 256 * SELECT_UNROLL - 1) / (256 * SELECT_UNROLL);
-  // every CTA ends with up to 512 global atomics onto the same 512 counters: keep the CTAs few (2 per SM);
-  // 8 loads in flight per thread still cover the latency
-  const int grid = (int)(want < 1 ? 1 : (want > 148 * 2 ? 148 * 2 : want));
+  // 8 CTAs per SM: measured faster than 2 per SM (0.19 vs 0.25 ms at 16.7 M values) although every CTA ends
+  // with up to 512 global atomics onto the same counters -- the passes want the parallelism
+  const int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     svgd_select_hist_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(values), n_values, shift, st);

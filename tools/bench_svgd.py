@@ -1,9 +1,10 @@
-"""Per-kernel times of one SVGD step (K11-K14, csrc/svgd.cu) and of the whole
-`next(sampler)` with the BNN cost kernel K4 supplying the gradients.
-    python tools/bench_svgd.py [--quick]
-Rooflines: K14 is FP32-pipe bound, 4 n^2 D flop (two products sharing the K operand) against
-74.4 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz); K11 is 3 n^2 D / 2 flop-equivalents on the
-same pipe (subtract + FMA per term, upper triangle only); K12/K13 are latency / L2 bound.
+"""Per-kernel times of one SVGD step (K11-K14, csrc/svgd*.cu), FFMA and tcgen05 implementations,
+and of the whole `next(sampler)` with the BNN cost kernel K4 supplying the gradients.
+    python tools/bench_svgd.py [--quick | --k14-sweep [n D]]
+Rooflines: K14 is 4 n^2 D flop (two products sharing the K operand): the FFMA kernel against the
+FP32 peak of 74.4 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz), the tcgen05 kernel (3 TF32 products
+per fp32 product) against the dense TF32 tensor peak; K11 is n^2 D / 2 MAC on the upper triangle;
+K12/K13 are latency / L2 bound.
 """
 import json
 import os
