@@ -291,6 +291,16 @@ int64_t sgmcmc_svgd_scratch_bytes(int64_t n_particles, int64_t n_dims);
 int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kernel_matrix, float* kernel_sum,
                                   float* bandwidth, void* scratch, int64_t scratch_bytes,
                                   int64_t n_particles, int64_t n_dims, void* stream);
+/* SVGD of at most 128 particles on a built-in test density (SGMCMC_TARGET_*), `n_steps` steps in
+ * ONE launch of one CTA (gradients, distances, exact median, kernel, Stein direction and update
+ * all in shared memory): the regime of docs/source/notebooks/SVGD.ipynb.  particles
+ * [n, D] (D = 2 banana, 1 gmm) and historical_grad [n, D] are updated in place; every
+ * keep_every-th particle set goes to trace [n_steps / keep_every, n, D] and the costs of the
+ * particles BEFORE that step to cost_trace [n_steps / keep_every, n] (either may be NULL). */
+int sgmcmc_svgd_target_run_f32(int target, float* particles, float* historical_grad, float* trace,
+                               float* cost_trace, int64_t n_particles, int64_t n_steps,
+                               int64_t keep_every, float epsilon, float alpha, float one_minus_alpha,
+                               float fudge_factor, void* stream);
 int sgmcmc_svgd_update_f32(float* particles, const float* grad, float* historical_grad,
                            const float* kernel_matrix, const float* kernel_sum, const float* bandwidth,
                            float* particles_scratch, int64_t n_particles, int64_t n_dims, float epsilon,

@@ -69,6 +69,8 @@ SIGNATURES = {
     "sgmcmc_median_f32": [_P, c_int64, _P, _P, _P],
     "sgmcmc_svgd_scratch_bytes": [c_int64, c_int64],
     "sgmcmc_svgd_kernel_matrix_f32": [_P] * 5 + [c_int64, c_int64, c_int64, _P],
+    "sgmcmc_svgd_target_run_f32": [c_int] + [_P] * 4 + [c_int64, c_int64, c_int64, c_float, c_float, c_float,
+                                                        c_float, _P],
     "sgmcmc_svgd_update_f32": [_P] * 7 + [c_int64, c_int64, c_float, c_float, c_float, c_float, _P],
 }
 _RESTYPES = {"sgmcmc_last_error": c_char_p, "sgmcmc_launch_count": c_int64, "sgmcmc_svgd_scratch_bytes": c_int64}

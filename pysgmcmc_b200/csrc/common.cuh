@@ -128,6 +128,37 @@ __device__ __forceinline__ void normal4(uint64_t group, uint64_t step, uint64_t 
   out[2] = r1 * __cosf(a1); out[3] = r1 * __sinf(a1);
 }
 
+// ---- radix-select helper: which of 256 histogram bins holds the element of rank `r`? -----------
+// Executed by one full warp (lane l scans bins 8l .. 8l+7, a shuffle scan finds the crossing lane).
+// Returns the bin (255 if r is beyond the total) and the number of elements in the bins before it.
+__device__ __forceinline__ void warp_pick_bin(const uint32_t* hist, uint32_t r, uint32_t& bin, uint32_t& before) {
+  const int lane = (int)(threadIdx.x & 31);
+  uint32_t c[8], s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    c[k] = hist[lane * 8 + k];
+    s += c[k];
+  }
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned crossing = __ballot_sync(0xFFFFFFFFu, r < incl);
+  const int L = crossing ? __ffs(crossing) - 1 : 31;
+  uint32_t b = 7, cum = incl - s;
+  if (lane == L) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (r < cum + c[k]) { b = (uint32_t)k; break; }
+      cum += c[k];
+    }
+  }
+  bin = __shfl_sync(0xFFFFFFFFu, (uint32_t)L * 8u + b, L);
+  before = __shfl_sync(0xFFFFFFFFu, cum, L);
+}
+
 // ---- streaming global memory access (single-use data: do not keep it in L1) --------
 template <typename V>
 __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }

@@ -271,17 +271,14 @@ svgd_select_small_kernel(const uint32_t* __restrict__ values, int n_values, floa
       }
     }
     __syncthreads();
-    if (tid < 2) {
-      const uint32_t* hh = same ? h[0] : h[tid];
-      const uint32_t r = rank[tid];
-      uint32_t cum = 0, bin = 255;
-      for (uint32_t b = 0; b < 256; ++b) {
-        const uint32_t c = hh[b];
-        if (r < cum + c) { bin = b; break; }
-        cum += c;
+    if (tid < 64) {                                     // warp 0 narrows rank 0, warp 1 rank 1
+      const int w = tid >> 5;
+      uint32_t bin, before;
+      warp_pick_bin(same ? h[0] : h[w], rank[w], bin, before);
+      if ((tid & 31) == 0) {
+        prefix[w] |= bin << shift;
+        rank[w] -= before;
       }
-      prefix[tid] |= bin << shift;
-      rank[tid] = r - cum;
     }
     __syncthreads();
   }

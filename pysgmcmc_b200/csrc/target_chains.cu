@@ -153,6 +153,152 @@ static GmmParams make_gmm(int target) {
   return P;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K6 for SVGD: a small particle set (n <= 128) on a built-in test density, many steps per launch in
+// ONE CTA.  Everything a step needs -- gradients, the n x n squared distances, the exact median
+// (radix select over the shared-memory copy), the RBF kernel, the Stein direction, the AdaGrad
+// history and the update (pysgmcmc/samplers/svgd.py:125-182, oracle/svgd.py) -- stays in shared
+// memory and registers; HBM sees the particles once per launch plus the thinned trace.  This is
+// the reference notebook's regime (docs/source/notebooks/SVGD.ipynb: 10 particles on the banana,
+// 50 000 steps), which is launch-latency bound when run kernel by kernel.
+// Arithmetic and summation orders follow the FFMA kernels of svgd.cu except the kernel row sums
+// (sequential here, a tree there): the two paths agree to fp32 rounding, not bit for bit.
+// ---------------------------------------------------------------------------------------------
+struct SvgdRunArgs {
+  float *X, *hist, *trace, *cost_trace;
+  int n;
+  int64_t n_steps, keep_every;
+  float eps, alpha, one_minus_alpha, fudge;
+  GmmParams gmm;
+};
+
+__device__ __forceinline__ uint32_t svgd_float_key(uint32_t b) { return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
+__device__ __forceinline__ uint32_t svgd_key_float(uint32_t k) { return k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu); }
+
+template <typename Target>
+__global__ void __launch_bounds__(256) svgd_target_run_kernel(SvgdRunArgs a) {
+  constexpr int D = Target::D;
+  extern __shared__ __align__(16) float sm[];
+  const int n = a.n, tid = threadIdx.x;
+  float* P = sm;                      // [n, n] distances, then the kernel matrix
+  float* x = P + n * n;               // [n, D]
+  float* g = x + n * D;               // [n, D]
+  float* ksum = g + n * D;            // [n]
+  float* cost = ksum + n;             // [n]
+  __shared__ uint32_t h[2][256];
+  __shared__ uint32_t prefix[2], rank[2];
+  __shared__ float bw[2];             // h, h^2
+
+  const bool owner = tid < n * D;     // one thread per coordinate
+  const int oi = owner ? tid / D : 0;
+  float hreg = owner ? a.hist[tid] : 0.0f;
+  if (owner) x[tid] = a.X[tid];
+  __syncthreads();
+  const uint32_t n_values = (uint32_t)(n * n);
+  const float nf = (float)n;
+
+  for (int64_t step = 0; step < a.n_steps; ++step) {
+    // gradients of the COST at the current particles (svgd.py:125)
+    if (tid < n) {
+      float gi[D];
+      cost[tid] = Target::cost_grad(&x[tid * D], gi, a.gmm);
+#pragma unroll
+      for (int d = 0; d < D; ++d) g[tid * D + d] = gi[d];
+    }
+    // squared distances (svgd.py:151-152), difference first
+    for (int idx = tid; idx < n * n; idx += 256) {
+      const int i = idx / n, j = idx - i * n;
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float df = x[i * D + d] - x[j * D + d];
+        s = fmaf(df, df, s);
+      }
+      const float nrm = __fsqrt_rn(s);
+      P[idx] = __fmul_rn(nrm, nrm);
+    }
+    if (tid == 0) {
+      rank[1] = n_values / 2;
+      rank[0] = (n_values & 1u) ? n_values / 2 : n_values / 2 - 1;
+      prefix[0] = prefix[1] = 0;
+    }
+    __syncthreads();
+    // exact median: 4 passes of 8 bits over order-preserving keys (tensor_utils.py:194-208)
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      h[0][tid] = 0;
+      h[1][tid] = 0;
+      __syncthreads();
+      const uint32_t p0 = prefix[0], p1 = prefix[1];
+      const uint32_t mask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int idx = tid; idx < n * n; idx += 256) {
+        const uint32_t key = svgd_float_key(__float_as_uint(P[idx]));
+        const uint32_t bin = (key >> shift) & 255u;
+        if ((key & mask) == p0) atomicAdd(&h[0][bin], 1u);
+        if (p0 != p1 && (key & mask) == p1) atomicAdd(&h[1][bin], 1u);
+      }
+      __syncthreads();
+      if (tid < 64) {                                   // warp 0 narrows rank 0, warp 1 rank 1
+        const int w = tid >> 5;
+        uint32_t bin, before;
+        warp_pick_bin((p0 == p1) ? h[0] : h[w], rank[w], bin, before);
+        if ((tid & 31) == 0) {
+          prefix[w] |= bin << shift;
+          rank[w] -= before;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const float lo = __uint_as_float(svgd_key_float(prefix[0])), hi = __uint_as_float(svgd_key_float(prefix[1]));
+      const float med = (prefix[0] == prefix[1]) ? lo : __fdiv_rn(__fadd_rn(hi, lo), 2.0f);
+      const float hb = __fsqrt_rn(__fdiv_rn(__fmul_rn(0.5f, med), logf(__fadd_rn(nf, 1.0f))));   // svgd.py:155-157
+      bw[0] = hb;
+      bw[1] = __fmul_rn(hb, hb);
+    }
+    __syncthreads();
+    const float h2 = bw[1];
+    for (int idx = tid; idx < n * n; idx += 256) P[idx] = expf(__fdiv_rn(__fdiv_rn(-P[idx], h2), 2.0f));
+    __syncthreads();
+    if (tid < n) {
+      float s = 0.0f;
+      for (int j = 0; j < n; ++j) s += P[tid * n + j];
+      ksum[tid] = s;
+    }
+    __syncthreads();
+    // Stein direction, AdaGrad history, update (svgd.py:130-148,162-167)
+    float xnew = 0.0f;
+    if (owner) {
+      const int d = tid - oi * D;
+      float kg = 0.0f, kx = 0.0f;
+      for (int j = 0; j < n; ++j) {
+        const float k = P[oi * n + j];
+        kg = fmaf(k, g[j * D + d], kg);
+        kx = fmaf(k, x[j * D + d], kx);
+      }
+      const float xv = x[tid];
+      const float kgrad = __fdiv_rn(__fadd_rn(-kx, __fmul_rn(xv, ksum[oi])), h2);
+      const float phi = __fdiv_rn(__fadd_rn(kg, kgrad), nf);
+      hreg = __fadd_rn(__fmul_rn(a.alpha, hreg), __fmul_rn(a.one_minus_alpha, __fmul_rn(phi, phi)));
+      const float adj = __fdiv_rn(phi, __fadd_rn(a.fudge, __fsqrt_rn(hreg)));
+      xnew = __fsub_rn(xv, __fmul_rn(a.eps, adj));
+    }
+    __syncthreads();                                    // every thread has read the old particles
+    if (owner) x[tid] = xnew;
+    if ((step + 1) % a.keep_every == 0) {
+      const int64_t k = (step + 1) / a.keep_every - 1;
+      if (owner && a.trace) a.trace[k * n * D + tid] = xnew;
+      if (tid < n && a.cost_trace) a.cost_trace[k * n + tid] = cost[tid];   // cost of the PRE-update particles
+    }
+    __syncthreads();
+  }
+  if (owner) {
+    a.X[tid] = x[tid];
+    a.hist[tid] = hreg;
+  }
+}
+
 }  // namespace sgmcmc
 
 using namespace sgmcmc;
@@ -195,4 +341,35 @@ extern "C" int sgmcmc_target_chains_run_f32(int sampler, int target, float* thet
   else { SG_LAUNCH_TC(SGMCMC_SAMPLER_RSGHMC) }
 #undef SG_LAUNCH_TC
   return check_launch("target_chains_kernel");
+}
+
+extern "C" int sgmcmc_svgd_target_run_f32(int target, float* particles, float* historical_grad, float* trace,
+                                          float* cost_trace, int64_t n_particles, int64_t n_steps,
+                                          int64_t keep_every, float epsilon, float alpha, float one_minus_alpha,
+                                          float fudge_factor, void* stream) {
+  SG_REQUIRE(target >= 0 && target <= 3, SGMCMC_E_INVALID, "unknown target id %d", target);
+  SG_REQUIRE(n_particles >= 1 && n_particles <= 128, SGMCMC_E_UNSUPPORTED,
+             "the fused SVGD kernel holds at most 128 particles (got %lld)", (long long)n_particles);
+  SG_REQUIRE(n_steps >= 0 && keep_every >= 1, SGMCMC_E_INVALID, "n_steps must be >= 0 and keep_every >= 1");
+  SG_REQUIRE(particles && historical_grad, SGMCMC_E_INVALID, "particles / historical_grad must not be NULL");
+  if (n_steps == 0) return SGMCMC_OK;
+  const int n = (int)n_particles, D = target == SGMCMC_TARGET_BANANA ? 2 : 1;
+  SvgdRunArgs a;
+  a.X = particles; a.hist = historical_grad; a.trace = trace; a.cost_trace = cost_trace;
+  a.n = n; a.n_steps = n_steps; a.keep_every = keep_every;
+  a.eps = epsilon; a.alpha = alpha; a.one_minus_alpha = one_minus_alpha; a.fudge = fudge_factor;
+  a.gmm = make_gmm(target);
+  const size_t smem = sizeof(float) * ((size_t)n * n + 2 * (size_t)n * D + 2 * (size_t)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (target == SGMCMC_TARGET_BANANA) {
+    e = cudaFuncSetAttribute(svgd_target_run_kernel<Banana>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd_target_run_kernel: %s", cudaGetErrorString(e));
+    svgd_target_run_kernel<Banana><<<1, 256, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(svgd_target_run_kernel<Gmm>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd_target_run_kernel: %s", cudaGetErrorString(e));
+    svgd_target_run_kernel<Gmm><<<1, 256, smem, st>>>(a);
+  }
+  return check_launch("svgd_target_run_kernel");
 }

@@ -29,7 +29,10 @@ class SVGDSampler(MCMCSampler):
         A callable with ``native_cost_and_grad(theta[n, D], grad_out) -> cost[n]``
         (e.g. ``BayesianNeuralNetworkNLL``) is evaluated by its CUDA kernel instead, and a
         callable with a true ``vectorized`` attribute is called once on the ``[n, D]``
-        matrix transposed to ``[D, n]`` (so ``x[0], x[1]`` index coordinates).
+        matrix transposed to ``[D, n]`` (so ``x[0], x[1]`` index coordinates).  The built-in test
+        densities (``to_negative_log_likelihood(banana_log_likelihood)``, gmm1-3) with at most
+        128 particles run in the fused one-CTA kernel (``sgmcmc_svgd_target_run_f32``): one
+        launch per ``next(sampler)``, ONE launch for a whole ``sampler.run(n_steps)``.
     """
 
     def __init__(self, particles, cost_fun, batch_generator=None,
@@ -79,6 +82,28 @@ class SVGDSampler(MCMCSampler):
         self._particles_scratch = torch.empty((n, D), dtype=torch.float32, device=dev)
         self._grad = torch.empty((n, D), dtype=torch.float32, device=dev)
         self._vmap_ok = None
+
+    # ------------------------------------------------------------------ fused small-problem path
+    def _detect_native_target(self):
+        tag = getattr(self.particle_cost_fun, "native_target", None)
+        if tag is None or tag[1] != -1 or not self.session.fused:
+            return None
+        n, D = len(self.params), self._sizes[0]
+        if n > 128 or D != (2 if tag[0] == "banana" else 1):
+            return None
+        return tag[0]
+
+    def _target_run(self, n_steps, keep_every, trace, costs, epsilon):
+        _native.call("sgmcmc_svgd_target_run_f32", _native.TARGET_IDS[self._native_target],
+                     _native.ptr(self.particles), _native.ptr(self.historical_grad), _native.ptr(trace),
+                     _native.ptr(costs), self.n_particles, n_steps, keep_every, epsilon, self.alpha,
+                     1. - self.alpha, self.fudge_factor, self._stream())
+
+    def _launch_fused_target(self, z, epsilon):
+        assert z is None, "SVGD is deterministic: there is no noise to inject"
+        cost = torch.empty((1, self.n_particles), dtype=torch.float32, device=self.device)
+        self._target_run(1, 1, None, cost, epsilon)
+        return cost[0]
 
     # ------------------------------------------------------------------ cost + gradient
     def _particle_costs(self, X):
@@ -152,6 +177,12 @@ class SVGDSampler(MCMCSampler):
         n_keep = n_steps // keep_every
         trace = torch.empty((n_keep, self.n_particles, self.n_dims), dtype=self.dtype, device=self.device)
         costs = torch.empty((n_keep, self.n_particles), dtype=self.dtype, device=self.device)
+        if n_steps > 0 and self._can_run_fused():
+            with torch.cuda.device(self.device):
+                self._target_run(n_steps, keep_every, trace if n_keep else None, costs if n_keep else None,
+                                 float(next(self.stepsize_schedule)))
+            self.n_iterations += n_steps
+            return trace, costs
         for s in range(n_steps):
             cost = self._step_on_device()
             if (s + 1) % keep_every == 0:

@@ -371,6 +371,49 @@ def test_svgd_sampler_against_the_golden_file(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("target,n,D", [("banana", 10, 2), ("banana", 128, 2), ("gmm1", 16, 1), ("gmm3", 33, 1)])
+def test_fused_small_svgd_kernel(target, n, D):
+    """The one-CTA kernel (sgmcmc_svgd_target_run_f32) behind SVGDSampler for the built-in densities:
+    against the float64 oracle (40 steps on the banana; 8 on the 1-d mixtures, where the float32 and
+    float64 ORACLES already differ by 2e-5 at step 12 and 1e-3 at step 16), `run(n)` == n x `next()`
+    bit for bit, and against the kernel-by-kernel path (same cost function with its native tag
+    hidden -> autograd + K11-K14)."""
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.diagnostics import objective_functions as of
+    from pysgmcmc_b200.samplers import SVGDSampler
+    loglik = {"banana": of.banana_log_likelihood, "gmm1": of.gmm1_log_likelihood, "gmm3": of.gmm3_log_likelihood}[target]
+    cost = of.to_negative_log_likelihood(loglik)
+    rng = np.random.RandomState(n + D)
+    X0 = (rng.randn(n, D) * 2.0).astype(np.float32)
+    mk = lambda: [torch.tensor(x, device=DEV) for x in X0]
+    sess = lambda: Session(device=DEV, output="torch")
+    fused = SVGDSampler(mk(), cost, session=sess())
+    assert fused._native_target == target
+    ref = osvgd.OracleSVGD(X0.astype(np.float64), otargets.cost_and_grad(target))
+    n_steps = 40 if target == "banana" else 8
+    trace, costs = fused.run(n_steps, keep_every=4)
+    assert trace.shape == (n_steps // 4, n, D) and costs.shape == (n_steps // 4, n) and fused.n_iterations == n_steps
+    for step in range(1, n_steps + 1):
+        t64, c64 = next(ref)
+        if step % 4 == 0:
+            k = step // 4 - 1
+            assert np.abs(trace[k].cpu().numpy() - t64).max() <= 2e-5 * max(1.0, np.abs(t64).max()), step
+            assert np.allclose(costs[k].cpu().numpy(), c64, rtol=1e-4, atol=1e-4), step
+    stepwise = SVGDSampler(mk(), cost, session=sess())
+    for step in range(1, n_steps + 1):
+        sample, c = next(stepwise)
+        if step % 4 == 0:
+            assert torch.equal(torch.stack(sample), trace[step // 4 - 1]), step
+            assert torch.equal(c, costs[step // 4 - 1]), step
+    assert torch.equal(stepwise.historical_grad, fused.historical_grad)
+    hidden = lambda x: cost(x if D == 2 else [x[0]])            # no native tag -> autograd + K11-K14
+    generic = SVGDSampler(mk(), hidden, session=sess())
+    assert generic._native_target is None
+    tr2, _ = generic.run(4, keep_every=4)
+    assert np.abs((tr2[0] - trace[0]).cpu().numpy()).max() <= 2e-5 * max(1.0, float(trace[0].abs().max()))
+
+
+@pytest.mark.gpu
 def test_svgd_sampler_interface_and_errors():
     from pysgmcmc_b200 import Session
     from pysgmcmc_b200.samplers import SVGDSampler
