@@ -11,7 +11,7 @@ from pysgmcmc_b200 import _native  # noqa: E402
 
 dev = torch.device("cuda:0")
 for impl in (1, 2):
-    for n, D in ((10, 2), (132, 260), (256, 128), (400, 64)):
+    for n, D in ((10, 2), (132, 260), (256, 128), (400, 64), (260, 512), (520, 256)):   # incl. sliced K11, two-tile K14
         g = torch.Generator(device=dev).manual_seed(n)
         X = 1.0 + torch.randn((n, D), device=dev, generator=g)
         G = torch.randn((n, D), device=dev, generator=g)
@@ -32,6 +32,17 @@ for impl in (1, 2):
         _native.call("sgmcmc_set_svgd_tuning", 0)
         assert torch.isfinite(X).all()
         print("impl", impl, "n", n, "D", D, "ok", float(bw[1]), flush=True)
+# fused one-CTA SVGD on the built-in densities
+for target, n, D in ((0, 10, 2), (0, 128, 2), (1, 33, 1)):
+    X = torch.randn((n, D), device=dev)
+    H = torch.zeros((n, D), device=dev)
+    trace = torch.empty((5, n, D), device=dev)
+    costs = torch.empty((5, n), device=dev)
+    _native.call("sgmcmc_svgd_target_run_f32", target, _native.ptr(X), _native.ptr(H), _native.ptr(trace),
+                 _native.ptr(costs), n, 10, 2, 0.1, 0.9, 0.1, 1e-6, _native.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.isfinite(trace).all()
+    print("fused target", target, "n", n, "ok", flush=True)
 big = torch.randn(300000, device=dev)
 out = torch.empty(1, device=dev)
 scratch = torch.zeros(512, dtype=torch.int64, device=dev)
