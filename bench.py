@@ -319,6 +319,14 @@ def run_b200(args):
     # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------
     e2e = end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks)
 
+    # ---- informational: the SVGD step (K11-K14 on the tcgen05 tensor cores), never fatal ----
+    svgd = None
+    if rank == 0 and world == 1:
+        try:
+            svgd = svgd_step_rates(torch, _native, dev)
+        except Exception as exc:      # the headline metric does not depend on this
+            svgd = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -343,9 +351,66 @@ def run_b200(args):
         "roofline": roofline,
         "kernels": kernels,
         "sampling_phase": sampling_phase,
+        "svgd": svgd,
         "cpu_baseline": cpu,
     }
     emit(line)
+
+
+def svgd_step_rates(torch, _native, dev, n=4096, D=5252, reps=10):
+    """One SVGD update of `n` particles x `D` dimensions (the BNN's parameter count) with a given
+    gradient: K11-K13 (kernel matrix) and K14 (Stein direction + update), CUDA events, inputs
+    resident.  Informational: SVGDSampler is the SURVEY 8 f-4 row, not the headline metric."""
+    g = torch.Generator(device=dev).manual_seed(1)
+    X = torch.randn((n, D), device=dev, generator=g)
+    G = torch.randn((n, D), device=dev, generator=g)
+    H = torch.zeros((n, D), device=dev)
+    Kmat = torch.empty((n, n), device=dev)
+    ksum = torch.empty(n, device=dev)
+    bw = torch.zeros(4, device=dev)
+    scratch = _native.svgd_scratch(n, D, dev)
+    Xs = torch.empty_like(X)
+    st, p = _native.stream_ptr(), _native.ptr
+
+    def kernel_matrix():
+        _native.call("sgmcmc_svgd_kernel_matrix_f32", p(X), p(Kmat), p(ksum), p(bw), p(scratch),
+                     scratch.numel() * 8, n, D, st)
+
+    def update():          # epsilon = 0: the particles stay put, every repetition does the same work
+        _native.call("sgmcmc_svgd_update_f32", p(X), p(G), p(H), p(Kmat), p(ksum), p(bw), p(Xs), n, D,
+                     0.0, 0.9, 0.1, 1e-6, st)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms_km, ms_up = timed(kernel_matrix), timed(update)
+    tf = 4.0 * n * n * D / ms_up / 1e9
+    return {"workload": "one SVGD update, %d particles x %d dims (informational)" % (n, D),
+            "kernel_matrix_ms": ms_km, "update_ms": ms_up, "step_ms": ms_km + ms_up,
+            "particle_updates_per_s": n / (ms_km + ms_up) * 1e3,
+            "update_kernel": {"kernel": "svgd_update_umma_kernel (K14: tcgen05 kind::tf32, 3 products per fp32 "
+                                        "product, TMEM accumulators)",
+                              "bound": "tensor", "achieved": 3 * tf, "unit": "TFLOP/s executed TF32",
+                              "fp32_equivalent_TFLOPs": tf,
+                              "peak": 0.5 * measured_bf16_peak(), "peak_source": "half of MEASURED_PEAKS.json "
+                              "bf16_tflops (dense TF32 = half the bf16 rate)",
+                              "frac": 3 * tf / (0.5 * measured_bf16_peak())}}
+
+
+def measured_bf16_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"])
+    except Exception:
+        return 1686.9          # this pool's B200s (driver-written figure of round 1)
 
 
 def per_kernel_times(sampler, gen, nll, torch, _native, n=30):
