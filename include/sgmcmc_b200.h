@@ -287,6 +287,9 @@ int sgmcmc_variogram_select_f32(const float* trace, const int64_t* dims, double*
  * 23 / 24 = 2 with 3 / 4 producer register buffers in K14 (sweeps). */
 int sgmcmc_set_svgd_tuning(int impl);
 int sgmcmc_median_f32(const float* values, int64_t n_values, float* out, void* scratch, void* stream);
+/* The same median over all n * n entries of a SYMMETRIC matrix with a ZERO diagonal (what the
+ * kernel-matrix entry point uses on the squared distances): only the upper triangle is read. */
+int sgmcmc_median_symmetric_f32(const float* matrix, int64_t n, float* out, void* scratch, void* stream);
 int64_t sgmcmc_svgd_scratch_bytes(int64_t n_particles, int64_t n_dims);
 int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kernel_matrix, float* kernel_sum,
                                   float* bandwidth, void* scratch, int64_t scratch_bytes,

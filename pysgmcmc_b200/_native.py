@@ -67,6 +67,7 @@ SIGNATURES = {
     "sgmcmc_variogram_select_f32": [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P],
     "sgmcmc_set_svgd_tuning": [c_int],
     "sgmcmc_median_f32": [_P, c_int64, _P, _P, _P],
+    "sgmcmc_median_symmetric_f32": [_P, c_int64, _P, _P, _P],
     "sgmcmc_svgd_scratch_bytes": [c_int64, c_int64],
     "sgmcmc_svgd_kernel_matrix_f32": [_P] * 5 + [c_int64, c_int64, c_int64, _P],
     "sgmcmc_svgd_target_run_f32": [c_int] + [_P] * 4 + [c_int64, c_int64, c_int64, c_float, c_float, c_float,

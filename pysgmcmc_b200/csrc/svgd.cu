@@ -189,24 +189,65 @@ svgd_select_hist_kernel(const uint32_t* __restrict__ values, int64_t n_values, i
   if (h[1][threadIdx.x]) atomicAdd(&st->hist[1][threadIdx.x], h[1][threadIdx.x]);
 }
 
+// The same histogram pass for a SYMMETRIC n x n matrix with a zero diagonal (the squared distances):
+// only the upper triangle is read, every element counts twice and the n zeros of the diagonal are added
+// by one thread -- half the traffic and half the atomics of the generic pass, same counts.
+// Work items are (row, chunk of 256 * SELECT_UNROLL columns), dealt round-robin to a persistent grid.
+__global__ void __launch_bounds__(256)
+svgd_select_hist_sym_kernel(const uint32_t* __restrict__ values, int n, int shift, SelectState* st) {
+  __shared__ uint32_t h[2][256];
+  h[0][threadIdx.x] = 0;
+  h[1][threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
+  const uint32_t mask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
+  const bool same = (p0 == p1);
+  constexpr int CHUNK = 256 * SELECT_UNROLL;
+  const int chunks = (n + CHUNK - 1) / CHUNK;
+  const int64_t items = (int64_t)n * chunks;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int i = (int)(item / chunks), c0 = (int)(item - (int64_t)i * chunks) * CHUNK;
+    if (c0 + CHUNK - 1 <= i) continue;                  // chunk entirely on or below the diagonal (block-uniform)
+    const uint32_t* row = values + (int64_t)i * n;
+    uint32_t key[SELECT_UNROLL];
+    bool in[SELECT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SELECT_UNROLL; ++u) {
+      const int j = c0 + u * 256 + (int)threadIdx.x;
+      in[u] = j > i && j < n;
+      key[u] = in[u] ? float_key(row[j]) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < SELECT_UNROLL; ++u) {
+      const uint32_t bin = (key[u] >> shift) & 255u;
+      warp_aggregated_inc(h[0], bin, in[u] && (key[u] & mask) == p0, shift == 24);
+      if (!same) warp_aggregated_inc(h[1], bin, in[u] && (key[u] & mask) == p1, shift == 24);
+    }
+  }
+  __syncthreads();
+  // every off-diagonal value appears twice in the full matrix
+  if (h[0][threadIdx.x]) atomicAdd(&st->hist[0][threadIdx.x], 2u * h[0][threadIdx.x]);
+  if (h[1][threadIdx.x]) atomicAdd(&st->hist[1][threadIdx.x], 2u * h[1][threadIdx.x]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {            // the n zeros of the diagonal
+    const uint32_t key0 = float_key(0u), bin0 = (key0 >> shift) & 255u;
+    if ((key0 & mask) == p0) atomicAdd(&st->hist[0][bin0], (uint32_t)n);
+    if (!same && (key0 & mask) == p1) atomicAdd(&st->hist[1][bin0], (uint32_t)n);
+  }
+}
+
 // Narrows both prefixes by 8 bits.  On the last pass writes out[0] = median and, when
 // n_particles > 0, the RBF bandwidth of svgd.py:155-157: out[1] = h, out[2] = h^2.
 __global__ void svgd_select_pick_kernel(SelectState* st, int shift, int last, float* out, float n_particles) {
   __shared__ uint32_t new_prefix[2];
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 64) {                               // warp 0 narrows rank 0, warp 1 rank 1 (counts < 2^31)
+    const int r = (int)(threadIdx.x >> 5);
     const bool same = (st->prefix[0] == st->prefix[1]);
-    for (int r = 0; r < 2; ++r) {
-      const uint32_t* h = same ? st->hist[0] : st->hist[r];
-      const unsigned long long rank = st->rank[r];
-      unsigned long long cum = 0;
-      uint32_t bin = 255;
-      for (uint32_t b = 0; b < 256; ++b) {
-        const unsigned long long c = h[b];
-        if (rank < cum + c) { bin = b; break; }
-        cum += c;
-      }
+    const unsigned long long rank = st->rank[r];
+    uint32_t bin, before;
+    warp_pick_bin(same ? st->hist[0] : st->hist[r], (uint32_t)rank, bin, before);
+    if ((threadIdx.x & 31) == 0) {
       new_prefix[r] = st->prefix[r] | (bin << shift);
-      st->rank[r] = rank - cum;
+      st->rank[r] = rank - before;
     }
   }
   __syncthreads();
@@ -296,8 +337,9 @@ svgd_select_small_kernel(const uint32_t* __restrict__ values, int n_values, floa
   }
 }
 
+// symmetric_n > 0: `values` is a symmetric symmetric_n x symmetric_n matrix with a zero diagonal
 static int launch_select(const float* values, int64_t n_values, float* out, void* scratch, float n_particles,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int symmetric_n = 0) {
   if (n_values <= SELECT_SMALL_MAX) {
     svgd_select_small_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const uint32_t*>(values), (int)n_values, out,
                                                      n_particles);
@@ -312,7 +354,11 @@ static int launch_select(const float* values, int64_t n_values, float* out, void
   const int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    svgd_select_hist_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(values), n_values, shift, st);
+    if (symmetric_n > 0)
+      svgd_select_hist_sym_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(values), symmetric_n,
+                                                               shift, st);
+    else
+      svgd_select_hist_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(values), n_values, shift, st);
     if (int rc = check_launch("svgd_select_hist_kernel")) return rc;
     svgd_select_pick_kernel<<<1, 256, 0, stream>>>(st, shift, pass == 3, out, n_particles);
     if (int rc = check_launch("svgd_select_pick_kernel")) return rc;
@@ -556,6 +602,13 @@ extern "C" int sgmcmc_median_f32(const float* values, int64_t n_values, float* o
   return launch_select(values, n_values, out, scratch, 0.0f, (cudaStream_t)stream);
 }
 
+extern "C" int sgmcmc_median_symmetric_f32(const float* matrix, int64_t n, float* out, void* scratch, void* stream) {
+  SG_REQUIRE(n >= 1 && n <= 46340, SGMCMC_E_INVALID, "median: n must be in [1, 46340]");
+  SG_REQUIRE(matrix && out && scratch, SGMCMC_E_INVALID, "median: NULL pointer");
+  SG_REQUIRE(aligned_to(matrix, 4) && aligned_to(out, 4) && aligned_to(scratch, 8), SGMCMC_E_ALIGN, "median: misaligned pointer");
+  return launch_select(matrix, n * n, out, scratch, 0.0f, (cudaStream_t)stream, (int)n);
+}
+
 extern "C" int64_t sgmcmc_svgd_scratch_bytes(int64_t n_particles, int64_t n_dims) {
   if (n_particles < 0 || n_dims < 0 || n_particles > 46340 || n_dims > ((int64_t)1 << 30)) return -1;
   const int n = (int)n_particles, D = (int)n_dims;
@@ -587,7 +640,7 @@ extern "C" int sgmcmc_svgd_kernel_matrix_f32(const float* particles, float* kern
     svgd_sqdist_kernel<<<dim3(nt, nt), 256, 0, s>>>(particles, kernel_matrix, n, D);
     if (int rc = check_launch("svgd_sqdist_kernel")) return rc;
   }
-  if (int rc = launch_select(kernel_matrix, n_particles * n_particles, bandwidth, scratch, (float)n, s)) return rc;
+  if (int rc = launch_select(kernel_matrix, n_particles * n_particles, bandwidth, scratch, (float)n, s, n)) return rc;
   svgd_kernel_matrix_kernel<<<n, 256, 0, s>>>(kernel_matrix, kernel_sum, bandwidth, n);
   return check_launch("svgd_kernel_matrix_kernel");
 }

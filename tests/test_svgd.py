@@ -152,6 +152,28 @@ def test_k12_median_is_exact(n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 3, 17, 362, 363, 400, 1001, 2500])
+def test_k12_symmetric_median_is_exact(n):
+    """The upper-triangle variant used on the squared distances (every value counted twice + n zeros of
+    the diagonal) against the plain median of the full matrix; n <= 362 takes the one-CTA path."""
+    rng = np.random.RandomState(n)
+    A = (rng.rand(n, n) * 10 ** rng.uniform(-2, 2, size=(n, n))).astype(np.float32)
+    M = np.triu(A, 1)
+    M = M + M.T
+    if n > 100:
+        M[rng.randint(0, n, 50), rng.randint(0, n, 50)] = 0.0          # a few more zeros / ties ...
+        M = np.minimum(M, M.T)                                          # ... kept symmetric
+        np.fill_diagonal(M, 0.0)
+    nat = _native()
+    Md = torch.tensor(M, device=DEV)
+    out = torch.empty(1, device=DEV)
+    scratch = torch.zeros(512, dtype=torch.int64, device=DEV)
+    nat.call("sgmcmc_median_symmetric_f32", nat.ptr(Md), n, nat.ptr(out), nat.ptr(scratch), nat.stream_ptr())
+    assert float(out[0]) == float(osvgd.median(M))
+    assert float(out[0]) == float(tensor_utils.median(Md))
+
+
+@pytest.mark.gpu
 def test_k12_median_of_special_values():
     for values in ([0.0, 0.0, 0.0, 0.0], [-1.0, -2.0, -3.0], [-0.0, 0.0], [3e38, -3e38, 1e-45, -1e-45],
                    [np.inf, 1.0, 2.0], [5.0]):
