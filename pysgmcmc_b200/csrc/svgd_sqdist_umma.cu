@@ -305,12 +305,10 @@ int svgd_sqdist_best_slices(int n, int D) {
 // aligned; the contraction is sliced only as far as `work_floats` allows.
 int launch_svgd_sqdist_umma(const float* X, float* P, float* work, int64_t work_floats, int n, int D,
                             cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  {   // per launch, not cached: the attribute belongs to the current device
     const cudaError_t e = cudaFuncSetAttribute(svgd_sqdist_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)SQ_SMEM);
     if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd_sqdist_umma_kernel: %s", cudaGetErrorString(e));
-    configured = true;
   }
   int n_slices = svgd_sqdist_best_slices(n, D);
   while (n_slices > 1 && svgd_sqdist_work_floats(n, D, n_slices) > work_floats) --n_slices;

@@ -268,12 +268,10 @@ template <int PF, int MT>
 static int launch_umma_pf(const float* K, const float* X, const float* G, const float* ksum, const float* bw,
                           float* hist, float* Xout, int n, int D, float eps, float alpha, float one_minus_alpha,
                           float fudge, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  {   // per launch, not cached: the attribute belongs to the current device
     const cudaError_t e = cudaFuncSetAttribute(svgd_update_umma_kernel<PF, MT>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmCfg<MT>::SMEM);
     if (e != cudaSuccess) return set_error(SGMCMC_E_CUDA, "svgd_update_umma_kernel: %s", cudaGetErrorString(e));
-    configured = true;
   }
   const dim3 grid((unsigned)((D + UM_BN - 1) / UM_BN), (unsigned)((n + UM_BM * MT - 1) / (UM_BM * MT)));
   SG_REQUIRE(grid.y <= 65535, SGMCMC_E_UNSUPPORTED, "svgd: too many particles");
