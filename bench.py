@@ -64,13 +64,36 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+KERNEL_SOURCES = {"k1": ["update_kernels.cu", "sampler_math.cuh", "common.cuh"],
+                  "k4": ["bnn_mma.cuh", "bnn.cu", "bnn_common.cuh"]}
+
+
+def source_hash(files):
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(ROOT, "pysgmcmc_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two kernels of the step at
-    the headline shape, from the committed `ncu --set full` capture (profiles/)."""
+    the headline shape, from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by tools/ncu_summary.py --traffic).  The file carries the commit and a hash of the
+    kernel sources it was captured from; a kernel whose sources changed since gets no traffic
+    figure (null) instead of a stale one."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         return {}
+    for key, field in (("k1", "k1_burn_in_bytes_per_launch"), ("k4", "k4_bytes_per_launch")):
+        try:
+            if t.get("source_hash", {}).get(key) != source_hash(KERNEL_SOURCES[key]):
+                t[field] = None
+        except OSError:
+            t[field] = None
+    return t
 
 
 # ------------------------------------------------------------------------------------
@@ -318,6 +341,14 @@ def run_b200(args):
 
     # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------
     e2e = end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks)
+    e2e_every = end_to_end(sampler, nll, torch, _native, dev, C, min(K, 10), 2, world, barrier, max_over_ranks,
+                           sample_every=1, lookahead=2)
+
+    # ---- config 4 in full: R-hat / ESS over ALL chains of the job (K8 + the one collective) ----
+    diagnostics = None
+    if not args.no_diagnostics:
+        diagnostics = chain_diagnostics(sampler, torch, dist, dev, world, rank, args.diag_draws, args.diag_thin,
+                                        barrier, max_over_ranks)
 
     # ---- informational: the SVGD step (K11-K14 on the tcgen05 tensor cores), never fatal ----
     svgd = None
@@ -347,6 +378,8 @@ def run_b200(args):
         "config": workload_config(C, world),
         "clocks": clocks.summary(),
         "e2e": e2e,
+        "e2e_every_sample": e2e_every,
+        "diagnostics": diagnostics,
         "gpu_launches": launches,
         "roofline": roofline,
         "kernels": kernels,
@@ -446,39 +479,108 @@ def per_kernel_times(sampler, gen, nll, torch, _native, n=30):
             "step_ms": k4 + k1 + k7, "launches_timed": n}
 
 
-def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks):
+def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks,
+               sample_every=None, lookahead=8):
     """K steps through the public host-facing iterator `SGHMCSampler.iter_host`: per step the
     minibatch start indices are copied from pinned host memory, K4 + K1 run through the C ABI
     (sgmcmc_bnn_sghmc_run_f32) and the per-chain cost is copied back to pinned host memory,
     where the host receives it (what `sample, cost = next(sampler)` means); every
-    SAMPLE_STEPS-th step the whole sample [C, D] is copied back as well.  The iterator keeps
-    up to 8 steps queued ahead and runs the copies on their own streams, so the device does not
-    idle while the host handles a result or a sample crosses PCIe."""
+    `sample_every`-th step the whole sample [C, D] is copied back as well and READ by the host.
+    Default thinning: BayesianNeuralNetwork's sample_steps = 100, shortened to the number of timed
+    steps when fewer are timed, so that at least one whole sample crosses PCIe inside every timed
+    region.  sample_every = 1 is the reference's literal `next()` (every step returns host
+    parameters, base_classes.py:298-304): PCIe-bound, reported as `e2e_every_sample`.  The
+    iterator keeps up to `lookahead` steps queued ahead and runs the copies on their own streams,
+    so the device does not idle while the host handles a result or a sample crosses PCIe."""
     K_e = min(K, 300)
+    if sample_every is None:
+        sample_every = min(SAMPLE_STEPS, K_e)
     rng = np.random.RandomState(7)
     host_starts = torch.from_numpy(
         rng.randint(0, N_EXAMPLES - BATCH + 1, size=(W + K_e, C)).astype(np.int32)).pin_memory()
     checksum = 0.0
-    for _ in sampler.iter_host(host_starts[:W], sample_every=SAMPLE_STEPS, lookahead=8):
+    for _ in sampler.iter_host(host_starts[:W], sample_every=sample_every, lookahead=lookahead):
         pass
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     n_samples = 0
-    for sample, cost in sampler.iter_host(host_starts[W:], sample_every=SAMPLE_STEPS, lookahead=8):
+    for sample, cost in sampler.iter_host(host_starts[W:], sample_every=sample_every, lookahead=lookahead):
         checksum += float(cost[0])                       # the host reads every step's result
-        n_samples += sample is not None
+        if sample is not None:
+            n_samples += 1
+            checksum += float(sample[0, 0]) + float(sample[-1, -1])   # ... and the sample when there is one
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     assert np.isfinite(checksum)
+    assert n_samples == K_e // sample_every and n_samples >= 1, "no sample crossed PCIe in the timed region"
     return {"value": C * world * K_e / (ms / 1e3), "unit": "chain-steps/s", "steps": K_e,
             "ms_per_step": ms / K_e, "wall_ms_per_step": wall_ms / K_e,
             "h2d_bytes_per_step": C * 4, "d2h_bytes_per_step": C * 4 + n_samples * C * D * 4 / K_e,
-            "api": "SGHMCSampler.iter_host -> sgmcmc_bnn_sghmc_run_f32 (C ABI), one call per step, pinned host "
-                   "buffers, host receives every step's cost, up to 8 steps queued ahead"}
+            "sample_every": sample_every, "samples_copied": n_samples,
+            "api": "SGHMCSampler.iter_host -> sgmcmc_bnn_host_pipeline_step (C ABI), one call per step, pinned "
+                   "host buffers, host receives every step's cost and every %d-th sample [C, D], up to %d steps "
+                   "queued ahead" % (sample_every, lookahead)}
+
+
+def chain_diagnostics(sampler, torch, dist, dev, world, rank, n_draws, thin, barrier, max_over_ranks):
+    """BASELINE.json configs[3] in full: after the timed sampling every rank keeps `n_draws`
+    thinned draws of each of its chains, reduces them to per-dimension chain sums (K8,
+    csrc/moments.cu), the ranks exchange those sums with all_reduce(SUM) over NCCL -- the ONLY
+    collective of the path -- and every rank finalises R-hat and ESS redundantly
+    (pysgmcmc/diagnostics/sampler_diagnostics.py:47-194).  Times are the max over ranks."""
+    from pysgmcmc_b200.diagnostics.sampler_diagnostics import diagnose_trace
+    C, Dp = sampler.n_chains, sampler.n_params_per_chain
+    trace, _ = sampler.run(n_draws * thin, keep_every=thin)
+    # warm the collective up (communicator / channel set-up is not part of the exchange)
+    if world > 1:
+        warm = torch.zeros(3 * Dp + 1, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            dist.all_reduce(warm)
+    diagnose_trace(trace[:, :, :64].contiguous())        # first-call set-up of the kernels (local, no collective)
+    barrier()
+    t = {}
+    r_hat, ess = diagnose_trace(trace, timings=t)
+    barrier()
+    # every rank must have finalised the same numbers
+    r = torch.nan_to_num(r_hat, nan=-1.0, posinf=-2.0)
+    lo, hi = r.clone(), r.clone()
+    e = torch.as_tensor(ess, dtype=torch.float64, device=dev)
+    elo, ehi = e.clone(), e.clone()
+    if world > 1:
+        for x, op in ((lo, dist.ReduceOp.MIN), (hi, dist.ReduceOp.MAX), (elo, dist.ReduceOp.MIN),
+                      (ehi, dist.ReduceOp.MAX)):
+            dist.all_reduce(x, op=op)
+    assert torch.equal(lo, hi) and torch.equal(elo, ehi), "ranks finalised different diagnostics"
+    finite = torch.isfinite(r_hat)
+    assert bool(finite.any()), "no finite R-hat"
+    # sqrt((n-1)/n) <= R-hat by construction (B >= 0); ESS in [1, m n]
+    assert float(r_hat[finite].min()) >= np.sqrt((n_draws - 1.0) / n_draws) - 1e-9
+    assert float(np.nanmin(ess)) >= 1.0 and float(np.nanmax(ess)) <= C * world * n_draws
+    out = {
+        "what": "R-hat and ESS of all %d chains x %d draws (every %d-th step) x %d dims: K8 -> NCCL "
+                "all_reduce(SUM) of float64 chain sums -> finalise on every rank" % (C * world, n_draws, thin, Dp),
+        "trace_gb_per_gpu": trace.numel() * 4 / 1e9,
+        "k8_ms": max_over_ranks(t["k8_ms"]),
+        "allreduce_us": 1e3 * max_over_ranks(t.get("allreduce_ms", 0.0)),
+        "allreduce_calls": t["allreduce_calls"], "bytes": t["allreduce_bytes"],
+        "finalize_ms": max_over_ranks(t["finalize_ms"]), "wall_ms": max_over_ranks(t["wall_ms"]),
+        "k8_trace_GBps": trace.numel() * 4 / 1e6 / t["k8_ms"],
+        "r_hat": {"median": float(r_hat[finite].median()), "max": float(r_hat[finite].max()),
+                  "finite_dims": int(finite.sum())},
+        "ess": {"median": float(np.nanmedian(ess)), "min": float(np.nanmin(ess)),
+                "of_draws": C * world * n_draws},
+        "identical_on_all_ranks": True,
+        "note": "chains start from independent random initialisations and are still in burn-in: R-hat >> 1 "
+                "is the correct report for them; the estimator itself is tested against the oracle "
+                "(tests/test_diagnostics_*.py)",
+    }
+    del trace
+    torch.cuda.empty_cache()
+    return out
 
 
 _REAL_STDOUT = None
@@ -509,6 +611,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains-per-gpu", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-diagnostics", action="store_true")
+    ap.add_argument("--diag-draws", type=int, default=100)
+    ap.add_argument("--diag-thin", type=int, default=10)
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     if args.impl == "reference":

@@ -27,13 +27,13 @@ struct sgmcmc_bnn_host_pipeline {
   int64_t n_chains = 0, D = 0;
   int depth = 0;
   int64_t next_ticket = 0;
-  bool sample_in_flight = false;
+  int64_t n_samples = 0;          // samples requested so far (stage buffer = n_samples % 2)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   int32_t* d_starts = nullptr;   // [depth, C]
   float* d_cost = nullptr;       // [depth, C]
-  float* d_stage = nullptr;      // [C, D] or NULL
+  float* d_stage = nullptr;      // [2, C, D] or NULL: two snapshots may be on their way out
   cudaEvent_t h2d[sgmcmc::MAX_DEPTH], step_done[sgmcmc::MAX_DEPTH], out_done[sgmcmc::MAX_DEPTH];
-  cudaEvent_t sample_done = nullptr;
+  cudaEvent_t sample_done[2] = {nullptr, nullptr};
 };
 
 using namespace sgmcmc;
@@ -53,7 +53,8 @@ extern "C" int sgmcmc_bnn_host_pipeline_destroy(sgmcmc_bnn_host_pipeline* p) {
     if (p->step_done[b]) cudaEventDestroy(p->step_done[b]);
     if (p->out_done[b]) cudaEventDestroy(p->out_done[b]);
   }
-  if (p->sample_done) cudaEventDestroy(p->sample_done);
+  for (int k = 0; k < 2; ++k)
+    if (p->sample_done[k]) cudaEventDestroy(p->sample_done[k]);
   if (p->d_starts) cudaFree(p->d_starts);
   if (p->d_cost) cudaFree(p->d_cost);
   if (p->d_stage) cudaFree(p->d_stage);
@@ -86,13 +87,14 @@ extern "C" int sgmcmc_bnn_host_pipeline_create(sgmcmc_bnn_host_pipeline** out, i
   ok(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking), "cudaStreamCreate");
   ok(cudaMalloc(&p->d_starts, sizeof(int32_t) * depth * n_chains), "cudaMalloc(starts)");
   ok(cudaMalloc(&p->d_cost, sizeof(float) * depth * n_chains), "cudaMalloc(cost)");
-  if (with_samples) ok(cudaMalloc(&p->d_stage, sizeof(float) * n_chains * p->D), "cudaMalloc(sample stage)");
+  if (with_samples) ok(cudaMalloc(&p->d_stage, sizeof(float) * 2 * n_chains * p->D), "cudaMalloc(sample stage)");
   for (int b = 0; b < depth; ++b) {
     ok(cudaEventCreateWithFlags(&p->h2d[b], cudaEventDisableTiming), "cudaEventCreate");
     ok(cudaEventCreateWithFlags(&p->step_done[b], cudaEventDisableTiming), "cudaEventCreate");
     ok(cudaEventCreateWithFlags(&p->out_done[b], cudaEventDisableTiming), "cudaEventCreate");
   }
-  ok(cudaEventCreateWithFlags(&p->sample_done, cudaEventDisableTiming), "cudaEventCreate");
+  for (int k = 0; k < 2; ++k)
+    ok(cudaEventCreateWithFlags(&p->sample_done[k], cudaEventDisableTiming), "cudaEventCreate");
   if (rc != SGMCMC_OK) {
     sgmcmc_bnn_host_pipeline_destroy(p);
     return rc;
@@ -134,17 +136,20 @@ extern "C" int sgmcmc_bnn_host_pipeline_step(sgmcmc_bnn_host_pipeline* p, float*
                                         n_burn_in, adapt_forever, 1, epsilon, mdecay, scale_grad, seed, step,
                                         chain_offset, stream))
     return rc;
+  const int sb = (int)(p->n_samples & 1);
+  float* stage = p->d_stage + (int64_t)sb * C * p->D;
   if (host_sample != nullptr) {
-    if (p->sample_in_flight) SG_CUDA(cudaStreamWaitEvent(main, p->sample_done, 0));
-    SG_CUDA(cudaMemcpyAsync(p->d_stage, theta, sizeof(float) * C * p->D, cudaMemcpyDeviceToDevice, main));
+    // the snapshot before last used this stage buffer: its D2H must have left the device
+    if (p->n_samples >= 2) SG_CUDA(cudaStreamWaitEvent(main, p->sample_done[sb], 0));
+    SG_CUDA(cudaMemcpyAsync(stage, theta, sizeof(float) * C * p->D, cudaMemcpyDeviceToDevice, main));
   }
   SG_CUDA(cudaEventRecord(p->step_done[b], main));
   SG_CUDA(cudaStreamWaitEvent(p->s_out, p->step_done[b], 0));
   SG_CUDA(cudaMemcpyAsync(host_cost, d_cost, sizeof(float) * C, cudaMemcpyDeviceToHost, p->s_out));
   if (host_sample != nullptr) {
-    SG_CUDA(cudaMemcpyAsync(host_sample, p->d_stage, sizeof(float) * C * p->D, cudaMemcpyDeviceToHost, p->s_out));
-    SG_CUDA(cudaEventRecord(p->sample_done, p->s_out));
-    p->sample_in_flight = true;
+    SG_CUDA(cudaMemcpyAsync(host_sample, stage, sizeof(float) * C * p->D, cudaMemcpyDeviceToHost, p->s_out));
+    SG_CUDA(cudaEventRecord(p->sample_done[sb], p->s_out));
+    ++p->n_samples;
   }
   SG_CUDA(cudaEventRecord(p->out_done[b], p->s_out));
   if (ticket != nullptr) *ticket = p->next_ticket;

@@ -128,13 +128,28 @@ class DeviceBatchGenerator(object):
                 self._side.wait_stream(torch.cuda.current_stream(self.device))
         return self._side
 
+    def _take_pending(self, n_steps):
+        """Rows of a block that ``next(gen)`` started and did not finish: they are the next
+        steps of every stream, so block requests hand them out first."""
+        if self._buf is None or self._pos == self._buf.shape[0]:
+            self._buf = None
+            return None
+        rows = self._buf[self._pos:self._pos + n_steps]
+        self._pos += rows.shape[0]
+        return rows
+
     def next_block_async(self, n_steps):
         """Start the generation of the next `n_steps` steps on the generator's side stream.
         Returns ``(starts, event)``: the consumer's stream must wait for `event` before it
         reads `starts` (int32 ``[n_steps, C]``) and call ``starts.record_stream(consumer)``.
-        Blocks are generated in call order."""
-        assert self._buf is None or self._pos == self._buf.shape[0], \
-            "next_block cannot be mixed with a partially consumed next() block"
+        Blocks are generated in call order.  Rows left over from ``next(gen)`` come first
+        (that case is served on the current stream)."""
+        if self._buf is not None and self._pos < self._buf.shape[0]:
+            out = self.next_block(n_steps)
+            with torch.cuda.device(self.device):
+                event = torch.cuda.Event()
+                event.record(torch.cuda.current_stream(self.device))
+            return out, event
         side = self._side_stream()
         with torch.cuda.device(self.device):
             if not getattr(self, "_side_owns_state", False):
@@ -160,15 +175,19 @@ class DeviceBatchGenerator(object):
             self._side_owns_state = False
 
     def next_block(self, n_steps):
-        """Start indices of the next `n_steps` steps: int32 ``[n_steps, C]``."""
-        assert self._buf is None or self._pos == self._buf.shape[0], \
-            "next_block cannot be mixed with a partially consumed next() block"
+        """Start indices of the next `n_steps` steps: int32 ``[n_steps, C]`` (rows left over
+        from a ``next(gen)`` block first, then newly generated ones)."""
         with torch.cuda.device(self.device):
             self._reclaim_state()
-            out = torch.empty((n_steps, self.n_chains), dtype=torch.int32, device=self.device)
-            _native.call("sgmcmc_mt19937_starts", _native.ptr(self.state), _native.ptr(out),
-                         self.n_chains, n_steps, self.n_examples - self.batch_size,
-                         _native.stream_ptr())
+            head = self._take_pending(n_steps)
+            n_new = n_steps - (0 if head is None else head.shape[0])
+            out = torch.empty((n_new, self.n_chains), dtype=torch.int32, device=self.device)
+            if n_new > 0:
+                _native.call("sgmcmc_mt19937_starts", _native.ptr(self.state), _native.ptr(out),
+                             self.n_chains, n_new, self.n_examples - self.batch_size,
+                             _native.stream_ptr())
+            if head is not None:
+                out = torch.cat([head, out], dim=0) if n_new > 0 else head.contiguous()
         return out
 
     def state_dict(self):

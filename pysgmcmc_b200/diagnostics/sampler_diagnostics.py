@@ -22,7 +22,7 @@ from .. import _native
 from ..tensor_utils import get_name
 
 __all__ = ("effective_sample_sizes", "gelman_rubin", "gelman_rubin_from_trace",
-           "effective_n_from_trace", "ChainSums")
+           "effective_n_from_trace", "diagnose_trace", "ChainSums")
 
 
 # ---------------------------------------------------------------------------------------
@@ -151,6 +151,90 @@ def effective_n_from_trace(trace, group=None):
     return effective_n_from_variograms(
         v_hat, cs.m, n, lambda lag0, k: _all_reduce_sum(local_variogram_sums(trace, lag0, k), group),
         lambda lag0, k, dims: _all_reduce_sum(local_variogram_select_sums(trace, dims, lag0, k), group))
+
+
+class _Stopwatch(object):
+    """Accumulates device time (CUDA events on the current stream) and host time per label;
+    a no-op when no `timings` dict was asked for."""
+
+    def __init__(self, timings, device):
+        self.t, self.device, self.pending = timings, device, []
+
+    def device_section(self, label, fn):
+        if self.t is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        out = fn()
+        e1.record(torch.cuda.current_stream(self.device))
+        self.pending.append((label, e0, e1))
+        return out
+
+    def host_section(self, label, fn):
+        if self.t is None:
+            return fn()
+        import time
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        out = fn()
+        self.t[label] = self.t.get(label, 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
+
+    def close(self):
+        if self.t is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for label, e0, e1 in self.pending:
+            self.t[label] = self.t.get(label, 0.0) + e0.elapsed_time(e1)
+        self.pending = []
+
+
+def diagnose_trace(trace, group=None, timings=None):
+    """R-hat and ESS per dimension of a device trace ``[n_draws, C_local, D]``, all ranks of
+    `group` together, in one pass: K8 moment sums -> all-reduce -> V_hat, W, R-hat; K8 variogram
+    sums per lag block -> all-reduce -> ESS (sampler_diagnostics.py:76-82,153-161).  Returns
+    ``(r_hat [D] float64 tensor, ess [D] float64 ndarray)``.
+
+    `timings` (a dict) receives, in milliseconds: ``k8_ms`` (the reduction kernels),
+    ``allreduce_ms`` (the collectives, device time on the current stream), ``finalize_ms``
+    (host arithmetic of the stopping rule), plus ``allreduce_calls`` and ``allreduce_bytes``."""
+    import time
+    n, C, D = trace.shape
+    sw = _Stopwatch(timings, trace.device)
+    if timings is not None:
+        timings.update({"allreduce_calls": 0, "allreduce_bytes": 0})
+        torch.cuda.synchronize(trace.device)
+    t_begin = time.perf_counter()
+
+    def reduce(t):
+        if timings is not None:
+            timings["allreduce_calls"] += 1
+            timings["allreduce_bytes"] += t.numel() * t.element_size()
+        return sw.device_section("allreduce_ms", lambda: _all_reduce_sum(t, group))
+
+    sums = sw.device_section("k8_ms", lambda: local_moment_sums(trace))
+    packed = torch.cat([sums.reshape(-1), torch.tensor([float(C)], dtype=torch.float64, device=trace.device)])
+    packed = reduce(packed)
+    cs = ChainSums.__new__(ChainSums)
+    cs.sums, cs.m, cs.n, cs.group = packed[:-1].reshape(3, -1), int(round(float(packed[-1]))), int(n), group
+    v_hat, W = cs.v_hat_and_w()
+    r_hat = torch.sqrt(v_hat / W)
+
+    def block(lag0, k):
+        return reduce(sw.device_section("k8_ms", lambda: local_variogram_sums(trace, lag0, k)))
+
+    def select(lag0, k, dims):
+        return reduce(sw.device_section("k8_ms", lambda: local_variogram_select_sums(trace, dims, lag0, k)))
+
+    ess = effective_n_from_variograms(v_hat, cs.m, n, block, select)
+    sw.close()
+    if timings is not None:
+        # the stopping rule runs on the host between the lag blocks: what is left of the wall
+        # time after the kernels and collectives it waited for
+        timings["wall_ms"] = (time.perf_counter() - t_begin) * 1e3
+        timings["finalize_ms"] = max(0.0, timings["wall_ms"] - timings.get("k8_ms", 0.0)
+                                     - timings.get("allreduce_ms", 0.0))
+    return r_hat, ess
 
 
 # ---------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ from ..placeholders import Placeholder
 from ..tensor_utils import safe_divide
 
 HIDDEN = 50
+MAX_NATIVE_BATCH = 256          # rows of one minibatch the BNN kernels accept (csrc/bnn.cu)
 
 
 def parameter_shapes(n_in):
@@ -131,14 +132,29 @@ class BayesianNeuralNetworkNLL(object):
         self.last_mse = None
 
     # ---- where the current minibatch comes from ---------------------------------------
+    def full_dataset_batch(self):
+        """Rows per chain when NO minibatch indices are fed: the cost is then over the WHOLE
+        resident dataset, like the differentiable path (`_torch_batch`).  The kernels hold one
+        minibatch per chain in shared memory, so this only exists for small datasets; a larger
+        one raises instead of silently using its first rows."""
+        n = int(self.X.shape[0])
+        if n > MAX_NATIVE_BATCH:
+            raise ValueError(
+                "BayesianNeuralNetworkNLL: the dataset is resident on the device (%d rows) but no "
+                "minibatch start indices were fed through `starts_placeholder`; the native cost "
+                "evaluates at most %d rows per chain. Pass a DeviceBatchGenerator as the sampler's "
+                "batch_generator (or feed starts)." % (n, MAX_NATIVE_BATCH))
+        return n
+
     def _device_batch(self):
         """(X, y, starts or None, batch) for the native kernels."""
         if self.X is not None:
             starts = None
             if self.starts_placeholder is not None and self.starts_placeholder.value is not None:
                 starts = self.starts_placeholder.tensor(self.device, torch.int32).contiguous()
-            batch = self.actual_batch if starts is not None else min(self.X.shape[0], 256)
-            return self.X, self.y, starts, batch
+            if starts is not None:
+                return self.X, self.y, starts, self.actual_batch
+            return self.X, self.y, None, self.full_dataset_batch()
         xb = self.x_placeholder.tensor(self.device, torch.float32).reshape(-1, self.n_in).contiguous()
         yb = self.y_placeholder.tensor(self.device, torch.float32).reshape(-1).contiguous()
         return xb, yb, None, xb.shape[0]

@@ -17,6 +17,7 @@ What changed underneath
 There is no CPU path: constructing a sampler without the CUDA library raises.
 """
 import abc
+import contextlib
 
 import numpy as np
 import torch
@@ -201,6 +202,25 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
     def _stream(self):
         return _native.stream_ptr(self.session.stream)
 
+    @contextlib.contextmanager
+    def _on_device(self):
+        """Everything a step does -- the cost / gradient (autograd or K4), the minibatch index
+        kernel, the update kernel, the snapshot of the sample -- runs on the session's device
+        and, when ``Session(stream=s)`` names one, on THAT stream (torch ops follow the current
+        stream, the native calls get its handle), so the producers and consumers of `grad` and
+        `theta` are ordered on one stream."""
+        with torch.cuda.device(self.device):
+            stream = self.session.stream
+            if stream is not None:
+                if not getattr(self, "_stream_joined", False):
+                    # the constructor(s) filled the state on the stream that was current then
+                    stream.wait_stream(torch.cuda.current_stream(self.device))
+                    self._stream_joined = True
+                with torch.cuda.stream(stream):
+                    yield
+            else:
+                yield
+
     # ------------------------------------------------------------------ outputs
     def _output_params(self):
         if self.session.output == "numpy":
@@ -236,8 +256,8 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         Returns the cost at the pre-update point (base_classes.py:298-300)."""
         feed(feed_dict)
         epsilon = float(self.epsilon.value)
-        z = self._noise_tensor()
-        with torch.cuda.device(self.device):
+        with self._on_device():
+            z = self._noise_tensor()
             if self._native_target is not None:
                 cost = self._launch_fused_target(z, epsilon, **kwargs)
             else:
@@ -255,10 +275,11 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         if feed_dict is None:
             feed_dict = dict()
 
-        feed_dict.update(self._next_batch())
-        feed_dict.update(self._next_stepsize())
-        cost = self._advance(feed_dict)
-        params, cost = self._output_params(), self._output_cost(cost)
+        with self._on_device():
+            feed_dict.update(self._next_batch())
+            feed_dict.update(self._next_stepsize())
+            cost = self._advance(feed_dict)
+            params, cost = self._output_params(), self._output_cost(cost)
 
         if len(params) == 1:
             # unravel single-element lists to scalars (base_classes.py:302-304)
@@ -318,6 +339,10 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         kernels on the device.
         """
         assert n_steps >= 0 and keep_every >= 1
+        with self._on_device():
+            return self._run(n_steps, keep_every)
+
+    def _run(self, n_steps, keep_every):
         n_keep = n_steps // keep_every
         C, D = self.n_chains, self.n_params_per_chain
         trace = torch.empty((n_keep, C, D), dtype=self.dtype, device=self.device)
@@ -325,8 +350,7 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         if n_steps == 0:
             return trace, costs
         if self._can_run_fused():
-            with torch.cuda.device(self.device):
-                self._launch_fused_run(n_steps, keep_every, trace, costs)
+            self._launch_fused_run(n_steps, keep_every, trace, costs)
             return trace, costs
         for s in range(n_steps):
             cost = self._step_on_device()
@@ -402,11 +426,12 @@ class BurnInMCMCSampler(MCMCSampler, metaclass=abc.ABCMeta):
             feed_dict = dict()
 
         if self.is_burning_in:
-            feed_dict.update(self._next_batch())
-            feed_dict.update(self._next_stepsize())
+            with self._on_device():
+                feed_dict.update(self._next_batch())
+                feed_dict.update(self._next_stepsize())
 
-            cost = self._advance(feed_dict, adapt=True)
-            params, cost = self._output_params(), self._output_cost(cost)
+                cost = self._advance(feed_dict, adapt=True)
+                params, cost = self._output_params(), self._output_cost(cost)
 
             self.stepsize_schedule.update(params, cost)
 

@@ -106,7 +106,9 @@ class SGHMCSampler(BurnInMCMCSampler):
         """K5 (csrc/bnn.cu: sgmcmc_bnn_sghmc_run_f32) in chunks of whole thinning periods, with
         the on-device minibatch indices (K7) of chunk i+1 generated concurrently with chunk i."""
         cf, gen = self.cost_fun, self.batch_generator
-        batch = cf.actual_batch if gen is not None else min(cf.X.shape[0], 256)
+        # no index generator: every step evaluates the whole resident dataset (what the
+        # per-step path and the differentiable cost do); raises when it is too large
+        batch = cf.actual_batch if gen is not None else cf.full_dataset_batch()
         if self._grad is None:
             self._grad = torch.empty_like(self._theta)
         cost_scratch = torch.empty(self.n_chains, dtype=self.dtype, device=self.device)
@@ -159,69 +161,84 @@ class SGHMCSampler(BurnInMCMCSampler):
         travels, so the result is the same as the synchronous loop, bit for bit.  The pipeline
         itself is native (csrc/host_pipeline.cu: two ctypes calls per step).
 
-        The yielded arrays are views of pinned buffers that are re-used `lookahead + 1`
-        (cost) / one (sample) yields later: copy what must be kept.
+        The yielded arrays are views of pinned buffers: a cost row is re-used `lookahead + 1`
+        yields later, a sample buffer only after the NEXT sample was yielded (every sample that
+        can be in flight while the caller still holds one has its own pinned slot) -- copy what
+        must be kept longer.
         """
         assert self._bnn_run_ok() and self._native_target is None, "iter_host needs the native BNN cost"
         assert host_starts.dtype == torch.int32 and host_starts.dim() == 2 and host_starts.shape[1] == self.n_chains
         assert host_starts.is_pinned() and host_starts.is_contiguous(), "host_starts must be pinned host memory"
         assert 0 <= lookahead < 64
-        cf, C, D, dev = self.cost_fun, self.n_chains, self.n_params_per_chain, self.device
+        assert sample_every is None or sample_every >= 1
+        cf, C, D = self.cost_fun, self.n_chains, self.n_params_per_chain
         n_steps, depth = host_starts.shape[0], lookahead + 1
         if self._grad is None:
-            self._grad = torch.empty_like(self._theta)
-        handle, h_cost, h_sample = self._host_pipeline(depth, bool(sample_every))
+            with self._on_device():
+                self._grad = torch.empty_like(self._theta)
+        # samples that can be queued before the caller lets go of the one it was handed: the
+        # caller holds sample k (step s_k) until it asks for step s_k + 1, by which time steps up
+        # to s_k + depth are enqueued; slot k is re-used by sample k + n_slots, at step
+        # s_k + n_slots * sample_every >= s_k + depth + sample_every
+        n_slots = min(depth + 1, depth // sample_every + 2) if sample_every else 0
+        handle, h_cost, h_sample = self._host_pipeline(depth, n_slots)
         epsilon = float(next(self.stepsize_schedule))
         arrays = [_native.ptr(a) for a in self._arrays()]
         X, y, grad = _native.ptr(cf.X), _native.ptr(cf.y), _native.ptr(self._grad)
         starts0, row_bytes = host_starts.data_ptr(), C * 4
         cost0 = h_cost.data_ptr()
-        sample_ptr = h_sample.data_ptr() if sample_every else None
-        stream = self._stream()
+        sample0, sample_bytes = (h_sample.data_ptr(), C * D * 4) if sample_every else (None, 0)
         ticket = ctypes.c_int64()
-        wants_sample = [False] * depth
+        sample_slot = [-1] * depth
         first = None
 
         def enqueue(s):
             nonlocal first
             b = s % depth
-            wants_sample[b] = bool(sample_every) and (s + 1) % sample_every == 0
-            _native.call("sgmcmc_bnn_host_pipeline_step", handle, *arrays, X, y, starts0 + s * row_bytes,
-                         cost0 + b * row_bytes, sample_ptr if wants_sample[b] else None, grad, cf.n_in,
-                         cf.actual_batch, float(cf.batch_size), cf.n_examples,
-                         min(2, max(0, self.burn_in_steps - self.n_iterations)),
-                         int(self.burn_in_steps == 0), epsilon, self.mdecay, self.scale_grad,
-                         self._noise_seed, self.n_iterations, self.session.chain_offset, stream,
-                         ctypes.byref(ticket))
+            wants = bool(sample_every) and (s + 1) % sample_every == 0
+            # samples are numbered over the life of the sampler, so a second iter_host() call
+            # does not start on the slot the caller may still be reading
+            sample_slot[b] = (self._host_samples % n_slots) if wants else -1
+            self._host_samples += int(wants)
+            with self._on_device():          # per call, not across yields: the caller's device stays its own
+                _native.call("sgmcmc_bnn_host_pipeline_step", handle, *arrays, X, y, starts0 + s * row_bytes,
+                             cost0 + b * row_bytes, sample0 + sample_slot[b] * sample_bytes if wants else None,
+                             grad, cf.n_in, cf.actual_batch, float(cf.batch_size), cf.n_examples,
+                             min(2, max(0, self.burn_in_steps - self.n_iterations)),
+                             int(self.burn_in_steps == 0), epsilon, self.mdecay, self.scale_grad,
+                             self._noise_seed, self.n_iterations, self.session.chain_offset, self._stream(),
+                             ctypes.byref(ticket))
             if first is None:
                 first = ticket.value                  # tickets count over the life of the handle
             self.n_iterations += 1
 
         queued = 0
-        with torch.cuda.device(dev):
-            for s in range(n_steps):
-                while queued < n_steps and queued <= s + lookahead:
-                    enqueue(queued)
-                    queued += 1
+        for s in range(n_steps):
+            while queued < n_steps and queued <= s + lookahead:
+                enqueue(queued)
+                queued += 1
+            with torch.cuda.device(self.device):
                 _native.call("sgmcmc_bnn_host_pipeline_wait", handle, first + s)   # step s is in host memory
-                b = s % depth
-                yield (h_sample.numpy() if wants_sample[b] else None), h_cost[b].numpy()
+            b = s % depth
+            yield (h_sample[sample_slot[b]].numpy() if sample_slot[b] >= 0 else None), h_cost[b].numpy()
 
-    def _host_pipeline(self, depth, with_samples):
+    _host_samples = 0
+
+    def _host_pipeline(self, depth, n_sample_slots):
         """The native stepper of `iter_host` and its pinned result buffers, kept between calls
         (pinning [C, D] floats costs tens of milliseconds)."""
         cached = getattr(self, "_host_pipe", None)
-        if cached is not None and cached[0] == (depth, with_samples):
+        if cached is not None and cached[0] == (depth, n_sample_slots):
             return cached[1:]
         self.close_host_pipeline()
         C, D = self.n_chains, self.n_params_per_chain
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _native.call("sgmcmc_bnn_host_pipeline_create", ctypes.byref(handle), C, self.cost_fun.n_in, depth,
-                         int(with_samples))
+                         int(n_sample_slots > 0))
         h_cost = torch.empty((depth, C), dtype=self.dtype).pin_memory()
-        h_sample = torch.empty((C, D), dtype=self.dtype).pin_memory() if with_samples else None
-        self._host_pipe = ((depth, with_samples), handle, h_cost, h_sample)
+        h_sample = torch.empty((n_sample_slots, C, D), dtype=self.dtype).pin_memory() if n_sample_slots else None
+        self._host_pipe = ((depth, n_sample_slots), handle, h_cost, h_sample)
         return handle, h_cost, h_sample
 
     def close_host_pipeline(self):

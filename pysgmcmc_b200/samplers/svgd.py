@@ -145,7 +145,7 @@ class SVGDSampler(MCMCSampler):
         (svgd.py:150-182): returns ``(kernel_matrix [n, n], kernel_gradients [n, D])``."""
         assert particles is None or particles is self.particles, \
             "the kernel is evaluated on the sampler's own particles"
-        with torch.cuda.device(self.device):
+        with self._on_device():
             self._launch_kernel_matrix()
             K, X = self._kernel_matrix.clone(), self.particles
             kernel_gradients = (-(K @ X) + X * self._kernel_sum[:, None]) / self._bandwidth[2]
@@ -174,13 +174,16 @@ class SVGDSampler(MCMCSampler):
         """`n_steps` updates without returning to the host; every `keep_every`-th particle
         set and cost vector: ``(trace [n_keep, n_particles, D], costs [n_keep, n_particles])``."""
         assert n_steps >= 0 and keep_every >= 1
+        with self._on_device():
+            return self._run(n_steps, keep_every)
+
+    def _run(self, n_steps, keep_every):
         n_keep = n_steps // keep_every
         trace = torch.empty((n_keep, self.n_particles, self.n_dims), dtype=self.dtype, device=self.device)
         costs = torch.empty((n_keep, self.n_particles), dtype=self.dtype, device=self.device)
         if n_steps > 0 and self._can_run_fused():
-            with torch.cuda.device(self.device):
-                self._target_run(n_steps, keep_every, trace if n_keep else None, costs if n_keep else None,
-                                 float(next(self.stepsize_schedule)))
+            self._target_run(n_steps, keep_every, trace if n_keep else None, costs if n_keep else None,
+                             float(next(self.stepsize_schedule)))
             self.n_iterations += n_steps
             return trace, costs
         for s in range(n_steps):

@@ -5,7 +5,10 @@ Tolerances: K4 accumulates 50-term dot products with FMA in fp32 and evaluates t
 SFU (|error| ~ 2e-7 per activation), the oracle is float64.  Cost: rtol 2e-6.  Gradient:
 |g - g_ref| <= 2e-5 * max|g_ref| per chain (element-wise rtol is meaningless for the many
 entries that are ~1e-8 of the largest one).  Trajectories (injected noise, scale_grad = N as
-BayesianNeuralNetwork.train sets it): 1e-5 relative to max|theta| after 200 steps.
+BayesianNeuralNetwork.train sets it): 1e-5 relative to max|theta| after 200 steps (N = 2000)
+and after 500 steps at the benchmarked shapes (N = 20 000), 3e-5 after 1000 -- float32 itself
+separates the float32 and float64 oracles by 1.4e-5 there; the update alone is bit-exact
+(teacher-forced test).
 """
 import os
 
@@ -209,11 +212,98 @@ def test_bnn_sghmc_sampler_trajectory_matches_oracle():
     got = sampler._theta.cpu().numpy()
     scale = np.abs(want_theta).max()
     assert np.abs(got - want_theta).max() <= 1e-5 * scale
-    # minv = v_hat^-1/2 of a running mean of grad^2: entries whose gradient is ~1e-3 of the
-    # largest carry the gradient's absolute error as a percent-level relative error
-    minv_rel = np.abs(sampler._state_array("minv").cpu().numpy() / chain.minv - 1.0)
-    assert np.median(minv_rel) < 1e-5 and minv_rel.max() < 5e-2
+    # the frozen mass matrix: compared like the parameters, against the scale of the array (its
+    # entries are v_hat^-1/2 of a running mean of grad^2; update error and gradient error are
+    # separated in the teacher-forced test below)
+    minv = sampler._state_array("minv").cpu().numpy()
+    assert np.abs(minv - chain.minv).max() <= 1e-4 * np.abs(chain.minv).max()
+    assert np.median(np.abs(minv / chain.minv - 1.0)) < 1e-5
     assert not sampler.is_burning_in
+
+
+@pytest.mark.parametrize("variant", [10, 0])
+def test_bnn_sghmc_teacher_forced_update_bit_exact_gradient_error_bounded(variant):
+    """Separates the two error sources of a BNN-SGHMC trajectory.  Every step the oracle update
+    (sghmc.py:165-251) is fed the GPU's OWN gradient and the GPU's state before the step: the
+    state after K1 -- theta, V, tau, g, v_hat and the inverse mass matrix -- must then be
+    bit-identical (update error = 0, across the burn-in boundary); and the GPU's gradient is
+    compared with the float64 oracle gradient at the same point (gradient error
+    <= 2e-5 max|g| per chain)."""
+    C, N, batch, steps, burn = 6, 20000, 20, 150, 100
+    X, y = sinc_data(N)
+    theta0 = obnn.init_theta(C, seed=11, dtype=np.float32)
+    seeds = np.arange(C) + 40
+    _native.call("sgmcmc_set_bnn_tuning", variant)
+    try:
+        gen = DeviceBatchGenerator(N, batch, seeds=seeds, device=DEV, block=64)
+        nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+        params, off = [], 0
+        for shp in parameter_shapes(1):
+            n = int(np.prod(shp))
+            params.append(torch.tensor(theta0[:, off:off + n].reshape((C,) + shp), device=DEV))
+            off += n
+        sampler = SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen, burn_in_steps=burn,
+                               scale_grad=float(N), stepsize_schedule=ConstantStepsizeSchedule(0.01),
+                               session=Session(device=DEV, n_chains=C, output="torch"))
+        streams = [omt.MT19937(int(s)) for s in seeds]
+        zr = np.random.RandomState(9)
+        names = ("v", "tau", "g", "v_hat", "minv")
+        frozen = None
+        worst_grad = 0.0
+        for s in range(steps):
+            before = {"theta": sampler._theta.cpu().numpy()}
+            before.update({n: sampler._state_array(n).cpu().numpy() for n in names})
+            starts = np.array([st.bounded(N - batch) for st in streams])
+            z = zr.standard_normal((C, 5252)).astype(np.float32)
+            sampler.__next__(feed_dict={sampler.noise: z})
+            g_gpu = sampler._grad.cpu().numpy()
+            # gradient error at the GPU's own point
+            Xb, yb = obnn.gather_minibatch(X, y, starts, batch)
+            _, g64, _ = obnn.nll_and_grad(before["theta"].astype(np.float64), Xb, yb, n_examples=N)
+            worst_grad = max(worst_grad, float((np.abs(g_gpu - g64) / np.abs(g64).max(axis=1, keepdims=True)).max()))
+            # update error: the oracle step on the GPU's state and gradient
+            adapt = s < burn
+            want = osamplers.sghmc_step(before, g_gpu, z, 0.01, mdecay=0.05, scale_grad=float(N), burn_in=adapt,
+                                        frozen_minv=frozen)
+            if adapt:
+                frozen = want["minv"]
+            got = {"theta": sampler._theta.cpu().numpy()}
+            got.update({n: sampler._state_array(n).cpu().numpy() for n in names})
+            check = ("theta", "v", "tau", "g", "v_hat") if adapt else ("theta", "v")
+            for n in check:
+                assert np.array_equal(got[n], want[n]), "%s differs at step %d" % (n, s)
+            if s == burn - 1:          # the mass matrix the sampling phase uses (base_classes.py:438,448-454)
+                assert np.array_equal(got["minv"], want["minv"]), "frozen minv"
+        assert np.array_equal(sampler._state_array("minv").cpu().numpy(), frozen)
+        assert worst_grad <= 2e-5, "max |dg| / max|g| over the run = %.3g" % worst_grad
+    finally:
+        _native.call("sgmcmc_set_bnn_tuning", 10)
+
+
+# float32 arithmetic alone separates the float32 and float64 ORACLES by ~1.4e-5 of max|theta|
+# after 1000 steps at these shapes (2.8e-6 at the end of burn-in, step 600; measured with
+# tools/bnn_trajectory_drift.py, recorded in profiles/r02_bnn_trajectory_drift.jsonl), so the
+# north star's 1e-5 is asserted where float32 itself can hold it and the end of the run is
+# bounded by twice the oracles' own separation.
+TRAJ_TOL_500, TRAJ_TOL_1000 = 1e-5, 3e-5
+
+
+@pytest.mark.parametrize("variant", [10, 0])
+def test_bnn_sghmc_1000_step_trajectory_at_the_benchmarked_shapes(variant):
+    """1000 steps of next(sampler) at BASELINE.json configs[2] shapes -- N = 20 000, minibatch 20,
+    scale_grad = N, eps = 0.01, burn-in boundary at step 600, injected noise, bit-exact
+    minibatch streams -- for both K4 implementations, against the float32 oracle
+    (sghmc.py:165-251 over bayesian_neural_network.py:337-388)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from bnn_trajectory_drift import drift_curves
+    line, = drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(variant,))
+    vs32 = dict(zip(line["checkpoints"], line["gpu_vs_oracle_f32"]))
+    assert all(np.isfinite(v) for v in vs32.values())
+    assert max(vs32[k] for k in vs32 if k <= 500) <= TRAJ_TOL_500, line
+    assert vs32[1000] <= TRAJ_TOL_1000, line
+    # never (much) further from the float64 oracle than the float32 oracle itself is
+    assert line["gpu_vs_oracle_f64"][-1] <= 2.0 * line["oracle_f32_vs_f64"][-1] + 1e-5, line
 
 
 def test_bnn_sghmc_run_equals_per_step_and_oracle():
@@ -276,12 +366,14 @@ def test_bnn_sghmc_chunked_run_with_side_stream_indices(keep_every, run_chunk, m
     assert torch.equal(a._theta, b._theta)
 
 
-@pytest.mark.parametrize("lookahead", [0, 1, 3])
-def test_iter_host_pipelined_equals_synchronous_steps(lookahead):
+@pytest.mark.parametrize("lookahead,every", [(0, 8), (1, 8), (3, 8), (3, 1), (4, 2), (8, 3)])
+def test_iter_host_pipelined_equals_synchronous_steps(lookahead, every):
     """sampler.iter_host (host minibatch indices in, cost and thinned samples out, copies and
     the next step overlapped) == the same steps through next(sampler) with the indices fed one
-    row at a time; crosses the burn-in boundary."""
-    C, N, batch, steps, burn, every = 6, 2000, 20, 40, 17, 8
+    row at a time; crosses the burn-in boundary.  sample_every <= lookahead: several samples are
+    in flight while the caller still holds one (each has its own pinned slot); the yielded
+    sample is compared BEFORE the next one is requested, without copying it first."""
+    C, N, batch, steps, burn = 6, 2000, 20, 40, 17
     X, y = sinc_data(N)
     rng = np.random.RandomState(3)
     host_starts = torch.from_numpy(rng.randint(0, N - batch + 1, size=(steps, C)).astype(np.int32)).pin_memory()
@@ -295,20 +387,98 @@ def test_iter_host_pipelined_equals_synchronous_steps(lookahead):
         return s, ph
     a, _ = build()
     b, ph = build()
-    got = [(None if smp is None else smp.copy(), cost.copy())
-           for smp, cost in a.iter_host(host_starts, sample_every=every, lookahead=lookahead)]
-    assert len(got) == steps and a.n_iterations == steps
-    for s in range(steps):
+    import time
+    n_got = 0
+    for s, (smp, cost) in enumerate(a.iter_host(host_starts, sample_every=every, lookahead=lookahead)):
         ph.value = host_starts[s].to(DEV)     # (a feed_dict would be dropped after burn-in, :454)
-        sample, cost = next(b)
-        assert np.array_equal(got[s][1], cost.cpu().numpy()), "cost at step %d" % s
+        sample, want_cost = next(b)
+        want_theta = b._theta.cpu().numpy()
+        time.sleep(0.002)                     # let the queued steps (and their copies) run ahead
+        assert np.array_equal(cost, want_cost.cpu().numpy()), "cost at step %d" % s
         if (s + 1) % every == 0:
-            assert np.array_equal(got[s][0], b._theta.cpu().numpy()), "sample at step %d" % s
+            assert np.array_equal(smp, want_theta), "sample at step %d" % s
         else:
-            assert got[s][0] is None
+            assert smp is None
+        n_got += 1
+    assert n_got == steps and a.n_iterations == steps
     for name in ("v", "tau", "g", "v_hat", "minv"):
         assert torch.equal(a._state_array(name), b._state_array(name)), name
     assert torch.equal(a._theta, b._theta) and not a.is_burning_in
+
+
+def test_session_stream_orders_cost_gradient_and_update():
+    """Session(stream=s): the cost / gradient (K4 or autograd), the index kernel and the update
+    all run on s; results are bit-identical to the default stream, per step and through run()."""
+    C, N, batch, steps = 5, 2000, 20, 24
+    X, y = sinc_data(N)
+
+    def build(stream, cls=SGHMCSampler):
+        with torch.cuda.stream(stream) if stream is not None else torch.cuda.device(DEV):
+            gen = DeviceBatchGenerator(N, batch, n_chains=C, seed=5, device=DEV, block=16)
+        torch.cuda.synchronize()
+        nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+        params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+        return cls(params=params, cost_fun=nll, batch_generator=gen, burn_in_steps=10, scale_grad=float(N),
+                   seed=4, session=Session(device=DEV, n_chains=C, output="torch", stream=stream))
+    side = torch.cuda.Stream(device=DEV)
+    for cls in (SGHMCSampler, SGLDSampler):
+        a, b = build(None, cls), build(side, cls)
+        for _ in range(steps // 2):
+            ca, cb = next(a)[1], next(b)[1]
+        side.synchronize()
+        assert torch.equal(ca, cb)
+        a.run(steps // 2, keep_every=4)
+        tb, _ = b.run(steps // 2, keep_every=4)
+        side.synchronize()
+        torch.cuda.synchronize()
+        assert torch.equal(a._theta, b._theta) and torch.equal(tb[-1], b._theta), cls.__name__
+
+
+def test_next_then_run_drains_the_pending_index_block():
+    """next(sampler) leaves a partially consumed block of minibatch indices in the generator;
+    a following run() continues with those rows (same stream of indices as stepping on)."""
+    C, N, batch = 4, 2000, 20
+    X, y = sinc_data(N)
+
+    def build():
+        gen = DeviceBatchGenerator(N, batch, n_chains=C, seed=5, device=DEV, block=16)
+        nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+        params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+        return SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen, burn_in_steps=10,
+                            scale_grad=float(N), seed=4, session=Session(device=DEV, n_chains=C, output="torch"))
+    a, b = build(), build()
+    for _ in range(5):
+        next(a)
+    a.run(30, keep_every=10)                   # 11 pending rows, then new blocks
+    next(a)
+    state = a.state_dict()
+    a.run(7)
+    for _ in range(43):
+        next(b)
+    assert torch.equal(a._theta, b._theta)
+    c = build()
+    c.load_state_dict(state)                   # resume with pending rows, then run()
+    c.run(7)
+    assert torch.equal(c._theta, b._theta)
+
+
+def test_resident_dataset_without_minibatch_indices():
+    """No start indices fed: a small resident dataset is evaluated as a whole by the native cost
+    (same value as the differentiable path), a large one raises instead of silently using its
+    first rows."""
+    C = 3
+    for N, ok in ((120, True), (2000, False)):
+        X, y = sinc_data(N)
+        nll = BayesianNeuralNetworkNLL(N, 20, X=X, y=y, device=DEV)
+        params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+        theta = torch.cat([p.reshape(C, -1) for p in params], dim=1).contiguous()
+        grad = torch.empty_like(theta)
+        if ok:
+            cost = nll.native_cost_and_grad(theta, grad)
+            np.testing.assert_allclose(cost.cpu().numpy(), nll(params).cpu().numpy(), rtol=2e-5)
+        else:
+            with pytest.raises(ValueError, match="start indices"):
+                nll.native_cost_and_grad(theta, grad)
 
 
 def test_reference_style_host_batches_single_chain():

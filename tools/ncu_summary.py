@@ -2,6 +2,11 @@
     python tools/ncu_summary.py launches <launches.csv>      -> per-kernel time share
     python tools/ncu_summary.py rep <file.ncu-rep> [regex]   -> key metrics per captured launch
     python tools/ncu_summary.py source <file.ncu-rep> [topN] -> hottest source lines (stall samples)
+    python tools/ncu_summary.py opcodes <file.ncu-rep> [topN] -> dynamic instruction mix
+    python tools/ncu_summary.py traffic <k4.ncu-rep> <k1.ncu-rep> [note]
+        -> rewrites profiles/ncu_traffic.json (dram bytes per launch of K4 / K1 from `ncu --set full`
+           captures at the headline shape), stamped with the commit and a hash of the kernel sources
+           so that bench.py drops the figure when those sources change
 """
 import collections
 import csv
@@ -130,3 +135,47 @@ def opcodes(path, top=25):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "opcodes":
     opcodes(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 25)
+
+
+def traffic(k4_rep, k1_rep, note=""):
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    def dram_bytes(path, flt):
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units = rows[0], rows[1]
+        vals = []
+        for r in rows[2:]:
+            if not re.search(flt, r[hdr.index("Kernel Name")]):
+                continue
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = float(r[hdr.index(k)].replace(",", "")), units[hdr.index(k)].lower()
+                tot += v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+            vals.append(tot)
+        return sum(vals) / len(vals)
+    path = os.path.join(root, "profiles", "ncu_traffic.json")
+    try:
+        t = json.load(open(path))
+    except Exception:
+        t = {}
+    t["k4_bytes_per_launch"] = int(dram_bytes(k4_rep, "bnn_"))
+    t["k1_burn_in_bytes_per_launch"] = int(dram_bytes(k1_rep, "sghmc_update"))
+    t["k1_burn_in_algorithmic_bytes"] = 44 * 8192 * 5252
+    t["k4_algorithmic_bytes"] = 8 * 8192 * 5252
+    t["source"] = ("ncu --set full --clock-control none, 8192 chains x D=5252 (%s, %s): dram__bytes_read.sum + "
+                   "dram__bytes_write.sum per launch%s" % (os.path.basename(k4_rep), os.path.basename(k1_rep),
+                                                          "; " + note if note else ""))
+    t["commit"] = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True,
+                                 text=True).stdout.strip()
+    t["source_hash"] = {k: bench.source_hash(v) for k, v in bench.KERNEL_SOURCES.items()}
+    json.dump(t, open(path, "w"), indent=1)
+    print(json.dumps(t, indent=1))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "traffic":
+    traffic(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
