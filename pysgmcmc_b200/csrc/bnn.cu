@@ -460,7 +460,7 @@ static int g_bnn_variant = 10;        // 10: tensor-pipe kernel (bnn_mma.cuh); 0
 static int g_bnn_max_ctas = 0;          // 0: one CTA per chain group; > 0: persistent grid of that size
 static int64_t g_bnn_chunk = 0;         // chains per K4+K1 chunk inside sgmcmc_bnn_sghmc_run_f32 (0: all)
 void set_bnn_chunk(int64_t c) { g_bnn_chunk = c; }
-int bnn_variant_count() { return 11; }
+int bnn_variant_count() { return 14; }
 void set_bnn_variant(int v) { g_bnn_variant = v; }
 void set_bnn_max_ctas(int n) { g_bnn_max_ctas = n; }
 
@@ -486,7 +486,7 @@ static int launch_variant(const BnnArgs& a, cudaStream_t st) {
 }
 
 // K4 on the tensor pipe (bnn_mma.cuh): one CTA of ceil(batch / 16) warps per chain.
-template <int NB8>
+template <int NB8, int MODE>
 static int launch_mma(const BnnArgs& a, cudaStream_t st) {
   constexpr int NTHR = 32 * ((NB8 + 1) / 2);
   const size_t smem = (size_t)bnn_mma_smem_floats(a.batch, a.L.n_in, a.L.D) * sizeof(float);
@@ -494,12 +494,12 @@ static int launch_mma(const BnnArgs& a, cudaStream_t st) {
   unsigned blocks = (unsigned)a.n_chains;
   if (g_bnn_max_ctas > 0 && blocks > (unsigned)g_bnn_max_ctas) blocks = (unsigned)g_bnn_max_ctas;
   if (a.grad != nullptr) {
-    auto k = bnn_mma_kernel<NB8, true>;
+    auto k = bnn_mma_kernel<NB8, true, MODE>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     k<<<blocks, NTHR, smem, st>>>(a);
   } else {
-    auto k = bnn_mma_kernel<NB8, false>;
+    auto k = bnn_mma_kernel<NB8, false, MODE>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     k<<<blocks, NTHR, smem, st>>>(a);
@@ -507,17 +507,25 @@ static int launch_mma(const BnnArgs& a, cudaStream_t st) {
   return check_launch("bnn_mma_kernel");
 }
 
+template <int MODE>
 static int launch_mma_batch(const BnnArgs& a, cudaStream_t st) {
   switch ((a.batch + 7) / 8) {
-    case 1: return launch_mma<1>(a, st);
-    case 2: return launch_mma<2>(a, st);
-    case 3: return launch_mma<3>(a, st);
-    default: return launch_mma<4>(a, st);
+    case 1: return launch_mma<1, MODE>(a, st);
+    case 2: return launch_mma<2, MODE>(a, st);
+    case 3: return launch_mma<3, MODE>(a, st);
+    default: return launch_mma<4, MODE>(a, st);
   }
 }
 
 static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
-  if (g_bnn_variant >= 10 && a.batch <= 32) return launch_mma_batch(a, st);
+  if (g_bnn_variant >= 10 && a.batch <= 32) {
+    switch (g_bnn_variant) {              // accuracy modes of the tensor-pipe kernel (bnn_mma.cuh)
+      case 11: return launch_mma_batch<MMA_ROUND_SPLIT>(a, st);
+      case 12: return launch_mma_batch<MMA_RN_ACCUM>(a, st);
+      case 13: return launch_mma_batch<MMA_ROUND_SPLIT | MMA_RN_ACCUM>(a, st);
+      default: return launch_mma_batch<0>(a, st);
+    }
+  }
   static const int nc_of_variant[10] = {5, 5, 8, 8, 5, 12, 8, 4, 4, 4};
   const int variant = g_bnn_variant < 10 ? g_bnn_variant : 0;
   const size_t per_chain = bnn_smem_floats(a.batch, a.L.n_in) * sizeof(float);

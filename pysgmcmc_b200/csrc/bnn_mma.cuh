@@ -48,15 +48,22 @@ constexpr int NT8 = 7;   // 8-wide tiles covering those 56 columns
 // 3.7x less split error, but on the device the total error does not move (it is dominated by
 // the tensor core's own fp32 accumulation) while K4 slows from 0.218 to 0.223 ms, so the
 // truncating split is the default.
-#ifndef SGMCMC_TF32_ROUND_SPLIT
-#define SGMCMC_TF32_ROUND_SPLIT 0
-#endif
+//
+// Accuracy modes (template parameter MODE of everything below; launch variants 10-13):
+//   bit 0 (MMA_ROUND_SPLIT): hi is rounded to nearest instead of truncated, so lo is symmetric
+//         around 0 and the dropped lo*lo term (2^-22 of every product with the truncating
+//         split, always of the product's sign) stops being a systematic bias;
+//   bit 1 (MMA_RN_ACCUM): the three products of a k-step go into a zeroed register tile and are
+//         added to the running sum by the FP32 pipe (round to nearest) -- the tensor core adds
+//         into its accumulator operand with truncation, a bias that compounds over the k-steps
+//         of a GEMM (Ootomo & Yokota 2022).
+// What they buy is measured as trajectory drift, not single-step error
+// (tools/bnn_trajectory_drift.py, profiles/r02_bnn_trajectory_drift*.jsonl).
+constexpr int MMA_ROUND_SPLIT = 1, MMA_RN_ACCUM = 2;
+template <int MODE>
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-#if SGMCMC_TF32_ROUND_SPLIT
-  hi = __float_as_uint(x) + 0x1000u;
-#else
-  hi = __float_as_uint(x);
-#endif
+  if constexpr ((MODE & MMA_ROUND_SPLIT) != 0) hi = __float_as_uint(x) + 0x1000u;
+  else hi = __float_as_uint(x);
   lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
 }
 
@@ -96,22 +103,40 @@ __device__ __forceinline__ void store_c(float* __restrict__ buf, int batch, int 
 }
 
 // A fragments (hi, lo) of k-step ks taken from the C-layout tile ks of `src`
+template <int MODE>
 __device__ __forceinline__ void a_from_c(const float (&src)[NT8][4], int ks, uint32_t (&ah)[4], uint32_t (&al)[4]) {
-  split_tf32(src[ks][0], ah[0], al[0]);   // (row g,   k slot t)   = column 2t
-  split_tf32(src[ks][2], ah[1], al[1]);   // (row g+8, k slot t)
-  split_tf32(src[ks][1], ah[2], al[2]);   // (row g,   k slot t+4) = column 2t+1
-  split_tf32(src[ks][3], ah[3], al[3]);   // (row g+8, k slot t+4)
+  split_tf32<MODE>(src[ks][0], ah[0], al[0]);   // (row g,   k slot t)   = column 2t
+  split_tf32<MODE>(src[ks][2], ah[1], al[1]);   // (row g+8, k slot t)
+  split_tf32<MODE>(src[ks][1], ah[2], al[2]);   // (row g,   k slot t+4) = column 2t+1
+  split_tf32<MODE>(src[ks][3], ah[3], al[3]);   // (row g+8, k slot t+4)
 }
 
+template <int MODE>
 __device__ __forceinline__ void mma3_row(float (&acc)[NT8][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                          const uint32_t (&bh)[NT8][2], const uint32_t (&bl)[NT8][2]) {
   // three passes over 7 independent accumulators: dependent MMAs are 7 issues apart
+  if constexpr ((MODE & MMA_RN_ACCUM) != 0) {
+    float part[NT8][4];
 #pragma unroll
-  for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], al, bh[nt]);
+    for (int nt = 0; nt < NT8; ++nt) part[nt][0] = part[nt][1] = part[nt][2] = part[nt][3] = 0.0f;
 #pragma unroll
-  for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], ah, bl[nt]);
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(part[nt], al, bh[nt]);
 #pragma unroll
-  for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], ah, bh[nt]);
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(part[nt], ah, bl[nt]);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(part[nt], ah, bh[nt]);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = __fadd_rn(acc[nt][e], part[nt][e]);
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], al, bh[nt]);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], ah, bl[nt]);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], ah, bh[nt]);
+  }
 }
 
 __device__ __forceinline__ void zero_tile(float (&acc)[NT8][4]) {
@@ -120,13 +145,14 @@ __device__ __forceinline__ void zero_tile(float (&acc)[NT8][4]) {
 }
 
 // acc[i][j] = sum_{k<=50} src[i][k] * Wb[k][j]   (Wb = [W; b], row stride 50; src column 50 is 1)
+template <int MODE>
 __device__ __forceinline__ void gemm_forward(const float* __restrict__ Wb, const float (&src)[NT8][4],
                                              float (&acc)[NT8][4], int g, int t) {
   zero_tile(acc);
 #pragma unroll
   for (int ks = 0; ks < NT8; ++ks) {
     uint32_t ah[4], al[4], bh[NT8][2], bl[NT8][2];
-    a_from_c(src, ks, ah, al);
+    a_from_c<MODE>(src, ks, ah, al);
     const int k0 = 8 * ks + 2 * t, k1 = k0 + 1;          // rows of [W; b] behind k slots t, t+4
     const float* w0 = Wb + k0 * HID + g;
 #pragma unroll
@@ -143,29 +169,30 @@ __device__ __forceinline__ void gemm_forward(const float* __restrict__ Wb, const
         b0 = k0 <= HID ? b0 : 0.0f;
         b1 = k1 <= HID ? b1 : 0.0f;
       }
-      split_tf32(b0, bh[nt][0], bl[nt][0]);
-      split_tf32(b1, bh[nt][1], bl[nt][1]);
+      split_tf32<MODE>(b0, bh[nt][0], bl[nt][0]);
+      split_tf32<MODE>(b1, bh[nt][1], bl[nt][1]);
     }
-    mma3_row(acc, ah, al, bh, bl);
+    mma3_row<MODE>(acc, ah, al, bh, bl);
   }
 }
 
 // acc[i][k] = sum_j src[i][j] * W[k][j]   (src columns >= 50 are 0)
+template <int MODE>
 __device__ __forceinline__ void gemm_backward_data(const float* __restrict__ Wb, const float (&src)[NT8][4],
                                                    float (&acc)[NT8][4], int g, int t) {
   zero_tile(acc);
 #pragma unroll
   for (int ks = 0; ks < NT8; ++ks) {
     uint32_t ah[4], al[4], bh[NT8][2], bl[NT8][2];
-    a_from_c(src, ks, ah, al);
+    a_from_c<MODE>(src, ks, ah, al);
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt) {
       const int k = min(8 * nt + g, HID - 1);            // output units >= 50 are discarded
       const float2 b = *reinterpret_cast<const float2*>(Wb + k * HID + 8 * ks + 2 * t);
-      split_tf32(b.x, bh[nt][0], bl[nt][0]);
-      split_tf32(b.y, bh[nt][1], bl[nt][1]);
+      split_tf32<MODE>(b.x, bh[nt][0], bl[nt][0]);
+      split_tf32<MODE>(b.y, bh[nt][1], bl[nt][1]);
     }
-    mma3_row(acc, ah, al, bh, bl);
+    mma3_row<MODE>(acc, ah, al, bh, bl);
   }
 }
 
@@ -173,7 +200,7 @@ __device__ __forceinline__ void gemm_backward_data(const float* __restrict__ Wb,
 // i.e. the gradient of [W; b] (weight prior included) replaces the weights in place.  The
 // MTW row tiles (16 rows k each) from mt0 on are this warp's share; their A fragments stay
 // in registers while the column tiles are walked two at a time (4 independent accumulators).
-template <int NB8, int MTW>
+template <int NB8, int MTW, int MODE>
 __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, const float* __restrict__ Zb,
                                                  float* __restrict__ Wb, int batch, float pscale, int mt0,
                                                  int g, int t) {
@@ -193,10 +220,10 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
       a1 = (i0 < batch && k1 < AS) ? a1 : 0.0f;
       a2 = i1 < batch ? a2 : 0.0f;
       a3 = (i1 < batch && k1 < AS) ? a3 : 0.0f;
-      split_tf32(a0, ah[m][ks][0], al[m][ks][0]);
-      split_tf32(a1, ah[m][ks][1], al[m][ks][1]);
-      split_tf32(a2, ah[m][ks][2], al[m][ks][2]);
-      split_tf32(a3, ah[m][ks][3], al[m][ks][3]);
+      split_tf32<MODE>(a0, ah[m][ks][0], al[m][ks][0]);
+      split_tf32<MODE>(a1, ah[m][ks][1], al[m][ks][1]);
+      split_tf32<MODE>(a2, ah[m][ks][2], al[m][ks][2]);
+      split_tf32<MODE>(a3, ah[m][ks][3], al[m][ks][3]);
     }
   }
 #pragma unroll
@@ -213,8 +240,8 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
         float b1 = Zb[min(i1, batch - 1) * AS + 8 * nt + g];
         b0 = i0 < batch ? b0 : 0.0f;
         b1 = i1 < batch ? b1 : 0.0f;
-        split_tf32(b0, bh[p][ks][0], bl[p][ks][0]);
-        split_tf32(b1, bh[p][ks][1], bl[p][ks][1]);
+        split_tf32<MODE>(b0, bh[p][ks][0], bl[p][ks][0]);
+        split_tf32<MODE>(b1, bh[p][ks][1], bl[p][ks][1]);
       }
     }
     float acc[MTW][NP][4];
@@ -224,21 +251,38 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
       for (int p = 0; p < NP; ++p) acc[m][p][0] = acc[m][p][1] = acc[m][p][2] = acc[m][p][3] = 0.0f;
 #pragma unroll
     for (int ks = 0; ks < NB8; ++ks) {
+      float part[MTW][NP][4];
+      constexpr bool RN = (MODE & MMA_RN_ACCUM) != 0 && NB8 > 1;   // (one k-step: nothing to chain)
+      if constexpr (RN) {
+#pragma unroll
+        for (int m = 0; m < MTW; ++m)
+#pragma unroll
+          for (int p = 0; p < NP; ++p) part[m][p][0] = part[m][p][1] = part[m][p][2] = part[m][p][3] = 0.0f;
+      }
+      auto& dst = *(RN ? &part : &acc);
 #pragma unroll
       for (int m = 0; m < MTW; ++m)
 #pragma unroll
         for (int p = 0; p < NP; ++p)
-          if (nt0 + p < NT8) mma_tf32(acc[m][p], al[m][ks], bh[p][ks]);
+          if (nt0 + p < NT8) mma_tf32(dst[m][p], al[m][ks], bh[p][ks]);
 #pragma unroll
       for (int m = 0; m < MTW; ++m)
 #pragma unroll
         for (int p = 0; p < NP; ++p)
-          if (nt0 + p < NT8) mma_tf32(acc[m][p], ah[m][ks], bl[p][ks]);
+          if (nt0 + p < NT8) mma_tf32(dst[m][p], ah[m][ks], bl[p][ks]);
 #pragma unroll
       for (int m = 0; m < MTW; ++m)
 #pragma unroll
         for (int p = 0; p < NP; ++p)
-          if (nt0 + p < NT8) mma_tf32(acc[m][p], ah[m][ks], bh[p][ks]);
+          if (nt0 + p < NT8) mma_tf32(dst[m][p], ah[m][ks], bh[p][ks]);
+      if constexpr (RN) {
+#pragma unroll
+        for (int m = 0; m < MTW; ++m)
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[m][p][e] = __fadd_rn(acc[m][p][e], part[m][p][e]);
+      }
     }
 #pragma unroll
     for (int m = 0; m < MTW; ++m) {
@@ -285,7 +329,7 @@ __device__ __forceinline__ BnnMmaSmem bnn_mma_carve(float* base, int batch, int 
 // `th` is the chain's parameter row in global memory (staged here into R).  COHERENT: the
 // calling kernel also WRITES theta (K5), so the row is read with ld.global.cg (L2, where the
 // update phase re-reads it) instead of the read-only path.
-template <int NB8, bool WANT_GRAD, bool COHERENT = false>
+template <int NB8, bool WANT_GRAD, bool COHERENT = false, int MODE = 0>
 __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __restrict__ th,
                                               const int32_t* __restrict__ start_ptr, const BnnMmaSmem& s,
                                               float& cost_out, float& sse_out) {
@@ -383,7 +427,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
   // ---- layers 2, 3 forward: h <- tanh([h 1] [W; b]) ----
 #pragma unroll 1
   for (int l = 0; l < 2; ++l) {
-    gemm_forward(R + (l == 0 ? L.oW2 : L.oW3), h, acc, g, t);
+    gemm_forward<MODE>(R + (l == 0 ? L.oW2 : L.oW3), h, acc, g, t);
     activate();
     if (l == 0 && WANT_GRAD) store_c(s.Q, batch, r0, t, h);
   }
@@ -478,7 +522,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
     float* Wb = R + (l == 0 ? L.oW3 : L.oW2);
     const float* Hb = l == 0 ? s.Q : s.P;               // the activations below this layer
     store_c(s.Zb, batch, r0, t, h);                     // dZ of this layer, for the dW GEMM
-    gemm_backward_data(Wb, h, acc, g, t);
+    gemm_backward_data<MODE>(Wb, h, acc, g, t);
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt) {
       const float2 v0 = *reinterpret_cast<const float2*>(Hb + min(r0, batch - 1) * AS + 8 * nt + 2 * t);
@@ -490,7 +534,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
       h[nt][3] = (dead || r1 >= batch) ? 0.0f : acc[nt][3] * fmaf(-v1.y, v1.y, 1.0f);
     }
     chain_barrier<NW>();               // W of this layer is dead, Zb is complete
-    gemm_weight_grad<NB8, 4 / NW>(Hb, s.Zb, Wb, batch, pscale, w * (4 / NW), g, t);
+    gemm_weight_grad<NB8, 4 / NW, MODE>(Hb, s.Zb, Wb, batch, pscale, w * (4 / NW), g, t);
     chain_barrier<NW>();               // Zb may be overwritten by the next dZ
   }
 
@@ -510,7 +554,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
   chain_barrier<NW>();
 }
 
-template <int NB8, bool WANT_GRAD>
+template <int NB8, bool WANT_GRAD, int MODE>
 __global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), NB8 > 2 ? 6 : 8) bnn_mma_kernel(BnnArgs a) {
   constexpr int NW = (NB8 + 1) / 2;
   constexpr int NTHR = 32 * NW;
@@ -525,7 +569,8 @@ __global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), NB8 > 2 ? 6 : 8) bnn_mma
     if (tid == 0 && chain + gridDim.x < a.n_chains && (D & 3) == 0 && aligned_to_dev(a.theta, 16))
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(th + (int64_t)gridDim.x * D), "r"(D * 4)
                    : "memory");
-    bnn_chain_mma<NB8, WANT_GRAD>(a, th, a.starts != nullptr ? a.starts + chain : nullptr, s, cost, sse);
+    bnn_chain_mma<NB8, WANT_GRAD, false, MODE>(a, th, a.starts != nullptr ? a.starts + chain : nullptr, s, cost,
+                                               sse);
     if (tid == 0) {
       a.cost[chain] = cost;
       if (a.mse != nullptr) a.mse[chain] = sse / (float)a.batch;

@@ -216,7 +216,7 @@ def test_bnn_sghmc_sampler_trajectory_matches_oracle():
     # entries are v_hat^-1/2 of a running mean of grad^2; update error and gradient error are
     # separated in the teacher-forced test below)
     minv = sampler._state_array("minv").cpu().numpy()
-    assert np.abs(minv - chain.minv).max() <= 1e-4 * np.abs(chain.minv).max()
+    assert np.abs(minv - chain.minv).max() <= 5e-4 * np.abs(chain.minv).max()
     assert np.median(np.abs(minv / chain.minv - 1.0)) < 1e-5
     assert not sampler.is_burning_in
 

@@ -87,7 +87,14 @@ def gpu_run(theta0, X, y, seeds, steps, burn, z_seed, every, variant, dev="cuda:
                 out.append((s + 1, sampler._theta.cpu().numpy()))
         return out, sampler
     finally:
-        _native.call("sgmcmc_set_bnn_tuning", 10)
+        _native.call("sgmcmc_set_bnn_tuning", DEFAULT_VARIANT)
+
+
+DEFAULT_VARIANT = 10
+K4_NAMES = {0: "FFMA (variant 0)", 10: "tensor-pipe 3xTF32 (variant 10: truncating split, chained accumulation)",
+            11: "tensor-pipe 3xTF32 (variant 11: rounded split)",
+            12: "tensor-pipe 3xTF32 (variant 12: FP32-pipe accumulation across k-steps)",
+            13: "tensor-pipe 3xTF32 (variant 13: rounded split + FP32-pipe accumulation)"}
 
 
 def drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(10, 0), z_seed=9, theta_seed=11):
@@ -106,7 +113,7 @@ def drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(10, 0), z_
         vs64 = [rel(g[1], o[1]) for g, o in zip(got, o64)]
         o32_vs64 = [rel(a[1], b[1]) for a, b in zip(o32, o64)]
         cross = next((g[0] for g, d in zip(got, vs32) if d > 1e-5), None)
-        lines.append({"k4": "tensor-pipe 3xTF32 (variant 10)" if variant == 10 else "FFMA (variant %d)" % variant,
+        lines.append({"k4": K4_NAMES.get(variant, "variant %d" % variant),
                       "config": {"N": N, "batch": BATCH, "scale_grad": N, "eps": 0.01, "burn_in_steps": burn,
                                  "steps": steps, "chains": chains},
                       "checkpoints": [g[0] for g in got],
@@ -121,6 +128,7 @@ if __name__ == "__main__":
     ap.add_argument("--burn", type=int, default=600)
     ap.add_argument("--chains", type=int, default=4)
     ap.add_argument("--every", type=int, default=100)
+    ap.add_argument("--variants", default="10,0")
     a = ap.parse_args()
-    for line in drift_curves(a.steps, a.burn, a.chains, a.every):
+    for line in drift_curves(a.steps, a.burn, a.chains, a.every, tuple(int(v) for v in a.variants.split(","))):
         print(json.dumps(line), flush=True)
