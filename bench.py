@@ -486,15 +486,19 @@ def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_o
     (sgmcmc_bnn_sghmc_run_f32) and the per-chain cost is copied back to pinned host memory,
     where the host receives it (what `sample, cost = next(sampler)` means); every
     `sample_every`-th step the whole sample [C, D] is copied back as well and READ by the host.
-    Default thinning: BayesianNeuralNetwork's sample_steps = 100, shortened to the number of timed
-    steps when fewer are timed, so that at least one whole sample crosses PCIe inside every timed
-    region.  sample_every = 1 is the reference's literal `next()` (every step returns host
+    Default thinning: BayesianNeuralNetwork's sample_steps = 100, and at least 100 steps are timed
+    (whatever --steps says), so that at least one whole sample crosses PCIe inside every timed
+    region -- at the rate the reference's model produces them, tail of the last copy included.  sample_every = 1 is the reference's literal `next()` (every step returns host
     parameters, base_classes.py:298-304): PCIe-bound, reported as `e2e_every_sample`.  The
     iterator keeps up to `lookahead` steps queued ahead and runs the copies on their own streams,
     so the device does not idle while the host handles a result or a sample crosses PCIe."""
-    K_e = min(K, 300)
     if sample_every is None:
-        sample_every = min(SAMPLE_STEPS, K_e)
+        # at least one whole thinning period of the reference (sample_steps = 100), so that exactly
+        # what BayesianNeuralNetwork.train moves per period crosses PCIe inside the timed region
+        # even when the driver asks for fewer steps
+        K_e, sample_every = min(max(K, SAMPLE_STEPS), 300), SAMPLE_STEPS
+    else:
+        K_e = min(K, 300)
     rng = np.random.RandomState(7)
     host_starts = torch.from_numpy(
         rng.randint(0, N_EXAMPLES - BATCH + 1, size=(W + K_e, C)).astype(np.int32)).pin_memory()

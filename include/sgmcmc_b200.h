@@ -53,10 +53,12 @@ const char* sgmcmc_last_error(void);
  * Measured on B200 (profiles/): 256 x 1 is fastest; more groups per thread cost occupancy. */
 int sgmcmc_set_update_tuning(int threads, int unroll);
 
-/* Implementation of the BNN kernel K4: 10 (the default) is the tensor-pipe kernel
- * (3xTF32 mma.sync, csrc/bnn_mma.cuh; minibatches of up to 32 rows, larger ones fall back to
- * 0); 0-9 are launch shapes of the FFMA kernel (units per thread, chains per CTA, rows in
- * flight) kept for the sweeps recorded under profiles/. */
+/* Implementation of the BNN kernel K4: 10-13 are the tensor-pipe kernel (3xTF32 mma.sync,
+ * csrc/bnn_mma.cuh; minibatches of up to 32 rows, larger ones fall back to 0) in its accuracy
+ * modes (10: truncating hi/lo split, sums chained through the tensor core's accumulator;
+ * 11: rounded split; 12: FP32-pipe accumulation across k-steps; 13: both); 0-9 are launch
+ * shapes of the FFMA kernel (units per thread, chains per CTA, rows in flight) kept for the
+ * sweeps recorded under profiles/. */
 int sgmcmc_set_bnn_tuning(int variant);
 
 /* K1 walks its arrays from the end (the first CTAs take the last elements): after K4, which
@@ -185,6 +187,27 @@ int sgmcmc_bnn_nll_grad_f32(const float* theta, const float* X, const float* y,
                             const int32_t* starts, float* cost, float* grad, float* mse,
                             int64_t n_chains, int n_in, int batch, float batch_size_cfg,
                             int64_t n_examples, void* stream);
+
+/* ---- K4 / K10 for any fully connected `get_net`: n_in -> h_1 -> ... -> h_L -> 1 with tanh
+ * hidden layers, a linear head and the learned log variance -- the architecture family of
+ * get_default_net (bayesian_neural_network.py:28-69) with user-chosen widths and depth, e.g. the
+ * 1000-512-512 network of BASELINE.json configs[4].  widths = {n_in, h_1, ..., h_L, 1}
+ * (n_widths = L + 2, 1 <= L <= 7).  Flat per-chain layout W_1 b_1 ... W_{L+1} b_{L+1} rho
+ * (sgmcmc_mlp_n_params values; kernels [in, out] row-major).  Cost, priors and gradient as
+ * sgmcmc_bnn_nll_grad_f32 (:77-141, :337-388); minibatches of up to 32 rows.  `workspace`
+ * (device, 16-byte aligned, sgmcmc_mlp_workspace_bytes(widths, n_widths, n_chains, batch) bytes)
+ * holds the activations between the layer kernels (csrc/mlp.cu).
+ * sgmcmc_mlp_predict_f32: out[k, i, 0] = f(x_i; theta_k), out[k, i, 1] = rho_k (:535-557);
+ * its workspace is sized with n_items = n_nets * ceil(n_points / 32), batch = 32. */
+int64_t sgmcmc_mlp_n_params(const int* widths, int n_widths);
+int64_t sgmcmc_mlp_workspace_bytes(const int* widths, int n_widths, int64_t n_items, int batch);
+int sgmcmc_mlp_nll_grad_f32(const float* theta, const float* X, const float* y, const int32_t* starts,
+                            float* cost, float* grad, float* mse, void* workspace, int64_t workspace_bytes,
+                            int64_t n_chains, const int* widths, int n_widths, int batch,
+                            float batch_size_cfg, int64_t n_examples, void* stream);
+int sgmcmc_mlp_predict_f32(const float* theta, const float* X, float* out, void* workspace,
+                           int64_t workspace_bytes, int64_t n_nets, const int* widths, int n_widths,
+                           int64_t n_points, void* stream);
 
 /* ---- K5: BNN-SGHMC chains: K4 + K1 for `n_steps` steps in one call with no host
  * synchronisation -- the whole next(sampler) of the BNN path

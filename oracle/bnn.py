@@ -27,11 +27,14 @@ from .tensor_utils import safe_divide
 
 
 def layout(n_in=1, hidden=(50, 50, 50)):
-    """[(name, shape, offset)] and total D."""
-    h1, h2, h3 = hidden
-    shapes = [("W1", (n_in, h1)), ("b1", (h1,)), ("W2", (h1, h2)), ("b2", (h2,)),
-              ("W3", (h2, h3)), ("b3", (h3,)), ("W4", (h3, 1)), ("b4", (1,)),
-              ("rho", (1, 1))]
+    """[(name, shape, offset)] and total D, for any number of hidden layers (a user `get_net`
+    of the shape of get_default_net with other widths: W_l, b_l per dense layer, then rho)."""
+    widths = [n_in] + list(hidden) + [1]
+    shapes = []
+    for l in range(1, len(widths)):
+        shapes.append(("W%d" % l, (widths[l - 1], widths[l])))
+        shapes.append(("b%d" % l, (widths[l],)))
+    shapes.append(("rho", (1, 1)))
     out, off = [], 0
     for name, shp in shapes:
         out.append((name, shp, off))
@@ -104,14 +107,16 @@ def weight_prior_log_like(parameters, wdecay=1.0, dtype=np.float64):
 # --------------------------- network + cost ------------------------------ #
 
 def forward(theta, X, n_in=1, hidden=(50, 50, 50)):
-    """get_default_net (:28-69). Returns (f_mean [C,B], rho [C], caches)."""
+    """get_default_net (:28-69) for any tuple of hidden widths.
+    Returns (f_mean [C,B], rho [C], (P, H_0 = X, H_1, ..., H_L))."""
     P = unpack(theta, n_in, hidden)
-    H1 = np.tanh(X @ P["W1"] + P["b1"][:, None, :])
-    H2 = np.tanh(H1 @ P["W2"] + P["b2"][:, None, :])
-    H3 = np.tanh(H2 @ P["W3"] + P["b3"][:, None, :])
-    f = (H3 @ P["W4"])[..., 0] + P["b4"]
+    L = len(hidden)
+    Hs = [X]
+    for l in range(1, L + 1):
+        Hs.append(np.tanh(Hs[-1] @ P["W%d" % l] + P["b%d" % l][:, None, :]))
+    f = (Hs[-1] @ P["W%d" % (L + 1)])[..., 0] + P["b%d" % (L + 1)]
     rho = P["rho"][:, 0, 0]
-    return f, rho, (P, H1, H2, H3)
+    return f, rho, (P,) + tuple(Hs)
 
 
 def nll_and_grad(theta, X, y, n_examples, batch_size=None, n_in=1, hidden=(50, 50, 50),
@@ -130,8 +135,10 @@ def nll_and_grad(theta, X, y, n_examples, batch_size=None, n_in=1, hidden=(50, 5
     bs = T(B if batch_size is None else batch_size)
     N = T(n_examples)
     D = theta.shape[-1]
+    L = len(hidden)
 
-    f, rho, (P, H1, H2, H3) = forward(theta, X, n_in, hidden)
+    f, rho, cache = forward(theta, X, n_in, hidden)
+    P, Hs = cache[0], cache[1:]
     f_var_inv = T(1.0) / (np.exp(rho) + T(1e-16))                       # :368
     diff = y - f
     mse = np.square(diff)                                               # :370
@@ -155,20 +162,16 @@ def nll_and_grad(theta, X, y, n_examples, batch_size=None, n_in=1, hidden=(50, 5
     drho_lv = (T(2.0) * (rho - np.log(T(1e-6))) / _sd_den(lv_den)) / N
 
     G = {}
-    G["W4"] = np.einsum("cbh,cb->ch", H3, dfm)[:, :, None]
-    G["b4"] = dfm.sum(axis=1)[:, None]
-    dH3 = dfm[:, :, None] * P["W4"][:, None, :, 0]
-    dZ3 = dH3 * (T(1.0) - H3 * H3)
-    G["W3"] = np.einsum("cbi,cbj->cij", H2, dZ3)
-    G["b3"] = dZ3.sum(axis=1)
-    dH2 = np.einsum("cbj,cij->cbi", dZ3, P["W3"])
-    dZ2 = dH2 * (T(1.0) - H2 * H2)
-    G["W2"] = np.einsum("cbi,cbj->cij", H1, dZ2)
-    G["b2"] = dZ2.sum(axis=1)
-    dH1 = np.einsum("cbj,cij->cbi", dZ2, P["W2"])
-    dZ1 = dH1 * (T(1.0) - H1 * H1)
-    G["W1"] = np.einsum("cbi,cbj->cij", X, dZ1)
-    G["b1"] = dZ1.sum(axis=1)
+    head = L + 1
+    G["W%d" % head] = np.einsum("cbh,cb->ch", Hs[L], dfm)[:, :, None]
+    G["b%d" % head] = dfm.sum(axis=1)[:, None]
+    dH = dfm[:, :, None] * P["W%d" % head][:, None, :, 0]
+    for l in range(L, 0, -1):
+        dZ = dH * (T(1.0) - Hs[l] * Hs[l])
+        G["W%d" % l] = np.einsum("cbi,cbj->cij", Hs[l - 1], dZ)
+        G["b%d" % l] = dZ.sum(axis=1)
+        if l > 1:
+            dH = np.einsum("cbj,cij->cbi", dZ, P["W%d" % l])
     G["rho"] = (drho_data + drho_lv)[:, None, None]
     grad = pack(G, n_in, hidden)
     # weight prior: d/dp of -(1/N) * sum(-0.5 p^2)/(D + 3e-16)

@@ -53,6 +53,10 @@ SIGNATURES = {
     "sgmcmc_mt19937_seed": [_P, _P, c_int64, _P],
     "sgmcmc_mt19937_starts": [_P, _P, c_int64, c_int64, c_uint32, _P],
     "sgmcmc_bnn_nll_grad_f32": [_P] * 7 + [c_int64, c_int, c_int, c_float, c_int64, _P],
+    "sgmcmc_mlp_n_params": [POINTER(c_int), c_int],
+    "sgmcmc_mlp_workspace_bytes": [POINTER(c_int), c_int, c_int64, c_int],
+    "sgmcmc_mlp_nll_grad_f32": [_P] * 8 + [c_int64, c_int64, POINTER(c_int), c_int, c_int, c_float, c_int64, _P],
+    "sgmcmc_mlp_predict_f32": [_P] * 4 + [c_int64, c_int64, POINTER(c_int), c_int, c_int64, _P],
     "sgmcmc_bnn_sghmc_run_f32": [_P] * 14 + [c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
                                              c_int, c_int64, c_float, c_float, c_float,
                                              c_uint64, c_uint64, c_uint64, _P],
@@ -74,7 +78,8 @@ SIGNATURES = {
                                                         c_float, _P],
     "sgmcmc_svgd_update_f32": [_P] * 7 + [c_int64, c_int64, c_float, c_float, c_float, c_float, _P],
 }
-_RESTYPES = {"sgmcmc_last_error": c_char_p, "sgmcmc_launch_count": c_int64, "sgmcmc_svgd_scratch_bytes": c_int64}
+_RESTYPES = {"sgmcmc_last_error": c_char_p, "sgmcmc_launch_count": c_int64, "sgmcmc_svgd_scratch_bytes": c_int64,
+             "sgmcmc_mlp_n_params": c_int64, "sgmcmc_mlp_workspace_bytes": c_int64}
 
 _lib = None
 
@@ -114,6 +119,12 @@ def svgd_scratch(n_particles, n_dims, device):
     if nbytes < 0:
         raise NativeError("sgmcmc_svgd_scratch_bytes: unsupported size %d x %d" % (n_particles, n_dims))
     return torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+
+
+def int_array(values):
+    """A C `int[]` for the `widths` arguments."""
+    values = [int(v) for v in values]
+    return (c_int * len(values))(*values), len(values)
 
 
 def launch_count():

@@ -163,17 +163,23 @@ chain_moments_vec_kernel(const float4* __restrict__ trace4, double* __restrict__
   }
 }
 
-// Lags 1 .. VW in ONE pass: a thread owns 2 dimensions and keeps the last VW draws of its
-// chain in a register ring (as doubles, converted once), so every trace element is read once
-// and costs one subtraction and one FMA per lag.  For many lags this kernel is bound by the
-// FP64 pipe (2 * VW instructions per element), not by HBM.
+// Lags shift + 1 .. shift + VW in ONE pass: a thread owns 2 dimensions and keeps VW consecutive
+// draws of its chain in a register ring (as doubles, converted once); draw i is paired with the
+// VW draws that precede draw i - shift.  For shift == 0 (lags 1 .. VW) every trace element is read
+// once; later lag blocks read a second, delayed stream of the same column (shift draws behind)
+// that feeds the ring.  Either way an element costs one subtraction and one FMA per lag: for
+// many lags the kernel is bound by the FP64 pipe (2 * VW instructions per element), not by HBM.
+// (The per-lag kernel this replaces for lag0 > 1 re-read the whole trace for every lag: 83 lags
+// of the 17 GB shard took 470 ms; as 6 blocks of 16 lags they take ~70 ms.)
 constexpr int VW = 16;
 constexpr int VW_THREADS = 128;
 constexpr int VW_CHAINS = 64;
 
-template <bool FIRST>
-__device__ __forceinline__ void variogram_block(const float2 (&v)[VW], int64_t base, int64_t n_draws,
-                                                double (&ring)[VW][2], double (&acc)[VW][2]) {
+// v: the current draws (index base + k), w: the draws that enter the ring (v itself, or the
+// delayed stream)
+template <bool FIRST, bool DELAYED>
+__device__ __forceinline__ void variogram_block(const float2 (&v)[VW], const float2 (&w)[VW], int64_t base,
+                                                int64_t n_draws, double (&ring)[VW][2], double (&acc)[VW][2]) {
 #pragma unroll
   for (int k = 0; k < VW; ++k) {
     if (base + k < n_draws) {
@@ -187,15 +193,16 @@ __device__ __forceinline__ void variogram_block(const float2 (&v)[VW], int64_t b
           acc[t - 1][1] = fma(d1, d1, acc[t - 1][1]);
         }
       }
-      ring[k][0] = x[0];
-      ring[k][1] = x[1];
+      ring[k][0] = DELAYED ? (double)w[k].x : x[0];
+      ring[k][1] = DELAYED ? (double)w[k].y : x[1];
     }
   }
 }
 
+template <bool DELAYED>
 __global__ void __launch_bounds__(VW_THREADS, 2)
 variogram_window_kernel(const float2* __restrict__ trace2, double* __restrict__ out, int64_t n_draws,
-                        int64_t n_chains, int64_t d2, int n_lags) {
+                        int64_t n_chains, int64_t d2, int n_lags, int64_t shift) {
   const int64_t q = (int64_t)blockIdx.x * VW_THREADS + threadIdx.x;
   if (q >= d2) return;
   const int64_t c0 = (int64_t)blockIdx.y * VW_CHAINS;
@@ -207,13 +214,23 @@ variogram_window_kernel(const float2* __restrict__ trace2, double* __restrict__ 
   for (int64_t j = c0; j < c1; ++j) {
     const float2* p = trace2 + j * d2 + q;
     double ring[VW][2];
-    for (int64_t base = 0; base < n_draws; base += VW) {
+    // draw i = shift + base + k is paired with draws base + k - t (t = 1 .. VW), i.e. lag shift + t
+    for (int64_t base = 0; shift + base < n_draws; base += VW) {
       float2 v[VW];
 #pragma unroll
       for (int k = 0; k < VW; ++k)
-        v[k] = base + k < n_draws ? __ldcs(p + (base + k) * stride) : make_float2(0.0f, 0.0f);
-      if (base == 0) variogram_block<true>(v, base, n_draws, ring, acc);
-      else variogram_block<false>(v, base, n_draws, ring, acc);
+        v[k] = shift + base + k < n_draws ? __ldcs(p + (shift + base + k) * stride) : make_float2(0.0f, 0.0f);
+      if constexpr (DELAYED) {
+        float2 w[VW];
+#pragma unroll
+        for (int k = 0; k < VW; ++k)        // (base + k < shift + base + k: in range whenever it is used)
+          w[k] = shift + base + k < n_draws ? __ldcs(p + (base + k) * stride) : make_float2(0.0f, 0.0f);
+        if (base == 0) variogram_block<true, true>(v, w, shift + base, n_draws, ring, acc);
+        else variogram_block<false, true>(v, w, shift + base, n_draws, ring, acc);
+      } else {
+        if (base == 0) variogram_block<true, false>(v, v, base, n_draws, ring, acc);
+        else variogram_block<false, false>(v, v, base, n_draws, ring, acc);
+      }
     }
   }
   const int64_t D = 2 * d2, d = 2 * q;
@@ -303,14 +320,25 @@ extern "C" int sgmcmc_variogram_f32(const float* trace, double* variogram, int64
   if (int rc = check_trace_args(trace, variogram, n_draws, n_chains, n_dims)) return rc;
   SG_REQUIRE(lag0 >= 1 && n_lags >= 0 && n_lags <= 65535, SGMCMC_E_INVALID, "lag0 must be >= 1, n_lags in [0, 65535]");
   if (n_draws == 0 || n_chains == 0 || n_dims == 0 || n_lags == 0) return SGMCMC_OK;
-  if (lag0 == 1 && n_lags <= VW && n_dims % 2 == 0 && aligned_to(trace, 8) &&
-      (n_chains + VW_CHAINS - 1) / VW_CHAINS <= 65535) {
-    // the first block of lags (what well-mixed chains need): one pass over the trace
+  if (n_dims % 2 == 0 && aligned_to(trace, 8) && (n_chains + VW_CHAINS - 1) / VW_CHAINS <= 65535) {
+    // blocks of VW lags, one (lags 1 .. VW: what well-mixed chains need) or two streams over the
+    // trace per block
     const int64_t d2 = n_dims / 2;
     const dim3 grid((unsigned)((d2 + VW_THREADS - 1) / VW_THREADS), (unsigned)((n_chains + VW_CHAINS - 1) / VW_CHAINS));
-    variogram_window_kernel<<<grid, VW_THREADS, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2*>(trace), variogram, n_draws, n_chains, d2, (int)n_lags);
-    return check_launch("variogram_window_kernel");
+    for (int64_t b = 0; b < n_lags; b += VW) {
+      const int64_t shift = lag0 - 1 + b;
+      if (shift >= n_draws) break;                       // (no pairs at these lags: the sums stay 0)
+      const int nl = (int)(n_lags - b < VW ? n_lags - b : VW);
+      const float2* t2 = reinterpret_cast<const float2*>(trace);
+      if (shift == 0)
+        variogram_window_kernel<false><<<grid, VW_THREADS, 0, (cudaStream_t)stream>>>(t2, variogram + b * n_dims,
+                                                                                      n_draws, n_chains, d2, nl, 0);
+      else
+        variogram_window_kernel<true><<<grid, VW_THREADS, 0, (cudaStream_t)stream>>>(t2, variogram + b * n_dims,
+                                                                                     n_draws, n_chains, d2, nl, shift);
+      if (int rc = check_launch("variogram_window_kernel")) return rc;
+    }
+    return SGMCMC_OK;
   }
   const dim3 block(MT_DX, MT_DY);
   const dim3 grid((unsigned)((n_dims + MT_DX - 1) / MT_DX),

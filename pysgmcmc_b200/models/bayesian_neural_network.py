@@ -9,10 +9,11 @@ schedule (burn-in, one network kept every `sample_steps` iterations after burn-i
 ``generate_batches(seed=seed)``), the predictive mean / variance formulas.
 What differs: `session` is a :class:`pysgmcmc_b200.Session` (with ``Session(n_chains=C)`` C
 independent chains sample in parallel and each kept iteration yields C networks); `dtype` is a
-torch dtype and
-defaults to float32; `get_net` other than `get_default_net` is not supported by the
-fused kernels (the network architecture is compiled in); weight initialisation uses a torch
-generator (TensorFlow's stream is not reproducible).
+torch dtype and defaults to float32 (float64 models sample through the differentiable torch cost
+and the float64 update kernels -- the fused BNN kernels are float32 only); `get_net` is
+`get_default_net`, an ``MLPNet(hidden=...)`` of any widths (native kernels: csrc/mlp.cu) or a
+``TorchNet`` (autograd), see models/networks.py; weight initialisation uses a torch generator
+(TensorFlow's stream is not reproducible).
 """
 import logging
 from collections import deque
@@ -31,6 +32,7 @@ from .base_model import (BaseModel, zero_mean_unit_var_normalization,
                          zero_mean_unit_var_unnormalization)
 from .bnn_cost import (BayesianNeuralNetworkNLL, default_net_params, log_variance_prior_log_like,  # noqa: F401
                        network_output, weight_prior_log_like)
+from .networks import DEFAULT_NET, MLPNet, TorchNet, as_network  # noqa: F401
 
 
 def get_default_net(inputs, params):
@@ -49,25 +51,15 @@ class BayesianNeuralNetwork(object):
                  burn_in_steps=1000, sample_steps=100,
                  normalize_input=True, normalize_output=True,
                  seed=None, dtype=torch.float32, **sampler_kwargs):
-        # Sanitize inputs (bayesian_neural_network.py:238-268)
-        assert isinstance(n_nets, int)
-        assert isinstance(n_iters, int)
-        assert isinstance(burn_in_steps, int)
-        assert isinstance(sample_steps, int)
-        assert isinstance(batch_size, int)
+        # input checks of bayesian_neural_network.py:238-268: wrong types / values raise
+        # AssertionError (pinned by tests/bayesian_neural_network/test_invalid_inputs.py:17-100)
+        counts = {"n_nets": (n_nets, 1), "n_iters": (n_iters, 1), "burn_in_steps": (burn_in_steps, 0),
+                  "sample_steps": (sample_steps, 1), "batch_size": (batch_size, 1)}
+        for name, (value, lowest) in counts.items():
+            assert isinstance(value, int) and value >= lowest, "%s must be an integer >= %d" % (name, lowest)
         assert isinstance(dtype, torch.dtype)
-
-        assert n_nets > 0
-        assert n_iters > 0
-        assert burn_in_steps >= 0
-        assert sample_steps > 0
-        assert batch_size > 0
-
-        assert callable(get_net)
-        assert callable(batch_generator)
-
-        assert hasattr(stepsize_schedule, "update")
-        assert hasattr(stepsize_schedule, "__next__")
+        assert callable(get_net) and callable(batch_generator)
+        assert all(hasattr(stepsize_schedule, a) for a in ("update", "__next__"))
 
         if not Sampler.is_supported(sampling_method):
             raise ValueError(
@@ -76,9 +68,8 @@ class BayesianNeuralNetwork(object):
                 "Supported sampling methods are enumerated in "
                 "'Sampler' enum type.".format(input=sampling_method)
             )
-        if get_net is not get_default_net:
-            raise ValueError("the B200 engine compiles the default architecture (get_default_net) "
-                             "into its kernels; custom `get_net` callables are not supported")
+        #: the architecture behind `get_net` (raises ValueError for callables without parameters)
+        self.net = as_network(get_net, default_callable=get_default_net)
 
         self.sampling_method = sampling_method
         self.stepsize_schedule = stepsize_schedule
@@ -129,7 +120,7 @@ class BayesianNeuralNetwork(object):
             batches = DeviceBatchGenerator(n_datapoints, self.batch_size, seeds=seeds, device=device)
             self.nll = BayesianNeuralNetworkNLL(n_datapoints, self.batch_size, X=self.X, y=self.y,
                                                 starts_placeholder=batches.starts_placeholder,
-                                                device=device, dtype=self.dtype)
+                                                device=device, dtype=self.dtype, net=self.net)
         else:
             if n_chains is not None:
                 raise ValueError("Session(n_chains=C) needs the default `generate_batches` (per-chain "
@@ -142,10 +133,11 @@ class BayesianNeuralNetwork(object):
             self.nll = BayesianNeuralNetworkNLL(n_datapoints, self.batch_size, n_in=n_inputs,
                                                 x_placeholder=self.X_Minibatch,
                                                 y_placeholder=self.Y_Minibatch,
-                                                device=device, dtype=self.dtype)
+                                                device=device, dtype=self.dtype, net=self.net)
 
-        self.network_params = default_net_params(n_inputs, n_chains=n_chains, seed=self.seed, dtype=self.dtype,
-                                                 device=device)
+        self.network_params = self.net.init_params(n_inputs, n_chains=n_chains, seed=self.seed, dtype=self.dtype,
+                                                   device=device)
+        self._param_shapes = self.net.parameter_shapes(n_inputs)
         self.samples.clear()
 
         self.sampler_kwargs.update({
@@ -230,22 +222,47 @@ class BayesianNeuralNetwork(object):
     def compute_network_output(self, params, input_data):
         """Network output ``(N, 2)`` = (mean, log variance) for one parameter sample
         (bayesian_neural_network.py:535-557); `params` is a flat ``[D]`` tensor or the list of
-        9 parameter arrays."""
+        parameter arrays."""
         device = self.session.device
         if isinstance(params, (list, tuple)):
             params = torch.cat([torch.as_tensor(np.asarray(p) if not isinstance(p, torch.Tensor) else p
                                                 ).reshape(-1) for p in params])
-        theta = params.to(device=device, dtype=torch.float32).reshape(1, -1).contiguous()
+        theta = params.to(device=device).reshape(1, -1).contiguous()
         return self._forward(theta, input_data)[0]
 
     def _forward(self, theta, input_data):
+        """(mean, log variance) of every stored network at every input: ``[n_nets, N, 2]``.
+        float32 models: K10 (default architecture) or the layer kernels (any MLPNet); float64
+        models and TorchNet architectures: the differentiable torch function, in the model's dtype."""
         device = self.session.device
-        X = torch.as_tensor(np.asarray(input_data), dtype=torch.float32, device=device).contiguous()
+        native = self.dtype == torch.float32 and isinstance(self.net, MLPNet)
+        X = torch.as_tensor(np.asarray(input_data), dtype=torch.float32 if native else self.dtype,
+                            device=device).contiguous()
         n_nets, n_points = theta.shape[0], X.shape[0]
+        if not native:
+            theta = theta.to(self.dtype)
+            params, off = [], 0
+            for shp in self.net.parameter_shapes(X.shape[1]):
+                n = int(np.prod(shp))
+                params.append(theta[:, off:off + n].reshape((n_nets,) + tuple(shp)))
+                off += n
+            with torch.no_grad():
+                out = self.net(X, params)
+            return out.cpu().numpy().astype(np.float64)
+        theta = theta.to(torch.float32).contiguous()
         out = torch.empty((n_nets, n_points, 2), dtype=torch.float32, device=device)
         with torch.cuda.device(device):
-            _native.call("sgmcmc_bnn_predict_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(out),
-                         n_nets, X.shape[1], n_points, _native.stream_ptr(self.session.stream))
+            stream = _native.stream_ptr(self.session.stream)
+            if self.net == DEFAULT_NET:
+                _native.call("sgmcmc_bnn_predict_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(out),
+                             n_nets, X.shape[1], n_points, stream)
+            else:
+                widths, n_w = _native.int_array(self.net.widths(X.shape[1]))
+                items = n_nets * ((n_points + 31) // 32)
+                nbytes = int(_native.load().sgmcmc_mlp_workspace_bytes(widths, n_w, items, 32))
+                ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+                _native.call("sgmcmc_mlp_predict_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(out),
+                             _native.ptr(ws), ws.numel() * 8, n_nets, widths, n_w, n_points, stream)
         return out.cpu().numpy().astype(np.float64)
 
     @BaseModel._check_shapes_predict
@@ -263,7 +280,7 @@ class BayesianNeuralNetwork(object):
         else:
             X_ = X_test
 
-        theta = torch.stack(list(self.samples)).to(torch.float32).contiguous()
+        theta = torch.stack(list(self.samples)).contiguous()
         out = self._forward(theta, X_)                      # [n_nets, N, 2]
         f_out = out[:, :, 0]
         theta_noise = np.exp(out[:, :, 1])

@@ -1,17 +1,20 @@
 """The BNN cost function of the hot path as a sampler `cost_fun`:
-negative log likelihood of the BOHAMIANN network (n_in-50-50-50-1 tanh MLP with a learned
-log-variance), i.e. pysgmcmc/models/bayesian_neural_network.py:28-69 (`get_default_net`),
-:77-141 (priors) and :337-388 (`negative_log_likelihood`).
+negative log likelihood of a network with a learned log-variance output, i.e.
+pysgmcmc/models/bayesian_neural_network.py:77-141 (priors) and :337-388
+(`negative_log_likelihood`) over a `get_net` architecture (:28-69; models/networks.py).
 
-* ``native_cost_and_grad`` runs kernel K4 (csrc/bnn.cu) for all chains at once;
-  `SGHMCSampler` recognises the object and drives K4 + K1 from C (K5) without returning
-  to Python between steps.
+* ``native_cost_and_grad`` runs kernel K4 for all chains at once: the specialised 50-50-50
+  kernels (csrc/bnn_mma.cuh, csrc/bnn.cu) for the BOHAMIANN default -- `SGHMCSampler` recognises
+  that case and drives K4 + K1 from C (K5) without returning to Python between steps -- and the
+  layer kernels of csrc/mlp.cu for every other `MLPNet` (any widths / depth, minibatches of up
+  to 32 rows).
 * ``__call__(params)`` is the same cost written in differentiable torch ops: it serves
-  float64 samplers, SGLD / relativistic samplers (generic autograd path) and the
-  full-dataset logging of `BayesianNeuralNetwork.train`.
+  float64 samplers, SGLD / relativistic samplers on wide minibatches, arbitrary `TorchNet`
+  architectures (generic autograd path) and the full-dataset logging of
+  `BayesianNeuralNetwork.train`.
 
-Flat per-chain layout = ``tf.trainable_variables()`` order of the reference:
-W1[n_in,50] b1[50] W2[50,50] b2[50] W3[50,50] b3[50] W4[50,1] b4[1] rho[1,1].
+Flat per-chain layout = ``tf.trainable_variables()`` order of the reference; for the default
+network: W1[n_in,50] b1[50] W2[50,50] b2[50] W3[50,50] b3[50] W4[50,1] b4[1] rho[1,1].
 """
 import math
 
@@ -21,6 +24,7 @@ import torch
 from .. import _native
 from ..placeholders import Placeholder
 from ..tensor_utils import safe_divide
+from .networks import DEFAULT_NET, MLPNet
 
 HIDDEN = 50
 MAX_NATIVE_BATCH = 256          # rows of one minibatch the BNN kernels accept (csrc/bnn.cu)
@@ -36,43 +40,16 @@ def n_parameters(n_in):
 
 
 def default_net_params(n_in, n_chains=None, seed=None, dtype=torch.float32, device="cuda:0"):
-    """Initial parameters of `get_default_net` (bayesian_neural_network.py:28-61): kernels
-    ~ truncated normal(0, sqrt(1.3 / fan_in)) (tf.contrib `variance_scaling_initializer`
-    with factor=1.0: FAN_IN, truncated at two standard deviations and rescaled), zero
-    biases, log-variance log(1e-3).  TensorFlow's random stream cannot be reproduced
-    (and the reference pins none, tests/bayesian_neural_network/test_seeding.py:14-46 only
-    asks for same seed -> same net), so the draws come from a seeded torch generator.
-
-    Returns a list of 9 tensors (with a leading chain axis when `n_chains` is given).
-    """
-    gen = torch.Generator(device="cpu")
-    gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed))
-    lead = () if n_chains is None else (n_chains,)
-    out = []
-    for shp in parameter_shapes(n_in):
-        if len(shp) == 2 and shp != (1, 1):
-            std = math.sqrt(1.3 / shp[0])
-            w = torch.empty(lead + shp, dtype=torch.float64)
-            torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=gen)
-            out.append((w * std).to(dtype))
-        elif shp == (1, 1):
-            out.append(torch.full(lead + shp, math.log(1e-3), dtype=dtype))
-        else:
-            out.append(torch.zeros(lead + shp, dtype=dtype))
-    return [p.to(device) for p in out]
+    """Initial parameters of `get_default_net` (bayesian_neural_network.py:28-61); see
+    `MLPNet.init_params`.  Returns a list of 9 tensors (with a leading chain axis when
+    `n_chains` is given)."""
+    return DEFAULT_NET.init_params(n_in, n_chains=n_chains, seed=seed, dtype=dtype, device=device)
 
 
 def network_output(params, X):
     """`get_default_net` in torch ops: returns ``[..., n_points, 2]`` = (mean, log variance).
     `params` may carry a leading chain axis (then X is ``[C, B, n_in]`` or ``[B, n_in]``)."""
-    W1, b1, W2, b2, W3, b3, W4, b4, rho = params
-    chains = W1.dim() == 3
-    bias = (lambda b: b[:, None, :]) if chains else (lambda b: b)
-    h = torch.tanh(X @ W1 + bias(b1))
-    h = torch.tanh(h @ W2 + bias(b2))
-    h = torch.tanh(h @ W3 + bias(b3))
-    f = h @ W4 + bias(b4)
-    return torch.cat([f, torch.ones_like(f) * rho], dim=-1)
+    return DEFAULT_NET(X, params)
 
 
 def log_variance_prior_log_like(log_var, mean=1e-6, var=0.01, dtype=None):
@@ -107,7 +84,8 @@ class BayesianNeuralNetworkNLL(object):
 
     def __init__(self, n_examples, batch_size=20, n_in=None, X=None, y=None, starts_placeholder=None,
                  x_placeholder=None, y_placeholder=None, n_chains=None, device="cuda:0",
-                 dtype=torch.float32):
+                 dtype=torch.float32, net=None):
+        self.net = DEFAULT_NET if net is None else net
         self.device = torch.device(device)
         self.dtype = dtype
         self.n_examples = int(n_examples)
@@ -126,10 +104,23 @@ class BayesianNeuralNetworkNLL(object):
             self.X = self.y = None
             self.n_in = int(n_in)
         self.actual_batch = min(self.batch_size, self.n_examples)    # data_batches.py:111
-        self.n_params = n_parameters(self.n_in)
-        self.bnn_native = True
+        self.n_params = self.net.n_parameters(self.n_in)
+        #: the default architecture: K4 + K1 can be driven from C (K5, `SGHMCSampler.run` / `iter_host`)
+        self.bnn_native = self.net == DEFAULT_NET
+        #: any MLPNet: cost + gradient by the layer kernels of csrc/mlp.cu
+        self.mlp_native = isinstance(self.net, MLPNet) and not self.bnn_native
         self._cost = None
+        self._mlp_ws = None
         self.last_mse = None
+
+    @property
+    def supports_native(self):
+        """Whether `native_cost_and_grad` exists for this architecture and minibatch (else the
+        sampler differentiates `__call__` with autograd)."""
+        if self.bnn_native:
+            return True
+        return self.mlp_native and self.actual_batch <= 32 and (self.X is None or self.starts_placeholder is not None
+                                                                 or self.X.shape[0] <= 32)
 
     # ---- where the current minibatch comes from ---------------------------------------
     def full_dataset_batch(self):
@@ -180,19 +171,39 @@ class BayesianNeuralNetworkNLL(object):
             self._cost = torch.empty(C, dtype=torch.float32, device=self.device)
         mse = torch.empty(C, dtype=torch.float32, device=self.device) if want_mse else None
         with torch.cuda.device(self.device):
-            _native.call("sgmcmc_bnn_nll_grad_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(y),
-                         _native.ptr(starts), _native.ptr(self._cost), _native.ptr(grad_out),
-                         _native.ptr(mse), C, self.n_in, batch, float(self.batch_size),
-                         self.n_examples, _native.stream_ptr())
+            if self.bnn_native:
+                _native.call("sgmcmc_bnn_nll_grad_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(y),
+                             _native.ptr(starts), _native.ptr(self._cost), _native.ptr(grad_out),
+                             _native.ptr(mse), C, self.n_in, batch, float(self.batch_size),
+                             self.n_examples, _native.stream_ptr())
+            else:
+                if batch > 32:
+                    raise ValueError("the layer kernels (csrc/mlp.cu) take minibatches of up to 32 rows (got %d)"
+                                     % batch)
+                widths, n_w = _native.int_array(self.net.widths(self.n_in))
+                ws = self._mlp_workspace(widths, n_w, C, batch)
+                _native.call("sgmcmc_mlp_nll_grad_f32", _native.ptr(theta), _native.ptr(X), _native.ptr(y),
+                             _native.ptr(starts), _native.ptr(self._cost), _native.ptr(grad_out), _native.ptr(mse),
+                             _native.ptr(ws), ws.numel() * 8, C, widths, n_w, batch, float(self.batch_size),
+                             self.n_examples, _native.stream_ptr())
         self.last_mse = mse
         return self._cost
+
+    def _mlp_workspace(self, widths, n_w, n_items, batch):
+        """Activation workspace of the layer kernels (int64 elements: 16-byte aligned), kept."""
+        nbytes = int(_native.load().sgmcmc_mlp_workspace_bytes(widths, n_w, n_items, batch))
+        if nbytes < 0:
+            raise _native.NativeError("sgmcmc_mlp_workspace_bytes: unsupported architecture %r" % (self.net,))
+        if self._mlp_ws is None or self._mlp_ws.numel() * 8 < nbytes:
+            self._mlp_ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=self.device)
+        return self._mlp_ws
 
     # ---- generic differentiable path ------------------------------------------------------
     def __call__(self, params, *_):
         params = list(params)
         chains = params[0].dim() == 3
         X, Y = self._torch_batch()
-        out = network_output(params, X)
+        out = self.net(X, params)
         f_mean, f_log_var = out[..., 0:1], out[..., 1:2]
         Y = Y.reshape(f_mean.shape)
         f_var_inv = 1.0 / (torch.exp(f_log_var) + 1e-16)

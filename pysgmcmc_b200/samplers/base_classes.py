@@ -165,7 +165,8 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         return cost, self._grad
 
     def _cost_and_grad(self):
-        if hasattr(self.cost_fun, "native_cost_and_grad") and self.dtype == torch.float32:
+        if (hasattr(self.cost_fun, "native_cost_and_grad") and self.dtype == torch.float32
+                and getattr(self.cost_fun, "supports_native", True)):
             return self._native_cost_and_grad()
         return self._autograd_cost_and_grad()
 

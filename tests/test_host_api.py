@@ -156,6 +156,33 @@ def test_bnn_unsupported_sampler_and_predict_before_train():
         bnn.predict(np.linspace(0, 1, 100)[:, None])                      # test_train_predict.py:51-72
 
 
+def test_get_net_architectures():
+    """get_net: the default callable, MLPNet of any widths, TorchNet; a TensorFlow-style callable
+    without parameters is rejected with an explanation (models/networks.py)."""
+    import torch
+    from pysgmcmc_b200.models import MLPNet, TorchNet
+    from pysgmcmc_b200.models.bayesian_neural_network import get_default_net
+    from pysgmcmc_b200.models.networks import DEFAULT_NET, as_network
+    assert as_network(get_default_net, get_default_net) is DEFAULT_NET
+    wide = MLPNet((1000, 512, 512))
+    assert wide.n_parameters(1) == 777682 and wide.widths(1) == [1, 1000, 512, 512, 1]
+    assert DEFAULT_NET.n_parameters(1) == 5252 and MLPNet((50, 50, 50)) == DEFAULT_NET != wide
+    assert DEFAULT_NET.parameter_shapes(1) == [(1, 50), (50,), (50, 50), (50,), (50, 50), (50,), (50, 1), (1,), (1, 1)]
+    p = MLPNet((6, 4)).init_params(3, n_chains=2, seed=1, device="cpu")
+    assert [tuple(t.shape) for t in p] == [(2, 3, 6), (2, 6), (2, 6, 4), (2, 4), (2, 4, 1), (2, 1), (2, 1, 1)]
+    assert float(p[-1][0, 0, 0]) == pytest.approx(np.log(1e-3)) and float(p[1].abs().sum()) == 0.0
+    out = MLPNet((6, 4))(torch.zeros(5, 3), p)
+    assert tuple(out.shape) == (2, 5, 2)
+    q = MLPNet((6, 4)).init_params(3, n_chains=2, seed=1, device="cpu")
+    assert all(torch.equal(a, b) for a, b in zip(p, q))                  # same seed, same network
+    t = TorchNet(lambda x, prm: x @ prm[0], lambda n_in: [(n_in, 2), (1, 1)])
+    assert t.n_parameters(3) == 7 and float(t.init_params(3, device="cpu")[-1]) == pytest.approx(np.log(1e-3))
+    with pytest.raises(ValueError, match="parameters are explicit"):
+        as_network(lambda inputs, seed=None, dtype=None: inputs, get_default_net)
+    with pytest.raises(ValueError):
+        MLPNet(())
+
+
 # ---- schedules, trace adapter, momentum initialiser, objective functions ----
 def test_schedules():
     s = ConstantStepsizeSchedule(0.01)

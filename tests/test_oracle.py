@@ -106,10 +106,10 @@ def test_target_gradients_match_autograd(name):
 def _torch_nll(theta, X, y, N, bs, n_in=1, hidden=(50, 50, 50)):
     lay, D = bnn.layout(n_in, hidden)
     P = {name: theta[:, off:off + int(np.prod(shp))].reshape((-1,) + shp) for name, shp, off in lay}
-    h = torch.tanh(X @ P["W1"] + P["b1"][:, None, :])
-    h = torch.tanh(h @ P["W2"] + P["b2"][:, None, :])
-    h = torch.tanh(h @ P["W3"] + P["b3"][:, None, :])
-    f = (h @ P["W4"])[..., 0] + P["b4"]
+    h, L = X, len(hidden)
+    for l in range(1, L + 1):
+        h = torch.tanh(h @ P["W%d" % l] + P["b%d" % l][:, None, :])
+    f = (h @ P["W%d" % (L + 1)])[..., 0] + P["b%d" % (L + 1)]
     rho = P["rho"][:, 0, 0]
     fvi = 1.0 / (torch.exp(rho) + 1e-16)
     ll = (-(y - f) ** 2 * (0.5 * fvi[:, None]) - 0.5 * rho[:, None]).sum(1) / bs
@@ -118,7 +118,8 @@ def _torch_nll(theta, X, y, N, bs, n_in=1, hidden=(50, 50, 50)):
     return -ll
 
 
-@pytest.mark.parametrize("n_in,hidden", [(1, (50, 50, 50)), (3, (8, 6, 5))])
+@pytest.mark.parametrize("n_in,hidden", [(1, (50, 50, 50)), (3, (8, 6, 5)), (2, (12,)), (1, (9, 4, 7, 3, 5)),
+                                         (1, (100, 64, 64))])
 def test_bnn_nll_grad_matches_autograd(n_in, hidden):
     rng = np.random.RandomState(3)
     C, B, N = 4, 20, 500
