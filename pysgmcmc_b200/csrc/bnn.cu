@@ -456,7 +456,12 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
 // profiles/ ---------------------------------------------------------------------------
 constexpr int K10_COLS = 1, K10_TPC = 50, K10_NC = 5;
 
-static int g_bnn_variant = 10;        // 10: tensor-pipe kernel (bnn_mma.cuh); 0-9: FFMA launch shapes
+// 10-13: tensor-pipe kernel (bnn_mma.cuh) in its accuracy modes; 0-9: FFMA launch shapes.  Default 13
+// (rounded hi/lo split + FP32-pipe accumulation across k-steps): the only tensor-pipe mode whose
+// 1000-step BNN-SGHMC trajectory stays within 1e-5 of the float32 oracle at the benchmarked shapes
+// (9.0e-6; mode 10: 4.6e-5, mode 11: 2.4e-5, FFMA kernel: 9.8e-6) -- 0.27 vs 0.22 ms for 8192 chains
+// (profiles/r02_bnn_trajectory_drift.jsonl, profiles/r02_k4_variants.jsonl)
+static int g_bnn_variant = 13;
 static int g_bnn_max_ctas = 0;          // 0: one CTA per chain group; > 0: persistent grid of that size
 static int64_t g_bnn_chunk = 0;         // chains per K4+K1 chunk inside sgmcmc_bnn_sghmc_run_f32 (0: all)
 void set_bnn_chunk(int64_t c) { g_bnn_chunk = c; }

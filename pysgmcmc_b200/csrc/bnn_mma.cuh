@@ -73,6 +73,13 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// d = a * b (a zero accumulator operand: the register-zero form, no tile to clear first)
+__device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.0f));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -118,9 +125,7 @@ __device__ __forceinline__ void mma3_row(float (&acc)[NT8][4], const uint32_t (&
   if constexpr ((MODE & MMA_RN_ACCUM) != 0) {
     float part[NT8][4];
 #pragma unroll
-    for (int nt = 0; nt < NT8; ++nt) part[nt][0] = part[nt][1] = part[nt][2] = part[nt][3] = 0.0f;
-#pragma unroll
-    for (int nt = 0; nt < NT8; ++nt) mma_tf32(part[nt], al, bh[nt]);
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32_zero(part[nt], al, bh[nt]);
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt) mma_tf32(part[nt], ah, bl[nt]);
 #pragma unroll
@@ -253,18 +258,15 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
     for (int ks = 0; ks < NB8; ++ks) {
       float part[MTW][NP][4];
       constexpr bool RN = (MODE & MMA_RN_ACCUM) != 0 && NB8 > 1;   // (one k-step: nothing to chain)
-      if constexpr (RN) {
-#pragma unroll
-        for (int m = 0; m < MTW; ++m)
-#pragma unroll
-          for (int p = 0; p < NP; ++p) part[m][p][0] = part[m][p][1] = part[m][p][2] = part[m][p][3] = 0.0f;
-      }
       auto& dst = *(RN ? &part : &acc);
 #pragma unroll
       for (int m = 0; m < MTW; ++m)
 #pragma unroll
         for (int p = 0; p < NP; ++p)
-          if (nt0 + p < NT8) mma_tf32(dst[m][p], al[m][ks], bh[p][ks]);
+          if (nt0 + p < NT8) {
+            if constexpr (RN) mma_tf32_zero(dst[m][p], al[m][ks], bh[p][ks]);
+            else mma_tf32(dst[m][p], al[m][ks], bh[p][ks]);
+          }
 #pragma unroll
       for (int m = 0; m < MTW; ++m)
 #pragma unroll
@@ -281,7 +283,8 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
 #pragma unroll
           for (int p = 0; p < NP; ++p)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[m][p][e] = __fadd_rn(acc[m][p][e], part[m][p][e]);
+            for (int e = 0; e < 4; ++e)
+              if (nt0 + p < NT8) acc[m][p][e] = __fadd_rn(acc[m][p][e], part[m][p][e]);
       }
     }
 #pragma unroll

@@ -29,15 +29,21 @@ namespace sgmcmc {
 
 constexpr int MLP_MAX_W = 8;        // weight matrices: up to 7 hidden layers + the head
 constexpr int MLP_THREADS = 128;
-constexpr int MLP_KC = 64;          // rows of the staged operand per shared-memory chunk
+constexpr int MLP_KMAX = 512;       // rows of the staged operand per shared-memory chunk (40 KB at 20 rows)
+
+// batch tile: minibatch rows padded to what the register tiles are compiled for
+__host__ __device__ __forceinline__ int mlp_bt(int batch) { return batch <= 8 ? 8 : batch <= 16 ? 16 : batch <= 20 ? 20 : 32; }
 
 struct MlpLayout {
   int n_w;                          // weight matrices = hidden layers + 1
   int width[MLP_MAX_W + 1];         // width[0] = n_in, width[1..n_w-1] hidden, width[n_w] = 1
   int64_t oW[MLP_MAX_W], ob[MLP_MAX_W], orho, D;
-  int wp[MLP_MAX_W + 1];            // widths rounded up to 4 (row strides in the workspace)
-  int64_t oH[MLP_MAX_W], oZ[MLP_MAX_W];   // workspace offsets (floats) of H_l and dZ_l, l = 1..n_w-1
-  int64_t oSq, oDf, ws_floats;      // partial sums of squares (prior), d cost / d f, total per chain
+  // workspace (floats per chain).  Activations and their gradients are stored TRANSPOSED,
+  // Ht_l[i * BT + b] = H_l[b][i] (BT = mlp_bt(batch), rows b >= batch are zero): the slice of
+  // rows a GEMM chunk needs is then one contiguous block, staged into shared memory with
+  // 128-bit copies and read back as 128-bit warp-broadcast loads (4 batch rows per load).
+  int64_t oH[MLP_MAX_W], oZ[MLP_MAX_W];   // Ht_l, dZt_l for l = 1..n_w-1
+  int64_t oSq, ws_floats;           // partial sums of squares (weight prior); total per chain
   int sq_slot[MLP_MAX_W];           // first partial-sum slot of layer l (one slot per column tile)
   int n_sq;
 };
@@ -46,7 +52,7 @@ struct MlpArgs {
   const float* theta;      // [n_theta_rows, D]
   const float* X;          // [n_rows, n_in]
   const float* y;          // [n_rows] (NULL for predict)
-  const int32_t* starts;   // [C] first row of each chain's minibatch, or NULL (see row0)
+  const int32_t* starts;   // [C] first row of each chain's minibatch, or NULL (see item_rows)
   float* ws;               // [C, ws_floats]
   float* cost;             // [C] or NULL
   float* grad;             // [C, D] or NULL
@@ -71,7 +77,6 @@ static int make_mlp_layout(MlpLayout& L, const int* widths, int n_widths, int ba
   for (int l = 0; l <= L.n_w; ++l) {
     SG_REQUIRE(widths[l] >= 1 && widths[l] <= (1 << 20), SGMCMC_E_UNSUPPORTED, "mlp: layer width out of range");
     L.width[l] = widths[l];
-    L.wp[l] = (widths[l] + 3) & ~3;
   }
   for (int l = 0; l < L.n_w; ++l) {
     L.oW[l] = o; o += (int64_t)L.width[l] * L.width[l + 1];
@@ -82,14 +87,13 @@ static int make_mlp_layout(MlpLayout& L, const int* widths, int n_widths, int ba
   L.orho = o; o += 1;
   L.D = o;
   L.n_sq = slot;
-  const int bp = (batch + 3) & ~3;
-  for (int l = 1; l < L.n_w; ++l) {
-    L.oH[l] = w; w += (int64_t)bp * L.wp[l];
-    L.oZ[l] = w; w += (int64_t)bp * L.wp[l];
-  }
+  const int bt = mlp_bt(batch);
   L.oH[0] = L.oZ[0] = 0;
+  for (int l = 1; l < L.n_w; ++l) {
+    L.oH[l] = w; w += (int64_t)bt * L.width[l];
+    L.oZ[l] = w; w += (int64_t)bt * L.width[l];
+  }
   L.oSq = w; w += (slot + 3) & ~3;
-  L.oDf = w; w += 32;
   L.ws_floats = (w + 3) & ~3;
   return SGMCMC_OK;
 }
@@ -120,25 +124,75 @@ __device__ __forceinline__ void item_rows(const MlpArgs& a, int64_t chain, int64
   rows = (int)(left < a.batch ? (left < 0 ? 0 : left) : a.batch);
 }
 
-// Stage rows [k0, k0 + kc) of the left operand of layer l (H_{l-1}, or the minibatch for l = 1)
-// transposed into shared memory: sH[ii * BT + b] = H_{l-1}[b][k0 + ii]; rows b >= rows are 0.
+// Stage rows [k0, k0 + kc) of the left operand of layer l into shared memory as sH[ii * BT + b]:
+// a contiguous 128-bit copy of Ht_{l-1} (l > 1), or the minibatch transposed (l = 1).
 template <int BT>
 __device__ __forceinline__ void stage_left(const MlpArgs& a, int l, const float* __restrict__ ws, int64_t row0,
                                            int rows, int k0, int kc, float* __restrict__ sH) {
-  const int n_in = a.L.width[l - 1];
-  for (int e = threadIdx.x; e < kc * BT; e += blockDim.x) {
-    const int b = e / kc, ii = e - b * kc;                       // ii fastest: coalesced global reads
-    float v = 0.0f;
-    if (b < rows)
-      v = l == 1 ? __ldg(a.X + (row0 + b) * n_in + k0 + ii) : ws[a.L.oH[l - 1] + (int64_t)b * a.L.wp[l - 1] + k0 + ii];
-    sH[ii * BT + b] = v;
+  if (l > 1) {
+    const float4* src = reinterpret_cast<const float4*>(ws + a.L.oH[l - 1] + (int64_t)k0 * BT);
+    float4* dst = reinterpret_cast<float4*>(sH);
+    for (int e = threadIdx.x; e < kc * (BT / 4); e += blockDim.x) dst[e] = src[e];
+  } else {
+    const int n_in = a.L.width[0];
+    for (int e = threadIdx.x; e < kc * BT; e += blockDim.x) {
+      const int b = e / kc, ii = e - b * kc;                     // ii fastest: coalesced global reads
+      sH[ii * BT + b] = b < rows ? __ldg(a.X + (row0 + b) * n_in + k0 + ii) : 0.0f;
+    }
   }
 }
 
+// CPT weights of one row, loaded with the widest access the alignment allows (VW floats per load)
+template <int CPT, int VW>
+__device__ __forceinline__ void load_w(const float* __restrict__ p, int n_valid, float (&w)[CPT]) {
+  if constexpr (CPT == 4 && VW == 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+  } else if constexpr (CPT == 4 && VW == 2) {
+    const float2 q0 = __ldg(reinterpret_cast<const float2*>(p)), q1 = __ldg(reinterpret_cast<const float2*>(p) + 1);
+    w[0] = q0.x; w[1] = q0.y; w[2] = q1.x; w[3] = q1.y;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) w[c] = c < n_valid ? __ldg(p + c) : 0.0f;
+  }
+}
+// widest vector access for CPT columns starting at a multiple of CPT in rows of n_out floats
+template <int CPT>
+__device__ __forceinline__ int vector_width(const float* base, int n_out) {
+  if (CPT != 4) return 1;
+  if ((n_out & 3) == 0 && aligned_to_dev(base, 16)) return 4;
+  if ((n_out & 1) == 0 && aligned_to_dev(base, 8)) return 2;      // (odd chains of a network with D % 4 == 2)
+  return 1;
+}
+
 // ---- forward: H_l = tanh(H_{l-1} W_l + b_l), thread = CPT consecutive columns x all rows ----------
+template <int BT, int CPT, int VW>
+__device__ __forceinline__ void fwd_rows(const float* __restrict__ wrow, int n_out, int n_valid, int kc,
+                                         const float* __restrict__ sH, float (&acc)[BT][CPT], float& sq) {
+#pragma unroll 8
+  for (int ii = 0; ii < kc; ++ii) {
+    float w[CPT];
+    load_w<CPT, VW>(wrow + (int64_t)ii * n_out, n_valid, w);
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) sq = fmaf(w[c], w[c], sq);
+    const float4* h4 = reinterpret_cast<const float4*>(sH + ii * BT);
+#pragma unroll
+    for (int b4 = 0; b4 < BT / 4; ++b4) {
+      const float4 h = h4[b4];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        acc[4 * b4 + 0][c] = fmaf(h.x, w[c], acc[4 * b4 + 0][c]);
+        acc[4 * b4 + 1][c] = fmaf(h.y, w[c], acc[4 * b4 + 1][c]);
+        acc[4 * b4 + 2][c] = fmaf(h.z, w[c], acc[4 * b4 + 2][c]);
+        acc[4 * b4 + 3][c] = fmaf(h.w, w[c], acc[4 * b4 + 3][c]);
+      }
+    }
+  }
+}
+
 template <int BT, int CPT>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpArgs a, int l) {
-  __shared__ __align__(16) float sH[MLP_KC * BT];
+  extern __shared__ __align__(16) float sH[];              // [min(n_in, MLP_KMAX)][BT]
   __shared__ float red[MLP_THREADS / 32];
   const int n_in = a.L.width[l - 1], n_out = a.L.width[l];
   const int n_ct = (n_out + CPT * MLP_THREADS - 1) / (CPT * MLP_THREADS);
@@ -152,65 +206,41 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpArgs a, int l) 
   int rows;
   item_rows(a, chain, row0, rows);
   const int j0 = (ct * MLP_THREADS + (int)threadIdx.x) * CPT;
-  const bool vec = CPT == 4 && (n_out & 3) == 0 && aligned_to_dev(W, 16);
-  const bool vec2 = CPT == 4 && (n_out & 1) == 0 && aligned_to_dev(W, 8);   // (rows of odd chains when D % 4 == 2)
+  const int n_valid = n_out - j0;                          // columns of this thread that exist (<= 0: none)
+  const int vw = vector_width<CPT>(W, n_out);
   float acc[BT][CPT];
 #pragma unroll
   for (int b = 0; b < BT; ++b)
 #pragma unroll
     for (int c = 0; c < CPT; ++c) acc[b][c] = 0.0f;
   float sq = 0.0f;
-  for (int k0 = 0; k0 < n_in; k0 += MLP_KC) {
-    const int kc = min(MLP_KC, n_in - k0);
-    __syncthreads();
+  for (int k0 = 0; k0 < n_in; k0 += MLP_KMAX) {
+    const int kc = min(MLP_KMAX, n_in - k0);
+    if (k0 > 0) __syncthreads();
     stage_left<BT>(a, l, ws, row0, rows, k0, kc, sH);
     __syncthreads();
-    if (j0 < n_out) {
+    if (n_valid > 0) {
       const float* __restrict__ wrow = W + (int64_t)k0 * n_out + j0;
-#pragma unroll 4
-      for (int ii = 0; ii < kc; ++ii) {
-        float w[CPT];
-        if (vec) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(wrow + (int64_t)ii * n_out));
-          w[0] = q.x;
-          if constexpr (CPT == 4) { w[1] = q.y; w[2] = q.z; w[3] = q.w; }
-        } else if (vec2 && j0 + 3 < n_out) {
-          const float2* p2 = reinterpret_cast<const float2*>(wrow + (int64_t)ii * n_out);
-          const float2 q0 = __ldg(p2), q1 = __ldg(p2 + 1);
-          w[0] = q0.x;
-          if constexpr (CPT == 4) { w[1] = q0.y; w[2] = q1.x; w[3] = q1.y; }
-        } else {
-#pragma unroll
-          for (int c = 0; c < CPT; ++c) w[c] = j0 + c < n_out ? __ldg(wrow + (int64_t)ii * n_out + c) : 0.0f;
-        }
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) sq = fmaf(w[c], w[c], sq);
-        const float4* h4 = reinterpret_cast<const float4*>(sH + ii * BT);
-#pragma unroll
-        for (int b4 = 0; b4 < BT / 4; ++b4) {
-          const float4 h = h4[b4];
-#pragma unroll
-          for (int c = 0; c < CPT; ++c) {
-            acc[4 * b4 + 0][c] = fmaf(h.x, w[c], acc[4 * b4 + 0][c]);
-            acc[4 * b4 + 1][c] = fmaf(h.y, w[c], acc[4 * b4 + 1][c]);
-            acc[4 * b4 + 2][c] = fmaf(h.z, w[c], acc[4 * b4 + 2][c]);
-            acc[4 * b4 + 3][c] = fmaf(h.w, w[c], acc[4 * b4 + 3][c]);
-          }
-        }
-      }
+      if (vw == 4) fwd_rows<BT, CPT, 4>(wrow, n_out, n_valid, kc, sH, acc, sq);
+      else if (vw == 2) fwd_rows<BT, CPT, 2>(wrow, n_out, n_valid, kc, sH, acc, sq);
+      else fwd_rows<BT, CPT, 1>(wrow, n_out, n_valid, kc, sH, acc, sq);
     }
   }
-  if (j0 < n_out) {
+  if (n_valid > 0) {
     float* __restrict__ Hout = ws + a.L.oH[l];
-    const int wp = a.L.wp[l];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-      if (j0 + c < n_out) {
+      if (c < n_valid) {
         const float bj = __ldg(bias + j0 + c);
         sq = fmaf(bj, bj, sq);
+        float4* out4 = reinterpret_cast<float4*>(Hout + (int64_t)(j0 + c) * BT);
 #pragma unroll
-        for (int b = 0; b < BT; ++b)
-          if (b < rows) Hout[(int64_t)b * wp + j0 + c] = fast_tanh(acc[b][c] + bj);
+        for (int b4 = 0; b4 < BT / 4; ++b4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = 4 * b4 + e < rows ? fast_tanh(acc[4 * b4 + e][c] + bj) : 0.0f;
+          out4[b4] = make_float4(v[0], v[1], v[2], v[3]);
+        }
       }
     }
   }
@@ -221,53 +251,74 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpArgs a, int l) 
 
 // ---- head: f = H_L W_{L+1} + b_{L+1}; loss (bayesian_neural_network.py:368-388); gradient of the
 // head parameters and rho; dZ_L = (df W_{L+1}^T) * (1 - H_L^2).  One CTA per work item. -------------
-template <bool WANT_GRAD>
+template <int BT, bool WANT_GRAD>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_head_kernel(MlpArgs a) {
-  __shared__ float sF[32], sDf[32], red[MLP_THREADS / 32];
+  __shared__ float sF[MLP_THREADS / 32][BT], sDf[BT], red[MLP_THREADS / 32];
   const int l = a.L.n_w;                       // the head is weight matrix n_w (1-based)
-  const int hL = a.L.width[l - 1], wp = a.L.wp[l - 1];
+  const int hL = a.L.width[l - 1];
   const int64_t chain = blockIdx.x;
   const int64_t trow = chain / a.theta_div;
   const float* __restrict__ th = a.theta + trow * a.L.D;
   const float* __restrict__ W = th + a.L.oW[l - 1];
   float* __restrict__ ws = a.ws + chain * a.L.ws_floats;
-  const float* __restrict__ H = ws + a.L.oH[l - 1];
+  const float* __restrict__ Ht = ws + a.L.oH[l - 1];
   int64_t row0;
   int rows;
   item_rows(a, chain, row0, rows);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float b4 = th[a.L.ob[l - 1]];
   const float rho = th[a.L.orho];
-  for (int b = w; b < rows; b += MLP_THREADS / 32) {
-    float f = 0.0f;
-    for (int i = lane; i < hL; i += 32) f = fmaf(H[(int64_t)b * wp + i], __ldg(W + i), f);
+  // f[b] = sum_i Ht[i][b] W[i]: a thread walks its units i, all rows at once
+  float f[BT];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
-    if (lane == 0) sF[b] = f + b4;
-  }
-  __syncthreads();
-  if (a.fout != nullptr) {                     // predict: (mean, log variance) per row (:535-557)
-    for (int b = tid; b < rows; b += MLP_THREADS) {
-      float* o = a.fout + (trow * a.n_rows + row0 + b) * 2;
-      o[0] = sF[b];
-      o[1] = rho;
+  for (int b = 0; b < BT; ++b) f[b] = 0.0f;
+  float sq = 0.0f;
+  for (int i = tid; i < hL; i += MLP_THREADS) {
+    const float wi = __ldg(W + i);
+    sq = fmaf(wi, wi, sq);
+    const float4* h4 = reinterpret_cast<const float4*>(Ht + (int64_t)i * BT);
+#pragma unroll
+    for (int b4 = 0; b4 < BT / 4; ++b4) {
+      const float4 h = h4[b4];
+      f[4 * b4 + 0] = fmaf(h.x, wi, f[4 * b4 + 0]); f[4 * b4 + 1] = fmaf(h.y, wi, f[4 * b4 + 1]);
+      f[4 * b4 + 2] = fmaf(h.z, wi, f[4 * b4 + 2]); f[4 * b4 + 3] = fmaf(h.w, wi, f[4 * b4 + 3]);
     }
   }
-  if (a.y == nullptr) return;
+#pragma unroll
+  for (int b = 0; b < BT; ++b) {
+    float v = f[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sF[w][b] = v;
+  }
+  const float sq_head = block_sum(sq, red);                           // (its barriers also publish sF)
   const float e_rho = expf(rho);
   const float fvi = 1.0f / (e_rho + 1e-16f);                          // :368
   float sse = 0.0f;
   if (tid < 32) {
-    float diff = tid < rows ? __ldg(a.y + row0 + tid) - sF[tid] : 0.0f;
-    if (tid < rows) sDf[tid] = -(diff * fvi) * a.inv_bs;              // d cost / d f_i
+    float diff = 0.0f;
+    if (tid < rows) {
+      float fb = b4;
+#pragma unroll
+      for (int ww = 0; ww < MLP_THREADS / 32; ++ww) fb += sF[ww][tid];
+      if (a.fout != nullptr) {                 // predict: (mean, log variance) per row (:535-557)
+        float* o = a.fout + (trow * a.n_rows + row0 + tid) * 2;
+        o[0] = fb;
+        o[1] = rho;
+      }
+      if (a.y != nullptr) {
+        diff = __ldg(a.y + row0 + tid) - fb;
+        sDf[tid] = -(diff * fvi) * a.inv_bs;                          // d cost / d f_i
+      }
+    } else if (tid < BT) {
+      sDf[tid] = 0.0f;
+    }
     sse = diff * diff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
   }
-  // squares of the head's own parameters
-  float sq = 0.0f;
-  for (int i = tid; i < hL; i += MLP_THREADS) { const float v = __ldg(W + i); sq = fmaf(v, v, sq); }
-  const float sq_head = block_sum(sq, red);                           // (also orders sDf / sse)
+  if (a.y == nullptr) return;
+  __syncthreads();
   const float pscale = a.prior_den_inv * a.inv_n;
   if (tid == 0) {
     float sq_t = sq_head + b4 * b4 + rho * rho;
@@ -291,14 +342,26 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_head_kernel(MlpArgs a) {
   }
   if (!WANT_GRAD) return;
   float* __restrict__ g = a.grad + chain * a.L.D + a.L.oW[l - 1];
-  float* __restrict__ dZ = ws + a.L.oZ[l - 1];
+  float* __restrict__ dZt = ws + a.L.oZ[l - 1];
+  float df[BT];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) df[b] = sDf[b];
   for (int i = tid; i < hL; i += MLP_THREADS) {
     const float wi = __ldg(W + i);
+    const float4* h4 = reinterpret_cast<const float4*>(Ht + (int64_t)i * BT);
+    float4* z4 = reinterpret_cast<float4*>(dZt + (int64_t)i * BT);
     float dw = 0.0f;
-    for (int b = 0; b < rows; ++b) {
-      const float h = H[(int64_t)b * wp + i];
-      dw = fmaf(h, sDf[b], dw);
-      dZ[(int64_t)b * wp + i] = (sDf[b] * wi) * fmaf(-h, h, 1.0f);
+#pragma unroll
+    for (int b4 = 0; b4 < BT / 4; ++b4) {
+      const float4 h = h4[b4];
+      const float hv[4] = {h.x, h.y, h.z, h.w};
+      float zv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dw = fmaf(hv[e], df[4 * b4 + e], dw);
+        zv[e] = (df[4 * b4 + e] * wi) * fmaf(-hv[e], hv[e], 1.0f);    // (rows >= batch: df = 0)
+      }
+      z4[b4] = make_float4(zv[0], zv[1], zv[2], zv[3]);
     }
     g[i] = fmaf(wi, pscale, dw);
   }
@@ -306,9 +369,47 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_head_kernel(MlpArgs a) {
 
 // ---- weight gradient: dW_l[i][j] = sum_b H_{l-1}[b][i] dZ_l[b][j] + pscale W_l[i][j] (and db_l);
 // thread = CPT consecutive columns (dZ of those columns in registers), the rows i of its slice ------
+template <int BT, int CPT, int VW>
+__device__ __forceinline__ void wgrad_rows(const float* __restrict__ W, float* __restrict__ gW, int n_out, int n_valid,
+                                           int kc, const float* __restrict__ sH, const float (&dz)[BT][CPT],
+                                           float pscale) {
+#pragma unroll 4
+  for (int ii = 0; ii < kc; ++ii) {
+    const int64_t o = (int64_t)ii * n_out;
+    float w[CPT], gsum[CPT];
+    load_w<CPT, VW>(W + o, n_valid, w);
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) gsum[c] = 0.0f;
+    const float4* h4 = reinterpret_cast<const float4*>(sH + ii * BT);
+#pragma unroll
+    for (int b4 = 0; b4 < BT / 4; ++b4) {
+      const float4 h = h4[b4];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        gsum[c] = fmaf(h.x, dz[4 * b4 + 0][c], gsum[c]);
+        gsum[c] = fmaf(h.y, dz[4 * b4 + 1][c], gsum[c]);
+        gsum[c] = fmaf(h.z, dz[4 * b4 + 2][c], gsum[c]);
+        gsum[c] = fmaf(h.w, dz[4 * b4 + 3][c], gsum[c]);
+      }
+    }
+    if constexpr (CPT == 4 && VW == 4) {
+      *reinterpret_cast<float4*>(gW + o) = make_float4(fmaf(w[0], pscale, gsum[0]), fmaf(w[1], pscale, gsum[1]),
+                                                       fmaf(w[2], pscale, gsum[2]), fmaf(w[3], pscale, gsum[3]));
+    } else if constexpr (CPT == 4 && VW == 2) {
+      float2* g2 = reinterpret_cast<float2*>(gW + o);
+      g2[0] = make_float2(fmaf(w[0], pscale, gsum[0]), fmaf(w[1], pscale, gsum[1]));
+      g2[1] = make_float2(fmaf(w[2], pscale, gsum[2]), fmaf(w[3], pscale, gsum[3]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+        if (c < n_valid) gW[o + c] = fmaf(w[c], pscale, gsum[c]);
+    }
+  }
+}
+
 template <int BT, int CPT>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_wgrad_kernel(MlpArgs a, int l, int n_is) {
-  __shared__ __align__(16) float sH[MLP_KC * BT];
+  extern __shared__ __align__(16) float sH[];              // [min(rows of the slice, MLP_KMAX)][BT]
   const int n_in = a.L.width[l - 1], n_out = a.L.width[l];
   const int n_ct = (n_out + CPT * MLP_THREADS - 1) / (CPT * MLP_THREADS);
   const int64_t chain = blockIdx.x / (n_ct * n_is);
@@ -322,20 +423,29 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_wgrad_kernel(MlpArgs a, int l
   int rows;
   item_rows(a, chain, row0, rows);
   const int j0 = (ct * MLP_THREADS + (int)threadIdx.x) * CPT;
+  const int n_valid = n_out - j0;
   const float pscale = a.prior_den_inv * a.inv_n;
-  const bool vec = CPT == 4 && (n_out & 3) == 0 && aligned_to_dev(W, 16) && aligned_to_dev(gW, 16);
-  const bool vec2 = CPT == 4 && (n_out & 1) == 0 && aligned_to_dev(W, 8) && aligned_to_dev(gW, 8);
+  const int vw = min(vector_width<CPT>(W, n_out), vector_width<CPT>(gW, n_out));
   float dz[BT][CPT];
-  const float* __restrict__ dZ = ws + a.L.oZ[l];
-  const int wp = a.L.wp[l];
+  const float* __restrict__ dZt = ws + a.L.oZ[l];
 #pragma unroll
-  for (int b = 0; b < BT; ++b)
+  for (int c = 0; c < CPT; ++c) {
+    if (c < n_valid) {
+      const float4* z4 = reinterpret_cast<const float4*>(dZt + (int64_t)(j0 + c) * BT);
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) dz[b][c] = (b < rows && j0 + c < n_out) ? dZ[(int64_t)b * wp + j0 + c] : 0.0f;
-  if (is == 0 && j0 < n_out) {
+      for (int b4 = 0; b4 < BT / 4; ++b4) {
+        const float4 z = z4[b4];
+        dz[4 * b4 + 0][c] = z.x; dz[4 * b4 + 1][c] = z.y; dz[4 * b4 + 2][c] = z.z; dz[4 * b4 + 3][c] = z.w;
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < BT; ++b) dz[b][c] = 0.0f;
+    }
+  }
+  if (is == 0) {
 #pragma unroll
     for (int c = 0; c < CPT; ++c)
-      if (j0 + c < n_out) {
+      if (c < n_valid) {
         float db = 0.0f;
 #pragma unroll
         for (int b = 0; b < BT; ++b) db += dz[b][c];
@@ -344,58 +454,16 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_wgrad_kernel(MlpArgs a, int l
   }
   const int ilen = (n_in + n_is - 1) / n_is;
   const int i_begin = is * ilen, i_end = min(n_in, i_begin + ilen);
-  for (int k0 = i_begin; k0 < i_end; k0 += MLP_KC) {
-    const int kc = min(MLP_KC, i_end - k0);
-    __syncthreads();
+  for (int k0 = i_begin; k0 < i_end; k0 += MLP_KMAX) {
+    const int kc = min(MLP_KMAX, i_end - k0);
+    if (k0 > i_begin) __syncthreads();
     stage_left<BT>(a, l, ws, row0, rows, k0, kc, sH);
     __syncthreads();
-    if (j0 < n_out) {
-#pragma unroll 2
-      for (int ii = 0; ii < kc; ++ii) {
-        const int64_t o = (int64_t)(k0 + ii) * n_out + j0;
-        float w[CPT], gsum[CPT];
-        if (vec) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(W + o));
-          w[0] = q.x;
-          if constexpr (CPT == 4) { w[1] = q.y; w[2] = q.z; w[3] = q.w; }
-        } else if (vec2 && j0 + 3 < n_out) {
-          const float2 q0 = __ldg(reinterpret_cast<const float2*>(W + o)), q1 = __ldg(reinterpret_cast<const float2*>(W + o) + 1);
-          w[0] = q0.x;
-          if constexpr (CPT == 4) { w[1] = q0.y; w[2] = q1.x; w[3] = q1.y; }
-        } else {
-#pragma unroll
-          for (int c = 0; c < CPT; ++c) w[c] = j0 + c < n_out ? __ldg(W + o + c) : 0.0f;
-        }
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) gsum[c] = 0.0f;
-        const float4* h4 = reinterpret_cast<const float4*>(sH + ii * BT);
-#pragma unroll
-        for (int b4 = 0; b4 < BT / 4; ++b4) {
-          const float4 h = h4[b4];
-#pragma unroll
-          for (int c = 0; c < CPT; ++c) {
-            gsum[c] = fmaf(h.x, dz[4 * b4 + 0][c], gsum[c]);
-            gsum[c] = fmaf(h.y, dz[4 * b4 + 1][c], gsum[c]);
-            gsum[c] = fmaf(h.z, dz[4 * b4 + 2][c], gsum[c]);
-            gsum[c] = fmaf(h.w, dz[4 * b4 + 3][c], gsum[c]);
-          }
-        }
-        if (vec) {
-          if constexpr (CPT == 4)
-            *reinterpret_cast<float4*>(gW + o) = make_float4(fmaf(w[0], pscale, gsum[0]), fmaf(w[1], pscale, gsum[1]),
-                                                             fmaf(w[2], pscale, gsum[2]), fmaf(w[3], pscale, gsum[3]));
-        } else if (vec2 && j0 + 3 < n_out) {
-          if constexpr (CPT == 4) {
-            float2* g2 = reinterpret_cast<float2*>(gW + o);
-            g2[0] = make_float2(fmaf(w[0], pscale, gsum[0]), fmaf(w[1], pscale, gsum[1]));
-            g2[1] = make_float2(fmaf(w[2], pscale, gsum[2]), fmaf(w[3], pscale, gsum[3]));
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < CPT; ++c)
-            if (j0 + c < n_out) gW[o + c] = fmaf(w[c], pscale, gsum[c]);
-        }
-      }
+    if (n_valid > 0) {
+      const int64_t o = (int64_t)k0 * n_out + j0;
+      if (vw == 4) wgrad_rows<BT, CPT, 4>(W + o, gW + o, n_out, n_valid, kc, sH, dz, pscale);
+      else if (vw == 2) wgrad_rows<BT, CPT, 2>(W + o, gW + o, n_out, n_valid, kc, sH, dz, pscale);
+      else wgrad_rows<BT, CPT, 1>(W + o, gW + o, n_out, n_valid, kc, sH, dz, pscale);
     }
   }
 }
@@ -404,7 +472,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_wgrad_kernel(MlpArgs a, int l
 // thread = RI rows i (interleaved, so a warp's rows are consecutive) x all batch rows -----------------
 template <int BT, int RI>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_data_kernel(MlpArgs a, int l) {
-  __shared__ __align__(16) float sZ[MLP_KC * BT];
+  extern __shared__ __align__(16) float sZ[];              // [min(n_out, MLP_KMAX)][BT]
   const int n_in = a.L.width[l - 1], n_out = a.L.width[l];
   const int n_rt = (n_in + RI * MLP_THREADS - 1) / (RI * MLP_THREADS);
   const int64_t chain = blockIdx.x / n_rt;
@@ -412,16 +480,11 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_data_kernel(MlpArgs a, in
   const float* __restrict__ th = a.theta + (chain / a.theta_div) * a.L.D;
   const float* __restrict__ W = th + a.L.oW[l - 1];
   float* __restrict__ ws = a.ws + chain * a.L.ws_floats;
-  int64_t row0;
-  int rows;
-  item_rows(a, chain, row0, rows);
-  const float* __restrict__ dZ = ws + a.L.oZ[l];
-  const int wpz = a.L.wp[l];
   int irow[RI];
 #pragma unroll
   for (int r = 0; r < RI; ++r) irow[r] = (rt * RI + r) * MLP_THREADS + (int)threadIdx.x;
-  // rows of W_l start at multiples of n_out floats: 128-bit loads need n_out % 4 == 0 and an
-  // aligned base; a base that is only 8-byte aligned (odd chains when D % 4 == 2) takes two 64-bit loads
+  // rows of W_l start at multiples of n_out floats: vector loads along a row need n_out % 4 == 0; a
+  // base that is only 8-byte aligned (odd chains when D % 4 == 2) takes two 64-bit loads
   const bool vec = (n_out & 3) == 0 && aligned_to_dev(W, 8);
   const bool a16 = aligned_to_dev(W, 16);
   float acc[RI][BT];
@@ -429,15 +492,17 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_data_kernel(MlpArgs a, in
   for (int r = 0; r < RI; ++r)
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[r][b] = 0.0f;
-  for (int k0 = 0; k0 < n_out; k0 += MLP_KC) {
-    const int kc = min(MLP_KC, n_out - k0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < kc * BT; e += blockDim.x) {      // sZ[jj * BT + b] = dZ_l[b][k0 + jj]
-      const int b = e / kc, jj = e - b * kc;
-      sZ[jj * BT + b] = b < rows ? dZ[(int64_t)b * wpz + k0 + jj] : 0.0f;
+  for (int k0 = 0; k0 < n_out; k0 += MLP_KMAX) {
+    const int kc = min(MLP_KMAX, n_out - k0);
+    if (k0 > 0) __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(ws + a.L.oZ[l] + (int64_t)k0 * BT);
+      float4* dst = reinterpret_cast<float4*>(sZ);
+      for (int e = threadIdx.x; e < kc * (BT / 4); e += blockDim.x) dst[e] = src[e];
     }
     __syncthreads();
-    if (vec && (kc & 3) == 0) {
+    if (vec) {                                             // (kc is a multiple of 4: n_out and MLP_KMAX are)
+#pragma unroll 2
       for (int jj = 0; jj < kc; jj += 4) {
         float w[RI][4];
 #pragma unroll
@@ -472,7 +537,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_data_kernel(MlpArgs a, in
         }
       }
     } else {
-#pragma unroll 2
+#pragma unroll 4
       for (int jj = 0; jj < kc; ++jj) {
         float w[RI];
 #pragma unroll
@@ -492,35 +557,48 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_data_kernel(MlpArgs a, in
       }
     }
   }
-  const float* __restrict__ H = ws + a.L.oH[l - 1];
+  const float* __restrict__ Ht = ws + a.L.oH[l - 1];
   float* __restrict__ dZp = ws + a.L.oZ[l - 1];
-  const int wp = a.L.wp[l - 1];
 #pragma unroll
   for (int r = 0; r < RI; ++r)
     if (irow[r] < n_in) {
+      const float4* h4 = reinterpret_cast<const float4*>(Ht + (int64_t)irow[r] * BT);
+      float4* z4 = reinterpret_cast<float4*>(dZp + (int64_t)irow[r] * BT);
 #pragma unroll
-      for (int b = 0; b < BT; ++b)
-        if (b < rows) {
-          const float h = H[(int64_t)b * wp + irow[r]];
-          dZp[(int64_t)b * wp + irow[r]] = acc[r][b] * fmaf(-h, h, 1.0f);
-        }
+      for (int b4 = 0; b4 < BT / 4; ++b4) {
+        const float4 h = h4[b4];                          // (rows >= batch: acc = 0, H = 0)
+        z4[b4] = make_float4(acc[r][4 * b4 + 0] * fmaf(-h.x, h.x, 1.0f), acc[r][4 * b4 + 1] * fmaf(-h.y, h.y, 1.0f),
+                             acc[r][4 * b4 + 2] * fmaf(-h.z, h.z, 1.0f), acc[r][4 * b4 + 3] * fmaf(-h.w, h.w, 1.0f));
+      }
     }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
+template <typename K>
+static void allow_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 template <int BT>
 static int launch_mlp_bt(const MlpArgs& a, bool want_grad, cudaStream_t st) {
   const MlpLayout& L = a.L;
   const int n_hidden = L.n_w - 1;
   const int64_t C = a.n_chains;
+  auto smem_rows = [](int n) { return (size_t)(n < MLP_KMAX ? n : MLP_KMAX) * BT * sizeof(float); };
   for (int l = 1; l <= n_hidden; ++l) {
     const int n_ct = mlp_col_tiles(L.width[l]);
-    if (mlp_cpt(L.width[l]) == 4) mlp_fwd_kernel<BT, 4><<<(unsigned)(C * n_ct), MLP_THREADS, 0, st>>>(a, l);
-    else mlp_fwd_kernel<BT, 1><<<(unsigned)(C * n_ct), MLP_THREADS, 0, st>>>(a, l);
+    const size_t smem = smem_rows(L.width[l - 1]);
+    if (mlp_cpt(L.width[l]) == 4) {
+      allow_smem(mlp_fwd_kernel<BT, 4>, smem);
+      mlp_fwd_kernel<BT, 4><<<(unsigned)(C * n_ct), MLP_THREADS, smem, st>>>(a, l);
+    } else {
+      allow_smem(mlp_fwd_kernel<BT, 1>, smem);
+      mlp_fwd_kernel<BT, 1><<<(unsigned)(C * n_ct), MLP_THREADS, smem, st>>>(a, l);
+    }
     if (int rc = check_launch("mlp_fwd_kernel")) return rc;
   }
-  if (want_grad) mlp_head_kernel<true><<<(unsigned)C, MLP_THREADS, 0, st>>>(a);
-  else mlp_head_kernel<false><<<(unsigned)C, MLP_THREADS, 0, st>>>(a);
+  if (want_grad) mlp_head_kernel<BT, true><<<(unsigned)C, MLP_THREADS, 0, st>>>(a);
+  else mlp_head_kernel<BT, false><<<(unsigned)C, MLP_THREADS, 0, st>>>(a);
   if (int rc = check_launch("mlp_head_kernel")) return rc;
   if (!want_grad) return SGMCMC_OK;
   for (int l = n_hidden; l >= 1; --l) {
@@ -529,17 +607,26 @@ static int launch_mlp_bt(const MlpArgs& a, bool want_grad, cudaStream_t st) {
     const bool quad = mlp_cpt(n_out) == 4;
     const int n_ct = mlp_col_tiles(n_out);
     int n_is = 1;
-    while (C * n_ct * n_is < 592 && n_is * 2 * MLP_KC <= n_in) n_is *= 2;
-    if (quad) mlp_wgrad_kernel<BT, 4><<<(unsigned)(C * n_ct * n_is), MLP_THREADS, 0, st>>>(a, l, n_is);
-    else mlp_wgrad_kernel<BT, 1><<<(unsigned)(C * n_ct * n_is), MLP_THREADS, 0, st>>>(a, l, n_is);
+    while (C * n_ct * n_is < 592 && n_is * 2 * 64 <= n_in) n_is *= 2;
+    const size_t smem = smem_rows((n_in + n_is - 1) / n_is);
+    if (quad) {
+      allow_smem(mlp_wgrad_kernel<BT, 4>, smem);
+      mlp_wgrad_kernel<BT, 4><<<(unsigned)(C * n_ct * n_is), MLP_THREADS, smem, st>>>(a, l, n_is);
+    } else {
+      allow_smem(mlp_wgrad_kernel<BT, 1>, smem);
+      mlp_wgrad_kernel<BT, 1><<<(unsigned)(C * n_ct * n_is), MLP_THREADS, smem, st>>>(a, l, n_is);
+    }
     if (int rc = check_launch("mlp_wgrad_kernel")) return rc;
     if (l > 1) {
-      if (n_in >= 4 * MLP_THREADS && C * ((n_in + 4 * MLP_THREADS - 1) / (4 * MLP_THREADS)) >= 296) {
-        const int n_rt = (n_in + 4 * MLP_THREADS - 1) / (4 * MLP_THREADS);
-        mlp_bwd_data_kernel<BT, 4><<<(unsigned)(C * n_rt), MLP_THREADS, 0, st>>>(a, l);
+      const size_t smem_z = smem_rows(n_out);
+      const int n_rt4 = (n_in + 4 * MLP_THREADS - 1) / (4 * MLP_THREADS);
+      if (BT <= 20 && n_in >= 4 * MLP_THREADS && C * n_rt4 >= 296) {
+        allow_smem(mlp_bwd_data_kernel<BT, 4>, smem_z);
+        mlp_bwd_data_kernel<BT, 4><<<(unsigned)(C * n_rt4), MLP_THREADS, smem_z, st>>>(a, l);
       } else {
         const int n_rt = (n_in + MLP_THREADS - 1) / MLP_THREADS;
-        mlp_bwd_data_kernel<BT, 1><<<(unsigned)(C * n_rt), MLP_THREADS, 0, st>>>(a, l);
+        allow_smem(mlp_bwd_data_kernel<BT, 1>, smem_z);
+        mlp_bwd_data_kernel<BT, 1><<<(unsigned)(C * n_rt), MLP_THREADS, smem_z, st>>>(a, l);
       }
       if (int rc = check_launch("mlp_bwd_data_kernel")) return rc;
     }
@@ -548,10 +635,12 @@ static int launch_mlp_bt(const MlpArgs& a, bool want_grad, cudaStream_t st) {
 }
 
 static int launch_mlp(const MlpArgs& a, bool want_grad, cudaStream_t st) {
-  if (a.batch <= 8) return launch_mlp_bt<8>(a, want_grad, st);
-  if (a.batch <= 16) return launch_mlp_bt<16>(a, want_grad, st);
-  if (a.batch <= 20) return launch_mlp_bt<20>(a, want_grad, st);
-  return launch_mlp_bt<32>(a, want_grad, st);
+  switch (mlp_bt(a.batch)) {
+    case 8: return launch_mlp_bt<8>(a, want_grad, st);
+    case 16: return launch_mlp_bt<16>(a, want_grad, st);
+    case 20: return launch_mlp_bt<20>(a, want_grad, st);
+    default: return launch_mlp_bt<32>(a, want_grad, st);
+  }
 }
 
 }  // namespace sgmcmc

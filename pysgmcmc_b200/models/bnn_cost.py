@@ -205,7 +205,8 @@ class BayesianNeuralNetworkNLL(object):
         X, Y = self._torch_batch()
         out = self.net(X, params)
         f_mean, f_log_var = out[..., 0:1], out[..., 1:2]
-        Y = Y.reshape(f_mean.shape)
+        # minibatches per chain: Y [C, B]; one batch for all chains: Y [B] broadcasts over them
+        Y = Y.reshape(Y.shape + (1,)) if Y.dim() == f_mean.dim() - 1 else Y.reshape(f_mean.shape[-2:])
         f_var_inv = 1.0 / (torch.exp(f_log_var) + 1e-16)
         mse = torch.square(Y - f_mean)
         log_like = (-mse * (0.5 * f_var_inv) - 0.5 * f_log_var).sum(dim=(-1, -2))

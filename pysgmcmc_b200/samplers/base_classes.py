@@ -273,6 +273,10 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         assert (feed_dict is None or hasattr(feed_dict, "update"))
         assert hasattr(self, "theta_t") or not hasattr(self, "cost")
 
+        if self._prefetching(feed_dict):
+            return self._next_prefetched(unwrap=True)
+        self._drop_prefetched()
+
         if feed_dict is None:
             feed_dict = dict()
 
@@ -292,8 +296,68 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
 
         return params, cost
 
+    # ------------------------------------------------------------------ next() from prefetched steps
+    _pf = None
+    _prefetch_supported = True
+
+    def _prefetching(self, feed_dict):
+        return (not feed_dict and self._prefetch_supported and self.session.prefetch > 1
+                and self._can_run_fused())
+
+    def _next_prefetched(self, unwrap):
+        """Session(prefetch=S): the next (sample, cost) pair out of a block of S steps computed by
+        one launch of the fused kernels (`run`).  `n_iterations` counts the pairs handed out, the
+        device state is `_pf["ahead"]` steps further."""
+        pf = self._pf
+        if pf is None or pf["pos"] == pf["n"]:
+            S = self.session.prefetch
+            if self._burn_in_remaining_for_prefetch() > 0:
+                # a block never crosses the end of burn-in: `next()` changes its return type there
+                S = min(S, self._burn_in_remaining_for_prefetch())
+            handed_out = self.n_iterations
+            with self._on_device():
+                trace, costs = self._run(S, 1)           # advances n_iterations by S
+                if self.session.output == "numpy":
+                    trace, costs = trace.cpu().numpy(), costs.cpu().numpy()
+            self.n_iterations = handed_out
+            pf = self._pf = {"trace": trace, "costs": costs, "pos": 0, "n": S}
+        i = pf["pos"]
+        pf["pos"] += 1
+        flat = pf["trace"][i]
+        if self.session.output == "numpy":
+            params = []
+            for shp, off, n in zip(self._shapes, self._offsets, self._sizes):
+                v = flat[:, off:off + n]
+                params.append(v.reshape((self.n_chains,) + shp) if self.multi_chain else v[0].reshape(shp))
+            c = pf["costs"][i]
+            cost = c if self.multi_chain else c.reshape(())[()]
+        else:
+            params = self._views(flat)
+            cost = self._output_cost(pf["costs"][i])
+        if unwrap and len(params) == 1:
+            params = params[0]
+        self.stepsize_schedule.update(params, cost)
+        self.n_iterations += 1
+        return params, cost
+
+    def _burn_in_remaining_for_prefetch(self):
+        return 0
+
+    def _drop_prefetched(self):
+        """Leaving the prefetched mode (something was fed, `run()` was called, ...): the steps that
+        were computed ahead but not handed out yet are skipped -- the chain continues from the
+        device state."""
+        pf = self._pf
+        if pf is not None:
+            self.n_iterations += pf["n"] - pf["pos"]
+            self._pf = None
+
     # ------------------------------------------------------------------ checkpoint / resume
     def state_dict(self):
+        self._drop_prefetched()
+        return self._state_dict()
+
+    def _state_dict(self):
         """Everything needed to continue this chain bit-identically: the flat state arrays,
         the iteration counter (= Philox step), the noise seed and, for on-device minibatch
         generators, the MT19937 streams.  (The reference keeps its state in TF session
@@ -314,6 +378,7 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
 
     def load_state_dict(self, state):
         assert tuple(state["theta"].shape) == tuple(self._theta.shape), "layout mismatch"
+        self._pf = None
         self._theta.copy_(state["theta"])
         if self._STATE_NAMES:
             assert tuple(state["state_names"]) == tuple(self._STATE_NAMES)
@@ -340,6 +405,7 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         kernels on the device.
         """
         assert n_steps >= 0 and keep_every >= 1
+        self._drop_prefetched()
         with self._on_device():
             return self._run(n_steps, keep_every)
 
@@ -423,6 +489,11 @@ class BurnInMCMCSampler(MCMCSampler, metaclass=abc.ABCMeta):
         samples are unwrapped (:302-304)."""
         assert (feed_dict is None or hasattr(feed_dict, "update"))
 
+        if self._prefetching(feed_dict):
+            # (burn-in steps return the parameter list as it is, later ones unwrap: :446 / :302-304)
+            return self._next_prefetched(unwrap=not self.is_burning_in)
+        self._drop_prefetched()
+
         if feed_dict is None:
             feed_dict = dict()
 
@@ -453,3 +524,6 @@ class BurnInMCMCSampler(MCMCSampler, metaclass=abc.ABCMeta):
 
     def _burn_in_remaining(self):
         return max(0, self.burn_in_steps - self.n_iterations)
+
+    def _burn_in_remaining_for_prefetch(self):
+        return self._burn_in_remaining()

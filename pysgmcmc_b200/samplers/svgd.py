@@ -177,6 +177,8 @@ class SVGDSampler(MCMCSampler):
         with self._on_device():
             return self._run(n_steps, keep_every)
 
+    _prefetch_supported = False      # (the particle layout of the trace differs from the chain layout)
+
     def _run(self, n_steps, keep_every):
         n_keep = n_steps // keep_every
         trace = torch.empty((n_keep, self.n_particles, self.n_dims), dtype=self.dtype, device=self.device)

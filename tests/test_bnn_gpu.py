@@ -6,9 +6,8 @@ SFU (|error| ~ 2e-7 per activation), the oracle is float64.  Cost: rtol 2e-6.  G
 |g - g_ref| <= 2e-5 * max|g_ref| per chain (element-wise rtol is meaningless for the many
 entries that are ~1e-8 of the largest one).  Trajectories (injected noise, scale_grad = N as
 BayesianNeuralNetwork.train sets it): 1e-5 relative to max|theta| after 200 steps (N = 2000)
-and after 500 steps at the benchmarked shapes (N = 20 000), 3e-5 after 1000 -- float32 itself
-separates the float32 and float64 oracles by 1.4e-5 there; the update alone is bit-exact
-(teacher-forced test).
+and after 1000 steps at the benchmarked shapes (N = 20 000) -- float32 itself separates the
+float32 and float64 oracles by 1.4e-5 there; the update alone is bit-exact (teacher-forced test).
 """
 import os
 
@@ -26,6 +25,7 @@ from pysgmcmc_b200.stepsize_schedules import ConstantStepsizeSchedule
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+K4_DEFAULT = 13      # tensor-pipe kernel, rounded split + FP32-pipe accumulation (csrc/bnn.cu: g_bnn_variant)
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -221,7 +221,7 @@ def test_bnn_sghmc_sampler_trajectory_matches_oracle():
     assert not sampler.is_burning_in
 
 
-@pytest.mark.parametrize("variant", [10, 0])
+@pytest.mark.parametrize("variant", [K4_DEFAULT, 0])
 def test_bnn_sghmc_teacher_forced_update_bit_exact_gradient_error_bounded(variant):
     """Separates the two error sources of a BNN-SGHMC trajectory.  Every step the oracle update
     (sghmc.py:165-251) is fed the GPU's OWN gradient and the GPU's state before the step: the
@@ -275,33 +275,33 @@ def test_bnn_sghmc_teacher_forced_update_bit_exact_gradient_error_bounded(varian
             if s == burn - 1:          # the mass matrix the sampling phase uses (base_classes.py:438,448-454)
                 assert np.array_equal(got["minv"], want["minv"]), "frozen minv"
         assert np.array_equal(sampler._state_array("minv").cpu().numpy(), frozen)
-        assert worst_grad <= 2e-5, "max |dg| / max|g| over the run = %.3g" % worst_grad
+        assert worst_grad <= 2e-5, "variant %d: max |dg| / max|g| over the run = %.3g" % (variant, worst_grad)
     finally:
-        _native.call("sgmcmc_set_bnn_tuning", 10)
+        _native.call("sgmcmc_set_bnn_tuning", K4_DEFAULT)
 
 
-# float32 arithmetic alone separates the float32 and float64 ORACLES by ~1.4e-5 of max|theta|
-# after 1000 steps at these shapes (2.8e-6 at the end of burn-in, step 600; measured with
-# tools/bnn_trajectory_drift.py, recorded in profiles/r02_bnn_trajectory_drift.jsonl), so the
-# north star's 1e-5 is asserted where float32 itself can hold it and the end of the run is
-# bounded by twice the oracles' own separation.
-TRAJ_TOL_500, TRAJ_TOL_1000 = 1e-5, 3e-5
+# BASELINE.json north_star: "1000-step trajectories match ... within 1e-5 relative in FP32".
+# Measured at these shapes (tools/bnn_trajectory_drift.py, profiles/r02_bnn_trajectory_drift.jsonl):
+# default K4 (tensor pipe, rounded split + FP32-pipe accumulation) 9.0e-6, FFMA K4 9.8e-6 of
+# max|theta| at step 1000 -- for scale: float32 arithmetic alone separates the float32 and float64
+# ORACLES by 1.4e-5 there.  The faster tensor-pipe modes (variants 10 / 11: 4.6e-5 / 2.4e-5) do
+# not meet the bar and are not the default.
+TRAJ_TOL = 1e-5
 
 
-@pytest.mark.parametrize("variant", [10, 0])
+@pytest.mark.parametrize("variant", [K4_DEFAULT, 0])
 def test_bnn_sghmc_1000_step_trajectory_at_the_benchmarked_shapes(variant):
     """1000 steps of next(sampler) at BASELINE.json configs[2] shapes -- N = 20 000, minibatch 20,
     scale_grad = N, eps = 0.01, burn-in boundary at step 600, injected noise, bit-exact
     minibatch streams -- for both K4 implementations, against the float32 oracle
-    (sghmc.py:165-251 over bayesian_neural_network.py:337-388)."""
+    (sghmc.py:165-251 over bayesian_neural_network.py:337-388), at the north star's tolerance."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
     from bnn_trajectory_drift import drift_curves
     line, = drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(variant,))
     vs32 = dict(zip(line["checkpoints"], line["gpu_vs_oracle_f32"]))
     assert all(np.isfinite(v) for v in vs32.values())
-    assert max(vs32[k] for k in vs32 if k <= 500) <= TRAJ_TOL_500, line
-    assert vs32[1000] <= TRAJ_TOL_1000, line
+    assert max(vs32.values()) <= TRAJ_TOL, line
     # never (much) further from the float64 oracle than the float32 oracle itself is
     assert line["gpu_vs_oracle_f64"][-1] <= 2.0 * line["oracle_f32_vs_f64"][-1] + 1e-5, line
 
@@ -527,13 +527,13 @@ def test_k4_launch_variants_agree():
     Xb, yb = obnn.gather_minibatch(X, y, starts, 20)
     wc, wg, _ = obnn.nll_and_grad(theta, Xb, yb, n_examples=N)
     try:
-        for v in range(11):
+        for v in range(14):
             _native.call("sgmcmc_set_bnn_tuning", v)
             cost, grad, _ = k4(theta, X, y, starts, 20, 20, N)
             np.testing.assert_allclose(cost, wc, rtol=3e-6, err_msg="variant %d" % v)
             assert_grad_close(grad, wg)
     finally:
-        _native.call("sgmcmc_set_bnn_tuning", 10)
+        _native.call("sgmcmc_set_bnn_tuning", K4_DEFAULT)
 
 
 def test_checkpoint_resume_is_bit_identical():

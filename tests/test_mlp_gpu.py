@@ -81,7 +81,7 @@ def test_mlp_cost_and_gradient_match_the_oracle(hidden, n_in, C, batch, N):
     assert err.max() <= 2e-5, "max |dg| / max|g| = %.3g" % err.max()
     # cost only (no gradient buffer): same cost
     cost2, _, _ = mlp_k4(theta, X, y, starts, widths, batch, 20, N, want_grad=False)
-    np.testing.assert_array_equal(cost, cost2)
+    np.testing.assert_allclose(cost, cost2, rtol=1e-6)
 
 
 def test_generic_kernels_agree_with_the_specialised_k4():

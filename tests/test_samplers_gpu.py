@@ -232,3 +232,35 @@ def test_invalid_constructor_inputs_assert():
                 dict(session="session")):
         with pytest.raises(AssertionError):
             SGHMCSampler(**{**good, **bad})
+
+
+@pytest.mark.parametrize("output", ["torch", "numpy"])
+@pytest.mark.parametrize("cls_name", ["sghmc", "sgld", "rsghmc"])
+def test_prefetched_next_returns_the_same_pairs(cls_name, output):
+    """Session(prefetch=S): next(sampler) hands out steps computed S at a time by one fused launch;
+    the (sample, cost) pairs, their container types across the burn-in boundary and n_iterations
+    are those of the step-by-step loop, bit for bit."""
+    from pysgmcmc_b200.samplers import RelativisticSGHMCSampler, SGHMCSampler, SGLDSampler
+    cls = {"sghmc": SGHMCSampler, "sgld": SGLDSampler, "rsghmc": RelativisticSGHMCSampler}[cls_name]
+    kw = {} if cls_name == "rsghmc" else {"burn_in_steps": 37}
+
+    def make(prefetch):
+        params = [torch.tensor(0.0, device=DEV), torch.tensor(6.0, device=DEV)]
+        return cls(params=params, cost_fun=to_negative_log_likelihood(banana_log_likelihood), seed=5,
+                   session=Session(device=DEV, output=output, prefetch=prefetch), **kw)
+    a, b = make(0), make(16)
+    if cls_name == "rsghmc":
+        b._state_array("p").copy_(a._state_array("p"))
+    for step in range(100):
+        (sa, ca), (sb, cb) = next(a), next(b)
+        assert type(sa) is type(sb) and a.n_iterations == b.n_iterations == step + 1
+        assert getattr(a, "is_burning_in", False) == getattr(b, "is_burning_in", False)
+        ha = [np.asarray(x.cpu() if output == "torch" else x) for x in sa]
+        hb = [np.asarray(x.cpu() if output == "torch" else x) for x in sb]
+        assert all(np.array_equal(x, y) for x, y in zip(ha, hb)), "sample at step %d" % step
+        assert np.array_equal(np.asarray(ca.cpu() if output == "torch" else ca),
+                              np.asarray(cb.cpu() if output == "torch" else cb)), "cost at step %d" % step
+    # leaving the prefetched mode: the steps computed ahead are skipped, the chain goes on from the device state
+    ahead = b._pf["n"] - b._pf["pos"]
+    b.run(3)
+    assert b.n_iterations == 100 + ahead + 3 and b._pf is None

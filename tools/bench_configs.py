@@ -40,10 +40,10 @@ n = 10000
 banana_nll = to_negative_log_likelihood(banana_log_likelihood)
 
 
-def single_chain(output, fused=True):
+def single_chain(output, fused=True, prefetch=0):
     params = [torch.tensor(0.0, device=DEV), torch.tensor(6.0, device=DEV)]
     return SGHMCSampler(params=params, cost_fun=banana_nll, burn_in_steps=3000, seed=1,
-                        session=Session(device=DEV, output=output, fused=fused))
+                        session=Session(device=DEV, output=output, fused=fused, prefetch=prefetch))
 
 s = single_chain("numpy")
 for _ in range(100):
@@ -57,6 +57,14 @@ for _ in range(100):
 dt = gpu_timed(lambda: [next(s) for _ in range(n)])
 emit(config="banana SGHMC, 1 chain, next(sampler) -> device tensors (no host sync)", steps=n, seconds=dt,
      chain_steps_per_s=n / dt)
+for out in ("torch", "numpy"):
+    for S in (64, 1024):
+        s = single_chain(out, prefetch=S)
+        for _ in range(2 * S):
+            next(s)
+        dt = gpu_timed(lambda: [next(s) for _ in range(n)])
+        emit(config="banana SGHMC, 1 chain, next(sampler) -> %s, Session(prefetch=%d): steps computed %d at a "
+                    "time by one K6 launch" % (out, S, S), steps=n, seconds=dt, chain_steps_per_s=n / dt)
 s = single_chain("torch", fused=False)
 for _ in range(100):
     next(s)
@@ -97,3 +105,62 @@ for _ in range(500):
 dt = time.perf_counter() - t0
 emit(config="gmm1 SGLD, 4096 chains, NumPy oracle on one host core", steps=500, seconds=dt,
      chain_steps_per_s=C * 500 / dt)
+
+# ---- config 2: ONE BOHAMIANN chain (N = 20 000, batch 20) -----------------------------------
+from oracle import bnn as obnn  # noqa: E402
+from pysgmcmc_b200.data_batches import DeviceBatchGenerator  # noqa: E402
+from pysgmcmc_b200.models.bnn_cost import BayesianNeuralNetworkNLL, default_net_params  # noqa: E402
+
+N, B = 20000, 20
+rs = np.random.RandomState(1)
+Xd = rs.uniform(0, 1, size=(N, 1))
+yd = np.sinc(Xd * 10 - 5).sum(axis=1)
+Xd = ((Xd - Xd.mean(0)) / Xd.std(0)).astype(np.float32)
+yd = ((yd - yd.mean()) / yd.std()).astype(np.float32)
+
+
+def bnn_chain(C, prefetch=0, output="torch"):
+    gen = DeviceBatchGenerator(N, B, n_chains=C, seed=1, device=DEV)
+    nll = BayesianNeuralNetworkNLL(N, B, X=Xd, y=yd, starts_placeholder=gen.starts_placeholder, device=DEV)
+    return SGHMCSampler(params=default_net_params(1, n_chains=C, seed=1, device=DEV), cost_fun=nll,
+                        batch_generator=gen, burn_in_steps=1000, scale_grad=float(N), seed=1,
+                        session=Session(device=DEV, n_chains=C, output=output, prefetch=prefetch))
+
+
+for C in (1, 8, 148):
+    s = bnn_chain(C)
+    s.run(1100, keep_every=10 ** 9)
+    dt = gpu_timed(lambda: s.run(5000, keep_every=100))
+    emit(config="BNN-SGHMC (1-50-50-50-1, N=20000, batch 20), %d chain(s), sampler.run(5000) after burn-in" % C,
+         steps=5000, seconds=dt, chain_steps_per_s=C * 5000 / dt, us_per_step=1e6 * dt / 5000)
+s = bnn_chain(1)
+for _ in range(1100):
+    next(s)
+dt = gpu_timed(lambda: [next(s) for _ in range(3000)])
+emit(config="BNN-SGHMC, 1 chain, next(sampler) -> device tensors, step by step", steps=3000, seconds=dt,
+     chain_steps_per_s=3000 / dt, us_per_step=1e6 * dt / 3000)
+for out in ("torch", "numpy"):
+    s = bnn_chain(1, prefetch=256, output=out)
+    for _ in range(1300):
+        next(s)
+    dt = gpu_timed(lambda: [next(s) for _ in range(5000)])
+    emit(config="BNN-SGHMC, 1 chain, next(sampler) -> %s, Session(prefetch=256)" % out, steps=5000, seconds=dt,
+         chain_steps_per_s=5000 / dt, us_per_step=1e6 * dt / 5000)
+theta = obnn.init_theta(1, seed=1, dtype=np.float32)
+holder = {}
+
+
+def _cg(th):
+    Xb, yb = obnn.gather_minibatch(Xd, yd, holder["s"], B)
+    c, g, _ = obnn.nll_and_grad(th, Xb, yb, n_examples=N)
+    return c, g
+
+
+chain = osamplers.OracleChain("sghmc", theta, _cg, epsilon=0.01, burn_in_steps=0, scale_grad=float(N))
+t0 = time.perf_counter()
+for _ in range(2000):
+    holder["s"] = rng.randint(0, N - B + 1, size=1)
+    chain.next(rng.standard_normal((1, 5252)).astype(np.float32))
+dt = time.perf_counter() - t0
+emit(config="BNN-SGHMC, 1 chain, NumPy oracle on one host core", steps=2000, seconds=dt, chain_steps_per_s=2000 / dt,
+     us_per_step=1e6 * dt / 2000)
