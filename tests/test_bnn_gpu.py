@@ -132,8 +132,9 @@ def test_k10_predict_matches_oracle():
     X = rng.uniform(-2, 2, size=(n_points, 1))
     t = torch.as_tensor(theta, dtype=torch.float32, device=DEV)
     out = torch.empty((n_nets, n_points, 2), device=DEV)
-    _native.call("sgmcmc_bnn_predict_f32", _native.ptr(t), _native.ptr(torch.as_tensor(X, dtype=torch.float32, device=DEV)),
-                 _native.ptr(out), n_nets, 1, n_points, _native.stream_ptr())
+    Xd = torch.as_tensor(X, dtype=torch.float32, device=DEV)
+    _native.call("sgmcmc_bnn_predict_f32", _native.ptr(t), _native.ptr(Xd), _native.ptr(out), n_nets, 1, n_points,
+                 _native.stream_ptr())
     f, rho, _ = obnn.forward(theta, np.repeat(X[None], n_nets, axis=0))
     np.testing.assert_allclose(out[..., 0].cpu().numpy(), f, rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(out[..., 1].cpu().numpy(), np.repeat(rho[:, None], n_points, 1), rtol=1e-6)
