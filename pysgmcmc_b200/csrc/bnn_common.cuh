@@ -52,9 +52,12 @@ struct BnnArgs {
 
 // tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx + rcp.approx): |error| ~ 2e-7,
 // saturates correctly at +-1.  3000 activations per chain-step make the libm tanhf
-// (~25 instructions) a third of the kernel; this is 6.
+// (~25 instructions) a third of the kernel; this is 5.  ex2.approx.ftz directly: __expf wraps the
+// same instruction in a denormal-range fix-up (3 more instructions) that only matters for
+// exp(2x) < 2^-126, where the result is -1 either way.
 __device__ __forceinline__ float fast_tanh(float x) {
-  const float e = __expf(2.0f * x);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));   // 2 log2(e)
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 

@@ -80,6 +80,14 @@ __device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const uint32_t (&a)
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.0f));
 }
 
+// acc(2) += part(2), round to nearest, one packed instruction (FADD2)
+__device__ __forceinline__ void add2_rn(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -131,9 +139,10 @@ __device__ __forceinline__ void mma3_row(float (&acc)[NT8][4], const uint32_t (&
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt) mma_tf32(part[nt], ah, bh[nt]);
 #pragma unroll
-    for (int nt = 0; nt < NT8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[nt][e] = __fadd_rn(acc[nt][e], part[nt][e]);
+    for (int nt = 0; nt < NT8; ++nt) {               // packed add.rn.f32x2: two accumulator elements per issue slot
+      add2_rn(acc[nt][0], acc[nt][1], part[nt][0], part[nt][1]);
+      add2_rn(acc[nt][2], acc[nt][3], part[nt][2], part[nt][3]);
+    }
   } else {
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], al, bh[nt]);
@@ -282,9 +291,10 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
         for (int m = 0; m < MTW; ++m)
 #pragma unroll
           for (int p = 0; p < NP; ++p)
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (nt0 + p < NT8) acc[m][p][e] = __fadd_rn(acc[m][p][e], part[m][p][e]);
+            if (nt0 + p < NT8) {
+              add2_rn(acc[m][p][0], acc[m][p][1], part[m][p][0], part[m][p][1]);
+              add2_rn(acc[m][p][2], acc[m][p][3], part[m][p][2], part[m][p][3]);
+            }
       }
     }
 #pragma unroll
