@@ -199,6 +199,11 @@ int sgmcmc_bnn_nll_grad_f32(const float* theta, const float* X, const float* y,
  * holds the activations between the layer kernels (csrc/mlp.cu).
  * sgmcmc_mlp_predict_f32: out[k, i, 0] = f(x_i; theta_k), out[k, i, 1] = rho_k (:535-557);
  * its workspace is sized with n_items = n_nets * ceil(n_points / 32), batch = 32. */
+/* sgmcmc_set_mlp_tuning(1) (the default): layers whose weight matrix is at least 128 x 128 (widths
+ * multiples of 4) run their forward and backward-data GEMMs on the tcgen05 tensor cores as 3xTF32
+ * (csrc/mlp_umma.cu); 0 keeps every layer on the FFMA kernels (the implementation the tests compare
+ * against).  Set it BEFORE sizing the workspace: the tensor-core layers keep split copies there. */
+int sgmcmc_set_mlp_tuning(int tensor_core_layers);
 int64_t sgmcmc_mlp_n_params(const int* widths, int n_widths);
 int64_t sgmcmc_mlp_workspace_bytes(const int* widths, int n_widths, int64_t n_items, int batch);
 int sgmcmc_mlp_nll_grad_f32(const float* theta, const float* X, const float* y, const int32_t* starts,

@@ -31,6 +31,7 @@ SIGNATURES = {
     "sgmcmc_last_error": [],
     "sgmcmc_set_update_tuning": [c_int, c_int],
     "sgmcmc_set_bnn_tuning": [c_int],
+    "sgmcmc_set_mlp_tuning": [c_int],
     "sgmcmc_set_persistent_grids": [c_int, c_int],
     "sgmcmc_set_bnn_chunk": [c_int64],
     "sgmcmc_set_bnn_pipeline": [c_int64, c_int],

@@ -21,7 +21,6 @@
 // therefore the lever (fewer operand loads per FFMA), paid for with 52 registers per unit.
 #include "bnn_common.cuh"
 #include "bnn_mma.cuh"
-#include "bnn_mma_t.cuh"
 namespace sgmcmc {
 
 // acc[r][c] += sum_k act[row r][k] * w[c][k]  for ROWS rows of a [B x HS] activation buffer.
@@ -466,7 +465,7 @@ static int g_bnn_variant = 13;
 static int g_bnn_max_ctas = 0;          // 0: one CTA per chain group; > 0: persistent grid of that size
 static int64_t g_bnn_chunk = 0;         // chains per K4+K1 chunk inside sgmcmc_bnn_sghmc_run_f32 (0: all)
 void set_bnn_chunk(int64_t c) { g_bnn_chunk = c; }
-int bnn_variant_count() { return 18; }
+int bnn_variant_count() { return 14; }
 void set_bnn_variant(int v) { g_bnn_variant = v; }
 void set_bnn_max_ctas(int n) { g_bnn_max_ctas = n; }
 
@@ -523,47 +522,7 @@ static int launch_mma_batch(const BnnArgs& a, cudaStream_t st) {
   }
 }
 
-// K4 on the tensor pipe, transposed formulation (bnn_mma_t.cuh): one CTA of 4 warps per chain;
-// variants 14-17 = operands split once into hi/lo planes (weights and activations, weights only,
-// activations only) or at every fragment load (none).
-template <int NB8, int RB, bool PRE_W, bool PRE_A>
-static int launch_mma_t(const BnnArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)bnn_t_smem_bytes<PRE_W, PRE_A>(RB, NB8, a.L.n_in);
-  SG_REQUIRE(smem <= 227 * 1024, SGMCMC_E_UNSUPPORTED, "bnn (mma_t): %zu B of shared memory per CTA", smem);
-  unsigned blocks = (unsigned)a.n_chains;
-  if (g_bnn_max_ctas > 0 && blocks > (unsigned)g_bnn_max_ctas) blocks = (unsigned)g_bnn_max_ctas;
-  if (a.grad != nullptr) {
-    auto k = bnn_mma_t_kernel<NB8, RB, true, PRE_W, PRE_A>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    k<<<blocks, T_THREADS, smem, st>>>(a);
-  } else {
-    auto k = bnn_mma_t_kernel<NB8, RB, false, PRE_W, PRE_A>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    k<<<blocks, T_THREADS, smem, st>>>(a);
-  }
-  return check_launch("bnn_mma_t_kernel");
-}
-
-template <bool PRE_W, bool PRE_A>
-static int launch_mma_t_batch(const BnnArgs& a, cudaStream_t st) {
-  if (a.batch <= 8) return launch_mma_t<1, 8, PRE_W, PRE_A>(a, st);
-  if (a.batch <= 16) return launch_mma_t<2, 16, PRE_W, PRE_A>(a, st);
-  if (a.batch <= 20) return launch_mma_t<3, 20, PRE_W, PRE_A>(a, st);
-  if (a.batch <= 24) return launch_mma_t<3, 24, PRE_W, PRE_A>(a, st);
-  return launch_mma_t<4, 32, PRE_W, PRE_A>(a, st);
-}
-
 static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
-  if (g_bnn_variant >= 14 && a.batch <= 32 && (a.grad == nullptr || aligned_to(a.grad, 8))) {
-    switch (g_bnn_variant) {
-      case 15: return launch_mma_t_batch<true, false>(a, st);
-      case 16: return launch_mma_t_batch<false, true>(a, st);
-      case 17: return launch_mma_t_batch<false, false>(a, st);
-      default: return launch_mma_t_batch<true, true>(a, st);
-    }
-  }
   if (g_bnn_variant >= 10 && a.batch <= 32) {
     switch (g_bnn_variant) {              // accuracy modes of the tensor-pipe kernel (bnn_mma.cuh)
       case 11: return launch_mma_batch<MMA_ROUND_SPLIT>(a, st);

@@ -24,8 +24,14 @@
 // Layout of a chain's parameters (the reference's tf.trainable_variables() order, kernels
 // [in, out] row-major): W_1 b_1 W_2 b_2 ... W_{L+1} b_{L+1} rho.
 #include "bnn_common.cuh"
+#include "mlp_umma.cuh"
 
 namespace sgmcmc {
+
+// wide layers on the tensor cores (csrc/mlp_umma.cu); sgmcmc_set_mlp_tuning(0) keeps every layer on
+// the FFMA kernels below (the second implementation the tests compare against)
+static int g_mlp_umma = 1;
+void set_mlp_umma(int on) { g_mlp_umma = on; }
 
 constexpr int MLP_MAX_W = 8;        // weight matrices: up to 7 hidden layers + the head
 constexpr int MLP_THREADS = 128;
@@ -45,7 +51,13 @@ struct MlpLayout {
   int64_t oH[MLP_MAX_W], oZ[MLP_MAX_W];   // Ht_l, dZt_l for l = 1..n_w-1
   int64_t oSq, ws_floats;           // partial sums of squares (weight prior); total per chain
   int sq_slot[MLP_MAX_W];           // first partial-sum slot of layer l (one slot per column tile)
+  int sq_n[MLP_MAX_W];              // partial sums layer l writes
   int n_sq;
+  // tensor-core layers (mlp_umma.cu): umma[l - 1] != 0 when weight matrix l runs its forward and
+  // backward-data GEMMs there; their activation operands live a second time in the workspace, split
+  // into hi / lo planes in the MMA's canonical order (mlp_umma.cuh): Hc_l = H_l, Zc_l = dZ_l
+  int umma[MLP_MAX_W];
+  int64_t oHc[MLP_MAX_W], oZc[MLP_MAX_W], cplane[MLP_MAX_W];   // -1: not kept
 };
 
 struct MlpArgs {
@@ -66,6 +78,13 @@ struct MlpArgs {
   MlpLayout L;
 };
 
+// columns per thread of the column-owner kernels (forward, weight gradient) for a layer of
+// n_out units, and the number of column tiles (CTAs per chain) that gives
+__host__ __device__ __forceinline__ int mlp_cpt(int n_out) { return n_out >= 256 ? 4 : 1; }
+__host__ __device__ __forceinline__ int mlp_col_tiles(int n_out) {
+  return (n_out + mlp_cpt(n_out) * MLP_THREADS - 1) / (mlp_cpt(n_out) * MLP_THREADS);
+}
+
 static int make_mlp_layout(MlpLayout& L, const int* widths, int n_widths, int batch) {
   SG_REQUIRE(widths != nullptr && n_widths >= 3 && n_widths <= MLP_MAX_W + 1, SGMCMC_E_UNSUPPORTED,
              "mlp: widths = [n_in, hidden..., 1] with 1 to %d hidden layers (got %d entries)", MLP_MAX_W - 1,
@@ -81,29 +100,41 @@ static int make_mlp_layout(MlpLayout& L, const int* widths, int n_widths, int ba
   for (int l = 0; l < L.n_w; ++l) {
     L.oW[l] = o; o += (int64_t)L.width[l] * L.width[l + 1];
     L.ob[l] = o; o += L.width[l + 1];
-    L.sq_slot[l] = slot;
-    slot += (L.width[l + 1] + MLP_THREADS - 1) / MLP_THREADS;     // >= the column tiles of either CPT
   }
   L.orho = o; o += 1;
   L.D = o;
+  for (int l = L.n_w; l >= 1; --l) {                              // weight matrix l: width[l-1] -> width[l]
+    const int wi = L.width[l - 1], wo = L.width[l];
+    // tensor-core layers: widths that fill a 128-unit tile, rows of W_l that 64-bit loads can walk
+    const bool ok = g_mlp_umma && l >= 2 && l < L.n_w && wi >= 128 && wo >= 128 && wi % 4 == 0 && wo % 4 == 0 &&
+                    L.D % 2 == 0 && L.oW[l - 1] % 2 == 0;
+    // bit 0: forward GEMM, bit 1: backward-data GEMM.  The backward one needs dZ_l split and in canonical
+    // order, which the head and the tensor-core backward of layer l + 1 write (the FFMA backward does not)
+    const bool bwd = ok && (l == L.n_w - 1 || (L.umma[l] & 2) != 0);
+    L.umma[l - 1] = (ok ? 1 : 0) | (bwd ? 2 : 0);
+  }
+  for (int l = 0; l < L.n_w; ++l) {
+    L.sq_slot[l] = slot;
+    L.sq_n[l] = (L.umma[l] & 1) ? (L.width[l + 1] + 127) / 128 : mlp_col_tiles(L.width[l + 1]);
+    slot += (L.width[l + 1] + MLP_THREADS - 1) / MLP_THREADS;     // >= the column tiles of either CPT / the 128-unit tiles
+  }
   L.n_sq = slot;
   const int bt = mlp_bt(batch);
   L.oH[0] = L.oZ[0] = 0;
+  L.oHc[0] = L.oZc[0] = -1;
   for (int l = 1; l < L.n_w; ++l) {
     L.oH[l] = w; w += (int64_t)bt * L.width[l];
     L.oZ[l] = w; w += (int64_t)bt * L.width[l];
+    L.cplane[l] = (int64_t)((L.width[l] + 15) & ~15) * MU_CN;
+    L.oHc[l] = L.oZc[l] = -1;
+    if (l + 1 < L.n_w && (L.umma[l] & 1)) { L.oHc[l] = w; w += 2 * L.cplane[l]; }    // operand of layer l+1's forward
+    if (L.umma[l - 1] & 2) { L.oZc[l] = w; w += 2 * L.cplane[l]; }                  // operand of layer l's backward
   }
   L.oSq = w; w += (slot + 3) & ~3;
   L.ws_floats = (w + 3) & ~3;
   return SGMCMC_OK;
 }
 
-// columns per thread of the column-owner kernels (forward, weight gradient) for a layer of
-// n_out units, and the number of column tiles (CTAs per chain) that gives
-__host__ __device__ __forceinline__ int mlp_cpt(int n_out) { return n_out >= 256 ? 4 : 1; }
-__host__ __device__ __forceinline__ int mlp_col_tiles(int n_out) {
-  return (n_out + mlp_cpt(n_out) * MLP_THREADS - 1) / (mlp_cpt(n_out) * MLP_THREADS);
-}
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
@@ -190,6 +221,35 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ wrow, int n_o
   }
 }
 
+// The split, canonically ordered copy of a layer's output for a tensor-core GEMM (mlp_umma.cuh): units
+// j0 .. j0 + CPT - 1 of this thread, all MU_CN rows (rows >= `rows` and units >= n_out are zeros).
+// ACT: the values are pre-activations, apply bias + tanh (forward); else they are taken as they are.
+template <int BT, int CPT>
+__device__ __forceinline__ void store_canonical(float* __restrict__ dst, int64_t plane, const float (&acc)[BT][CPT],
+                                                int j0, int n_out, int rows, bool act, const float* __restrict__ bias) {
+  const int n_pad = (n_out + 15) & ~15;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int j = j0 + c;
+    if (j < n_pad) {
+      const float bj = (act && j < n_out) ? __ldg(bias + j) : 0.0f;
+      float* q = dst + ((int64_t)(j >> 2) * MU_CN) * 4 + (j & 3);
+#pragma unroll
+      for (int n = 0; n < MU_CN; ++n) {
+        float v = 0.0f;
+        if (n < BT) {
+          v = acc[n < BT ? n : 0][c];
+          if (act) v = fast_tanh(v + bj);
+          v = (n < rows && j < n_out) ? v : 0.0f;
+        }
+        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+        q[4 * n] = hi;
+        q[plane + 4 * n] = v - hi;
+      }
+    }
+  }
+}
+
 template <int BT, int CPT>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpArgs a, int l) {
   extern __shared__ __align__(16) float sH[];              // [min(n_in, MLP_KMAX)][BT]
@@ -244,6 +304,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_fwd_kernel(MlpArgs a, int l) 
       }
     }
   }
+  if (a.L.oHc[l] >= 0) store_canonical<BT, CPT>(ws + a.L.oHc[l], a.L.cplane[l], acc, j0, n_out, rows, true, bias);
   // sum of squares of this tile's weights and biases, for the weight prior (:131-141)
   const float tot = block_sum(sq, red);
   if (threadIdx.x == 0) ws[a.L.oSq + a.L.sq_slot[l - 1] + ct] = tot;
@@ -323,7 +384,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_head_kernel(MlpArgs a) {
   if (tid == 0) {
     float sq_t = sq_head + b4 * b4 + rho * rho;
     for (int q = 1; q < l; ++q)                                       // one partial per column tile of layer q
-      for (int ct = 0; ct < mlp_col_tiles(a.L.width[q]); ++ct) sq_t += ws[a.L.oSq + a.L.sq_slot[q - 1] + ct];
+      for (int ct = 0; ct < a.L.sq_n[q - 1]; ++ct) sq_t += ws[a.L.oSq + a.L.sq_slot[q - 1] + ct];
     const float lv_den = 0.02f + 3e-16f;                              // safe_divide(., 2 * var)
     const float dl = rho - logf(1e-6f);
     const float log_like_data = (-sse * (0.5f * fvi) - 0.5f * rho * (float)rows) * a.inv_bs;
@@ -346,10 +407,12 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_head_kernel(MlpArgs a) {
   float df[BT];
 #pragma unroll
   for (int b = 0; b < BT; ++b) df[b] = sDf[b];
+  const int64_t oZc = a.L.oZc[l - 1], zplane = a.L.cplane[l - 1];    // tensor-core backward of layer L: split copy of dZ_L
   for (int i = tid; i < hL; i += MLP_THREADS) {
     const float wi = __ldg(W + i);
     const float4* h4 = reinterpret_cast<const float4*>(Ht + (int64_t)i * BT);
     float4* z4 = reinterpret_cast<float4*>(dZt + (int64_t)i * BT);
+    float* zc = ws + oZc + ((int64_t)(i >> 2) * MU_CN) * 4 + (i & 3);
     float dw = 0.0f;
 #pragma unroll
     for (int b4 = 0; b4 < BT / 4; ++b4) {
@@ -360,11 +423,24 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_head_kernel(MlpArgs a) {
       for (int e = 0; e < 4; ++e) {
         dw = fmaf(hv[e], df[4 * b4 + e], dw);
         zv[e] = (df[4 * b4 + e] * wi) * fmaf(-hv[e], hv[e], 1.0f);    // (rows >= batch: df = 0)
+        if (oZc >= 0) {
+          const float hi = __uint_as_float((__float_as_uint(zv[e]) + 0x1000u) & 0xffffe000u);
+          zc[4 * (4 * b4 + e)] = hi;
+          zc[zplane + 4 * (4 * b4 + e)] = zv[e] - hi;
+        }
       }
       z4[b4] = make_float4(zv[0], zv[1], zv[2], zv[3]);
     }
+    if (oZc >= 0)
+      for (int n = BT; n < MU_CN; ++n) zc[4 * n] = zc[zplane + 4 * n] = 0.0f;
     g[i] = fmaf(wi, pscale, dw);
   }
+  if (oZc >= 0)                                                       // units hL .. round_up(hL, 16): zeros
+    for (int e = tid; e < (((hL + 15) & ~15) - hL) * MU_CN; e += MLP_THREADS) {
+      const int i = hL + e / MU_CN, n = e % MU_CN;
+      float* zc = ws + oZc + ((int64_t)(i >> 2) * MU_CN + n) * 4 + (i & 3);
+      zc[0] = zc[zplane] = 0.0f;
+    }
 }
 
 // ---- weight gradient: dW_l[i][j] = sum_b H_{l-1}[b][i] dZ_l[b][j] + pscale W_l[i][j] (and db_l);
@@ -559,6 +635,8 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_data_kernel(MlpArgs a, in
   }
   const float* __restrict__ Ht = ws + a.L.oH[l - 1];
   float* __restrict__ dZp = ws + a.L.oZ[l - 1];
+  // (a layer whose backward runs on the tensor cores gets its dZ from mlp_umma.cu or the head, never from here:
+  // see make_mlp_layout)
 #pragma unroll
   for (int r = 0; r < RI; ++r)
     if (irow[r] < n_in) {
@@ -585,7 +663,33 @@ static int launch_mlp_bt(const MlpArgs& a, bool want_grad, cudaStream_t st) {
   const int n_hidden = L.n_w - 1;
   const int64_t C = a.n_chains;
   auto smem_rows = [](int n) { return (size_t)(n < MLP_KMAX ? n : MLP_KMAX) * BT * sizeof(float); };
+  auto umma_args = [&](int l, bool fwd) {        // weight matrix l on the tensor cores (mlp_umma.cu)
+    MuArgs m;
+    m.theta = a.theta; m.D = L.D; m.theta_div = a.theta_div;
+    m.oW = L.oW[l - 1]; m.ob = L.ob[l - 1]; m.ldw = L.width[l];
+    m.ws = a.ws; m.ws_floats = L.ws_floats;
+    m.starts = a.starts; m.n_rows = a.n_rows; m.batch = a.batch; m.bt = BT;
+    if (fwd) {                                   // H_l = tanh(H_{l-1} W_l + b_l)
+      m.M = L.width[l]; m.K = L.width[l - 1];
+      m.oBc = L.oHc[l - 1]; m.b_plane = L.cplane[l - 1];
+      m.oHin = 0; m.oOut = L.oH[l];
+      m.oOutc = L.oHc[l]; m.out_plane = L.cplane[l];
+      m.oSq = L.oSq + L.sq_slot[l - 1];
+    } else {                                     // dZ_{l-1} = (dZ_l W_l^T) * (1 - H_{l-1}^2)
+      m.M = L.width[l - 1]; m.K = L.width[l];
+      m.oBc = L.oZc[l]; m.b_plane = L.cplane[l];
+      m.oHin = L.oH[l - 1]; m.oOut = L.oZ[l - 1];
+      m.oOutc = L.oZc[l - 1]; m.out_plane = L.cplane[l - 1];
+      m.oSq = 0;
+    }
+    m.Mpad = (m.M + 15) & ~15;
+    return m;
+  };
   for (int l = 1; l <= n_hidden; ++l) {
+    if (L.umma[l - 1] & 1) {
+      if (int rc = launch_mlp_gemm_umma(umma_args(l, true), true, C, st)) return rc;
+      continue;
+    }
     const int n_ct = mlp_col_tiles(L.width[l]);
     const size_t smem = smem_rows(L.width[l - 1]);
     if (mlp_cpt(L.width[l]) == 4) {
@@ -617,7 +721,9 @@ static int launch_mlp_bt(const MlpArgs& a, bool want_grad, cudaStream_t st) {
       mlp_wgrad_kernel<BT, 1><<<(unsigned)(C * n_ct * n_is), MLP_THREADS, smem, st>>>(a, l, n_is);
     }
     if (int rc = check_launch("mlp_wgrad_kernel")) return rc;
-    if (l > 1) {
+    if (l > 1 && (L.umma[l - 1] & 2)) {
+      if (int rc = launch_mlp_gemm_umma(umma_args(l, false), false, C, st)) return rc;
+    } else if (l > 1) {
       const size_t smem_z = smem_rows(n_out);
       const int n_rt4 = (n_in + 4 * MLP_THREADS - 1) / (4 * MLP_THREADS);
       if (BT <= 20 && n_in >= 4 * MLP_THREADS && C * n_rt4 >= 296) {
@@ -634,6 +740,12 @@ static int launch_mlp_bt(const MlpArgs& a, bool want_grad, cudaStream_t st) {
   return SGMCMC_OK;
 }
 
+static bool uses_umma(const MlpLayout& L) {
+  for (int l = 0; l < L.n_w; ++l)
+    if (L.umma[l]) return true;
+  return false;
+}
+
 static int launch_mlp(const MlpArgs& a, bool want_grad, cudaStream_t st) {
   switch (mlp_bt(a.batch)) {
     case 8: return launch_mlp_bt<8>(a, want_grad, st);
@@ -646,6 +758,11 @@ static int launch_mlp(const MlpArgs& a, bool want_grad, cudaStream_t st) {
 }  // namespace sgmcmc
 
 using namespace sgmcmc;
+
+extern "C" int sgmcmc_set_mlp_tuning(int tensor_core_layers) {
+  set_mlp_umma(tensor_core_layers != 0);
+  return SGMCMC_OK;
+}
 
 extern "C" int64_t sgmcmc_mlp_n_params(const int* widths, int n_widths) {
   MlpLayout L;
@@ -674,6 +791,7 @@ extern "C" int sgmcmc_mlp_nll_grad_f32(const float* theta, const float* X, const
   SG_REQUIRE(workspace_bytes >= (int64_t)sizeof(float) * a.L.ws_floats * n_chains, SGMCMC_E_INVALID,
              "mlp: workspace too small (sgmcmc_mlp_workspace_bytes)");
   SG_REQUIRE(aligned_to(theta, 4) && (grad == nullptr || aligned_to(grad, 4)), SGMCMC_E_ALIGN, "mlp: misaligned pointer");
+  SG_REQUIRE(!uses_umma(a.L) || aligned_to(theta, 8), SGMCMC_E_ALIGN, "mlp: theta must be 8-byte aligned");
   SG_REQUIRE(n_chains * (int64_t)((a.L.width[1] + MLP_THREADS - 1) / MLP_THREADS) * 64 < (int64_t)1 << 31,
              SGMCMC_E_UNSUPPORTED, "mlp: grid too large");
   if (n_chains == 0) return SGMCMC_OK;
@@ -702,6 +820,7 @@ extern "C" int sgmcmc_mlp_predict_f32(const float* theta, const float* X, float*
   SG_REQUIRE(workspace_bytes >= (int64_t)sizeof(float) * a.L.ws_floats * n_nets * tiles, SGMCMC_E_INVALID,
              "mlp_predict: workspace too small (sgmcmc_mlp_workspace_bytes with n_items = n_nets * ceil(n_points / 32), "
              "batch = 32)");
+  SG_REQUIRE(!uses_umma(a.L) || aligned_to(theta, 8), SGMCMC_E_ALIGN, "mlp: theta must be 8-byte aligned");
   a.theta = theta; a.X = X; a.y = nullptr; a.starts = nullptr; a.ws = (float*)workspace;
   a.cost = nullptr; a.grad = nullptr; a.mse = nullptr; a.fout = out;
   a.n_chains = n_nets * tiles; a.n_rows = n_points; a.theta_div = (int)tiles; a.batch = batch;

@@ -84,6 +84,39 @@ def test_mlp_cost_and_gradient_match_the_oracle(hidden, n_in, C, batch, N):
     np.testing.assert_allclose(cost, cost2, rtol=1e-6)
 
 
+@pytest.mark.parametrize("hidden,n_in,C,batch,N", [
+    ((1000, 512, 512), 1, 3, 20, 20000),     # both wide layers forward and backward on the tensor cores
+    ((256, 256), 4, 2, 32, 900),             # the largest minibatch
+    ((128, 260, 128), 2, 3, 13, 700),        # partial 128-unit tiles, contraction lengths that are not multiples of 16
+    ((512, 7, 256, 256), 1, 2, 20, 500),     # a narrow layer in between: only the last matrix qualifies
+    ((256, 256, 64), 1, 2, 8, 300),          # forward on the tensor cores, backward from an FFMA layer above
+])
+def test_tensor_core_layers_agree_with_the_ffma_layers(hidden, n_in, C, batch, N):
+    """csrc/mlp_umma.cu (tcgen05, 3xTF32) against the FFMA layer kernels on the same inputs, and both
+    against the float64 oracle."""
+    X, y = sinc_data(N, n_in)
+    theta = obnn.init_theta(C, n_in=n_in, hidden=hidden, seed=3, dtype=np.float64)
+    theta += 0.05 * np.random.RandomState(4).standard_normal(theta.shape)
+    starts = np.random.RandomState(5).randint(0, N - batch + 1, size=C)
+    widths = [n_in] + list(hidden) + [1]
+    try:
+        _native.call("sgmcmc_set_mlp_tuning", 0)
+        c0, g0, m0 = mlp_k4(theta, X, y, starts, widths, batch, 20, N)
+    finally:
+        _native.call("sgmcmc_set_mlp_tuning", 1)
+    c1, g1, m1 = mlp_k4(theta, X, y, starts, widths, batch, 20, N)
+    Xb, yb = obnn.gather_minibatch(X, y, starts, batch)
+    wc, wg, wm = obnn.nll_and_grad(theta.astype(np.float32).astype(np.float64), Xb, yb, n_examples=N,
+                                   batch_size=20, n_in=n_in, hidden=hidden)
+    for cost, grad, mse in ((c0, g0, m0), (c1, g1, m1)):
+        np.testing.assert_allclose(cost, wc, rtol=3e-6)
+        np.testing.assert_allclose(mse, wm, rtol=2e-5)
+        assert np.isfinite(grad).all()
+        err = np.abs(grad - wg).max(axis=1) / np.abs(wg).max(axis=1)
+        assert err.max() <= 2e-5, "max |dg| / max|g| = %.3g" % err.max()
+    assert (np.abs(g1 - g0).max(axis=1) <= 1e-5 * np.abs(g0).max(axis=1)).all()
+
+
 def test_generic_kernels_agree_with_the_specialised_k4():
     """Same network, same inputs: csrc/mlp.cu against the tensor-pipe K4 (bnn_mma.cuh)."""
     C, N, batch = 16, 2000, 20
