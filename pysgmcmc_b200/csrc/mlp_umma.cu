@@ -25,7 +25,13 @@
 //   epilogue   (warps 0-7, a thread owns one unit = one TMEM lane): bias + tanh (forward) or
 //              * (1 - H^2) (backward), then the result leaves twice: plain [unit][BT] for the FFMA
 //              kernels (head, weight gradient) and split + canonical for the next tensor-core GEMM.
-// Shared memory 91 KB per CTA -> 2 CTAs per SM, TMEM 32 columns each.
+// Accumulation: tcgen05.mma adds into its TMEM accumulator with truncation, a bias of up to one ulp of
+// the running sum per instruction that compounds over the 3 x K / 8 instructions of a long contraction
+// (K = 1000: measured 1e-5 relative on the cost with a single accumulator).  So a tile keeps EIGHT
+// accumulators of 32 columns: the k-blocks go round-robin into seven of them, which only ever take the
+// exact hi*hi products, and the two small cross terms of every block go into the eighth, whose sum --
+// and therefore whose ulp -- is 2^-11 of the others'.  The epilogue adds the eight in fp32, round to nearest.
+// Shared memory 91 KB per CTA -> 2 CTAs per SM, TMEM 256 columns each (all 512 of the SM).
 #include "bnn_common.cuh"
 #include "umma.cuh"
 #include "mlp_umma.cuh"
@@ -42,6 +48,7 @@ constexpr uint32_t MU_STAGE = 2 * MU_A_PART + 2 * MU_B_PART;                    
 constexpr int MU_STAGES = 4;
 constexpr uint32_t MU_SMEM = MU_STAGES * MU_STAGE;                                               // 91136 B
 constexpr int MU_PF = 3;
+constexpr int MU_NACC = 7;                               // hi*hi accumulators (+ 1 for the cross terms): 8 x 32 TMEM columns
 
 struct MuRegs {
   float4 a[2], b;
@@ -80,7 +87,7 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
     umma::mbar_init(umma::smem_u32(&accum_bar), 1);
     umma::mbar_init_fence();
   }
-  if (warp == MU_PRODUCERS / 32) umma::tmem_alloc<32>(umma::smem_u32(&tmem_slot));
+  if (warp == MU_PRODUCERS / 32) umma::tmem_alloc<32 * (MU_NACC + 1)>(umma::smem_u32(&tmem_slot));
   umma::fence_before_thread_sync();
   __syncthreads();
   umma::fence_after_thread_sync();
@@ -183,7 +190,17 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
     const int q = warp & 3, hcol = warp >> 2;
     const int u = m0 + 32 * q + lane;                  // this thread's unit = its TMEM lane
     float v[16];
-    umma::tmem_ld16(taddr + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * hcol), v);
+    {
+      const uint32_t tbase = taddr + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * hcol);
+      umma::tmem_ld16(tbase + 32 * MU_NACC, v);          // the cross terms first (smallest)
+      const int n_main = nkb < MU_NACC ? nkb : MU_NACC;
+      for (int j = 0; j < n_main; ++j) {
+        float p[16];
+        umma::tmem_ld16(tbase + 32 * (uint32_t)j, p);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __fadd_rn(v[c], p[c]);
+      }
+    }
     int64_t row0;
     int rows;
     {
@@ -255,9 +272,10 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
           const uint32_t b_hi = stage + 2 * MU_A_PART + (uint32_t)ks * 2 * MU_B_LBO, b_lo = b_hi + MU_B_PART;
           const uint64_t da_hi = umma::smem_desc(a_hi, MU_A_LBO, MU_A_SBO), da_lo = umma::smem_desc(a_lo, MU_A_LBO, MU_A_SBO);
           const uint64_t db_hi = umma::smem_desc(b_hi, MU_B_LBO, MU_B_SBO), db_lo = umma::smem_desc(b_lo, MU_B_LBO, MU_B_SBO);
-          umma::mma_tf32(taddr, da_lo, db_hi, idesc, (kb | ks) != 0);      // small terms first
-          umma::mma_tf32(taddr, da_hi, db_lo, idesc, 1);
-          umma::mma_tf32(taddr, da_hi, db_hi, idesc, 1);
+          const uint32_t t_main = taddr + 32u * (uint32_t)(kb % MU_NACC), t_small = taddr + 32u * MU_NACC;
+          umma::mma_tf32(t_small, da_lo, db_hi, idesc, (kb | ks) != 0);
+          umma::mma_tf32(t_small, da_hi, db_lo, idesc, 1);
+          umma::mma_tf32(t_main, da_hi, db_hi, idesc, (kb >= MU_NACC) || ks != 0);
         }
         umma::commit(umma::smem_u32(&empty_bar[s]));                      // stage free once these MMAs retire
         if (kb == nkb - 1) umma::commit(umma::smem_u32(&accum_bar));      // accumulator complete
@@ -270,7 +288,7 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
   __syncthreads();
   if (warp == MU_PRODUCERS / 32) {
     umma::fence_after_thread_sync();
-    umma::tmem_dealloc<32>(taddr);
+    umma::tmem_dealloc<32 * (MU_NACC + 1)>(taddr);
   }
 }
 

@@ -26,6 +26,7 @@ ap.add_argument("--hidden", default="1000,512,512")
 ap.add_argument("--chains", default="1,8,64,256")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--n-in", type=int, default=1)
+ap.add_argument("--layers", default="tcgen05,ffma", help="implementations of the wide layers to time")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 hidden = tuple(int(h) for h in args.hidden.split(","))
@@ -56,7 +57,8 @@ def timed(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-for C in [int(c) for c in args.chains.split(",")]:
+for impl, C in [(m, int(c)) for m in args.layers.split(",") for c in args.chains.split(",")]:
+    _native.call("sgmcmc_set_mlp_tuning", 1 if impl == "tcgen05" else 0)
     gen = DeviceBatchGenerator(N, B, n_chains=C, seed=1, device=dev)
     nll = BayesianNeuralNetworkNLL(N, B, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=dev, net=net)
     params = net.init_params(args.n_in, n_chains=C, seed=1, device=dev)
@@ -68,7 +70,7 @@ for C in [int(c) for c in args.chains.split(",")]:
     ms_step = timed(lambda: sampler.run(1, keep_every=10 ** 9), args.iters)
     gbs = 8.0 * C * D / ms_k4 / 1e6
     print(json.dumps({
-        "net": "%d-%s-1" % (args.n_in, "-".join(map(str, hidden))), "params_per_chain": D, "chains": C, "batch": B,
+        "net": "%d-%s-1" % (args.n_in, "-".join(map(str, hidden))), "wide_layers": impl, "params_per_chain": D, "chains": C, "batch": B,
         "k4_layer_kernels_ms": round(ms_k4, 4), "k4_us_per_chain": round(1e3 * ms_k4 / C, 3),
         "k4_algorithmic_GBps": round(gbs, 1), "k4_frac_of_measured_hbm_peak": round(gbs / peak, 4),
         "k4_fp32_TFLOPs": round(flop * C / ms_k4 / 1e9, 2), "k4_frac_of_fp32_peak_74.4": round(flop * C / ms_k4 / 1e9 / 74.45, 3),
@@ -76,3 +78,4 @@ for C in [int(c) for c in args.chains.split(",")]:
         "step_state_GBps_52B_per_param": round(52.0 * C * D / ms_step / 1e6, 1)}), flush=True)
     del sampler, nll, gen, params
     torch.cuda.empty_cache()
+_native.call("sgmcmc_set_mlp_tuning", 1)
