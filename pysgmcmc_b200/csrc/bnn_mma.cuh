@@ -59,12 +59,41 @@ constexpr int NT8 = 7;   // 8-wide tiles covering those 56 columns
 //         of a GEMM (Ootomo & Yokota 2022).
 // What they buy is measured as trajectory drift, not single-step error
 // (tools/bnn_trajectory_drift.py, profiles/r02_bnn_trajectory_drift*.jsonl).
-constexpr int MMA_ROUND_SPLIT = 1, MMA_RN_ACCUM = 2;
+constexpr int MMA_ROUND_SPLIT = 1, MMA_RN_ACCUM = 2, MMA_PACKED_SPLIT = 4;
 template <int MODE>
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   if constexpr ((MODE & MMA_ROUND_SPLIT) != 0) hi = __float_as_uint(x) + 0x1000u;
   else hi = __float_as_uint(x);
   lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
+}
+
+// Two operand words at once.  MMA_PACKED_SPLIT (launch variant 14 = 13 + this, for the weight fragments):
+// Veltkamp's splitting on the FP32 pipe, packed
+//   p = 8193 x;  hi = p - 8192 x  (x rounded to 11 significant bits, exactly a TF32 value);  lo = x - hi
+// = FMUL2 + FFMA2 + FADD2 for the pair, 1.5 issue slots per word instead of 3 (integer add, mask,
+// subtract): the hi/lo split is 32 % of the instructions K4 executes (profiles/r02_ncu_k4_mode13_summary.txt)
+// and the kernel is bound by issue slots, not by the FP32 pipe the packed instructions occupy for two cycles.
+// Measured: 0.255 against 0.266 ms -- and a 1000-step trajectory that ends just ABOVE 1e-5 where the
+// integer split ends just below it (both are roundings to nearest; the difference is the trajectory's
+// own sensitivity), so it is not the default.
+template <int MODE>
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
+  if constexpr ((MODE & MMA_PACKED_SPLIT) != 0) {
+    asm("{\n\t.reg .b64 x, p, h, l, c1, c2;\n\t"
+        "mov.b64 x, {%4, %5};\n\t"
+        "mov.b64 c1, {%6, %6};\n\t"
+        "mov.b64 c2, {%7, %7};\n\t"
+        "mul.rn.f32x2 p, x, c1;\n\t"
+        "fma.rn.f32x2 h, x, c2, p;\n\t"
+        "sub.rn.f32x2 l, x, h;\n\t"
+        "mov.b64 {%0, %1}, h;\n\t"
+        "mov.b64 {%2, %3}, l;\n\t}"
+        : "=r"(h0), "=r"(h1), "=r"(l0), "=r"(l1)
+        : "f"(x0), "f"(x1), "f"(8193.0f), "f"(-8192.0f));
+  } else {
+    split_tf32<MODE>(x0, h0, l0);
+    split_tf32<MODE>(x1, h1, l1);
+  }
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -120,10 +149,11 @@ __device__ __forceinline__ void store_c(float* __restrict__ buf, int batch, int 
 // A fragments (hi, lo) of k-step ks taken from the C-layout tile ks of `src`
 template <int MODE>
 __device__ __forceinline__ void a_from_c(const float (&src)[NT8][4], int ks, uint32_t (&ah)[4], uint32_t (&al)[4]) {
-  split_tf32<MODE>(src[ks][0], ah[0], al[0]);   // (row g,   k slot t)   = column 2t
-  split_tf32<MODE>(src[ks][2], ah[1], al[1]);   // (row g+8, k slot t)
-  split_tf32<MODE>(src[ks][1], ah[2], al[2]);   // (row g,   k slot t+4) = column 2t+1
-  split_tf32<MODE>(src[ks][3], ah[3], al[3]);   // (row g+8, k slot t+4)
+  // (row g, k slot t) = column 2t, (row g+8, k slot t) | (row g, k slot t+4) = column 2t+1, (row g+8, k slot t+4)
+  split_tf32<MODE>(src[ks][0], ah[0], al[0]);
+  split_tf32<MODE>(src[ks][2], ah[1], al[1]);
+  split_tf32<MODE>(src[ks][1], ah[2], al[2]);
+  split_tf32<MODE>(src[ks][3], ah[3], al[3]);
 }
 
 template <int MODE>
@@ -183,8 +213,7 @@ __device__ __forceinline__ void gemm_forward(const float* __restrict__ Wb, const
         b0 = k0 <= HID ? b0 : 0.0f;
         b1 = k1 <= HID ? b1 : 0.0f;
       }
-      split_tf32<MODE>(b0, bh[nt][0], bl[nt][0]);
-      split_tf32<MODE>(b1, bh[nt][1], bl[nt][1]);
+      split_pair<MODE>(b0, b1, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
     }
     mma3_row<MODE>(acc, ah, al, bh, bl);
   }
@@ -203,8 +232,7 @@ __device__ __forceinline__ void gemm_backward_data(const float* __restrict__ Wb,
     for (int nt = 0; nt < NT8; ++nt) {
       const int k = min(8 * nt + g, HID - 1);            // output units >= 50 are discarded
       const float2 b = *reinterpret_cast<const float2*>(Wb + k * HID + 8 * ks + 2 * t);
-      split_tf32<MODE>(b.x, bh[nt][0], bl[nt][0]);
-      split_tf32<MODE>(b.y, bh[nt][1], bl[nt][1]);
+      split_pair<MODE>(b.x, b.y, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
     }
     mma3_row<MODE>(acc, ah, al, bh, bl);
   }
@@ -234,10 +262,8 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
       a1 = (i0 < batch && k1 < AS) ? a1 : 0.0f;
       a2 = i1 < batch ? a2 : 0.0f;
       a3 = (i1 < batch && k1 < AS) ? a3 : 0.0f;
-      split_tf32<MODE>(a0, ah[m][ks][0], al[m][ks][0]);
-      split_tf32<MODE>(a1, ah[m][ks][1], al[m][ks][1]);
-      split_tf32<MODE>(a2, ah[m][ks][2], al[m][ks][2]);
-      split_tf32<MODE>(a3, ah[m][ks][3], al[m][ks][3]);
+      split_pair<MODE>(a0, a1, ah[m][ks][0], ah[m][ks][1], al[m][ks][0], al[m][ks][1]);
+      split_pair<MODE>(a2, a3, ah[m][ks][2], ah[m][ks][3], al[m][ks][2], al[m][ks][3]);
     }
   }
 #pragma unroll
@@ -254,8 +280,7 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
         float b1 = Zb[min(i1, batch - 1) * AS + 8 * nt + g];
         b0 = i0 < batch ? b0 : 0.0f;
         b1 = i1 < batch ? b1 : 0.0f;
-        split_tf32<MODE>(b0, bh[p][ks][0], bl[p][ks][0]);
-        split_tf32<MODE>(b1, bh[p][ks][1], bl[p][ks][1]);
+        split_pair<MODE>(b0, b1, bh[p][ks][0], bh[p][ks][1], bl[p][ks][0], bl[p][ks][1]);
       }
     }
     float acc[MTW][NP][4];

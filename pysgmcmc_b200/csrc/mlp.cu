@@ -125,7 +125,7 @@ static int make_mlp_layout(MlpLayout& L, const int* widths, int n_widths, int ba
   for (int l = 1; l < L.n_w; ++l) {
     L.oH[l] = w; w += (int64_t)bt * L.width[l];
     L.oZ[l] = w; w += (int64_t)bt * L.width[l];
-    L.cplane[l] = (int64_t)((L.width[l] + 15) & ~15) * MU_CN;
+    L.cplane[l] = (int64_t)((L.width[l] + MU_KPAD - 1) & ~(MU_KPAD - 1)) * MU_CN;
     L.oHc[l] = L.oZc[l] = -1;
     if (l + 1 < L.n_w && (L.umma[l] & 1)) { L.oHc[l] = w; w += 2 * L.cplane[l]; }    // operand of layer l+1's forward
     if (L.umma[l - 1] & 2) { L.oZc[l] = w; w += 2 * L.cplane[l]; }                  // operand of layer l's backward
@@ -227,25 +227,34 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ wrow, int n_o
 template <int BT, int CPT>
 __device__ __forceinline__ void store_canonical(float* __restrict__ dst, int64_t plane, const float (&acc)[BT][CPT],
                                                 int j0, int n_out, int rows, bool act, const float* __restrict__ bias) {
-  const int n_pad = (n_out + 15) & ~15;
+  const int n_pad = (n_out + MU_KPAD - 1) & ~(MU_KPAD - 1);
+  if (j0 >= n_pad) return;
+  float bj[CPT];
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int j = j0 + c;
-    if (j < n_pad) {
-      const float bj = (act && j < n_out) ? __ldg(bias + j) : 0.0f;
-      float* q = dst + ((int64_t)(j >> 2) * MU_CN) * 4 + (j & 3);
+  for (int c = 0; c < CPT; ++c) bj[c] = (act && j0 + c < n_out) ? __ldg(bias + j0 + c) : 0.0f;
+  // a quad of units (j0 is a multiple of CPT) is one 16-byte piece per minibatch row: 128-bit stores
+  float* q = dst + ((int64_t)(j0 >> 2) * MU_CN) * 4 + (j0 & 3);
 #pragma unroll
-      for (int n = 0; n < MU_CN; ++n) {
-        float v = 0.0f;
-        if (n < BT) {
-          v = acc[n < BT ? n : 0][c];
-          if (act) v = fast_tanh(v + bj);
-          v = (n < rows && j < n_out) ? v : 0.0f;
-        }
-        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-        q[4 * n] = hi;
-        q[plane + 4 * n] = v - hi;
+  for (int n = 0; n < MU_CN; ++n) {
+    float hi[CPT], lo[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      float v = 0.0f;
+      if (n < BT) {
+        v = acc[n < BT ? n : 0][c];
+        if (act) v = fast_tanh(v + bj[c]);
+        v = (n < rows && j0 + c < n_out) ? v : 0.0f;
       }
+      hi[c] = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+      lo[c] = v - hi[c];
+    }
+    if constexpr (CPT == 4) {
+      *reinterpret_cast<float4*>(q + 4 * n) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(q + plane + 4 * n) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+        if (j0 + c < n_pad) { q[4 * n + c] = hi[c]; q[plane + 4 * n + c] = lo[c]; }
     }
   }
 }
@@ -435,8 +444,8 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_head_kernel(MlpArgs a) {
       for (int n = BT; n < MU_CN; ++n) zc[4 * n] = zc[zplane + 4 * n] = 0.0f;
     g[i] = fmaf(wi, pscale, dw);
   }
-  if (oZc >= 0)                                                       // units hL .. round_up(hL, 16): zeros
-    for (int e = tid; e < (((hL + 15) & ~15) - hL) * MU_CN; e += MLP_THREADS) {
+  if (oZc >= 0)                                                       // units hL .. round_up(hL, MU_KPAD): zeros
+    for (int e = tid; e < (((hL + MU_KPAD - 1) & ~(MU_KPAD - 1)) - hL) * MU_CN; e += MLP_THREADS) {
       const int i = hL + e / MU_CN, n = e % MU_CN;
       float* zc = ws + oZc + ((int64_t)(i >> 2) * MU_CN + n) * 4 + (i & 3);
       zc[0] = zc[zplane] = 0.0f;
@@ -682,7 +691,7 @@ static int launch_mlp_bt(const MlpArgs& a, bool want_grad, cudaStream_t st) {
       m.oOutc = L.oZc[l - 1]; m.out_plane = L.cplane[l - 1];
       m.oSq = 0;
     }
-    m.Mpad = (m.M + 15) & ~15;
+    m.Mpad = (m.M + MU_KPAD - 1) & ~(MU_KPAD - 1);
     return m;
   };
   for (int l = 1; l <= n_hidden; ++l) {

@@ -13,14 +13,19 @@
 // fp32 accuracy on the TF32 datapath as in csrc/svgd_umma.cu (3xTF32): operands are split into
 // hi = tf32_rn(x), lo = x - hi, each product issued as lo*hi + hi*lo + hi*hi into the fp32 TMEM
 // accumulator.  Structure per CTA (one chain x one 128-unit tile), 288 threads:
-//   warps 0-7  producers: coalesced global loads of the weight block (3 register buffers ahead),
-//              split, stores into a 4-stage shared-memory ring in the no-swizzle K-major canonical
-//              layout of the MMA descriptors (forward: W is contiguous along the NON-contracted index,
-//              so the producers transpose while storing, conflict-free thanks to 144-byte row groups;
-//              backward: 128-bit stores, the core-matrix columns 2336 B apart for the same reason);
+//   warps 0-7  producers: a block of 32 k x 128 units per step.  Forward (W contiguous along the NON-contracted
+//              index): a thread loads one quad of units at four consecutive k -- a 4 x 4 piece in registers --
+//              and stores it transposed, four consecutive k of one unit per 128-bit store, straight into
+//              the no-swizzle K-major canonical layout of the MMA descriptors (144-byte row groups make the
+//              eight lanes of a store phase hit eight different 16-byte bank groups).  Backward (W contiguous
+//              along k): 128-bit loads and stores, core-matrix columns 2320 B apart for the same reason.
+//              The split is Veltkamp's, packed (FMUL2 / FFMA2 / FADD2 per pair).  The first version moved one
+//              float4 per thread and block of 16 k with scalar transposing stores and ran at 0.33 of the
+//              DRAM peak, issue bound (~60 instructions per float4; cp.async in place of register
+//              prefetch changed nothing -- profiles/r02_ncu_mlp_umma_register_prefetch_summary.txt);
 //              the activation operand arrives ALREADY split and in canonical order -- the epilogue
-//              that produced it wrote it that way -- so its staging is a plain 4 KB copy per block;
-//   warp 8     one lane issues 2 k-steps x 3 products of tcgen05.mma (M = 128, N = 32, K = 8),
+//              that produced it wrote it that way -- so its staging is a plain 8 KB copy per block;
+//   warp 8     one lane issues 4 k-steps x 3 products of tcgen05.mma (M = 128, N = 32, K = 8),
 //              tcgen05.commit releases the stage / publishes the accumulator through mbarriers;
 //   epilogue   (warps 0-7, a thread owns one unit = one TMEM lane): bias + tanh (forward) or
 //              * (1 - H^2) (backward), then the result leaves twice: plain [unit][BT] for the FFMA
@@ -31,33 +36,54 @@
 // accumulators of 32 columns: the k-blocks go round-robin into seven of them, which only ever take the
 // exact hi*hi products, and the two small cross terms of every block go into the eighth, whose sum --
 // and therefore whose ulp -- is 2^-11 of the others'.  The epilogue adds the eight in fp32, round to nearest.
-// Shared memory 91 KB per CTA -> 2 CTAs per SM, TMEM 256 columns each (all 512 of the SM).
+// Shared memory 89 KB per CTA -> 2 CTAs per SM, TMEM 256 columns each (all 512 of the SM).
 #include "bnn_common.cuh"
 #include "umma.cuh"
 #include "mlp_umma.cuh"
 
 namespace sgmcmc {
 
-constexpr int MU_BM = 128, MU_BK = 16;
+constexpr int MU_BM = 128, MU_BK = 32;
 constexpr int MU_PRODUCERS = 256, MU_THREADS = MU_PRODUCERS + 32;
-constexpr uint32_t MU_A_SBO = 144;                      // 8 rows x 16 B, padded (transposing stores hit 32 banks)
-constexpr uint32_t MU_A_LBO = 16 * MU_A_SBO + 32;       // 128 rows = 16 groups; +32: the 128-bit stores spread too
-constexpr uint32_t MU_A_PART = MU_A_LBO * (MU_BK / 4);  // hi (or lo) of the weight block: 9344 B
-constexpr uint32_t MU_B_SBO = 128, MU_B_LBO = 16 * MU_CN, MU_B_PART = MU_B_LBO * (MU_BK / 4);   // 2048 B
-constexpr uint32_t MU_STAGE = 2 * MU_A_PART + 2 * MU_B_PART;                                     // 22784 B
-constexpr int MU_STAGES = 4;
-constexpr uint32_t MU_SMEM = MU_STAGES * MU_STAGE;                                               // 91136 B
-constexpr int MU_PF = 3;
+constexpr uint32_t MU_A_SBO = 144;                      // 8 rows x 16 B, padded (see the producers)
+constexpr uint32_t MU_A_LBO = 16 * MU_A_SBO + 16;       // 128 rows = 16 groups; +16: the backward stores spread too
+constexpr uint32_t MU_A_PART = MU_A_LBO * (MU_BK / 4);  // hi (or lo) of the weight block: 18560 B
+constexpr uint32_t MU_B_SBO = 128, MU_B_LBO = 16 * MU_CN, MU_B_PART = MU_B_LBO * (MU_BK / 4);   // 4096 B
+constexpr uint32_t MU_STAGE = 2 * MU_A_PART + 2 * MU_B_PART;                                     // 45312 B
+constexpr int MU_STAGES = 2;
+constexpr uint32_t MU_SMEM = MU_STAGES * MU_STAGE;                                               // 90624 B
+constexpr int MU_PF = 2;                                 // register buffers of the producers (one block ahead)
 constexpr int MU_NACC = 7;                               // hi*hi accumulators (+ 1 for the cross terms): 8 x 32 TMEM columns
 
 struct MuRegs {
-  float4 a[2], b;
+  float4 a[4], b[2];
 };
 
+// (16-byte aligned source, or 8 for the odd chains of a network whose parameter count is 2 mod 4)
 __device__ __forceinline__ float4 ld4_al(const float* p, bool a16) {
   if (a16) return __ldg(reinterpret_cast<const float4*>(p));
   const float2 u = __ldg(reinterpret_cast<const float2*>(p)), v = __ldg(reinterpret_cast<const float2*>(p) + 1);
   return make_float4(u.x, u.y, v.x, v.y);
+}
+
+// Veltkamp's splitting of two words at once: p = 8193 x, hi = p - 8192 x (11 significant bits: a TF32 value),
+// lo = x - hi (exact) -- FMUL2 + FFMA2 + FADD2
+__device__ __forceinline__ void split2(float x0, float x1, float& h0, float& h1, float& l0, float& l1) {
+  asm("{\n\t.reg .b64 x, p, h, l, c1, c2;\n\t"
+      "mov.b64 x, {%4, %5};\n\t"
+      "mov.b64 c1, {%6, %6};\n\t"
+      "mov.b64 c2, {%7, %7};\n\t"
+      "mul.rn.f32x2 p, x, c1;\n\t"
+      "fma.rn.f32x2 h, x, c2, p;\n\t"
+      "sub.rn.f32x2 l, x, h;\n\t"
+      "mov.b64 {%0, %1}, h;\n\t"
+      "mov.b64 {%2, %3}, l;\n\t}"
+      : "=f"(h0), "=f"(h1), "=f"(l0), "=f"(l1)
+      : "f"(x0), "f"(x1), "f"(8193.0f), "f"(-8192.0f));
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  split2(v.x, v.y, hi.x, hi.y, lo.x, lo.y);
+  split2(v.z, v.w, hi.z, hi.w, lo.z, lo.w);
 }
 
 template <bool FWD>
@@ -96,75 +122,89 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
   if (warp < MU_PRODUCERS / 32) {
     // ------------------------------------------------------------------ producers
     const bool a16 = aligned_to_dev(W, 16);
-    // weight block of 16 k x 128 units: two float4 per thread
-    int64_t a_goff[2];       // offset of the float4 inside the block (relative to k0 * stride)
-    uint32_t a_off[2];
-    bool a_in[2];
-    int a_k[2];              // FWD: row k of the float4 inside the block (the K edge is per row)
+    // weight block of 32 k x 128 units: four float4 per thread
+    int64_t a_goff[4];       // offsets of the float4s inside the block
+    uint32_t a_off[4];       // FWD: store of unit 4 dq + i;  BWD: store of float4 j
+    bool a_in[4];
+    int kq;
     if (FWD) {
-      // W[k][m], m contiguous: lane -> (k within a quad kr, quad of units dql); a warp-load reads 4 rows x 128
-      // contiguous bytes, the matching warp-store writes 4 k x 32 units as 32-bit words into 32 distinct banks
-      const int kr = lane & 3, dql = lane >> 2;
+      // W[k][m], m contiguous: warp = quad of k (rows k0 + 4 kq + j), lane = quad of units dq: a warp-load
+      // reads 512 contiguous bytes of one row; the 4 x 4 piece leaves as 4 k of one unit per store
+      kq = warp;
+      const int dq = lane;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int tau = 2 * warp + e, kq = tau & 3, dq = 8 * (tau >> 2) + dql;
-        a_k[e] = 4 * kq + kr;
-        a_in[e] = m0 + 4 * dq < M;
-        a_goff[e] = (int64_t)a_k[e] * a.ldw + m0 + 4 * dq;
-        a_off[e] = (uint32_t)(dq >> 1) * MU_A_SBO + (uint32_t)(4 * (dq & 1)) * 16 + (uint32_t)kq * MU_A_LBO +
-                   (uint32_t)kr * 4;
+      for (int j = 0; j < 4; ++j) {
+        a_in[j] = m0 + 4 * dq < M;
+        a_goff[j] = (int64_t)(4 * kq + j) * a.ldw + m0 + 4 * dq;
+        a_off[j] = (uint32_t)(dq >> 1) * MU_A_SBO + (uint32_t)(4 * (dq & 1) + j) * 16 + (uint32_t)kq * MU_A_LBO;
       }
     } else {
-      // W[m][k], k contiguous: a thread moves 4 consecutive k of one unit with 128-bit accesses
+      // W[m][k], k contiguous: lane = (row within a group of 4, quad of k): a warp-load reads 4 rows x 128 bytes
+      kq = lane & 7;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int idx = tid + MU_PRODUCERS * e, m = idx >> 2, kq = idx & 3;
-        a_k[e] = 4 * kq;
-        a_in[e] = m0 + m < M;
-        a_goff[e] = (int64_t)(m0 + m) * a.ldw + 4 * kq;
-        a_off[e] = (uint32_t)(m >> 3) * MU_A_SBO + (uint32_t)(m & 7) * 16 + (uint32_t)kq * MU_A_LBO;
+      for (int j = 0; j < 4; ++j) {
+        const int m = 16 * warp + 4 * j + (lane >> 3);
+        a_in[j] = m0 + m < M;
+        a_goff[j] = (int64_t)(m0 + m) * a.ldw + 4 * kq;
+        a_off[j] = (uint32_t)(m >> 3) * MU_A_SBO + (uint32_t)(m & 7) * 16 + (uint32_t)kq * MU_A_LBO;
       }
     }
-    // activation operand: 2 planes x 2 KB per block, already split and in canonical order
-    const float* __restrict__ Bsrc = ws + a.oBc + (int64_t)(tid >> 7) * a.b_plane + (tid & 127) * 4;
-    const uint32_t b_off = 2 * MU_A_PART + (uint32_t)(tid >> 7) * MU_B_PART + (uint32_t)(tid & 127) * 16;
+    // activation operand: 2 planes x 4 KB per block, already split and in canonical order
+    const float* Bsrc[2];
+    uint32_t b_off[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int idx = tid + MU_PRODUCERS * e;
+      Bsrc[e] = ws + a.oBc + (int64_t)(idx >> 8) * a.b_plane + (idx & 255) * 4;
+      b_off[e] = 2 * MU_A_PART + (uint32_t)(idx >> 8) * MU_B_PART + (uint32_t)(idx & 255) * 16;
+    }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sq = 0.0f;
+    float sq = 0.0f, sq1 = 0.0f;
 
     auto load = [&](MuRegs& r, int kb) {
       const int k0 = kb * MU_BK;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool in = a_in[e] && (k0 + a_k[e] < K);
-        r.a[e] = in ? ld4_al(W + (FWD ? (int64_t)k0 * a.ldw : (int64_t)k0) + a_goff[e], a16) : zero4;
+      for (int j = 0; j < 4; ++j) {
+        const bool in = a_in[j] && (k0 + 4 * kq + (FWD ? j : 0) < K);
+        r.a[j] = in ? ld4_al(W + (FWD ? (int64_t)k0 * a.ldw : (int64_t)k0) + a_goff[j], a16) : zero4;
       }
-      r.b = *reinterpret_cast<const float4*>(Bsrc + (int64_t)kb * (MU_BK / 4) * MU_CN * 4);
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        r.b[e] = *reinterpret_cast<const float4*>(Bsrc[e] + (int64_t)kb * (MU_BK / 4) * MU_CN * 4);
     };
     auto produce = [&](const MuRegs& r, int kb) {
       const int s = kb % MU_STAGES;
       const uint32_t parity = ((uint32_t)(kb / MU_STAGES) & 1u) ^ 1u;
-      umma::mbar_wait(umma::smem_u32(&empty_bar[s]), parity);
-      uint8_t* stage = smem + (uint32_t)s * MU_STAGE;
+      float4 hi[4], lo[4];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float4 hi, lo;
-        umma::split_tf32(r.a[e].x, hi.x, lo.x);
-        umma::split_tf32(r.a[e].y, hi.y, lo.y);
-        umma::split_tf32(r.a[e].z, hi.z, lo.z);
-        umma::split_tf32(r.a[e].w, hi.w, lo.w);
-        if (FWD) {
-          sq = fmaf(r.a[e].x, r.a[e].x, sq); sq = fmaf(r.a[e].y, r.a[e].y, sq);
-          sq = fmaf(r.a[e].z, r.a[e].z, sq); sq = fmaf(r.a[e].w, r.a[e].w, sq);
-          float* ph = reinterpret_cast<float*>(stage + a_off[e]);
-          float* pl = reinterpret_cast<float*>(stage + MU_A_PART + a_off[e]);
-          ph[0] = hi.x; ph[4] = hi.y; ph[8] = hi.z; ph[12] = hi.w;      // consecutive units = consecutive rows, 16 B apart
-          pl[0] = lo.x; pl[4] = lo.y; pl[8] = lo.z; pl[12] = lo.w;
-        } else {
-          *reinterpret_cast<float4*>(stage + a_off[e]) = hi;
-          *reinterpret_cast<float4*>(stage + MU_A_PART + a_off[e]) = lo;
+      for (int j = 0; j < 4; ++j) split4(r.a[j], hi[j], lo[j]);
+      if (FWD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sq = fmaf(r.a[j].x, r.a[j].x, sq); sq1 = fmaf(r.a[j].y, r.a[j].y, sq1);
+          sq = fmaf(r.a[j].z, r.a[j].z, sq); sq1 = fmaf(r.a[j].w, r.a[j].w, sq1);
         }
       }
-      *reinterpret_cast<float4*>(stage + b_off) = r.b;
+      umma::mbar_wait(umma::smem_u32(&empty_bar[s]), parity);
+      uint8_t* stage = smem + (uint32_t)s * MU_STAGE;
+      if (FWD) {                                        // transposed: unit 4 dq + i gets its 4 consecutive k
+        *reinterpret_cast<float4*>(stage + a_off[0]) = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
+        *reinterpret_cast<float4*>(stage + a_off[1]) = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
+        *reinterpret_cast<float4*>(stage + a_off[2]) = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
+        *reinterpret_cast<float4*>(stage + a_off[3]) = make_float4(hi[0].w, hi[1].w, hi[2].w, hi[3].w);
+        *reinterpret_cast<float4*>(stage + MU_A_PART + a_off[0]) = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
+        *reinterpret_cast<float4*>(stage + MU_A_PART + a_off[1]) = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
+        *reinterpret_cast<float4*>(stage + MU_A_PART + a_off[2]) = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
+        *reinterpret_cast<float4*>(stage + MU_A_PART + a_off[3]) = make_float4(lo[0].w, lo[1].w, lo[2].w, lo[3].w);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<float4*>(stage + a_off[j]) = hi[j];
+          *reinterpret_cast<float4*>(stage + MU_A_PART + a_off[j]) = lo[j];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) *reinterpret_cast<float4*>(stage + b_off[e]) = r.b[e];
       umma::fence_proxy_async_smem();
       umma::mbar_arrive(umma::smem_u32(&full_bar[s]));
     };
@@ -183,6 +223,7 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
         }
       }
     }
+    sq += sq1;
 
     // ------------------------------------------------------------------ epilogue
     umma::mbar_wait(umma::smem_u32(&accum_bar), 0);

@@ -9,10 +9,10 @@ namespace sgmcmc {
 
 // The activation operand of a tensor-core layer GEMM lives in the workspace already split into a hi
 // and a lo plane and in the MMA's canonical K-major order, MU_CN = 32 minibatch rows (N) per unit k:
-//   float index inside a plane = ((k / 4) * MU_CN + n) * 4 + k % 4,   plane = round_up(width, 16) * MU_CN floats
-// (rows n >= batch and units k >= width are zeros), so that a block of 16 k is one contiguous 2 KB
-// piece per plane and its staging a plain copy.
-constexpr int MU_CN = 32;
+//   float index inside a plane = ((k / 4) * MU_CN + n) * 4 + k % 4,   plane = round_up(width, MU_KPAD) * MU_CN floats
+// (rows n >= batch and units k >= width are zeros), so that a block of MU_KPAD = 32 k is one contiguous
+// 4 KB piece per plane and its staging a plain copy.
+constexpr int MU_CN = 32, MU_KPAD = 32;
 
 struct MuArgs {
   const float* theta;      // [n_theta_rows, D]
@@ -20,7 +20,7 @@ struct MuArgs {
   int theta_div;           // theta row of work item c = c / theta_div
   int64_t oW, ob;          // offsets of W_l and b_l inside a parameter row
   int ldw;                 // row length of W_l = its n_out
-  int M, K, Mpad;          // units produced, contraction length, round_up(M, 16)
+  int M, K, Mpad;          // units produced, contraction length, round_up(M, MU_KPAD)
   float* ws;               // [n_items, ws_floats]
   int64_t ws_floats;
   int64_t oBc, b_plane;    // canonical activation operand (hi plane; lo plane b_plane floats further)

@@ -94,7 +94,8 @@ DEFAULT_VARIANT = 13
 K4_NAMES = {0: "FFMA (variant 0)", 10: "tensor-pipe 3xTF32 (variant 10: truncating split, chained accumulation)",
             11: "tensor-pipe 3xTF32 (variant 11: rounded split)",
             12: "tensor-pipe 3xTF32 (variant 12: FP32-pipe accumulation across k-steps)",
-            13: "tensor-pipe 3xTF32 (variant 13: rounded split + FP32-pipe accumulation)"}
+            13: "tensor-pipe 3xTF32 (variant 13: rounded split + FP32-pipe accumulation)",
+            14: "tensor-pipe 3xTF32 (variant 14: 13 with packed FP32 splitting of the weight fragments)"}
 
 
 def drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(13, 0), z_seed=9, theta_seed=11):
