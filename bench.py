@@ -358,6 +358,17 @@ def run_b200(args):
         except Exception as exc:      # the headline metric does not depend on this
             svgd = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
+    # ---- informational: BASELINE.json configs[4]'s wide 1000-512-512 network (layer kernels of
+    #      csrc/mlp.cu, its wide layers on tcgen05: csrc/mlp_umma.cu), never fatal ----
+    wide_net = None
+    if rank == 0 and world == 1:
+        try:
+            del sampler
+            torch.cuda.empty_cache()
+            wide_net = wide_net_rates(torch, _native, dev)
+        except Exception as exc:
+            wide_net = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -385,6 +396,7 @@ def run_b200(args):
         "kernels": kernels,
         "sampling_phase": sampling_phase,
         "svgd": svgd,
+        "wide_net": wide_net,
         "cpu_baseline": cpu,
     }
     emit(line)
@@ -436,6 +448,63 @@ def svgd_step_rates(torch, _native, dev, n=4096, D=5252, reps=10):
                               "peak": 0.5 * measured_bf16_peak(), "peak_source": "half of MEASURED_PEAKS.json "
                               "bf16_tflops (dense TF32 = half the bf16 rate)",
                               "frac": 3 * tf / (0.5 * measured_bf16_peak())}}
+
+
+def wide_net_rates(torch, _native, dev, hidden=(1000, 512, 512), C=256, N=20000, B=20, reps=5):
+    """Cost + gradient (K4 for any architecture) and the whole BNN-SGHMC step of `C` chains of the
+    1-1000-512-512-1 network (D = 777 682), CUDA events, state resident (2.4 GB of theta + gradient per
+    pass: larger than L2).  The pass is HBM bound on paper: theta is read by the forward, the backward-data
+    and the weight-gradient kernels and the gradient written once = 16 B per parameter."""
+    import numpy as np
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.data_batches import DeviceBatchGenerator
+    from pysgmcmc_b200.models import MLPNet
+    from pysgmcmc_b200.models.bnn_cost import BayesianNeuralNetworkNLL
+    from pysgmcmc_b200.samplers import SGHMCSampler
+    net = MLPNet(hidden)
+    D = net.n_parameters(1)
+    rng = np.random.RandomState(1)
+    X = rng.standard_normal((N, 1)).astype(np.float32)
+    y = rng.standard_normal(N).astype(np.float32)
+    gen = DeviceBatchGenerator(N, B, n_chains=C, seed=1, device=dev)
+    nll = BayesianNeuralNetworkNLL(N, B, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=dev, net=net)
+    sampler = SGHMCSampler(params=net.init_params(1, n_chains=C, seed=1, device=dev), cost_fun=nll,
+                           batch_generator=gen, burn_in_steps=10 ** 9, scale_grad=float(N), seed=1,
+                           session=Session(device=dev, n_chains=C, output="torch"))
+    next(sampler)
+    theta, grad = sampler._theta, sampler._grad
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms_k4 = timed(lambda: nll.native_cost_and_grad(theta, grad))
+    ms_step = timed(lambda: sampler.run(1, keep_every=10 ** 9))
+    peak = measured_hbm_peak()
+    gbs = 16.0 * C * D / ms_k4 / 1e6
+    return {"workload": "BNN-SGHMC on the 1-1000-512-512-1 network, %d chains x %d parameters, minibatch %d "
+                        "(informational)" % (C, D, B),
+            "k4_ms": ms_k4, "step_ms": ms_step, "chain_steps_per_s": C / ms_step * 1e3,
+            "roofline": {"kernel": "layer kernels of K4 (mlp_fwd, mlp_gemm_umma fwd/bwd on tcgen05, mlp_head, mlp_wgrad)",
+                         "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes": "16 B per parameter and chain-step: theta read by forward, "
+                                              "backward-data and weight gradient, gradient written once"},
+            "step_GBps_60B_per_param": 60.0 * C * D / ms_step / 1e6}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
 
 
 def measured_bf16_peak():
