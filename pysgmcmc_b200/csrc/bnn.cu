@@ -491,7 +491,7 @@ static int launch_variant(const BnnArgs& a, cudaStream_t st) {
 }
 
 // K4 on the tensor pipe (bnn_mma.cuh): one CTA of ceil(batch / 16) warps per chain.
-template <int NB8, int MODE>
+template <int NB8, int MODE, int MINB = (NB8 > 2 ? 6 : 8)>
 static int launch_mma(const BnnArgs& a, cudaStream_t st) {
   constexpr int NTHR = 32 * ((NB8 + 1) / 2);
   const size_t smem = (size_t)bnn_mma_smem_floats(a.batch, a.L.n_in, a.L.D) * sizeof(float);
@@ -499,12 +499,12 @@ static int launch_mma(const BnnArgs& a, cudaStream_t st) {
   unsigned blocks = (unsigned)a.n_chains;
   if (g_bnn_max_ctas > 0 && blocks > (unsigned)g_bnn_max_ctas) blocks = (unsigned)g_bnn_max_ctas;
   if (a.grad != nullptr) {
-    auto k = bnn_mma_kernel<NB8, true, MODE>;
+    auto k = bnn_mma_kernel<NB8, true, MODE, MINB>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     k<<<blocks, NTHR, smem, st>>>(a);
   } else {
-    auto k = bnn_mma_kernel<NB8, false, MODE>;
+    auto k = bnn_mma_kernel<NB8, false, MODE, MINB>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     k<<<blocks, NTHR, smem, st>>>(a);

@@ -592,8 +592,8 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
   chain_barrier<NW>();
 }
 
-template <int NB8, bool WANT_GRAD, int MODE>
-__global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), NB8 > 2 ? 6 : 8) bnn_mma_kernel(BnnArgs a) {
+template <int NB8, bool WANT_GRAD, int MODE, int MINB = (NB8 > 2 ? 6 : 8)>
+__global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), MINB) bnn_mma_kernel(BnnArgs a) {
   constexpr int NW = (NB8 + 1) / 2;
   constexpr int NTHR = 32 * NW;
   extern __shared__ __align__(16) float smem[];
