@@ -458,7 +458,7 @@ template <int BT, int CPT, int VW>
 __device__ __forceinline__ void wgrad_rows(const float* __restrict__ W, float* __restrict__ gW, int n_out, int n_valid,
                                            int kc, const float* __restrict__ sH, const float (&dz)[BT][CPT],
                                            float pscale) {
-#pragma unroll 4
+#pragma unroll 8
   for (int ii = 0; ii < kc; ++ii) {
     const int64_t o = (int64_t)ii * n_out;
     float w[CPT], gsum[CPT];
@@ -493,7 +493,7 @@ __device__ __forceinline__ void wgrad_rows(const float* __restrict__ W, float* _
 }
 
 template <int BT, int CPT>
-__global__ void __launch_bounds__(MLP_THREADS) mlp_wgrad_kernel(MlpArgs a, int l, int n_is) {
+__global__ void __launch_bounds__(MLP_THREADS, CPT == 4 ? 4 : 1) mlp_wgrad_kernel(MlpArgs a, int l, int n_is) {
   extern __shared__ __align__(16) float sH[];              // [min(rows of the slice, MLP_KMAX)][BT]
   const int n_in = a.L.width[l - 1], n_out = a.L.width[l];
   const int n_ct = (n_out + CPT * MLP_THREADS - 1) / (CPT * MLP_THREADS);
