@@ -34,50 +34,49 @@ def generate_batches(x, y, x_placeholder, y_placeholder, batch_size=20, seed=Non
     >>> batch_dict[xp].shape, batch_dict[yp].shape
     ((20, 3), (20, 1))
     """
-    # Sanitize inputs
-    assert(isinstance(batch_size, int)), "generate_batches: batch size must be an integer."
-    assert(batch_size > 0), "generate_batches: batch size must be greater than zero."
-    assert(seed is None or isinstance(seed, int)), "generate_batches: seed must be an integer or `None`"
-    assert seed is None or (0 <= seed <= 2 ** 32 - 1)
-    assert(y.shape[0] == x.shape[0]), "Not exactly one label per datapoint!"
+    return _HostBatches(x, y, x_placeholder, y_placeholder, batch_size, seed)
 
-    n_examples = x.shape[0]
 
-    if seed is None:
-        seed = np.random.randint(1, 100000)
+def _checked_seed(seed, who):
+    """The reference asserts on its arguments (tests/test_data_batches.py:78-98 expect AssertionError
+    for a non-integer or non-positive batch size and for a non-integer or negative seed)."""
+    assert seed is None or (isinstance(seed, int) and 0 <= seed <= 2 ** 32 - 1), \
+        "%s: seed must be `None` or an integer in [0, 2**32 - 1]" % who
+    return int(np.random.randint(1, 100000)) if seed is None else seed      # data_batches.py:99-100
 
-    rng = np.random.RandomState()
-    rng.seed(seed)
 
-    initial_batch_size = batch_size
-    batch_size = min(initial_batch_size, n_examples)
+class _HostBatches(object):
+    """Iterator behind `generate_batches`: one legacy NumPy stream, one `randint` per batch -- the draw
+    order `DeviceBatchGenerator` reproduces on the GPU."""
 
-    if initial_batch_size != batch_size:
-        logging.error("Not enough datapoints to form a minibatch. "
-                      "Batchsize was set to %s", batch_size)
+    def __init__(self, x, y, x_placeholder, y_placeholder, batch_size, seed):
+        assert isinstance(batch_size, int) and batch_size > 0, \
+            "generate_batches: batch size must be an integer greater than zero."
+        assert y.shape[0] == x.shape[0], "Not exactly one label per datapoint!"
+        self.rng = np.random.RandomState(_checked_seed(seed, "generate_batches"))
+        self.x, self.y, self.keys = x, y, (x_placeholder, y_placeholder)
+        self.rows = min(batch_size, x.shape[0])                    # data_batches.py:111
+        if self.rows != batch_size:
+            logging.error("Not enough datapoints to form a minibatch. Batchsize was set to %s", self.rows)
 
-    while True:
-        start = rng.randint(0, (n_examples - batch_size + 1))
-        minibatch_x = x[start:start + batch_size]
-        minibatch_y = y[start:start + batch_size, None]
-        yield {x_placeholder: minibatch_x, y_placeholder: minibatch_y.reshape(-1, 1)}
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        first = self.rng.randint(0, self.x.shape[0] - self.rows + 1)       # end-exclusive (:120)
+        rows = slice(first, first + self.rows)
+        return {self.keys[0]: self.x[rows], self.keys[1]: self.y[rows].reshape(-1, 1)}
 
 
 def generate_shuffled_batches(x, y, x_placeholder, y_placeholder, batch_size=20, seed=None):
-    """`generate_batches` with the rows of every batch shuffled, x and y alike
-    (data_batches.py:132-206)."""
-    if seed is None:
-        seed = np.random.randint(1, 100000)
-
-    rng_x, rng_y = np.random.RandomState(), np.random.RandomState()
-    rng_x.seed(seed)
-    rng_y.seed(seed)
-
+    """`generate_batches` with the rows of every batch shuffled, x and y by two generators in the same
+    state (data_batches.py:132-206).  Like the reference this shuffles the slice VIEWS, i.e. it permutes
+    the rows of the caller's x and y in place (the pairs stay matched): data_batches.py:203-205."""
+    seed = _checked_seed(seed, "generate_shuffled_batches")
+    shufflers = np.random.RandomState(seed), np.random.RandomState(seed)
     for batch in generate_batches(x, y, x_placeholder, y_placeholder, batch_size, seed):
-        # like the reference, this shuffles the slice VIEWS, i.e. permutes the rows of
-        # the caller's x and y in place (pairs stay matched): data_batches.py:203-205
-        rng_x.shuffle(batch[x_placeholder])
-        rng_y.shuffle(batch[y_placeholder])
+        for rng, key in zip(shufflers, (x_placeholder, y_placeholder)):
+            rng.shuffle(batch[key])
         yield batch
 
 
