@@ -88,8 +88,11 @@ int sgmcmc_set_bnn_pipeline(int64_t chunk_chains, int ring);
  * K4 then K1, 40 instead of 52 B of HBM traffic per element-step and no grad_scratch, but
  * slower at large chain counts (too few warps per SM for the update's instruction stream,
  * DESIGN.md "K5"), so on = 0 (K4 then K1) is the default.  on = 1 selects the fused kernel,
- * on = 3 the fused kernel without the TMA L2 prefetch of the state rows.  max_ctas > 0 caps
- * its grid (persistent CTAs looping over chains). */
+ * on = 3 the fused kernel without the TMA L2 prefetch of the state rows, on = 4 (6: without the
+ * prefetch) its warp-specialised form: persistent CTAs of two 2-warp MMA groups and four update warps,
+ * the gradient handed over through two shared-memory buffers per group, so the issue-bound gradient and the
+ * HBM-bound update overlap inside every SM.  max_ctas > 0 caps the grid (persistent CTAs looping over
+ * chains; the warp-specialised kernel is always persistent, 2 CTAs per SM by default). */
 int sgmcmc_set_bnn_fused(int on, int max_ctas);
 
 /* Number of kernel launches issued by this library since load (all threads). */

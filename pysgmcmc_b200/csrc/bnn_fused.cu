@@ -162,7 +162,85 @@ bnn_sghmc_fused_kernel(BnnArgs a, FusedStepArgs f) {
   }
 }
 
-static int g_bnn_fused = 0;   // measured slower than K4 then K1 at large chain counts (DESIGN.md "K5")
+// ---- the warp-specialised form of the same step -----------------------------------------------------
+// One persistent CTA of 8 warps, two per SM: warps 0-3 are two MMA groups (2 warps each, one chain at a
+// time per group: bnn_chain_mma, unchanged), warps 4-7 are update warps that apply K1's arithmetic to the
+// chains the groups have finished.  A group owns two gradient buffers in shared memory: while the update
+// warps consume chain j from one, the group computes chain j + 1 into the other, so the issue-bound
+// gradient and the HBM-bound update overlap INSIDE an SM at all times instead of in alternating kernels
+// (or in a CTA that does one after the other, above), and the gradient never touches HBM (40 B per
+// element and step).  Hand-over through named barriers (bar.arrive / bar.sync, 64 + 128 threads):
+//   ready[g][b]: group g -> update warps (the gradient of its current chain is complete in buffer b)
+//   free [g][b]: update warps -> group g (buffer b may be overwritten)
+// 128 registers per thread (K4 runs as fast at 128 as at 168: profiles/r02_k4_occupancy_experiment.jsonl),
+// 110 KB of shared memory per CTA.  Bit-identical to K4 then K1 (same noise counters, same arithmetic).
+constexpr int WS_GROUP_THREADS = 64, WS_UPDATE_THREADS = 128, WS_THREADS = 2 * WS_GROUP_THREADS + WS_UPDATE_THREADS;
+
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__host__ __device__ inline int bnn_ws_group_floats(int batch, int n_in, int D) {
+  return ((D + 3) & ~3) + bnn_mma_smem_floats(batch, n_in, D);      // second gradient buffer + one chain's K4 buffers
+}
+
+template <int NB8, bool BURN_IN>
+__global__ void __launch_bounds__(WS_THREADS, 2) bnn_sghmc_ws_kernel(BnnArgs a, FusedStepArgs f) {
+  static_assert((NB8 + 1) / 2 == 2, "two MMA warps per chain");
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int D = a.L.D, D4 = (D + 3) & ~3;
+  const int group_floats = bnn_ws_group_floats(a.batch, a.L.n_in, D);
+  const int64_t stride = (int64_t)gridDim.x * 2;
+  constexpr int HANDOVER = WS_GROUP_THREADS + WS_UPDATE_THREADS;
+  if (warp < 4) {
+    // ------------------------------------------------------------------ MMA group g
+    const int g = warp >> 1, tid0 = g * WS_GROUP_THREADS;
+    float* base = smem + g * group_floats;                          // [R0 | R1 | P | Q | Zb | X | y | scratch]
+    BnnMmaSmem s = bnn_mma_carve(base + D4, a.batch, a.L.n_in, D);
+    int j = 0;
+    for (int64_t chain = (int64_t)blockIdx.x * 2 + g; chain < a.n_chains; chain += stride, ++j) {
+      const int b = j & 1;
+      if (j >= 2) named_sync(7 + 2 * g + b, HANDOVER);              // the update of chain j - 2 has read buffer b
+      s.R = base + b * D4;
+      if (f.prefetch && tid == tid0) prefetch_chain_state<BURN_IN>(f, chain, D);
+      float cost = 0.0f, sse = 0.0f;
+      bnn_chain_mma<NB8, true, true, MMA_ROUND_SPLIT | MMA_RN_ACCUM>(
+          a, f.theta + chain * D, a.starts != nullptr ? a.starts + chain : nullptr, s, cost, sse, tid0, 1 + g);
+      if (tid == tid0) {
+        a.cost[chain] = cost;                                        // U(theta_{t-1}): base_classes.py:298-300
+        if (a.mse != nullptr) a.mse[chain] = sse / (float)a.batch;
+      }
+      named_arrive(3 + 2 * g + b, HANDOVER);                         // gradient of `chain` complete in buffer b
+    }
+  } else {
+    // ------------------------------------------------------------------ update warps
+    const int ut = tid - 2 * WS_GROUP_THREADS;
+    for (int j = 0;; ++j) {
+      const int b = j & 1;
+      bool any = false;
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const int64_t chain = (int64_t)blockIdx.x * 2 + g + (int64_t)j * stride;
+        if (chain >= a.n_chains) continue;
+        any = true;
+        named_sync(3 + 2 * g + b, HANDOVER);
+        sghmc_update_chain<BURN_IN, WS_UPDATE_THREADS>(f, smem + g * group_floats + b * D4, chain, D, ut);
+        if (chain + 2 * stride < a.n_chains) named_arrive(7 + 2 * g + b, HANDOVER);
+      }
+      if (!any) break;
+    }
+  }
+}
+
+static int g_bnn_fused = 0;   // 0: K4 then K1; 1: one CTA does both in turn; 2: warp-specialised (see DESIGN.md "K5")
+static int g_fused_max_ctas = 0;
+static int g_fused_prefetch = 1;
+void set_bnn_fused_max_ctas(int n) { g_fused_max_ctas = n; }
+void set_bnn_fused_prefetch(int on) { g_fused_prefetch = on; }
 int bnn_fused_enabled() { return g_bnn_fused; }
 void set_bnn_fused(int on) { g_bnn_fused = on; }
 
@@ -174,10 +252,32 @@ bool bnn_fused_supported(const BnnArgs& a, const FusedStepArgs& f) {
   return (size_t)bnn_mma_smem_floats(a.batch, a.L.n_in, a.L.D) * sizeof(float) <= 227 * 1024;
 }
 
-static int g_fused_max_ctas = 0;
-static int g_fused_prefetch = 1;
-void set_bnn_fused_max_ctas(int n) { g_fused_max_ctas = n; }
-void set_bnn_fused_prefetch(int on) { g_fused_prefetch = on; }
+template <int NB8>
+static int launch_ws(const BnnArgs& a, const FusedStepArgs& f, cudaStream_t st) {
+  const size_t smem = (size_t)2 * bnn_ws_group_floats(a.batch, a.L.n_in, a.L.D) * sizeof(float);
+  SG_REQUIRE(smem <= 113 * 1024, SGMCMC_E_UNSUPPORTED, "warp-specialised BNN-SGHMC step: %zu B of shared memory per CTA", smem);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  unsigned blocks = (unsigned)((a.n_chains + 1) / 2);
+  const unsigned cap = g_fused_max_ctas > 0 ? (unsigned)g_fused_max_ctas : 2u * (unsigned)n_sm;   // persistent: 2 CTAs per SM
+  if (blocks > cap) blocks = cap;
+  if (f.burn_in) {
+    auto k = bnn_sghmc_ws_kernel<NB8, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    k<<<blocks, WS_THREADS, smem, st>>>(a, f);
+  } else {
+    auto k = bnn_sghmc_ws_kernel<NB8, false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    k<<<blocks, WS_THREADS, smem, st>>>(a, f);
+  }
+  return check_launch("bnn_sghmc_ws_kernel");
+}
 
 template <int NB8>
 static int launch_fused(const BnnArgs& a, const FusedStepArgs& f, cudaStream_t st) {
@@ -204,6 +304,10 @@ int launch_bnn_sghmc_fused(const BnnArgs& a, const FusedStepArgs& f_in, cudaStre
   f.prefetch = g_fused_prefetch;
   SG_REQUIRE(bnn_fused_supported(a, f), SGMCMC_E_UNSUPPORTED,
              "fused BNN-SGHMC step: needs batch <= 32, D %% 4 == 0 and 16-byte aligned state");
+  if (g_bnn_fused == 2 && a.batch > 16) {
+    const size_t smem_ws = (size_t)2 * bnn_ws_group_floats(a.batch, a.L.n_in, a.L.D) * sizeof(float);
+    if (smem_ws <= 113 * 1024) return a.batch <= 24 ? launch_ws<3>(a, f, st) : launch_ws<4>(a, f, st);
+  }
   switch ((a.batch + 7) / 8) {
     case 1: return launch_fused<1>(a, f, st);
     case 2: return launch_fused<2>(a, f, st);

@@ -123,9 +123,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Barrier among the NW warps that work on one chain.  bar_id == 0: they are the whole CTA; bar_id > 0: they
+// are one group of a warp-specialised CTA (bnn_fused.cu) and meet at that named barrier.
 template <int NW>
-__device__ __forceinline__ void chain_barrier() {
-  if constexpr (NW == 1) __syncwarp(); else __syncthreads();
+__device__ __forceinline__ void chain_barrier(int bar_id = 0) {
+  if constexpr (NW == 1) {
+    __syncwarp();
+  } else {
+    if (bar_id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NW) : "memory");
+  }
 }
 
 constexpr int MMA_SCRATCH = 192;   // cross-warp partial sums: [2][64] dW4 columns, [64] scalars
@@ -370,10 +377,10 @@ __device__ __forceinline__ BnnMmaSmem bnn_mma_carve(float* base, int batch, int 
 template <int NB8, bool WANT_GRAD, bool COHERENT = false, int MODE = 0>
 __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __restrict__ th,
                                               const int32_t* __restrict__ start_ptr, const BnnMmaSmem& s,
-                                              float& cost_out, float& sse_out) {
+                                              float& cost_out, float& sse_out, int tid0 = 0, int bar_id = 0) {
   constexpr int NW = (NB8 + 1) / 2;
   constexpr int NTHR = 32 * NW;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tid = threadIdx.x - tid0, lane = tid & 31, w = tid >> 5;     // (tid0: first thread of this chain's group)
   const int g = lane >> 2, t = lane & 3;
   const BnnLayout L = a.L;
   const int batch = a.batch, n_in = L.n_in, D = L.D;
@@ -412,7 +419,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
   for (int q = tid; q < batch * n_in; q += NTHR) s.sX[q] = __ldg(a.X + start * n_in + q);
   for (int q = tid; q < batch; q += NTHR) s.sY[q] = __ldg(a.y + start + q);
   sq = warp_sum(sq);
-  chain_barrier<NW>();
+  chain_barrier<NW>(bar_id);
 
   // ---- layer 1 (n_in -> 50), element-wise in the C layout: h <- [tanh(X W1 + b1) 1 0..] ----
   const int r0 = 16 * w + g, r1 = r0 + 8;
@@ -525,7 +532,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
         h[nt][e] = (df[e >> 1] * wv) * fmaf(-v, v, 1.0f);
       }
   }
-  chain_barrier<NW>();                 // every thread has read W4, b4, rho; partial sums are visible
+  chain_barrier<NW>(bar_id);                 // every thread has read W4, b4, rho; partial sums are visible
   if (tid == 0) {
     float sse_t = 0.0f, sq_t = 0.0f;
 #pragma unroll
@@ -543,7 +550,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
     }
   }
   if (!WANT_GRAD) {
-    chain_barrier<NW>();
+    chain_barrier<NW>(bar_id);
     return;
   }
   // dW4: one column per thread (two for a single-warp chain)
@@ -571,14 +578,14 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
       h[nt][2] = (dead || r1 >= batch) ? 0.0f : acc[nt][2] * fmaf(-v1.x, v1.x, 1.0f);
       h[nt][3] = (dead || r1 >= batch) ? 0.0f : acc[nt][3] * fmaf(-v1.y, v1.y, 1.0f);
     }
-    chain_barrier<NW>();               // W of this layer is dead, Zb is complete
+    chain_barrier<NW>(bar_id);               // W of this layer is dead, Zb is complete
     gemm_weight_grad<NB8, 4 / NW, MODE>(Hb, s.Zb, Wb, batch, pscale, w * (4 / NW), g, t);
-    chain_barrier<NW>();               // Zb may be overwritten by the next dZ
+    chain_barrier<NW>(bar_id);               // Zb may be overwritten by the next dZ
   }
 
   // ---- layer 1 backward: dW1 = X^T dZ1, db1 = 1^T dZ1 (columns of dZ1 through Zb) ----
   store_c(s.Zb, batch, r0, t, h);
-  chain_barrier<NW>();
+  chain_barrier<NW>(bar_id);
   for (int j = tid; j < HID; j += NTHR) {
     float db = 0.0f;
     for (int i = 0; i < batch; ++i) db += s.Zb[i * AS + j];
@@ -589,7 +596,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
       R[L.oW1 + m * HID + j] = fmaf(R[L.oW1 + m * HID + j], pscale, dw);
     }
   }
-  chain_barrier<NW>();
+  chain_barrier<NW>(bar_id);
 }
 
 template <int NB8, bool WANT_GRAD, int MODE, int MINB = (NB8 > 2 ? 6 : 8)>

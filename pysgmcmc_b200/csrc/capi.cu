@@ -91,7 +91,7 @@ int sgmcmc_set_bnn_chunk(int64_t chains) {
 
 int sgmcmc_set_bnn_fused(int on, int max_ctas) {
   if (max_ctas < 0) return sgmcmc::set_error(SGMCMC_E_INVALID, "max_ctas must be >= 0");
-  sgmcmc::set_bnn_fused(on != 0);
+  sgmcmc::set_bnn_fused((on & 4) ? 2 : (on != 0 ? 1 : 0));
   sgmcmc::set_bnn_fused_prefetch((on & 2) == 0);
   sgmcmc::set_bnn_fused_max_ctas(max_ctas);
   return SGMCMC_OK;

@@ -660,10 +660,22 @@ def test_fused_step_is_bit_identical_to_k4_then_k1(z_injected):
         _native.call("sgmcmc_set_bnn_fused", 1, 5)        # persistent grid: 5 CTAs loop over 37 chains
         out[2] = _run_c(state, X, y, starts, z, C, 1, batch, N, steps, burn, 3, seed=99, step0=1000,
                         chain_offset=64)
+        # warp-specialised form (two MMA groups + update warps per CTA, gradient through shared-memory
+        # buffers): its default persistent grid, and 3 CTAs = 6 groups looping over the 37 chains (every
+        # group takes several chains: both gradient buffers and both hand-over barriers are recycled)
+        _native.call("sgmcmc_set_bnn_fused", 4, 0)
+        out[3] = _run_c(state, X, y, starts, z, C, 1, batch, N, steps, burn, 3, seed=99, step0=1000,
+                        chain_offset=64)
+        _native.call("sgmcmc_set_bnn_fused", 4, 3)
+        out[4] = _run_c(state, X, y, starts, z, C, 1, batch, N, steps, burn, 3, seed=99, step0=1000,
+                        chain_offset=64)
+        _native.call("sgmcmc_set_bnn_fused", 6, 1)        # one CTA, no L2 prefetch of the state rows
+        out[5] = _run_c(state, X, y, starts, z, C, 1, batch, N, steps, burn, 3, seed=99, step0=1000,
+                        chain_offset=64)
     finally:
         _native.call("sgmcmc_set_bnn_fused", 0, 0)
     names = ("theta", "v", "tau", "g", "v_hat", "minv")
-    for other in (0, 2):
+    for other in (0, 2, 3, 4, 5):
         for i, name in enumerate(names):
             assert np.array_equal(out[1][0][i], out[other][0][i]), (name, other)
         assert np.array_equal(out[1][1], out[other][1]) and np.array_equal(out[1][2], out[other][2])

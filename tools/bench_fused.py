@@ -20,7 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--chains", type=int, default=8192)
 ap.add_argument("--steps", type=int, default=300)
 ap.add_argument("--caps", default="0")
-ap.add_argument("--modes", default="1", help="fused modes to time: 1 = fused, 3 = fused without L2 prefetch")
+ap.add_argument("--modes", default="1", help="fused modes to time: 1 = fused, 3 = fused without L2 prefetch, 4 = warp-specialised, 6 = the same without prefetch")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 C, D = args.chains, 5252
@@ -55,4 +55,4 @@ for burn_in in (True, False):
                           "ms_per_step": round(ms, 4), "chain_steps_per_s": round(C / ms * 1e3),
                           "hbm_GBps_algorithmic": round(bytes_per_elem * C * D / ms / 1e6, 1),
                           "bit_identical_to_unfused": bool(torch.equal(ref, theta))}), flush=True)
-_native.call("sgmcmc_set_bnn_fused", 1, 0)
+_native.call("sgmcmc_set_bnn_fused", 0, 0)
