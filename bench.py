@@ -557,7 +557,10 @@ def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_o
     `sample_every`-th step the whole sample [C, D] is copied back as well and READ by the host.
     Default thinning: BayesianNeuralNetwork's sample_steps = 100, and at least 100 steps are timed
     (whatever --steps says), so that at least one whole sample crosses PCIe inside every timed
-    region -- at the rate the reference's model produces them, tail of the last copy included.  sample_every = 1 is the reference's literal `next()` (every step returns host
+    region -- at the rate the reference's model produces them.  The region is placed so that its sample
+    falls in the middle (`sample_phase`: the copy is pipelined under the following steps, as every sample's is
+    in a long run); `with_exposed_tail` is the same region ending WITH its sample, so that the whole D2H of
+    the last sample is an un-overlapped tail (the convention of the earlier records).  sample_every = 1 is the reference's literal `next()` (every step returns host
     parameters, base_classes.py:298-304): PCIe-bound, reported as `e2e_every_sample`.  The
     iterator keeps up to `lookahead` steps queued ahead and runs the copies on their own streams,
     so the device does not idle while the host handles a result or a sample crosses PCIe."""
@@ -569,31 +572,47 @@ def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_o
     else:
         K_e = min(K, 300)
     rng = np.random.RandomState(7)
-    host_starts = torch.from_numpy(
-        rng.randint(0, N_EXAMPLES - BATCH + 1, size=(W + K_e, C)).astype(np.int32)).pin_memory()
-    checksum = 0.0
-    for _ in sampler.iter_host(host_starts[:W], sample_every=sample_every, lookahead=lookahead):
-        pass
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n_samples = 0
-    for sample, cost in sampler.iter_host(host_starts[W:], sample_every=sample_every, lookahead=lookahead):
-        checksum += float(cost[0])                       # the host reads every step's result
-        if sample is not None:
-            n_samples += 1
-            checksum += float(sample[0, 0]) + float(sample[-1, -1])   # ... and the sample when there is one
-    e1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
-    assert np.isfinite(checksum)
-    assert n_samples == K_e // sample_every and n_samples >= 1, "no sample crossed PCIe in the timed region"
+
+    def timed_region(phase):
+        """`K_e` steps of the iterator after `W` untimed ones.  phase = 0: the region ends with its sample,
+        so the whole D2H of that sample is an exposed tail; phase = sample_every / 2: the sample falls in
+        the middle of the region and its copy is pipelined under the following steps, as every sample's is
+        in a long run."""
+        host_starts = torch.from_numpy(
+            rng.randint(0, N_EXAMPLES - BATCH + 1, size=(W + K_e, C)).astype(np.int32)).pin_memory()
+        for _ in sampler.iter_host(host_starts[:W], sample_every=sample_every, lookahead=lookahead,
+                                   sample_phase=phase + 1):        # (no sample in the warm-up)
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        checksum, n_samples = 0.0, 0
+        for sample, cost in sampler.iter_host(host_starts[W:], sample_every=sample_every, lookahead=lookahead,
+                                              sample_phase=phase):
+            checksum += float(cost[0])                       # the host reads every step's result
+            if sample is not None:
+                n_samples += 1
+                checksum += float(sample[0, 0]) + float(sample[-1, -1])   # ... and the sample when there is one
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+        assert np.isfinite(checksum)
+        return ms, wall_ms, n_samples
+
+    lead = sample_every // 2 if sample_every > 1 else 0
+    ms, wall_ms, n_samples = timed_region(lead)
+    tail = None
+    if lead > 0:
+        ms_t, wall_t, n_t = timed_region(0)
+        tail = {"value": C * world * K_e / (ms_t / 1e3), "ms_per_step": ms_t / K_e, "samples_copied": n_t,
+                "note": "the same region ending WITH its sample: the whole D2H of the last sample is an exposed tail"}
+    assert n_samples >= 1, "no sample crossed PCIe in the timed region"
     return {"value": C * world * K_e / (ms / 1e3), "unit": "chain-steps/s", "steps": K_e,
             "ms_per_step": ms / K_e, "wall_ms_per_step": wall_ms / K_e,
             "h2d_bytes_per_step": C * 4, "d2h_bytes_per_step": C * 4 + n_samples * C * D * 4 / K_e,
-            "sample_every": sample_every, "samples_copied": n_samples,
+            "sample_every": sample_every, "samples_copied": n_samples, "with_exposed_tail": tail,
             "api": "SGHMCSampler.iter_host -> sgmcmc_bnn_host_pipeline_step (C ABI), one call per step, pinned "
                    "host buffers, host receives every step's cost and every %d-th sample [C, D], up to %d steps "
                    "queued ahead" % (sample_every, lookahead)}

@@ -165,6 +165,10 @@ class BayesianNeuralNetworkNLL(object):
     def native_cost_and_grad(self, theta, grad_out, want_mse=False):
         C, D = theta.shape
         assert D == self.n_params, "parameter layout does not match the %d-input network" % self.n_in
+        if theta.dtype != torch.float32 or grad_out.dtype != torch.float32:
+            raise TypeError("the native BNN cost + gradient kernels are float32 (got %s); float64 samplers use the "
+                            "differentiable cost (call the object) with the float64 update kernels"
+                            % str(theta.dtype))
         X, y, starts, batch = self._device_batch()
         assert starts is None or starts.shape[0] == C
         if self._cost is None or self._cost.shape[0] != C:

@@ -145,7 +145,7 @@ class SGHMCSampler(BurnInMCMCSampler):
         self.cost = cost_scratch
 
     # ---- next(sampler) with HOST minibatches, pipelined ---------------------------------
-    def iter_host(self, host_starts, sample_every=None, lookahead=4):
+    def iter_host(self, host_starts, sample_every=None, lookahead=4, sample_phase=0):
         """Generator over ``(sample, cost)`` like ``next(sampler)``, for the BNN cost with the
         dataset resident on the device and the minibatch choice made on the HOST: row s of
         `host_starts` (pinned int32 ``[n_steps, C]``) holds the start index of every chain's
@@ -154,7 +154,9 @@ class SGHMCSampler(BurnInMCMCSampler):
         Every step copies its row host->device, runs K4 + K1 and copies the per-chain cost
         back into pinned host memory; every `sample_every`-th step the whole sample ``[C, D]``
         comes back as well (``None`` otherwise) -- the thinning of
-        ``BayesianNeuralNetwork.train`` (bayesian_neural_network.py:510-531).  Unlike a plain
+        ``BayesianNeuralNetwork.train`` (bayesian_neural_network.py:510-531); `sample_phase` shifts
+        which steps those are (a call that continues a thinning period started earlier: the samples
+        are the steps s with ``(s + 1 + sample_phase) % sample_every == 0``).  Unlike a plain
         ``next()`` loop the device never waits for the host: up to `lookahead` further steps
         are already queued when ``(sample_s, cost_s)`` is yielded, the copies run on their own
         streams (one per direction) and the sample is snapshotted device-to-device before it
@@ -195,7 +197,7 @@ class SGHMCSampler(BurnInMCMCSampler):
         def enqueue(s):
             nonlocal first
             b = s % depth
-            wants = bool(sample_every) and (s + 1) % sample_every == 0
+            wants = bool(sample_every) and (s + 1 + sample_phase) % sample_every == 0
             # samples are numbered over the life of the sampler, so a second iter_host() call
             # does not start on the slot the caller may still be reading
             sample_slot[b] = (self._host_samples % n_slots) if wants else -1

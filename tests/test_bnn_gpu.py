@@ -186,6 +186,16 @@ def oracle_bnn_chain(theta0, X, y, seeds, N, batch, steps, burn, z_seed, eps=0.0
     return theta, np.stack(costs), chain
 
 
+def test_native_cost_refuses_float64_instead_of_casting():
+    """The fused cost + gradient kernels are float32; handing them float64 parameters is an error
+    (float64 samplers go through the differentiable cost and the float64 update kernels)."""
+    X, y = sinc_data(64)
+    nll = BayesianNeuralNetworkNLL(64, 20, X=X[:20], y=y[:20], device=DEV)
+    theta = torch.zeros((2, 5252), dtype=torch.float64, device=DEV)
+    with pytest.raises(TypeError, match="float32"):
+        nll.native_cost_and_grad(theta, torch.empty_like(theta))
+
+
 def test_bnn_sghmc_sampler_trajectory_matches_oracle():
     """next(sampler) on the BNN cost with per-chain on-device minibatch streams and
     injected noise, 200 steps across the burn-in boundary, vs the fp32 oracle."""
