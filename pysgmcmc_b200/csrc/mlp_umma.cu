@@ -5,7 +5,7 @@
 //   backward data  dZ_{l-1}^T [n_in x batch] = W_l [n_in x n_out]  dZ_l^T [n_out x batch]    (* (1 - H_{l-1}^2))
 // (pysgmcmc/models/bayesian_neural_network.py:28-69 forward, tf.gradients backward).  The chain's
 // PRIVATE weight matrix is the M operand (tiles of 128 units), the minibatch the N operand (padded to
-// 32 rows), the contraction streams over the other layer width in blocks of 16.  Every weight is read
+// 32 rows), the contraction streams over the other layer width in blocks of 32.  Every weight is read
 // from HBM exactly once per pass and used for `batch` FMAs: 10 flop per weight byte, which the FP32
 // pipe cannot sustain at HBM speed (the FFMA kernels of mlp.cu run at 0.14 of the copy peak) and the
 // tensor pipe can.
@@ -36,7 +36,10 @@
 // accumulators of 32 columns: the k-blocks go round-robin into seven of them, which only ever take the
 // exact hi*hi products, and the two small cross terms of every block go into the eighth, whose sum --
 // and therefore whose ulp -- is 2^-11 of the others'.  The epilogue adds the eight in fp32, round to nearest.
-// Shared memory 89 KB per CTA -> 2 CTAs per SM, TMEM 256 columns each (all 512 of the SM).
+// Shared memory 89 KB per CTA -> 2 CTAs per SM, TMEM 256 columns each (all 512 of the SM).  What bounds it now
+// (profiles/r02_ncu_mlp_umma_summary.txt): DRAM 39-45 % busy, 43 % of the stall samples on the first use of a
+// loaded weight block -- one block ahead is all the 96 registers of 2 x 288 threads allow (a third buffer
+// spills and halves the rate; see profiles/r02_mlp_wide_tcgen05_bk32.jsonl for what else was tried).
 #include "bnn_common.cuh"
 #include "umma.cuh"
 #include "mlp_umma.cuh"
@@ -96,8 +99,8 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
   __shared__ float red[MU_PRODUCERS / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * MU_BM;
-  const int64_t chain = blockIdx.y;
+  const int m0 = blockIdx.y * MU_BM;
+  const int64_t chain = blockIdx.x;
   const int M = a.M, K = a.K;
   const int nkb = (K + MU_BK - 1) / MU_BK;
   const uint32_t smem_base = umma::smem_u32(smem);
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
         float s = 0.0f;
 #pragma unroll
         for (int i = 0; i < MU_PRODUCERS / 32; ++i) s += red[i];
-        ws[a.oSq + blockIdx.x] = s;
+        ws[a.oSq + blockIdx.y] = s;
       }
     }
   } else {
@@ -334,8 +337,9 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
 }
 
 int launch_mlp_gemm_umma(const MuArgs& a, bool fwd, int64_t n_items, cudaStream_t st) {
-  SG_REQUIRE(n_items <= 65535, SGMCMC_E_UNSUPPORTED, "mlp (tensor-core layers): at most 65535 chains per launch");
-  const dim3 grid((unsigned)((a.M + MU_BM - 1) / MU_BM), (unsigned)n_items);
+  SG_REQUIRE(n_items < ((int64_t)1 << 31) && (a.M + MU_BM - 1) / MU_BM <= 65535, SGMCMC_E_UNSUPPORTED,
+             "mlp (tensor-core layers): grid too large");
+  const dim3 grid((unsigned)n_items, (unsigned)((a.M + MU_BM - 1) / MU_BM));
   if (fwd) {
     cudaFuncSetAttribute(mlp_gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MU_SMEM);
     mlp_gemm_umma_kernel<true><<<grid, MU_THREADS, MU_SMEM, st>>>(a);
