@@ -64,6 +64,32 @@ def test_version_and_error_reporting_without_gpu():
     assert lib.sgmcmc_svgd_scratch_bytes(50000, 2) == -1
 
 
+def test_generic_network_layout_is_host_arithmetic():
+    """Parameter count and workspace of `get_net` specs (csrc/mlp.cu: make_mlp_layout): the layout of
+    tf.trainable_variables() order W_1 b_1 ... W_{L+1} b_{L+1} rho, and the workspace that grows by the
+    split canonical operand copies when wide layers go to the tensor cores."""
+    lib = _native.load()
+    wide, n = _native.int_array([1, 1000, 512, 512, 1])
+    assert lib.sgmcmc_mlp_n_params(wide, n) == 777682            # BASELINE.json configs[4]'s network
+    default, nd = _native.int_array([1, 50, 50, 50, 1])
+    assert lib.sgmcmc_mlp_n_params(default, nd) == 5252          # get_default_net (bayesian_neural_network.py:28-69)
+    bad, nb = _native.int_array([1, 50, 2])
+    assert lib.sgmcmc_mlp_n_params(bad, nb) == -1                # the output width must be 1
+    try:
+        assert lib.sgmcmc_set_mlp_tuning(0) == 0
+        ffma = lib.sgmcmc_mlp_workspace_bytes(wide, n, 3, 20)
+        narrow_ffma = lib.sgmcmc_mlp_workspace_bytes(default, nd, 3, 20)
+    finally:
+        assert lib.sgmcmc_set_mlp_tuning(1) == 0
+    umma = lib.sgmcmc_mlp_workspace_bytes(wide, n, 3, 20)
+    # plain activations + gradients: 2 x 20 x (1000 + 512 + 512) floats per chain (+ the partial sums)
+    assert 3 * 4 * 2 * 20 * 2024 <= ffma <= 3 * 4 * (2 * 20 * 2024 + 64)
+    # + hi / lo planes [round_up(width, 32)][32]: H_1, H_2 for the forward GEMMs of layers 2, 3; dZ_2, dZ_3
+    assert umma - ffma == 3 * 4 * 2 * 32 * (1024 + 512 + 512 + 512)
+    assert lib.sgmcmc_mlp_workspace_bytes(default, nd, 3, 20) == narrow_ffma     # no layer qualifies
+    assert lib.sgmcmc_mlp_workspace_bytes(wide, n, 3, 33) == -1                  # minibatches of up to 32 rows
+
+
 def test_no_product_module_imports_the_oracle():
     pkg = os.path.join(ROOT, "pysgmcmc_b200")
     for dirpath, _, files in os.walk(pkg):
