@@ -393,15 +393,19 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
     const float4* src = reinterpret_cast<const float4*>(th);
     float4* dst = reinterpret_cast<float4*>(R);
     const int n4 = D / 4;
-    for (int q0 = 0; q0 < n4; q0 += 8 * NTHR) {          // 8 independent 128-bit loads per thread in flight
-      float4 v[8];
+    // STAGE_U independent 128-bit loads per thread in flight: the whole row of the default network (1313
+    // float4 over 64 threads) in ONE round -- the registers are free at this point, and every further round
+    // exposes another global-memory latency at the head of the chain (10 % of K4's stall samples with 8)
+    constexpr int STAGE_U = NW == 2 ? 21 : 16;
+    for (int q0 = 0; q0 < n4; q0 += STAGE_U * NTHR) {
+      float4 v[STAGE_U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < STAGE_U; ++u) {
         const int q = q0 + u * NTHR + tid;
         v[u] = q < n4 ? (COHERENT ? __ldcg(src + q) : __ldg(src + q)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < STAGE_U; ++u) {
         const int q = q0 + u * NTHR + tid;
         if (q < n4) dst[q] = v[u];
         sq = fmaf(v[u].x, v[u].x, sq); sq = fmaf(v[u].y, v[u].y, sq);
