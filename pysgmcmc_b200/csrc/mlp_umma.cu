@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
   __shared__ float red[MU_PRODUCERS / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * MU_BM;
-  const int64_t chain = blockIdx.x;
+  const int m0 = blockIdx.x * MU_BM;                   // the tiles of a chain are neighbours in the grid: they share
+  const int64_t chain = a.chain0 + blockIdx.y;         // the chain's activation operand while it is hot in L2
   const int M = a.M, K = a.K;
   const int nkb = (K + MU_BK - 1) / MU_BK;
   const uint32_t smem_base = umma::smem_u32(smem);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
         float s = 0.0f;
 #pragma unroll
         for (int i = 0; i < MU_PRODUCERS / 32; ++i) s += red[i];
-        ws[a.oSq + blockIdx.y] = s;
+        ws[a.oSq + blockIdx.x] = s;
       }
     }
   } else {
@@ -336,18 +336,20 @@ __global__ void __launch_bounds__(MU_THREADS, 2) mlp_gemm_umma_kernel(MuArgs a) 
   }
 }
 
-int launch_mlp_gemm_umma(const MuArgs& a, bool fwd, int64_t n_items, cudaStream_t st) {
-  SG_REQUIRE(n_items < ((int64_t)1 << 31) && (a.M + MU_BM - 1) / MU_BM <= 65535, SGMCMC_E_UNSUPPORTED,
-             "mlp (tensor-core layers): grid too large");
-  const dim3 grid((unsigned)n_items, (unsigned)((a.M + MU_BM - 1) / MU_BM));
-  if (fwd) {
-    cudaFuncSetAttribute(mlp_gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MU_SMEM);
-    mlp_gemm_umma_kernel<true><<<grid, MU_THREADS, MU_SMEM, st>>>(a);
-  } else {
-    cudaFuncSetAttribute(mlp_gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MU_SMEM);
-    mlp_gemm_umma_kernel<false><<<grid, MU_THREADS, MU_SMEM, st>>>(a);
+int launch_mlp_gemm_umma(const MuArgs& a_in, bool fwd, int64_t n_items, cudaStream_t st) {
+  MuArgs a = a_in;
+  SG_REQUIRE((a.M + MU_BM - 1) / MU_BM <= 65535 * 32, SGMCMC_E_UNSUPPORTED, "mlp (tensor-core layers): layer too wide");
+  if (fwd) cudaFuncSetAttribute(mlp_gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MU_SMEM);
+  else cudaFuncSetAttribute(mlp_gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MU_SMEM);
+  for (int64_t c0 = 0; c0 < n_items; c0 += 65535) {      // grid.y holds the chains: 65535 per launch
+    const int64_t nc = n_items - c0 < 65535 ? n_items - c0 : 65535;
+    a.chain0 = c0;
+    const dim3 grid((unsigned)((a.M + MU_BM - 1) / MU_BM), (unsigned)nc);
+    if (fwd) mlp_gemm_umma_kernel<true><<<grid, MU_THREADS, MU_SMEM, st>>>(a);
+    else mlp_gemm_umma_kernel<false><<<grid, MU_THREADS, MU_SMEM, st>>>(a);
+    if (int rc = check_launch("mlp_gemm_umma_kernel")) return rc;
   }
-  return check_launch("mlp_gemm_umma_kernel");
+  return SGMCMC_OK;
 }
 
 }  // namespace sgmcmc

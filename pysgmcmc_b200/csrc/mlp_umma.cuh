@@ -31,6 +31,7 @@ struct MuArgs {
   const int32_t* starts;   // minibatch starts (NULL: row tiles, see item_rows in mlp.cu)
   int64_t n_rows;
   int batch, bt;           // rows per item; row stride of the plain layouts
+  int64_t chain0;          // first work item of this launch (set by launch_mlp_gemm_umma)
 };
 
 int launch_mlp_gemm_umma(const MuArgs& a, bool fwd, int64_t n_items, cudaStream_t st);
