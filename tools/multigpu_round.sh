@@ -1,3 +1,7 @@
+# Multi-GPU records of a round on an N-GPU box:   gpurun --gpus N -- bash tools/multigpu_round.sh N
+#   * the NCCL test of the one collective of the path (tests/test_diagnostics_multigpu.py, needs >= 2 GPUs)
+#   * BASELINE.json configs[4]: relativistic update sweep D = 1e5 ... 1e9, weak and strong, under torchrun
+#   * bench.py --gpus N under torchrun (chain-steps/s, e2e, R-hat / ESS of all chains with the all-reduce)
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
