@@ -374,7 +374,10 @@ __device__ __forceinline__ BnnMmaSmem bnn_mma_carve(float* base, int batch, int 
 // `th` is the chain's parameter row in global memory (staged here into R).  COHERENT: the
 // calling kernel also WRITES theta (K5), so the row is read with ld.global.cg (L2, where the
 // update phase re-reads it) instead of the read-only path.
-template <int NB8, bool WANT_GRAD, bool COHERENT = false, int MODE = 0>
+// BATCH_CT > 0: the minibatch has exactly that many rows (the launcher checked), so every row mask of the
+// fragment loads folds at compile time -- for the reference's 20 rows (16 + 4: the k slots t / t + 4 of the
+// third k-step are all live / all dead) that is every FSEL and most ISETPs of the weight-gradient GEMMs.
+template <int NB8, bool WANT_GRAD, bool COHERENT = false, int MODE = 0, int BATCH_CT = 0>
 __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __restrict__ th,
                                               const int32_t* __restrict__ start_ptr, const BnnMmaSmem& s,
                                               float& cost_out, float& sse_out, int tid0 = 0, int bar_id = 0) {
@@ -383,7 +386,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
   const int tid = threadIdx.x - tid0, lane = tid & 31, w = tid >> 5;     // (tid0: first thread of this chain's group)
   const int g = lane >> 2, t = lane & 3;
   const BnnLayout L = a.L;
-  const int batch = a.batch, n_in = L.n_in, D = L.D;
+  const int batch = BATCH_CT > 0 ? BATCH_CT : a.batch, n_in = L.n_in, D = L.D;
   float* __restrict__ R = s.R;
 
   // ---- stage theta (natural layout) and the minibatch; sum of squares for the weight prior ----
@@ -543,14 +546,20 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
     for (int ww = 0; ww < NW; ++ww) { sse_t += scr[128 + ww]; sq_t += scr[136 + ww]; }
     const float lv_den = 0.02f + 3e-16f;                            // safe_divide(., 2 * var)
     const float dl = rho - logf(1e-6f);
-    const float log_like_data = (-sse_t * (0.5f * fvi) - 0.5f * rho * (float)batch) * a.inv_bs;
-    const float lv = -(dl * dl) / lv_den - 0.5f * logf(0.01f);      // :102-107
-    const float wp = (-0.5f * sq_t) * a.prior_den_inv;              // :131-141
-    cost_out = -(log_like_data + (lv + wp) * a.inv_n);
+    // un-contracted on purpose: which product the compiler fuses into an FMA depends on what it knows at
+    // compile time (BATCH_CT), and every instantiation of this function has to produce the same bits
+    const float nb = (float)batch;
+    const float log_like_data = __fmul_rn(__fsub_rn(__fmul_rn(-sse_t, __fmul_rn(0.5f, fvi)),
+                                                    __fmul_rn(__fmul_rn(0.5f, rho), nb)), a.inv_bs);
+    const float lv = __fsub_rn(__fdiv_rn(-__fmul_rn(dl, dl), lv_den), 0.5f * logf(0.01f));      // :102-107
+    const float wp = __fmul_rn(__fmul_rn(-0.5f, sq_t), a.prior_den_inv);                         // :131-141
+    cost_out = -__fadd_rn(log_like_data, __fmul_rn(__fadd_rn(lv, wp), a.inv_n));
     sse_out = sse_t;
     if (WANT_GRAD) {
-      const float drho_data = -(0.5f * sse_t * e_rho * fvi * fvi - 0.5f * (float)batch) * a.inv_bs;
-      R[L.orho] = drho_data + (2.0f * dl / lv_den) * a.inv_n + rho * pscale;
+      const float drho_data = __fmul_rn(-__fsub_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(0.5f, sse_t), e_rho), fvi), fvi),
+                                                   __fmul_rn(0.5f, nb)), a.inv_bs);
+      R[L.orho] = __fadd_rn(__fadd_rn(drho_data, __fmul_rn(__fdiv_rn(__fmul_rn(2.0f, dl), lv_den), a.inv_n)),
+                            __fmul_rn(rho, pscale));
     }
   }
   if (!WANT_GRAD) {
@@ -603,7 +612,7 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
   chain_barrier<NW>(bar_id);
 }
 
-template <int NB8, bool WANT_GRAD, int MODE, int MINB = (NB8 > 2 ? 6 : 8)>
+template <int NB8, bool WANT_GRAD, int MODE, int MINB = (NB8 > 2 ? 6 : 8), int BATCH_CT = 0>
 __global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), MINB) bnn_mma_kernel(BnnArgs a) {
   constexpr int NW = (NB8 + 1) / 2;
   constexpr int NTHR = 32 * NW;
@@ -618,7 +627,7 @@ __global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), MINB) bnn_mma_kernel(Bnn
     if (tid == 0 && chain + gridDim.x < a.n_chains && (D & 3) == 0 && aligned_to_dev(a.theta, 16))
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(th + (int64_t)gridDim.x * D), "r"(D * 4)
                    : "memory");
-    bnn_chain_mma<NB8, WANT_GRAD, false, MODE>(a, th, a.starts != nullptr ? a.starts + chain : nullptr, s, cost,
+    bnn_chain_mma<NB8, WANT_GRAD, false, MODE, BATCH_CT>(a, th, a.starts != nullptr ? a.starts + chain : nullptr, s, cost,
                                                sse);
     if (tid == 0) {
       a.cost[chain] = cost;
