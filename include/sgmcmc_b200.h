@@ -53,11 +53,12 @@ const char* sgmcmc_last_error(void);
  * Measured on B200 (profiles/): 256 x 1 is fastest; more groups per thread cost occupancy. */
 int sgmcmc_set_update_tuning(int threads, int unroll);
 
-/* Implementation of the BNN kernel K4: 10-14 are the tensor-pipe kernel (3xTF32 mma.sync,
+/* Implementation of the BNN kernel K4: 10-16 are the tensor-pipe kernel (3xTF32 mma.sync,
  * csrc/bnn_mma.cuh; minibatches of up to 32 rows, larger ones fall back to 0) in its accuracy
  * modes (10: truncating hi/lo split, sums chained through the tensor core's accumulator;
- * 11: rounded split; 12: FP32-pipe accumulation across k-steps; 13: both, the default; 14: 13 with the
- * weight fragments split by packed FP32 instructions); 0-9 are launch
+ * 11: rounded split; 12: FP32-pipe accumulation across k-steps; 13: both; 14: 13 with the weight
+ * fragments split by packed FP32 instructions; 15: 13 with the cross terms of the 3xTF32 products in their
+ * own accumulator; 16: 15 + 14, the default); 0-9 are launch
  * shapes of the FFMA kernel (units per thread, chains per CTA, rows in flight) kept for the
  * sweeps recorded under profiles/. */
 int sgmcmc_set_bnn_tuning(int variant);

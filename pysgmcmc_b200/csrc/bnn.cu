@@ -456,16 +456,17 @@ bnn_predict_kernel(const float* __restrict__ theta, const float* __restrict__ X,
 // profiles/ ---------------------------------------------------------------------------
 constexpr int K10_COLS = 1, K10_TPC = 50, K10_NC = 5;
 
-// 10-14: tensor-pipe kernel (bnn_mma.cuh) in its accuracy modes; 0-9: FFMA launch shapes.  Default 13
-// (rounded hi/lo split + FP32-pipe accumulation across k-steps): the only tensor-pipe mode whose
-// 1000-step BNN-SGHMC trajectory stays within 1e-5 of the float32 oracle at the benchmarked shapes
-// (9.0e-6; mode 10: 4.6e-5, mode 11: 2.4e-5, FFMA kernel: 9.8e-6) -- 0.27 vs 0.22 ms for 8192 chains
-// (profiles/r02_bnn_trajectory_drift.jsonl, profiles/r02_k4_variants.jsonl)
-static int g_bnn_variant = 13;
+// 10-16: tensor-pipe kernel (bnn_mma.cuh) in its accuracy modes; 0-9: FFMA launch shapes.  Default 16: rounded
+// hi/lo split, FP32-pipe accumulation of the k-steps' exact hi*hi sums, cross terms in their own accumulator,
+// weight fragments split by packed FP32 instructions.  1000-step BNN-SGHMC trajectory at the benchmarked
+// shapes: 9.2e-6 from the float32 oracle and 1.32e-5 from the float64 one (the float32 ORACLE: 1.39e-5; mode
+// 13: 9.0e-6 / 1.82e-5; mode 10, round 1's default: 4.6e-5 / 4.1e-5; FFMA kernel: 9.8e-6 / 1.5e-5) at 0.238 ms
+// for 8192 chains (13: 0.247, 10: 0.202) -- profiles/r02_bnn_trajectory_drift*.jsonl, profiles/r02_k4_variants.jsonl
+static int g_bnn_variant = 16;
 static int g_bnn_max_ctas = 0;          // 0: one CTA per chain group; > 0: persistent grid of that size
 static int64_t g_bnn_chunk = 0;         // chains per K4+K1 chunk inside sgmcmc_bnn_sghmc_run_f32 (0: all)
 void set_bnn_chunk(int64_t c) { g_bnn_chunk = c; }
-int bnn_variant_count() { return 15; }
+int bnn_variant_count() { return 17; }
 void set_bnn_variant(int v) { g_bnn_variant = v; }
 void set_bnn_max_ctas(int n) { g_bnn_max_ctas = n; }
 
@@ -530,6 +531,8 @@ static int launch_nll_grad(const BnnArgs& a, cudaStream_t st) {
       case 12: return launch_mma_batch<MMA_RN_ACCUM>(a, st);
       case 13: return launch_mma_batch<MMA_ROUND_SPLIT | MMA_RN_ACCUM>(a, st);
       case 14: return launch_mma_batch<MMA_ROUND_SPLIT | MMA_RN_ACCUM | MMA_PACKED_SPLIT>(a, st);
+      case 15: return launch_mma_batch<MMA_ROUND_SPLIT | MMA_RN_ACCUM | MMA_SEP_CROSS>(a, st);
+      case 16: return launch_mma_batch<MMA_ROUND_SPLIT | MMA_RN_ACCUM | MMA_SEP_CROSS | MMA_PACKED_SPLIT>(a, st);
       default: return launch_mma_batch<0>(a, st);
     }
   }

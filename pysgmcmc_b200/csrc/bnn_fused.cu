@@ -151,7 +151,7 @@ bnn_sghmc_fused_kernel(BnnArgs a, FusedStepArgs f) {
   for (int64_t chain = blockIdx.x; chain < a.n_chains; chain += gridDim.x) {
     float cost = 0.0f, sse = 0.0f;
     if (f.prefetch && tid == 0) prefetch_chain_state<BURN_IN>(f, chain, D);
-    bnn_chain_mma<NB8, true, true, MMA_ROUND_SPLIT | MMA_RN_ACCUM>(a, f.theta + chain * D, a.starts != nullptr ? a.starts + chain : nullptr,
+    bnn_chain_mma<NB8, true, true, MMA_DEFAULT_MODE>(a, f.theta + chain * D, a.starts != nullptr ? a.starts + chain : nullptr,
                                    s, cost, sse);
     if (tid == 0) {
       a.cost[chain] = cost;                            // U(theta_{t-1}): base_classes.py:298-300
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) bnn_sghmc_ws_kernel(BnnArgs a, 
       s.R = base + b * D4;
       if (f.prefetch && tid == tid0) prefetch_chain_state<BURN_IN>(f, chain, D);
       float cost = 0.0f, sse = 0.0f;
-      bnn_chain_mma<NB8, true, true, MMA_ROUND_SPLIT | MMA_RN_ACCUM>(
+      bnn_chain_mma<NB8, true, true, MMA_DEFAULT_MODE>(
           a, f.theta + chain * D, a.starts != nullptr ? a.starts + chain : nullptr, s, cost, sse, tid0, 1 + g);
       if (tid == tid0) {
         a.cost[chain] = cost;                                        // U(theta_{t-1}): base_classes.py:298-300

@@ -59,7 +59,10 @@ constexpr int NT8 = 7;   // 8-wide tiles covering those 56 columns
 //         of a GEMM (Ootomo & Yokota 2022).
 // What they buy is measured as trajectory drift, not single-step error
 // (tools/bnn_trajectory_drift.py, profiles/r02_bnn_trajectory_drift*.jsonl).
-constexpr int MMA_ROUND_SPLIT = 1, MMA_RN_ACCUM = 2, MMA_PACKED_SPLIT = 4;
+constexpr int MMA_ROUND_SPLIT = 1, MMA_RN_ACCUM = 2, MMA_PACKED_SPLIT = 4, MMA_SEP_CROSS = 8;
+// the default (launch variant 16): every fused / pipelined caller of bnn_chain_mma uses it, so that all of
+// them stay bit-identical to K4 then K1
+constexpr int MMA_DEFAULT_MODE = MMA_ROUND_SPLIT | MMA_RN_ACCUM | MMA_SEP_CROSS | MMA_PACKED_SPLIT;
 template <int MODE>
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   if constexpr ((MODE & MMA_ROUND_SPLIT) != 0) hi = __float_as_uint(x) + 0x1000u;
@@ -163,11 +166,49 @@ __device__ __forceinline__ void a_from_c(const float (&src)[NT8][4], int ks, uin
   split_tf32<MODE>(src[ks][3], ah[3], al[3]);
 }
 
-template <int MODE>
-__device__ __forceinline__ void mma3_row(float (&acc)[NT8][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                         const uint32_t (&bh)[NT8][2], const uint32_t (&bl)[NT8][2]) {
+//   bit 3 (MMA_SEP_CROSS, with MMA_RN_ACCUM): the two cross terms of every k-step are chained through the
+//         tensor core into their OWN accumulator `corr` -- their sum is 2^-11 of the result, so is the ulp that
+//         the tensor core truncates at -- and only the exact hi*hi products of a k-step go through a zero C
+//         operand and the FP32-pipe addition; `corr` is added once at the end of the GEMM.  Mode 13 adds the
+//         cross terms and the hi*hi products inside the tensor core, one truncation at the ulp of the k-step's
+//         sum per k-step; this removes it.
+// FIRST: the first k-step of a GEMM -- the products go straight into the (not yet initialised) accumulators
+// through the zero-C form (0 + x = x exactly: the same bits as clearing the tile and adding)
+template <int MODE, bool FIRST = false>
+__device__ __forceinline__ void mma3_row(float (&acc)[NT8][4], float (&corr)[NT8][4], const uint32_t (&ah)[4],
+                                         const uint32_t (&al)[4], const uint32_t (&bh)[NT8][2],
+                                         const uint32_t (&bl)[NT8][2]) {
   // three passes over 7 independent accumulators: dependent MMAs are 7 issues apart
-  if constexpr ((MODE & MMA_RN_ACCUM) != 0) {
+  if constexpr ((MODE & MMA_SEP_CROSS) != 0) {
+    if constexpr (FIRST) {
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) mma_tf32_zero(corr[nt], al, bh[nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) mma_tf32_zero(acc[nt], ah, bh[nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) mma_tf32(corr[nt], ah, bl[nt]);
+    } else {
+      float part[NT8][4];
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) mma_tf32(corr[nt], al, bh[nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) mma_tf32_zero(part[nt], ah, bh[nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) mma_tf32(corr[nt], ah, bl[nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) {
+        add2_rn(acc[nt][0], acc[nt][1], part[nt][0], part[nt][1]);
+        add2_rn(acc[nt][2], acc[nt][3], part[nt][2], part[nt][3]);
+      }
+    }
+  } else if constexpr (FIRST) {
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32_zero(acc[nt], al, bh[nt]);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], ah, bl[nt]);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) mma_tf32(acc[nt], ah, bh[nt]);
+  } else if constexpr ((MODE & MMA_RN_ACCUM) != 0) {
     float part[NT8][4];
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt) mma_tf32_zero(part[nt], al, bh[nt]);
@@ -190,6 +231,18 @@ __device__ __forceinline__ void mma3_row(float (&acc)[NT8][4], const uint32_t (&
   }
 }
 
+// acc += corr at the end of a GEMM (MMA_SEP_CROSS)
+template <int MODE>
+__device__ __forceinline__ void add_cross(float (&acc)[NT8][4], const float (&corr)[NT8][4]) {
+  if constexpr ((MODE & MMA_SEP_CROSS) != 0) {
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      add2_rn(acc[nt][0], acc[nt][1], corr[nt][0], corr[nt][1]);
+      add2_rn(acc[nt][2], acc[nt][3], corr[nt][2], corr[nt][3]);
+    }
+  }
+}
+
 __device__ __forceinline__ void zero_tile(float (&acc)[NT8][4]) {
 #pragma unroll
   for (int nt = 0; nt < NT8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
@@ -199,7 +252,7 @@ __device__ __forceinline__ void zero_tile(float (&acc)[NT8][4]) {
 template <int MODE>
 __device__ __forceinline__ void gemm_forward(const float* __restrict__ Wb, const float (&src)[NT8][4],
                                              float (&acc)[NT8][4], int g, int t) {
-  zero_tile(acc);
+  float corr[NT8][4];                                    // (MMA_SEP_CROSS only; dead otherwise)
 #pragma unroll
   for (int ks = 0; ks < NT8; ++ks) {
     uint32_t ah[4], al[4], bh[NT8][2], bl[NT8][2];
@@ -222,15 +275,17 @@ __device__ __forceinline__ void gemm_forward(const float* __restrict__ Wb, const
       }
       split_pair<MODE>(b0, b1, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
     }
-    mma3_row<MODE>(acc, ah, al, bh, bl);
+    if (ks == 0) mma3_row<MODE, true>(acc, corr, ah, al, bh, bl);
+    else mma3_row<MODE>(acc, corr, ah, al, bh, bl);
   }
+  add_cross<MODE>(acc, corr);
 }
 
 // acc[i][k] = sum_j src[i][j] * W[k][j]   (src columns >= 50 are 0)
 template <int MODE>
 __device__ __forceinline__ void gemm_backward_data(const float* __restrict__ Wb, const float (&src)[NT8][4],
                                                    float (&acc)[NT8][4], int g, int t) {
-  zero_tile(acc);
+  float corr[NT8][4];                                    // (MMA_SEP_CROSS only; dead otherwise)
 #pragma unroll
   for (int ks = 0; ks < NT8; ++ks) {
     uint32_t ah[4], al[4], bh[NT8][2], bl[NT8][2];
@@ -241,8 +296,10 @@ __device__ __forceinline__ void gemm_backward_data(const float* __restrict__ Wb,
       const float2 b = *reinterpret_cast<const float2*>(Wb + k * HID + 8 * ks + 2 * t);
       split_pair<MODE>(b.x, b.y, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
     }
-    mma3_row<MODE>(acc, ah, al, bh, bl);
+    if (ks == 0) mma3_row<MODE, true>(acc, corr, ah, al, bh, bl);
+    else mma3_row<MODE>(acc, corr, ah, al, bh, bl);
   }
+  add_cross<MODE>(acc, corr);
 }
 
 // Wb[k][j] <- pscale * Wb[k][j] + sum_i Hb[i][k] * Zb[i][j]   for k <= 50 (row 50: bias), j < 50
@@ -290,35 +347,49 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
         split_pair<MODE>(b0, b1, bh[p][ks][0], bh[p][ks][1], bl[p][ks][0], bl[p][ks][1]);
       }
     }
-    float acc[MTW][NP][4];
-#pragma unroll
-    for (int m = 0; m < MTW; ++m)
-#pragma unroll
-      for (int p = 0; p < NP; ++p) acc[m][p][0] = acc[m][p][1] = acc[m][p][2] = acc[m][p][3] = 0.0f;
+    float acc[MTW][NP][4], corr[MTW][NP][4];
+    constexpr bool SEP = (MODE & MMA_SEP_CROSS) != 0;
 #pragma unroll
     for (int ks = 0; ks < NB8; ++ks) {
       float part[MTW][NP][4];
-      constexpr bool RN = (MODE & MMA_RN_ACCUM) != 0 && NB8 > 1;   // (one k-step: nothing to chain)
+      // FP32-pipe accumulation: every k-step after the first goes into `part` (zero C operand) and is added
+      // RN; the first one -- and all of them in the chained modes -- goes straight into the accumulators.
+      // SEP: the cross terms chain into `corr`, only hi*hi takes that route.
+      const bool RN = (MODE & MMA_RN_ACCUM) != 0 && ks > 0;        // (compile time: the loop is unrolled)
       auto& dst = *(RN ? &part : &acc);
+      auto& small = *(SEP ? &corr : &dst);
 #pragma unroll
       for (int m = 0; m < MTW; ++m)
 #pragma unroll
         for (int p = 0; p < NP; ++p)
           if (nt0 + p < NT8) {
-            if constexpr (RN) mma_tf32_zero(dst[m][p], al[m][ks], bh[p][ks]);
-            else mma_tf32(dst[m][p], al[m][ks], bh[p][ks]);
+            if ((SEP ? ks == 0 : (RN || ks == 0))) mma_tf32_zero(small[m][p], al[m][ks], bh[p][ks]);
+            else mma_tf32(small[m][p], al[m][ks], bh[p][ks]);
           }
+      if (SEP) {
 #pragma unroll
-      for (int m = 0; m < MTW; ++m)
+        for (int m = 0; m < MTW; ++m)
 #pragma unroll
-        for (int p = 0; p < NP; ++p)
-          if (nt0 + p < NT8) mma_tf32(dst[m][p], ah[m][ks], bl[p][ks]);
+          for (int p = 0; p < NP; ++p)
+            if (nt0 + p < NT8) mma_tf32_zero(dst[m][p], ah[m][ks], bh[p][ks]);
 #pragma unroll
-      for (int m = 0; m < MTW; ++m)
+        for (int m = 0; m < MTW; ++m)
 #pragma unroll
-        for (int p = 0; p < NP; ++p)
-          if (nt0 + p < NT8) mma_tf32(dst[m][p], ah[m][ks], bh[p][ks]);
-      if constexpr (RN) {
+          for (int p = 0; p < NP; ++p)
+            if (nt0 + p < NT8) mma_tf32(small[m][p], ah[m][ks], bl[p][ks]);
+      } else {
+#pragma unroll
+        for (int m = 0; m < MTW; ++m)
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+            if (nt0 + p < NT8) mma_tf32(dst[m][p], ah[m][ks], bl[p][ks]);
+#pragma unroll
+        for (int m = 0; m < MTW; ++m)
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+            if (nt0 + p < NT8) mma_tf32(dst[m][p], ah[m][ks], bh[p][ks]);
+      }
+      if (RN) {
 #pragma unroll
         for (int m = 0; m < MTW; ++m)
 #pragma unroll
@@ -328,6 +399,16 @@ __device__ __forceinline__ void gemm_weight_grad(const float* __restrict__ Hb, c
               add2_rn(acc[m][p][2], acc[m][p][3], part[m][p][2], part[m][p][3]);
             }
       }
+    }
+    if (SEP) {
+#pragma unroll
+      for (int m = 0; m < MTW; ++m)
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+          if (nt0 + p < NT8) {
+            add2_rn(acc[m][p][0], acc[m][p][1], corr[m][p][0], corr[m][p][1]);
+            add2_rn(acc[m][p][2], acc[m][p][3], corr[m][p][2], corr[m][p][3]);
+          }
     }
 #pragma unroll
     for (int m = 0; m < MTW; ++m) {

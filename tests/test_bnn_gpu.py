@@ -25,7 +25,7 @@ from pysgmcmc_b200.stepsize_schedules import ConstantStepsizeSchedule
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-K4_DEFAULT = 13      # tensor-pipe kernel, rounded split + FP32-pipe accumulation (csrc/bnn.cu: g_bnn_variant)
+K4_DEFAULT = 16      # tensor-pipe kernel: rounded split, FP32-pipe accumulation, separate cross-term accumulator (csrc/bnn.cu: g_bnn_variant)
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -292,11 +292,12 @@ def test_bnn_sghmc_teacher_forced_update_bit_exact_gradient_error_bounded(varian
 
 
 # BASELINE.json north_star: "1000-step trajectories match ... within 1e-5 relative in FP32".
-# Measured at these shapes (tools/bnn_trajectory_drift.py, profiles/r02_bnn_trajectory_drift.jsonl):
-# default K4 (tensor pipe, rounded split + FP32-pipe accumulation) 9.0e-6, FFMA K4 9.8e-6 of
-# max|theta| at step 1000 -- for scale: float32 arithmetic alone separates the float32 and float64
-# ORACLES by 1.4e-5 there.  The faster tensor-pipe modes (variants 10 / 11: 4.6e-5 / 2.4e-5) do
-# not meet the bar and are not the default.
+# Measured at these shapes (tools/bnn_trajectory_drift.py, profiles/r02_bnn_trajectory_drift*.jsonl):
+# default K4 (tensor pipe: rounded split, FP32-pipe accumulation, separate cross-term accumulator) 9.2e-6,
+# FFMA K4 9.8e-6 of max|theta| at step 1000 -- for scale: float32 arithmetic alone separates the float32
+# and float64 ORACLES by 1.4e-5 there, and the default K4 ends 1.3e-5 from the float64 oracle, i.e. closer
+# to exact arithmetic than the float32 oracle it is gated against.  The faster tensor-pipe modes (variants
+# 10 / 11: 4.6e-5 / 2.4e-5) do not meet the bar and are not the default.
 TRAJ_TOL = 1e-5
 
 
@@ -315,6 +316,8 @@ def test_bnn_sghmc_1000_step_trajectory_at_the_benchmarked_shapes(variant):
     assert max(vs32.values()) <= TRAJ_TOL, line
     # never (much) further from the float64 oracle than the float32 oracle itself is
     assert line["gpu_vs_oracle_f64"][-1] <= 2.0 * line["oracle_f32_vs_f64"][-1] + 1e-5, line
+    if variant == K4_DEFAULT:      # the default tensor-pipe mode is at least as close to exact arithmetic
+        assert line["gpu_vs_oracle_f64"][-1] <= 1.05 * line["oracle_f32_vs_f64"][-1], line
 
 
 def test_bnn_sghmc_run_equals_per_step_and_oracle():

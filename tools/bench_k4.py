@@ -66,5 +66,5 @@ for v, cap in [(int(x), int(c)) for x in args.variants.split(",") for c in args.
     print(json.dumps({"variant": v, "max_ctas": cap, "ms": round(ms, 4), "chain_steps_per_s": round(C / ms * 1e3),
                       "fp32_TFLOPs": round(tf, 2), "frac_of_74.4": round(tf / 74.45, 3),
                       "matches_variant0": ok}), flush=True)
-_native.call("sgmcmc_set_bnn_tuning", 13)
+_native.call("sgmcmc_set_bnn_tuning", 16)
 _native.call("sgmcmc_set_persistent_grids", 0, 0)

@@ -90,15 +90,17 @@ def gpu_run(theta0, X, y, seeds, steps, burn, z_seed, every, variant, dev="cuda:
         _native.call("sgmcmc_set_bnn_tuning", DEFAULT_VARIANT)
 
 
-DEFAULT_VARIANT = 13
+DEFAULT_VARIANT = 16
 K4_NAMES = {0: "FFMA (variant 0)", 10: "tensor-pipe 3xTF32 (variant 10: truncating split, chained accumulation)",
             11: "tensor-pipe 3xTF32 (variant 11: rounded split)",
             12: "tensor-pipe 3xTF32 (variant 12: FP32-pipe accumulation across k-steps)",
             13: "tensor-pipe 3xTF32 (variant 13: rounded split + FP32-pipe accumulation)",
-            14: "tensor-pipe 3xTF32 (variant 14: 13 with packed FP32 splitting of the weight fragments)"}
+            14: "tensor-pipe 3xTF32 (variant 14: 13 with packed FP32 splitting of the weight fragments)",
+            15: "tensor-pipe 3xTF32 (variant 15: 13 with the cross terms in their own accumulator)",
+            16: "tensor-pipe 3xTF32 (variant 16: 15 with packed FP32 splitting of the weight fragments)"}
 
 
-def drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(13, 0), z_seed=9, theta_seed=11):
+def drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(16, 0), z_seed=9, theta_seed=11):
     from oracle import bnn as obnn
     X, y = sinc_data()
     theta0 = obnn.init_theta(chains, seed=theta_seed, dtype=np.float32)
@@ -129,7 +131,7 @@ if __name__ == "__main__":
     ap.add_argument("--burn", type=int, default=600)
     ap.add_argument("--chains", type=int, default=4)
     ap.add_argument("--every", type=int, default=100)
-    ap.add_argument("--variants", default="13,0")
+    ap.add_argument("--variants", default="16,13,0")
     a = ap.parse_args()
     for line in drift_curves(a.steps, a.burn, a.chains, a.every, tuple(int(v) for v in a.variants.split(","))):
         print(json.dumps(line), flush=True)
