@@ -138,6 +138,7 @@ __device__ __forceinline__ void chain_barrier(int bar_id = 0) {
   }
 }
 
+constexpr int K4_PREFETCH_AHEAD = 1024;   // chains between a CTA and the row it prefetches into L2 (0: off)
 constexpr int MMA_SCRATCH = 192;   // cross-warp partial sums: [2][64] dW4 columns, [64] scalars
 // shared memory per chain (floats): R[D rounded to 4] | P | Q | Z ([batch x AS] each) | X | y | scratch
 __host__ __device__ inline int bnn_mma_smem_floats(int batch, int n_in, int D) {
@@ -704,10 +705,15 @@ __global__ void __launch_bounds__(32 * ((NB8 + 1) / 2), MINB) bnn_mma_kernel(Bnn
   for (int64_t chain = blockIdx.x; chain < a.n_chains; chain += gridDim.x) {
     const float* th = a.theta + chain * D;
     float cost = 0.0f, sse = 0.0f;
-    // persistent grid: pull the next chain's parameter row towards L2 while this one computes
-    if (tid == 0 && chain + gridDim.x < a.n_chains && (D & 3) == 0 && aligned_to_dev(a.theta, 16))
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(th + (int64_t)gridDim.x * D), "r"(D * 4)
-                   : "memory");
+    // Pull a LATER chain's parameter row towards L2 while this one computes: the row this CTA takes next
+    // (persistent grid), or -- one CTA per chain -- the row of the chain about one wave of CTAs further on
+    // (6 CTAs x 148 SMs are resident at a time; 1024 rows are 21 MB of the 126 MB L2).  Waiting for the row at
+    // the head of a chain was the largest single stall of the kernel (16 % of the samples, ncu).
+    {
+      const int64_t ahead = gridDim.x < a.n_chains ? (int64_t)gridDim.x : (int64_t)K4_PREFETCH_AHEAD;
+      if (tid == 0 && K4_PREFETCH_AHEAD > 0 && chain + ahead < a.n_chains && (D & 3) == 0 && aligned_to_dev(a.theta, 16))
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(th + ahead * D), "r"(D * 4) : "memory");
+    }
     bnn_chain_mma<NB8, WANT_GRAD, false, MODE, BATCH_CT>(a, th, a.starts != nullptr ? a.starts + chain : nullptr, s, cost,
                                                sse);
     if (tid == 0) {
