@@ -551,7 +551,7 @@ def per_kernel_times(sampler, gen, nll, torch, _native, n=30):
 
 
 def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_over_ranks,
-               sample_every=None, lookahead=8):
+               sample_every=None, lookahead=24):
     """K steps through the public host-facing iterator `SGHMCSampler.iter_host`: per step the
     minibatch start indices are copied from pinned host memory, K4 + K1 run through the C ABI
     (sgmcmc_bnn_sghmc_run_f32) and the per-chain cost is copied back to pinned host memory,
@@ -565,7 +565,9 @@ def end_to_end(sampler, nll, torch, _native, dev, C, K, W, world, barrier, max_o
     the last sample is an un-overlapped tail (the convention of the earlier records).  sample_every = 1 is the reference's literal `next()` (every step returns host
     parameters, base_classes.py:298-304): PCIe-bound, reported as `e2e_every_sample`.  The
     iterator keeps up to `lookahead` steps queued ahead and runs the copies on their own streams,
-    so the device does not idle while the host handles a result or a sample crosses PCIe."""
+    so the device does not idle while the host handles a result or a sample crosses PCIe (24 steps =
+    13 ms of queued work: a 172 MB sample needs 3.4 ms of PCIe alone on this box and several times that
+    when eight ranks pull theirs through one host at the same time)."""
     if sample_every is None:
         # at least one whole thinning period of the reference (sample_steps = 100), so that exactly
         # what BayesianNeuralNetwork.train moves per period crosses PCIe inside the timed region
