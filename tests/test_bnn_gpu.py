@@ -403,13 +403,15 @@ def test_iter_host_pipelined_equals_synchronous_steps(lookahead, every):
     b, ph = build()
     import time
     n_got = 0
-    for s, (smp, cost) in enumerate(a.iter_host(host_starts, sample_every=every, lookahead=lookahead)):
+    phase = 3 if every == 8 else 0            # a call that continues a thinning period started earlier
+    for s, (smp, cost) in enumerate(a.iter_host(host_starts, sample_every=every, lookahead=lookahead,
+                                                sample_phase=phase)):
         ph.value = host_starts[s].to(DEV)     # (a feed_dict would be dropped after burn-in, :454)
         sample, want_cost = next(b)
         want_theta = b._theta.cpu().numpy()
         time.sleep(0.002)                     # let the queued steps (and their copies) run ahead
         assert np.array_equal(cost, want_cost.cpu().numpy()), "cost at step %d" % s
-        if (s + 1) % every == 0:
+        if (s + 1 + phase) % every == 0:
             assert np.array_equal(smp, want_theta), "sample at step %d" % s
         else:
             assert smp is None
