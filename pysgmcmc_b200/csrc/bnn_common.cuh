@@ -61,6 +61,30 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
+// fast_tanh of two values with the FP32-pipe part packed (FMUL2 / FADD2 / FFMA2 around the four SFU
+// instructions: 7 issue slots instead of 10); the same arithmetic, bit for bit
+__device__ __forceinline__ void fast_tanh2(float x0, float x1, float& y0, float& y1) {
+  asm("{\n\t.reg .b64 x, c, one, m2, r;\n\t.reg .f32 e0, e1;\n\t"
+      "mov.b64 x, {%2, %3};\n\t"
+      "mov.b64 c, {%4, %4};\n\t"
+      "mov.b64 one, {%5, %5};\n\t"
+      "mov.b64 m2, {%6, %6};\n\t"
+      "mul.rn.f32x2 x, x, c;\n\t"
+      "mov.b64 {e0, e1}, x;\n\t"
+      "ex2.approx.ftz.f32 e0, e0;\n\t"
+      "ex2.approx.ftz.f32 e1, e1;\n\t"
+      "mov.b64 x, {e0, e1};\n\t"
+      "add.rn.f32x2 x, x, one;\n\t"
+      "mov.b64 {e0, e1}, x;\n\t"
+      "rcp.approx.ftz.f32 e0, e0;\n\t"
+      "rcp.approx.ftz.f32 e1, e1;\n\t"
+      "mov.b64 r, {e0, e1};\n\t"
+      "fma.rn.f32x2 r, r, m2, one;\n\t"
+      "mov.b64 {%0, %1}, r;\n\t}"
+      : "=f"(y0), "=f"(y1)
+      : "f"(x0), "f"(x1), "f"(2.885390081777927f), "f"(1.0f), "f"(-2.0f));
+}
+
 __device__ __forceinline__ bool aligned_to_dev(const void* p, size_t a) {
   return (reinterpret_cast<uintptr_t>(p) % a) == 0;
 }

@@ -539,16 +539,18 @@ __device__ __forceinline__ void bnn_chain_mma(const BnnArgs& a, const float* __r
     for (int half = 0; half < 2; ++half) {
       if (half == 0 || live1) {
 #pragma unroll
-        for (int nt = 0; nt < NT8; ++nt)
+        for (int nt = 0; nt < NT8; ++nt) {
+          float v[2];
+          fast_tanh2(acc[nt][2 * half], acc[nt][2 * half + 1], v[0], v[1]);
 #pragma unroll
-          for (int e = 2 * half; e < 2 * half + 2; ++e) {
-            float v = fast_tanh(acc[nt][e]);
+          for (int e = 0; e < 2; ++e) {
             if (nt == NT8 - 1) {
-              const int c = 2 * t + (e & 1);
-              v = c < 2 ? v : (c == 2 ? 1.0f : 0.0f);
+              const int c = 2 * t + e;
+              v[e] = c < 2 ? v[e] : (c == 2 ? 1.0f : 0.0f);
             }
-            h[nt][e] = v;
+            h[nt][2 * half + e] = v[e];
           }
+        }
       } else {
 #pragma unroll
         for (int nt = 0; nt < NT8; ++nt) h[nt][2] = h[nt][3] = 0.0f;
