@@ -237,6 +237,30 @@ int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float
                              float epsilon, float mdecay, float scale_grad,
                              uint64_t seed, uint64_t step0, uint64_t chain_offset, void* stream);
 
+/* ---- K5r: the same `n_steps` steps with every chain RESIDENT on one SM (csrc/bnn_resident.cu): one CTA per
+ * chain loads theta, V, tau, g, v_hat, minv into shared memory once, runs all n_steps steps there (cost +
+ * gradient on the FP32 pipe in the accumulation order of K4's FFMA kernel, then K1's arithmetic with K1's
+ * Philox counters) and writes the state back: HBM traffic per chain and CALL instead of per chain and step,
+ * and no launch per step -- the path for few chains (the reference's single-chain BOHAMIANN runs,
+ * bayesian_neural_network.py:436-531) and the faster one at any chain count.  Chains never interact, so the
+ * result does not depend on how a run is cut into calls.  Needs sgmcmc_bnn_resident_supported(n_in, batch)
+ * (odd n_in so that D % 4 == 0, batch <= 32, state + activations within 227 KB); E_UNSUPPORTED otherwise.
+ * cost_last [C] receives the cost of the last step; cost_all (NULL or [n_steps, C]) the cost of every step;
+ * grad_out (NULL or [C, D]) the gradient of the last step; the other arguments as in
+ * sgmcmc_bnn_sghmc_run_f32.  sgmcmc_set_bnn_resident_threads: threads per chain (448, 672 or 1024; 0 = the
+ * default 672), a tuning knob for the measurements in profiles/. */
+int sgmcmc_bnn_resident_supported(int n_in, int batch);
+int sgmcmc_set_bnn_resident_threads(int threads);
+int sgmcmc_bnn_sghmc_run_resident_f32(float* theta, float* v, float* tau, float* g, float* v_hat, float* minv,
+                                      const float* X, const float* y, const int32_t* starts,
+                                      const float* z, float* trace, float* cost_trace,
+                                      float* cost_all, float* cost_last, float* grad_out,
+                                      int64_t n_chains, int n_in, int batch, float batch_size_cfg,
+                                      int64_t n_examples, int64_t n_steps, int64_t n_burn_in,
+                                      int adapt_forever, int64_t keep_every,
+                                      float epsilon, float mdecay, float scale_grad,
+                                      uint64_t seed, uint64_t step0, uint64_t chain_offset, void* stream);
+
 /* ---- K5 with HOST buffers: the pipelined `sample, cost = next(sampler)` of the BNN path
  * (samplers/base_classes.py:258-310,408-456; csrc/host_pipeline.cu).  Every `step` copies
  * that step's minibatch start indices from pinned host memory (host_starts [C]), runs

@@ -61,6 +61,11 @@ SIGNATURES = {
     "sgmcmc_bnn_sghmc_run_f32": [_P] * 14 + [c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
                                              c_int, c_int64, c_float, c_float, c_float,
                                              c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_bnn_sghmc_run_resident_f32": [_P] * 15 + [c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
+                                                      c_int, c_int64, c_float, c_float, c_float,
+                                                      c_uint64, c_uint64, c_uint64, _P],
+    "sgmcmc_bnn_resident_supported": [c_int, c_int],
+    "sgmcmc_set_bnn_resident_threads": [c_int],
     "sgmcmc_bnn_host_pipeline_create": [POINTER(_P), c_int64, c_int, c_int, c_int],
     "sgmcmc_bnn_host_pipeline_destroy": [_P],
     "sgmcmc_bnn_host_pipeline_step": [_P] * 13 + [c_int, c_int, c_float, c_int64, c_int, c_int, c_float, c_float,

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libsgmcmc_b200.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 
-SOURCES = ["capi.cu", "update_kernels.cu", "target_chains.cu", "mt19937.cu", "bnn.cu", "mlp.cu", "mlp_umma.cu", "bnn_fused.cu", "host_pipeline.cu", "moments.cu", "svgd.cu", "svgd_umma.cu", "svgd_sqdist_umma.cu"]
+SOURCES = ["capi.cu", "update_kernels.cu", "target_chains.cu", "mt19937.cu", "bnn.cu", "mlp.cu", "mlp_umma.cu", "bnn_fused.cu", "bnn_resident.cu", "host_pipeline.cu", "moments.cu", "svgd.cu", "svgd_umma.cu", "svgd_sqdist_umma.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

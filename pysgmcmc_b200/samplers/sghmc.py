@@ -89,6 +89,15 @@ class SGHMCSampler(BurnInMCMCSampler):
     def _can_run_fused(self):
         return super()._can_run_fused() or self._bnn_run_ok()
 
+    #: `run()` keeps every chain resident on one SM for a whole chunk of steps (csrc/bnn_resident.cu) when the
+    #: sampler has at most this many chains and the shape fits; otherwise K4 then K1 per step.  0 switches
+    #: the resident kernel off.
+    RESIDENT_MAX_CHAINS = 1 << 30
+
+    def _resident_ok(self, batch):
+        return (0 < self.n_chains <= self.RESIDENT_MAX_CHAINS
+                and _native.load().sgmcmc_bnn_resident_supported(int(self.cost_fun.n_in), int(batch)) == 1)
+
     def _launch_fused_run(self, n_steps, keep_every, trace, costs):
         epsilon = float(next(self.stepsize_schedule))
         n_burn_in = min(n_steps, self._burn_in_remaining())
@@ -109,7 +118,8 @@ class SGHMCSampler(BurnInMCMCSampler):
         # no index generator: every step evaluates the whole resident dataset (what the
         # per-step path and the differentiable cost do); raises when it is too large
         batch = cf.actual_batch if gen is not None else cf.full_dataset_batch()
-        if self._grad is None:
+        resident = self._resident_ok(batch)
+        if self._grad is None and not resident:
             self._grad = torch.empty_like(self._theta)
         cost_scratch = torch.empty(self.n_chains, dtype=self.dtype, device=self.device)
         if gen is None or n_steps <= self.RUN_CHUNK:
@@ -133,10 +143,12 @@ class SGHMCSampler(BurnInMCMCSampler):
             k0 = done // keep_every                       # chunks start on a thinning boundary
             tr = trace[k0:] if trace is not None and k0 < trace.shape[0] else None
             co = costs[k0:] if costs is not None and k0 < costs.shape[0] else None
-            _native.call("sgmcmc_bnn_sghmc_run_f32", *[_native.ptr(a) for a in self._arrays()],
+            # every chain resident on an SM for the whole chunk (csrc/bnn_resident.cu), or K4 then K1 per step
+            fn, work = (("sgmcmc_bnn_sghmc_run_resident_f32", (None, _native.ptr(cost_scratch), None)) if resident else
+                        ("sgmcmc_bnn_sghmc_run_f32", (_native.ptr(self._grad), _native.ptr(cost_scratch))))
+            _native.call(fn, *[_native.ptr(a) for a in self._arrays()],
                          _native.ptr(cf.X), _native.ptr(cf.y), _native.ptr(starts), None,
-                         _native.ptr(tr), _native.ptr(co), _native.ptr(self._grad),
-                         _native.ptr(cost_scratch), C, cf.n_in, batch, float(cf.batch_size),
+                         _native.ptr(tr), _native.ptr(co), *work, C, cf.n_in, batch, float(cf.batch_size),
                          cf.n_examples, n, min(n, max(0, n_burn_in - done)), int(self.burn_in_steps == 0),
                          keep_every, epsilon, self.mdecay, self.scale_grad, self._noise_seed,
                          self.n_iterations, self.session.chain_offset, self._stream())

@@ -66,6 +66,8 @@ def gpu_run(theta0, X, y, seeds, steps, burn, z_seed, every, variant, dev="cuda:
     from pysgmcmc_b200.samplers import SGHMCSampler
     from pysgmcmc_b200.stepsize_schedules import ConstantStepsizeSchedule
     C = theta0.shape[0]
+    if variant == "resident":
+        return gpu_run_resident(theta0, X, y, seeds, steps, burn, z_seed, every, dev), None
     _native.call("sgmcmc_set_bnn_tuning", variant)
     try:
         gen = DeviceBatchGenerator(N, BATCH, seeds=seeds, device=dev, block=256)
@@ -90,6 +92,33 @@ def gpu_run(theta0, X, y, seeds, steps, burn, z_seed, every, variant, dev="cuda:
         _native.call("sgmcmc_set_bnn_tuning", DEFAULT_VARIANT)
 
 
+def gpu_run_resident(theta0, X, y, seeds, steps, burn, z_seed, every, dev="cuda:0"):
+    """The same chain through the resident kernel (csrc/bnn_resident.cu): one call per checkpoint interval,
+    the chains on their SMs in between; minibatch indices from the device generator (K7), z injected."""
+    import torch
+    from pysgmcmc_b200 import _native
+    from pysgmcmc_b200.data_batches import DeviceBatchGenerator
+    C = theta0.shape[0]
+    gen = DeviceBatchGenerator(N, BATCH, seeds=seeds, device=dev, block=256)
+    Xd, yd = torch.tensor(X, dtype=torch.float32, device=dev), torch.tensor(y, dtype=torch.float32, device=dev)
+    theta = torch.tensor(theta0, device=dev)
+    state = [theta, torch.zeros_like(theta)] + [torch.ones_like(theta) for _ in range(4)]   # theta, V, tau, g, v_hat, minv
+    cost = torch.empty(C, device=dev)
+    zr = np.random.RandomState(z_seed)
+    out, done = [], 0
+    while done < steps:
+        n = min(every, steps - done)
+        starts = gen.next_block(n)
+        z = torch.tensor(np.stack([zr.standard_normal((C, D)).astype(np.float32) for _ in range(n)]), device=dev)
+        _native.call("sgmcmc_bnn_sghmc_run_resident_f32", *[_native.ptr(a) for a in state], _native.ptr(Xd),
+                     _native.ptr(yd), _native.ptr(starts), _native.ptr(z), None, None, None, _native.ptr(cost), None,
+                     C, 1, BATCH, float(BATCH), N, n, min(n, max(0, burn - done)), 0, 1, 0.01, 0.05, float(N),
+                     0, done, 0, _native.stream_ptr())
+        done += n
+        out.append((done, theta.cpu().numpy()))
+    return out
+
+
 DEFAULT_VARIANT = 16
 K4_NAMES = {0: "FFMA (variant 0)", 10: "tensor-pipe 3xTF32 (variant 10: truncating split, chained accumulation)",
             11: "tensor-pipe 3xTF32 (variant 11: rounded split)",
@@ -97,7 +126,8 @@ K4_NAMES = {0: "FFMA (variant 0)", 10: "tensor-pipe 3xTF32 (variant 10: truncati
             13: "tensor-pipe 3xTF32 (variant 13: rounded split + FP32-pipe accumulation)",
             14: "tensor-pipe 3xTF32 (variant 14: 13 with packed FP32 splitting of the weight fragments)",
             15: "tensor-pipe 3xTF32 (variant 15: 13 with the cross terms in their own accumulator)",
-            16: "tensor-pipe 3xTF32 (variant 16: 15 with packed FP32 splitting of the weight fragments)"}
+            16: "tensor-pipe 3xTF32 (variant 16: 15 with packed FP32 splitting of the weight fragments)",
+            "resident": "resident kernel (csrc/bnn_resident.cu: FFMA accumulation order, chain on one SM)"}
 
 
 def drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(16, 0), z_seed=9, theta_seed=11):
@@ -116,7 +146,7 @@ def drift_curves(steps=1000, burn=600, chains=4, every=100, variants=(16, 0), z_
         vs64 = [rel(g[1], o[1]) for g, o in zip(got, o64)]
         o32_vs64 = [rel(a[1], b[1]) for a, b in zip(o32, o64)]
         cross = next((g[0] for g, d in zip(got, vs32) if d > 1e-5), None)
-        lines.append({"k4": K4_NAMES.get(variant, "variant %d" % variant),
+        lines.append({"k4": K4_NAMES.get(variant, "variant %s" % variant),
                       "config": {"N": N, "batch": BATCH, "scale_grad": N, "eps": 0.01, "burn_in_steps": burn,
                                  "steps": steps, "chains": chains},
                       "checkpoints": [g[0] for g in got],
@@ -133,5 +163,5 @@ if __name__ == "__main__":
     ap.add_argument("--every", type=int, default=100)
     ap.add_argument("--variants", default="16,13,0")
     a = ap.parse_args()
-    for line in drift_curves(a.steps, a.burn, a.chains, a.every, tuple(int(v) for v in a.variants.split(","))):
+    for line in drift_curves(a.steps, a.burn, a.chains, a.every, tuple(v if v == "resident" else int(v) for v in a.variants.split(","))):
         print(json.dumps(line), flush=True)
