@@ -92,7 +92,7 @@ class SGHMCSampler(BurnInMCMCSampler):
     #: `run()` keeps every chain resident on one SM for a whole chunk of steps (csrc/bnn_resident.cu) when the
     #: sampler has at most this many chains and the shape fits; otherwise K4 then K1 per step.  0 switches
     #: the resident kernel off.
-    RESIDENT_MAX_CHAINS = 1 << 30
+    RESIDENT_MAX_CHAINS = 0
 
     def _resident_ok(self, batch):
         return (0 < self.n_chains <= self.RESIDENT_MAX_CHAINS
