@@ -250,7 +250,7 @@ int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float
  * sgmcmc_bnn_sghmc_run_f32.  sgmcmc_set_bnn_resident_threads: threads per chain (448, 672 or 1024; 0 = the
  * default 672), a tuning knob for the measurements in profiles/. */
 int sgmcmc_bnn_resident_supported(int n_in, int batch);
-int sgmcmc_set_bnn_resident_threads(int threads);
+int sgmcmc_set_bnn_resident_overlap(int on);
 int sgmcmc_bnn_sghmc_run_resident_f32(float* theta, float* v, float* tau, float* g, float* v_hat, float* minv,
                                       const float* X, const float* y, const int32_t* starts,
                                       const float* z, float* trace, float* cost_trace,

@@ -65,7 +65,7 @@ SIGNATURES = {
                                                       c_int, c_int64, c_float, c_float, c_float,
                                                       c_uint64, c_uint64, c_uint64, _P],
     "sgmcmc_bnn_resident_supported": [c_int, c_int],
-    "sgmcmc_set_bnn_resident_threads": [c_int],
+    "sgmcmc_set_bnn_resident_overlap": [c_int],
     "sgmcmc_bnn_host_pipeline_create": [POINTER(_P), c_int64, c_int, c_int, c_int],
     "sgmcmc_bnn_host_pipeline_destroy": [_P],
     "sgmcmc_bnn_host_pipeline_step": [_P] * 13 + [c_int, c_int, c_float, c_int64, c_int, c_int, c_float, c_float,

@@ -32,9 +32,12 @@
 namespace sgmcmc {
 
 constexpr int RS_T = 672;        // 21 warps: D/4 = 1313 update groups are 2 rounds of 672 (97.7 % of the slots)
-constexpr int RS_SLOT = 64;
-constexpr int RS_KG = 12;        // k values per worker of a weight-gradient GEMM (5 slots cover 50 + 2 padding)
+constexpr int RS_GW = 10;        // warps 0 .. 9: the gradient (320 threads); warps 10 .. 20: the update's gradient-free part
+constexpr int RS_GT = 32 * RS_GW;
+constexpr int RS_UT = RS_T - RS_GT;
+constexpr int RS_KG = 12;        // k values per worker of a weight-gradient GEMM (5 warps cover 50 + 2 padding)
 constexpr int RS_NKG = 5;
+constexpr int RS_HALF = HID / 2; // a gradient worker owns 2 units: (2 jj, 2 jj + 1) or (kk, kk + 25)
 constexpr int RS_MAX_BATCH = 32;
 
 struct ResidentArgs {
@@ -46,7 +49,7 @@ struct ResidentArgs {
   float *cost_last, *cost_all;                    // [C]; [n_steps, C] or NULL
   float* grad_out;                                // [C, D] or NULL: the gradient of the LAST step (tests)
   int64_t n_chains, n_steps, n_burn_in, keep_every;
-  int batch, adapt_forever;
+  int batch, adapt_forever, pre;
   float inv_bs, inv_n, prior_den_inv;
   BnnLayout L;
   SghmcScalars<float> s;
@@ -55,17 +58,18 @@ struct ResidentArgs {
 
 struct ResidentSmem {
   float *TH, *G, *V, *TAU, *GG, *VH, *MINV;
+  float *PS, *PR;                                 // pre mode: sigma * z and r_t of the step (else NULL)
   float *H1, *H2, *H3, *Z3, *Z2, *Z1;             // [BP][HS]
   float *H1t, *H2t, *Z3t, *Z2t;                   // [HID][TS]
   float *X0, *Y0;                                 // two buffers each, XB / YB floats apart
   int XB, YB;
   float *sDf, *sSe, *sW4, *scr;
-  int BP, TS, total;
+  int BP, TS, total, zero_from;
 };
 
 // rows padded to a multiple of 4; the transposed buffers' row stride TS has TS / 4 odd, so that the 128-bit
 // accesses of 8 consecutive units fall into 8 different 16-byte bank groups
-__host__ __device__ inline ResidentSmem resident_carve(float* base, int batch, int n_in, int D) {
+__host__ __device__ inline ResidentSmem resident_carve(float* base, int batch, int n_in, int D, int pre) {
   ResidentSmem s;
   s.BP = (batch + 3) & ~3;
   s.TS = ((s.BP >> 2) & 1) ? s.BP : s.BP + 4;
@@ -73,6 +77,9 @@ __host__ __device__ inline ResidentSmem resident_carve(float* base, int batch, i
   float* p = base;
   s.TH = p; p += D; s.G = p; p += D; s.V = p; p += D; s.TAU = p; p += D;
   s.GG = p; p += D; s.VH = p; p += D; s.MINV = p; p += D;
+  s.PS = s.PR = nullptr;
+  if (pre) { s.PS = p; p += D; s.PR = p; p += D; }
+  s.zero_from = (int)(p - base);
   s.H1 = p; p += RB; s.H2 = p; p += RB; s.H3 = p; p += RB;
   s.Z3 = p; p += RB; s.Z2 = p; p += RB; s.Z1 = p; p += RB;
   s.H1t = p; p += TB; s.H2t = p; p += TB; s.Z3t = p; p += TB; s.Z2t = p; p += TB;
@@ -89,316 +96,447 @@ __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
                "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// named barriers: 1 = the gradient warps among themselves, 2 = "head done" from the gradient warps to warp 20
+__device__ __forceinline__ void grad_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RS_GT) : "memory"); }
+__device__ __forceinline__ void head_done_arrive() {
+  __threadfence_block();
+  asm volatile("bar.arrive 2, %0;" ::"n"(RS_GT + 32) : "memory");
+}
+__device__ __forceinline__ void head_done_wait() { asm volatile("bar.sync 2, %0;" ::"n"(RS_GT + 32) : "memory"); }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 
-// rows i0 .. i0+3 of a tanh layer for unit j: out = tanh(b[j] + sum_k in[.][k] W[k][j]), k ascending
+// rows i0 .. i0+3 of a tanh layer for units 2 jj, 2 jj + 1: out = tanh(b + sum_k in[.][k] W[k][.]), k ascending
 __device__ __forceinline__ void rs_forward(const float* __restrict__ TH, int oW, int ob,
                                            const float* __restrict__ inT, float* __restrict__ outR,
-                                           float* __restrict__ outT, int TS, int i0, int j) {
-  const float b = TH[ob + j];
-  float a0 = b, a1 = b, a2 = b, a3 = b;
-  const float* w = TH + oW + j;
+                                           float* __restrict__ outT, const int TS, int i0, int jj) {
+  const float2 b = ld2(TH + ob + 2 * jj);
+  float a0[4], a1[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { a0[r] = b.x; a1[r] = b.y; }
+  const float* w = TH + oW + 2 * jj;
   const float* h = inT + i0;
 #pragma unroll 10
   for (int k = 0; k < HID; ++k) {
-    const float wv = w[k * HID];
+    const float2 wv = ld2(w + k * HID);
     const float4 hv = ld4(h + k * TS);
-    a0 = fmaf(hv.x, wv, a0); a1 = fmaf(hv.y, wv, a1); a2 = fmaf(hv.z, wv, a2); a3 = fmaf(hv.w, wv, a3);
+    a0[0] = fmaf(hv.x, wv.x, a0[0]); a0[1] = fmaf(hv.y, wv.x, a0[1]); a0[2] = fmaf(hv.z, wv.x, a0[2]); a0[3] = fmaf(hv.w, wv.x, a0[3]);
+    a1[0] = fmaf(hv.x, wv.y, a1[0]); a1[1] = fmaf(hv.y, wv.y, a1[1]); a1[2] = fmaf(hv.z, wv.y, a1[2]); a1[3] = fmaf(hv.w, wv.y, a1[3]);
   }
-  a0 = fast_tanh(a0); a1 = fast_tanh(a1); a2 = fast_tanh(a2); a3 = fast_tanh(a3);
-  outR[(i0 + 0) * HS + j] = a0; outR[(i0 + 1) * HS + j] = a1;
-  outR[(i0 + 2) * HS + j] = a2; outR[(i0 + 3) * HS + j] = a3;
-  if (outT != nullptr) st4(outT + j * TS + i0, a0, a1, a2, a3);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    a0[r] = fast_tanh(a0[r]); a1[r] = fast_tanh(a1[r]);
+    st2(outR + (i0 + r) * HS + 2 * jj, a0[r], a1[r]);
+  }
+  if (outT != nullptr) {
+    st4(outT + (2 * jj) * TS + i0, a0[0], a0[1], a0[2], a0[3]);
+    st4(outT + (2 * jj + 1) * TS + i0, a1[0], a1[1], a1[2], a1[3]);
+  }
 }
 
-// rows i0 .. i0+3 of dZ_{l-1}[.][k] = (sum_m dZ_l[.][m] W_l[k][m]) * (1 - H_{l-1}[.][k]^2), m ascending
+// rows i0 .. i0+3 of dZ_{l-1}[.][k] = (sum_m dZ_l[.][m] W_l[k][m]) * (1 - H_{l-1}[.][k]^2) for k = kk and kk + 25,
+// m ascending
 __device__ __forceinline__ void rs_backward_data(const float* __restrict__ TH, int oW,
                                                  const float* __restrict__ zT, const float* __restrict__ hT,
-                                                 float* __restrict__ outR, float* __restrict__ outT, int TS,
-                                                 int i0, int k) {
-  const float2* wrow = reinterpret_cast<const float2*>(TH + oW + k * HID);
+                                                 float* __restrict__ outR, float* __restrict__ outT, const int TS,
+                                                 int i0, int kk) {
+  const int k0 = kk, k1 = kk + RS_HALF;
+  const float* w0 = TH + oW + k0 * HID;
+  const float* w1 = TH + oW + k1 * HID;
   const float* zt = zT + i0;
-  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  float a0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, a1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 5
   for (int m2 = 0; m2 < HID / 2; ++m2) {
-    const float2 w = wrow[m2];
+    const float2 wa = ld2(w0 + 2 * m2), wb = ld2(w1 + 2 * m2);
     const float4 z0 = ld4(zt + (2 * m2) * TS), z1 = ld4(zt + (2 * m2 + 1) * TS);
-    a0 = fmaf(z0.x, w.x, a0); a1 = fmaf(z0.y, w.x, a1); a2 = fmaf(z0.z, w.x, a2); a3 = fmaf(z0.w, w.x, a3);
-    a0 = fmaf(z1.x, w.y, a0); a1 = fmaf(z1.y, w.y, a1); a2 = fmaf(z1.z, w.y, a2); a3 = fmaf(z1.w, w.y, a3);
+    a0[0] = fmaf(z0.x, wa.x, a0[0]); a0[1] = fmaf(z0.y, wa.x, a0[1]); a0[2] = fmaf(z0.z, wa.x, a0[2]); a0[3] = fmaf(z0.w, wa.x, a0[3]);
+    a1[0] = fmaf(z0.x, wb.x, a1[0]); a1[1] = fmaf(z0.y, wb.x, a1[1]); a1[2] = fmaf(z0.z, wb.x, a1[2]); a1[3] = fmaf(z0.w, wb.x, a1[3]);
+    a0[0] = fmaf(z1.x, wa.y, a0[0]); a0[1] = fmaf(z1.y, wa.y, a0[1]); a0[2] = fmaf(z1.z, wa.y, a0[2]); a0[3] = fmaf(z1.w, wa.y, a0[3]);
+    a1[0] = fmaf(z1.x, wb.y, a1[0]); a1[1] = fmaf(z1.y, wb.y, a1[1]); a1[2] = fmaf(z1.z, wb.y, a1[2]); a1[3] = fmaf(z1.w, wb.y, a1[3]);
   }
-  const float4 hv = ld4(hT + k * TS + i0);
-  a0 = a0 * fmaf(-hv.x, hv.x, 1.0f); a1 = a1 * fmaf(-hv.y, hv.y, 1.0f);
-  a2 = a2 * fmaf(-hv.z, hv.z, 1.0f); a3 = a3 * fmaf(-hv.w, hv.w, 1.0f);
-  outR[(i0 + 0) * HS + k] = a0; outR[(i0 + 1) * HS + k] = a1;
-  outR[(i0 + 2) * HS + k] = a2; outR[(i0 + 3) * HS + k] = a3;
-  if (outT != nullptr) st4(outT + k * TS + i0, a0, a1, a2, a3);
+  const float4 h0 = ld4(hT + k0 * TS + i0), h1 = ld4(hT + k1 * TS + i0);
+  a0[0] = a0[0] * fmaf(-h0.x, h0.x, 1.0f); a0[1] = a0[1] * fmaf(-h0.y, h0.y, 1.0f);
+  a0[2] = a0[2] * fmaf(-h0.z, h0.z, 1.0f); a0[3] = a0[3] * fmaf(-h0.w, h0.w, 1.0f);
+  a1[0] = a1[0] * fmaf(-h1.x, h1.x, 1.0f); a1[1] = a1[1] * fmaf(-h1.y, h1.y, 1.0f);
+  a1[2] = a1[2] * fmaf(-h1.z, h1.z, 1.0f); a1[3] = a1[3] * fmaf(-h1.w, h1.w, 1.0f);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    outR[(i0 + r) * HS + k0] = a0[r];
+    outR[(i0 + r) * HS + k1] = a1[r];
+  }
+  if (outT != nullptr) {
+    st4(outT + k0 * TS + i0, a0[0], a0[1], a0[2], a0[3]);
+    st4(outT + k1 * TS + i0, a1[0], a1[1], a1[2], a1[3]);
+  }
 }
 
-// G[W_l[k][j]] = theta * pscale + sum_i H_{l-1}[i][k] dZ_l[i][j] for k = 12 kg .. 12 kg + 11 (< 50), i ascending;
-// kg == 0 also sums db[j]
+// G[W_l[k][j]] = theta * pscale + sum_i H_{l-1}[i][k] dZ_l[i][j] for j = 2 jj, 2 jj + 1 and k = 12 kg .. 12 kg + 11
+// (< 50), i ascending; kg == 0 also sums db[j]
+template <int BATCH_CT>
 __device__ __forceinline__ void rs_weight_grad(const float* __restrict__ TH, float* __restrict__ G, int oW, int ob,
                                                const float* __restrict__ hR, const float* __restrict__ zR,
-                                               int batch, float pscale, int kg, int j) {
-  float acc[RS_KG], db = 0.0f;
+                                               int batch_rt, float pscale, int kg, int jj) {
+  const int batch = BATCH_CT > 0 ? BATCH_CT : batch_rt;
+  float acc0[RS_KG], acc1[RS_KG], db0 = 0.0f, db1 = 0.0f;
 #pragma unroll
-  for (int kk = 0; kk < RS_KG; ++kk) acc[kk] = 0.0f;
-  const int nq = kg < RS_NKG - 1 ? 3 : 1;          // the last group holds k = 48, 49 (and the padding 50, 51)
+  for (int kk = 0; kk < RS_KG; ++kk) { acc0[kk] = 0.0f; acc1[kk] = 0.0f; }
+  const bool full = kg < RS_NKG - 1;               // the last group holds k = 48, 49 (and the padding 50, 51)
   const float* hp = hR + RS_KG * kg;
+  const float* zp = zR + 2 * jj;
+#pragma unroll 4
   for (int i = 0; i < batch; ++i) {
-    const float d = zR[i * HS + j];
-    db += d;
+    const float2 d = ld2(zp + i * HS);
+    db0 += d.x; db1 += d.y;
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-      if (q < nq) {
+      if (q == 0 || full) {
         const float4 h = ld4(hp + i * HS + 4 * q);
-        acc[4 * q + 0] = fmaf(h.x, d, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(h.y, d, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(h.z, d, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(h.w, d, acc[4 * q + 3]);
+        acc0[4 * q + 0] = fmaf(h.x, d.x, acc0[4 * q + 0]); acc0[4 * q + 1] = fmaf(h.y, d.x, acc0[4 * q + 1]);
+        acc0[4 * q + 2] = fmaf(h.z, d.x, acc0[4 * q + 2]); acc0[4 * q + 3] = fmaf(h.w, d.x, acc0[4 * q + 3]);
+        acc1[4 * q + 0] = fmaf(h.x, d.y, acc1[4 * q + 0]); acc1[4 * q + 1] = fmaf(h.y, d.y, acc1[4 * q + 1]);
+        acc1[4 * q + 2] = fmaf(h.z, d.y, acc1[4 * q + 2]); acc1[4 * q + 3] = fmaf(h.w, d.y, acc1[4 * q + 3]);
       }
   }
 #pragma unroll
   for (int kk = 0; kk < RS_KG; ++kk) {
     const int k = RS_KG * kg + kk;
-    if (k < HID) G[oW + k * HID + j] = fmaf(TH[oW + k * HID + j], pscale, acc[kk]);
+    if (k < HID) {
+      const float2 t = ld2(TH + oW + k * HID + 2 * jj);
+      st2(G + oW + k * HID + 2 * jj, fmaf(t.x, pscale, acc0[kk]), fmaf(t.y, pscale, acc1[kk]));
+    }
   }
-  if (kg == 0) G[ob + j] = fmaf(TH[ob + j], pscale, db);
+  if (kg == 0) {
+    const float2 t = ld2(TH + ob + 2 * jj);
+    st2(G + ob + 2 * jj, fmaf(t.x, pscale, db0), fmaf(t.y, pscale, db1));
+  }
 }
 
 __device__ __forceinline__ void rs_unpack(const float4& q, float (&r)[4]) { r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
+__device__ __forceinline__ float4 rs_pack(const float (&r)[4]) { return make_float4(r[0], r[1], r[2], r[3]); }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 1) bnn_sghmc_resident_kernel(ResidentArgs a) {
+// The update of sampler_math.cuh cut in two at the gradient: `pre` needs only the state (it runs on the update
+// warps WHILE the gradient warps compute), `post` is what is left once the gradient exists.  Same operations,
+// same order, same rounding as adapt() + sghmc_apply(): the tests compare with the oracle bit for bit.
+__device__ __forceinline__ float rs_sample(float minv_t, float z, const SghmcScalars<float>& s) {
+  using F = ieee<float>;
+  const float noise_scale = F::sub(F::mul(s.a, minv_t), s.c4);                     // sghmc.py:211-217
+  return F::mul(F::sqrt(F::max(noise_scale, 1e-16f)), z);                          // :220, base_classes.py:218
+}
+__device__ __forceinline__ void rs_adapt_pre(float& tau, float g, float v_hat, float& r_t, float& minv_t) {
+  using F = ieee<float>;
+  r_t = F::div(1.0f, F::add(tau, 1.0f));                                           // sghmc.py:168
+  minv_t = safe_divide(1.0f, safe_sqrt(v_hat));                                    // :179-183
+  tau = F::add(tau, F::add(safe_divide(F::mul(F::mul(-g, g), tau), v_hat), 1.0f)); // :172-176
+}
+__device__ __forceinline__ void rs_adapt_post(float& g, float& v_hat, float r_t, float grad) {
+  using F = ieee<float>;
+  const float g_t = F::add(g, F::add(F::mul(-r_t, g), F::mul(r_t, grad)));                          // :186-190
+  v_hat = F::add(v_hat, F::add(F::mul(-r_t, v_hat), F::mul(r_t, F::mul(grad, grad))));              // :192-196
+  g = g_t;
+}
+__device__ __forceinline__ void rs_apply_post(float& theta, float& v, float minv_t, float grad, float sample,
+                                              const SghmcScalars<float>& s) {
+  using F = ieee<float>;
+  const float drift = F::sub(F::mul(F::mul(s.neg_eps2, minv_t), grad), F::mul(s.mdecay, v));
+  const float v_t = F::add(v, F::add(drift, sample));                              // :233-238
+  v = v_t;
+  theta = F::add(theta, v_t);                                                      // :241-243
+}
+
+template <int BATCH_CT>
+__global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArgs a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int NW = NT / 32, NSLOT = NT / RS_SLOT;
+  constexpr int NT = RS_T, NW = RS_T / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = tid / RS_SLOT, j = tid % RS_SLOT;
   const int64_t chain = blockIdx.x;
   const BnnLayout L = a.L;
-  const int D = L.D, n4 = D >> 2, batch = a.batch, n_in = L.n_in;
-  const ResidentSmem s = resident_carve(smem, batch, n_in, D);
+  const int D = L.D, n4 = D >> 2, n_in = L.n_in;
+  const int batch = BATCH_CT > 0 ? BATCH_CT : a.batch;
+  const bool pre = a.pre != 0;
+  const ResidentSmem s = resident_carve(smem, batch, n_in, D, a.pre);
   const int TS = s.TS, nrg = s.BP >> 2;
   const float pscale = a.prior_den_inv * a.inv_n;
-  const bool split = RS_NKG + nrg <= NSLOT;         // the halves of a backward phase on different slots
-  const int dw4_slot = nrg < NSLOT ? nrg : 0;
+  const int64_t g0 = chain * n4;                    // first element group of this chain in the [C, D] arrays
 
-  // ---- the chain's state -> shared memory; activation buffers and minibatch rows zeroed -------------------
+  // ---- the chain's state -> shared memory; sum(theta^2); activation buffers and minibatch rows zeroed ----
   {
-    const int64_t g0 = chain * n4;
     const float4 *t4 = reinterpret_cast<const float4*>(a.theta) + g0, *v4 = reinterpret_cast<const float4*>(a.v) + g0,
                  *ta4 = reinterpret_cast<const float4*>(a.tau) + g0, *g4 = reinterpret_cast<const float4*>(a.g) + g0,
                  *h4 = reinterpret_cast<const float4*>(a.v_hat) + g0, *m4 = reinterpret_cast<const float4*>(a.minv) + g0;
+    float sq = 0.0f;
     for (int q = tid; q < n4; q += NT) {
-      reinterpret_cast<float4*>(s.TH)[q] = __ldcs(t4 + q);
+      const float4 t = __ldcs(t4 + q);
+      sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
+      reinterpret_cast<float4*>(s.TH)[q] = t;
       reinterpret_cast<float4*>(s.V)[q] = __ldcs(v4 + q);
       reinterpret_cast<float4*>(s.TAU)[q] = __ldcs(ta4 + q);
       reinterpret_cast<float4*>(s.GG)[q] = __ldcs(g4 + q);
       reinterpret_cast<float4*>(s.VH)[q] = __ldcs(h4 + q);
       reinterpret_cast<float4*>(s.MINV)[q] = __ldcs(m4 + q);
     }
-    for (int q = tid; q < s.total - 7 * D; q += NT) s.H1[q] = 0.0f;     // everything after the state arrays
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) s.scr[warp] = sq;
+    for (int q = s.zero_from + tid; q < s.total - 64; q += NT) smem[q] = 0.0f;      // everything but scr
   }
   __syncthreads();
   auto fetch_rows = [&](int64_t step, int buf) {     // X[start : start + B], y[start : start + B] of `step`
     const int64_t start = a.starts != nullptr ? (int64_t)a.starts[step * a.n_chains + chain] : 0;
     const float* xs = a.X + start * n_in;
     const float* ys = a.y + start;
-    for (int t = tid; t < batch * n_in; t += NT) cp_async4(s.X0 + buf * s.XB + t, xs + t);
-    for (int t = tid; t < batch; t += NT) cp_async4(s.Y0 + buf * s.YB + t, ys + t);
+    for (int t = tid; t < batch * n_in; t += RS_GT) cp_async4(s.X0 + buf * s.XB + t, xs + t);
+    for (int t = tid; t < batch; t += RS_GT) cp_async4(s.Y0 + buf * s.YB + t, ys + t);
   };
-  if (a.n_steps > 0) fetch_rows(0, 0);
+  if (tid < RS_GT && a.n_steps > 0) fetch_rows(0, 0);
 
   for (int64_t st = 0; st < a.n_steps; ++st) {
     const int cur = (int)(st & 1);
     const float* sX = s.X0 + cur * s.XB;
     const float* sY = s.Y0 + cur * s.YB;
+    const bool burn_in = a.adapt_forever || st < a.n_burn_in;
+    const float4* z4 = a.z != nullptr ? reinterpret_cast<const float4*>(a.z) + (st * a.n_chains + chain) * n4 : nullptr;
     cp_async_wait_all();
-    __syncthreads();                                 // rows of this step landed; theta of the last update visible
+    __syncthreads();                                 // rows of this step landed; the last update is visible
 
-    // ---- A: rows of the next step; sum(theta^2); W4; layer 1 ----
-    if (st + 1 < a.n_steps) fetch_rows(st + 1, cur ^ 1);
-    {
-      float sq = 0.0f;
-      for (int q = tid; q < n4; q += NT) {
-        const float4 t = reinterpret_cast<const float4*>(s.TH)[q];
-        sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
-      }
+    if (tid < RS_GT) {
+      // =================== gradient warps: cost + gradient of this step into G ===================
+      const int jj = lane;                           // the worker's pair of units (active: jj < 25)
+      const bool act = jj < RS_HALF;
+      // ---- A: rows of the next step; aligned copy of W4; layer 1 ----
+      if (st + 1 < a.n_steps) fetch_rows(st + 1, cur ^ 1);
+      if (warp == RS_GW - 1)
+        for (int t = lane; t < 64; t += 32) s.sW4[t] = t < HID ? s.TH[L.oW4 + t] : 0.0f;
+      if (act)
+        for (int rg = warp; rg < nrg; rg += RS_GW) {
+          const int i0 = 4 * rg;
+          const float2 b = ld2(s.TH + L.ob1 + 2 * jj);
+          float z0[4], z1[4];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      if (lane == 0) s.scr[warp] = sq;
-    }
-    if (tid >= NT - 64) {
-      const int t = tid - (NT - 64);
-      s.sW4[t] = t < HID ? s.TH[L.oW4 + t] : 0.0f;
-    }
-    if (j < HID) for (int rg = slot; rg < nrg; rg += NSLOT) {
-      const int i0 = 4 * rg;
-      const float b = s.TH[L.ob1 + j];
-      float z0 = b, z1 = b, z2 = b, z3 = b;
-      for (int m = 0; m < n_in; ++m) {
-        const float w = s.TH[L.oW1 + m * HID + j];
-        z0 = fmaf(sX[(i0 + 0) * n_in + m], w, z0); z1 = fmaf(sX[(i0 + 1) * n_in + m], w, z1);
-        z2 = fmaf(sX[(i0 + 2) * n_in + m], w, z2); z3 = fmaf(sX[(i0 + 3) * n_in + m], w, z3);
-      }
-      z0 = fast_tanh(z0); z1 = fast_tanh(z1); z2 = fast_tanh(z2); z3 = fast_tanh(z3);
-      s.H1[(i0 + 0) * HS + j] = z0; s.H1[(i0 + 1) * HS + j] = z1;
-      s.H1[(i0 + 2) * HS + j] = z2; s.H1[(i0 + 3) * HS + j] = z3;
-      st4(s.H1t + j * TS + i0, z0, z1, z2, z3);
-    }
-    __syncthreads();
-    // ---- B, C: layers 2 and 3 ----
-    if (j < HID)
-      for (int rg = slot; rg < nrg; rg += NSLOT) rs_forward(s.TH, L.oW2, L.ob2, s.H1t, s.H2, s.H2t, TS, 4 * rg, j);
-    __syncthreads();
-    if (j < HID)
-      for (int rg = slot; rg < nrg; rg += NSLOT) rs_forward(s.TH, L.oW3, L.ob3, s.H2t, s.H3, nullptr, TS, 4 * rg, j);
-    __syncthreads();
-    // ---- D: head f_i = b4 + H3[i, :] . W4, one thread per row (k ascending) ----
-    const float rho = s.TH[L.orho], b4 = s.TH[L.ob4];
-    const float e_rho = expf(rho);
-    const float fvi = __fdiv_rn(1.0f, e_rho + 1e-16f);                  // :368
-    if (tid < batch) {
-      const float* hr = s.H3 + tid * HS;
-      float f = b4;
+          for (int r = 0; r < 4; ++r) { z0[r] = b.x; z1[r] = b.y; }
+          for (int m = 0; m < n_in; ++m) {
+            const float2 w = ld2(s.TH + L.oW1 + m * HID + 2 * jj);
 #pragma unroll
-      for (int k4 = 0; k4 < K4S; ++k4) {
-        const float4 h = ld4(hr + 4 * k4), w = ld4(s.sW4 + 4 * k4);
-        f = fmaf(h.x, w.x, f); f = fmaf(h.y, w.y, f); f = fmaf(h.z, w.z, f); f = fmaf(h.w, w.w, f);
-      }
-      const float diff = sY[tid] - f;
-      s.sDf[tid] = -(diff * fvi) * a.inv_bs;                            // d cost / d f_i
-      s.sSe[tid] = diff * diff;                                         // :370
-    }
-    __syncthreads();
-    // ---- E: dZ3 = (df W4^T) * (1 - H3^2) | dW4 | scalar tail of the cost (:372-388), d/d rho, d/d b4 ----
-    if (j < HID) for (int rg = slot; rg < nrg; rg += NSLOT) {
-      const int i0 = 4 * rg;
-      const float w4 = s.sW4[j];
-      float o[4];
+            for (int r = 0; r < 4; ++r) {
+              const float x = sX[(i0 + r) * n_in + m];
+              z0[r] = fmaf(x, w.x, z0[r]); z1[r] = fmaf(x, w.y, z1[r]);
+            }
+          }
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float h = s.H3[(i0 + r) * HS + j];
-        o[r] = (s.sDf[i0 + r] * w4) * fmaf(-h, h, 1.0f);
-        s.Z3[(i0 + r) * HS + j] = o[r];
+          for (int r = 0; r < 4; ++r) {
+            z0[r] = fast_tanh(z0[r]); z1[r] = fast_tanh(z1[r]);
+            st2(s.H1 + (i0 + r) * HS + 2 * jj, z0[r], z1[r]);
+          }
+          st4(s.H1t + (2 * jj) * TS + i0, z0[0], z0[1], z0[2], z0[3]);
+          st4(s.H1t + (2 * jj + 1) * TS + i0, z1[0], z1[1], z1[2], z1[3]);
+        }
+      grad_sync();
+      // ---- B, C: layers 2 and 3 ----
+      if (act)
+        for (int rg = warp; rg < nrg; rg += RS_GW) rs_forward(s.TH, L.oW2, L.ob2, s.H1t, s.H2, s.H2t, TS, 4 * rg, jj);
+      grad_sync();
+      if (act)
+        for (int rg = warp; rg < nrg; rg += RS_GW) rs_forward(s.TH, L.oW3, L.ob3, s.H2t, s.H3, nullptr, TS, 4 * rg, jj);
+      grad_sync();
+      // ---- D: head f_i = b4 + H3[i, :] . W4, one thread per row (k ascending) ----
+      if (tid < batch) {
+        const float fvi = __fdiv_rn(1.0f, expf(s.TH[L.orho]) + 1e-16f);         // :368
+        const float* hr = s.H3 + tid * HS;
+        float f = s.TH[L.ob4];
+#pragma unroll
+        for (int k4 = 0; k4 < K4S; ++k4) {
+          const float4 h = ld4(hr + 4 * k4), w = ld4(s.sW4 + 4 * k4);
+          f = fmaf(h.x, w.x, f); f = fmaf(h.y, w.y, f); f = fmaf(h.z, w.z, f); f = fmaf(h.w, w.w, f);
+        }
+        const float diff = sY[tid] - f;
+        s.sDf[tid] = -(diff * fvi) * a.inv_bs;                                  // d cost / d f_i
+        s.sSe[tid] = diff * diff;                                               // :370
       }
-      st4(s.Z3t + j * TS + i0, o[0], o[1], o[2], o[3]);
-    }
-    if (slot == dw4_slot && j < HID) {
-      float dw = 0.0f;
-      for (int i = 0; i < batch; ++i) dw = fmaf(s.H3[i * HS + j], s.sDf[i], dw);
-      s.G[L.oW4 + j] = fmaf(s.sW4[j], pscale, dw);
-    }
-    if (tid == NT - 1) {
-      float sse = 0.0f, sdf = 0.0f, sq_t = 0.0f;
-      for (int i = 0; i < batch; ++i) { sse += s.sSe[i]; sdf += s.sDf[i]; }
-      for (int w = 0; w < NW; ++w) sq_t += s.scr[w];
-      const float lv_den = 0.02f + 3e-16f;                              // safe_divide(., 2 * var)
-      const float dl = rho - logf(1e-6f);
-      const float nb = (float)batch;
-      const float log_like_data = __fmul_rn(__fsub_rn(__fmul_rn(-sse, __fmul_rn(0.5f, fvi)),
-                                                      __fmul_rn(__fmul_rn(0.5f, rho), nb)), a.inv_bs);
-      const float lv = __fsub_rn(__fdiv_rn(-__fmul_rn(dl, dl), lv_den), 0.5f * logf(0.01f));     // :102-107
-      const float wp = __fmul_rn(__fmul_rn(-0.5f, sq_t), a.prior_den_inv);                        // :131-141
-      const float cost = -__fadd_rn(log_like_data, __fmul_rn(__fadd_rn(lv, wp), a.inv_n));
-      const float drho_data = __fmul_rn(-__fsub_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(0.5f, sse), e_rho), fvi), fvi),
-                                                   __fmul_rn(0.5f, nb)), a.inv_bs);
-      s.G[L.orho] = __fadd_rn(__fadd_rn(drho_data, __fmul_rn(__fdiv_rn(__fmul_rn(2.0f, dl), lv_den), a.inv_n)),
-                              __fmul_rn(rho, pscale));
-      s.G[L.ob4] = fmaf(b4, pscale, sdf);
-      // the cost of this step (at the parameters BEFORE its update, base_classes.py:258-310)
-      if (a.cost_all != nullptr) a.cost_all[st * a.n_chains + chain] = cost;
-      if (st == a.n_steps - 1) a.cost_last[chain] = cost;
-      if (a.cost_trace != nullptr && (st + 1) % a.keep_every == 0)
-        a.cost_trace[((st + 1) / a.keep_every - 1) * a.n_chains + chain] = cost;
-    }
-    __syncthreads();
-    // ---- F: dW3, db3 | dZ2;   G: dW2, db2 | dZ1 ----
-    if (split) {
-      if (slot < RS_NKG) { if (j < HID) rs_weight_grad(s.TH, s.G, L.oW3, L.ob3, s.H2, s.Z3, batch, pscale, slot, j); }
-      else if (slot < RS_NKG + nrg && j < HID)
-        rs_backward_data(s.TH, L.oW3, s.Z3t, s.H2t, s.Z2, s.Z2t, TS, 4 * (slot - RS_NKG), j);
+      head_done_arrive();                            // warp 20 computes the scalar tail of the cost from here on
+      grad_sync();
+      // ---- E: dZ3 = (df W4^T) * (1 - H3^2) | dW4 ----
+      if (act)
+        for (int rg = warp; rg < nrg; rg += RS_GW) {
+          const int i0 = 4 * rg;
+          const float2 w4 = ld2(s.sW4 + 2 * jj);
+          float o0[4], o1[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float2 h = ld2(s.H3 + (i0 + r) * HS + 2 * jj);
+            const float df = s.sDf[i0 + r];
+            o0[r] = (df * w4.x) * fmaf(-h.x, h.x, 1.0f);
+            o1[r] = (df * w4.y) * fmaf(-h.y, h.y, 1.0f);
+            st2(s.Z3 + (i0 + r) * HS + 2 * jj, o0[r], o1[r]);
+          }
+          st4(s.Z3t + (2 * jj) * TS + i0, o0[0], o0[1], o0[2], o0[3]);
+          st4(s.Z3t + (2 * jj + 1) * TS + i0, o1[0], o1[1], o1[2], o1[3]);
+        }
+      if (warp == RS_GW - 1 && act) {                // nrg <= 8: this warp has no rows of dZ3
+        const float2 w4 = ld2(s.sW4 + 2 * jj);
+        float dw0 = 0.0f, dw1 = 0.0f;
+        for (int i = 0; i < batch; ++i) {
+          const float2 h = ld2(s.H3 + i * HS + 2 * jj);
+          const float df = s.sDf[i];
+          dw0 = fmaf(h.x, df, dw0); dw1 = fmaf(h.y, df, dw1);
+        }
+        st2(s.G + L.oW4 + 2 * jj, fmaf(w4.x, pscale, dw0), fmaf(w4.y, pscale, dw1));
+      }
+      grad_sync();
+      // ---- F: dW3, db3 (warps 0-4) | dZ2 (warps 5-9);   G: dW2, db2 | dZ1 ----
+      if (warp < RS_NKG) { if (act) rs_weight_grad<BATCH_CT>(s.TH, s.G, L.oW3, L.ob3, s.H2, s.Z3, batch, pscale, warp, jj); }
+      else if (act)
+        for (int rg = warp - RS_NKG; rg < nrg; rg += RS_GW - RS_NKG)
+          rs_backward_data(s.TH, L.oW3, s.Z3t, s.H2t, s.Z2, s.Z2t, TS, 4 * rg, jj);
+      grad_sync();
+      if (warp < RS_NKG) { if (act) rs_weight_grad<BATCH_CT>(s.TH, s.G, L.oW2, L.ob2, s.H1, s.Z2, batch, pscale, warp, jj); }
+      else if (act)
+        for (int rg = warp - RS_NKG; rg < nrg; rg += RS_GW - RS_NKG)
+          rs_backward_data(s.TH, L.oW2, s.Z2t, s.H1t, s.Z1, nullptr, TS, 4 * rg, jj);
+      grad_sync();
+      // ---- H: db1[j] = sum_i dZ1[i][j];  dW1[m][j] = sum_i X[i][m] dZ1[i][j] ----
+      for (int item = tid; item < (n_in + 1) * HID; item += RS_GT) {
+        const int m = item / HID, j = item - m * HID;
+        if (m == n_in) {
+          float db = 0.0f;
+          for (int i = 0; i < batch; ++i) db += s.Z1[i * HS + j];
+          s.G[L.ob1 + j] = fmaf(s.TH[L.ob1 + j], pscale, db);
+        } else {
+          float dw = 0.0f;
+          for (int i = 0; i < batch; ++i) dw = fmaf(sX[i * n_in + m], s.Z1[i * HS + j], dw);
+          s.G[L.oW1 + m * HID + j] = fmaf(s.TH[L.oW1 + m * HID + j], pscale, dw);
+        }
+      }
     } else {
-      if (slot < RS_NKG && j < HID) rs_weight_grad(s.TH, s.G, L.oW3, L.ob3, s.H2, s.Z3, batch, pscale, slot, j);
-      if (j < HID)
-        for (int rg = slot; rg < nrg; rg += NSLOT) rs_backward_data(s.TH, L.oW3, s.Z3t, s.H2t, s.Z2, s.Z2t, TS, 4 * rg, j);
-    }
-    __syncthreads();
-    if (split) {
-      if (slot < RS_NKG) { if (j < HID) rs_weight_grad(s.TH, s.G, L.oW2, L.ob2, s.H1, s.Z2, batch, pscale, slot, j); }
-      else if (slot < RS_NKG + nrg && j < HID)
-        rs_backward_data(s.TH, L.oW2, s.Z2t, s.H1t, s.Z1, nullptr, TS, 4 * (slot - RS_NKG), j);
-    } else {
-      if (slot < RS_NKG && j < HID) rs_weight_grad(s.TH, s.G, L.oW2, L.ob2, s.H1, s.Z2, batch, pscale, slot, j);
-      if (j < HID)
-        for (int rg = slot; rg < nrg; rg += NSLOT) rs_backward_data(s.TH, L.oW2, s.Z2t, s.H1t, s.Z1, nullptr, TS, 4 * rg, j);
-    }
-    __syncthreads();
-    // ---- H: db1[j] = sum_i dZ1[i][j];  dW1[m][j] = sum_i X[i][m] dZ1[i][j] ----
-    for (int item = tid; item < (n_in + 1) * HID; item += NT) {
-      const int m = item / HID, jj = item - m * HID;
-      if (m == n_in) {
-        float db = 0.0f;
-        for (int i = 0; i < batch; ++i) db += s.Z1[i * HS + jj];
-        s.G[L.ob1 + jj] = fmaf(s.TH[L.ob1 + jj], pscale, db);
-      } else {
-        float dw = 0.0f;
-        for (int i = 0; i < batch; ++i) dw = fmaf(sX[i * n_in + m], s.Z1[i * HS + jj], dw);
-        s.G[L.oW1 + m * HID + jj] = fmaf(s.TH[L.oW1 + m * HID + jj], pscale, dw);
+      // =================== update warps: everything of the update that does not need the gradient ===================
+      if (pre) {
+        for (int q = tid - RS_GT; q < n4; q += RS_UT) {
+          float zf[4], ps[4];
+          if (z4 != nullptr) rs_unpack(__ldcs(z4 + q), zf);
+          else normal4((uint64_t)(g0 + q) + a.group_offset, a.step0 + (uint64_t)st, a.seed, zf);
+          if (burn_in) {
+            float ta[4], g[4], h[4], r[4], mi[4];
+            rs_unpack(reinterpret_cast<const float4*>(s.TAU)[q], ta);
+            rs_unpack(reinterpret_cast<const float4*>(s.GG)[q], g);
+            rs_unpack(reinterpret_cast<const float4*>(s.VH)[q], h);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              rs_adapt_pre(ta[i], g[i], h[i], r[i], mi[i]);
+              ps[i] = rs_sample(mi[i], zf[i], a.s);
+            }
+            reinterpret_cast<float4*>(s.TAU)[q] = rs_pack(ta);
+            reinterpret_cast<float4*>(s.PR)[q] = rs_pack(r);
+            reinterpret_cast<float4*>(s.MINV)[q] = rs_pack(mi);     // the inverse mass matrix of this step
+          } else {
+            float mi[4];
+            rs_unpack(reinterpret_cast<const float4*>(s.MINV)[q], mi);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ps[i] = rs_sample(mi[i], zf[i], a.s);
+          }
+          reinterpret_cast<float4*>(s.PS)[q] = rs_pack(ps);
+        }
+      }
+      if (warp == NW - 1) {
+        // ---- the scalar tail of the cost (:372-388), d/d rho, d/d b4: one thread, in the shadow of E .. H ----
+        head_done_wait();
+        if (lane == 0) {
+          const float rho = s.TH[L.orho], b4 = s.TH[L.ob4];
+          const float e_rho = expf(rho);
+          const float fvi = __fdiv_rn(1.0f, e_rho + 1e-16f);
+          float sse = 0.0f, sdf = 0.0f, sq_t = 0.0f;
+          for (int i = 0; i < batch; ++i) { sse += s.sSe[i]; sdf += s.sDf[i]; }
+          for (int w = 0; w < NW; ++w) sq_t += s.scr[w];
+          const float lv_den = 0.02f + 3e-16f;                              // safe_divide(., 2 * var)
+          const float dl = rho - logf(1e-6f);
+          const float nb = (float)batch;
+          const float log_like_data = __fmul_rn(__fsub_rn(__fmul_rn(-sse, __fmul_rn(0.5f, fvi)),
+                                                          __fmul_rn(__fmul_rn(0.5f, rho), nb)), a.inv_bs);
+          const float lv = __fsub_rn(__fdiv_rn(-__fmul_rn(dl, dl), lv_den), 0.5f * logf(0.01f));     // :102-107
+          const float wp = __fmul_rn(__fmul_rn(-0.5f, sq_t), a.prior_den_inv);                        // :131-141
+          const float cost = -__fadd_rn(log_like_data, __fmul_rn(__fadd_rn(lv, wp), a.inv_n));
+          const float drho_data = __fmul_rn(-__fsub_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(0.5f, sse), e_rho), fvi), fvi),
+                                                       __fmul_rn(0.5f, nb)), a.inv_bs);
+          s.G[L.orho] = __fadd_rn(__fadd_rn(drho_data, __fmul_rn(__fdiv_rn(__fmul_rn(2.0f, dl), lv_den), a.inv_n)),
+                                  __fmul_rn(rho, pscale));
+          s.G[L.ob4] = fmaf(b4, pscale, sdf);
+          // the cost of this step (at the parameters BEFORE its update, base_classes.py:258-310)
+          if (a.cost_all != nullptr) a.cost_all[st * a.n_chains + chain] = cost;
+          if (st == a.n_steps - 1) a.cost_last[chain] = cost;
+          if (a.cost_trace != nullptr && (st + 1) % a.keep_every == 0)
+            a.cost_trace[((st + 1) / a.keep_every - 1) * a.n_chains + chain] = cost;
+        }
       }
     }
-    __syncthreads();
-    // ---- I: the SGHMC update (sampler_math.cuh; K1's element group -> Philox counter mapping) ----
+    __syncthreads();                                 // the gradient is complete; so is the gradient-free part
+    // ---- the rest of the SGHMC update, all warps (K1's element group -> Philox counter mapping) ----
     {
-      const bool burn_in = a.adapt_forever || st < a.n_burn_in;
       const bool store_minv = burn_in && (st == a.n_burn_in - 1 || (a.adapt_forever && st == a.n_steps - 1));
       const bool snap = a.trace != nullptr && (st + 1) % a.keep_every == 0;
-      const int64_t g0 = chain * n4;
-      const float4* z4 = a.z != nullptr ? reinterpret_cast<const float4*>(a.z) + (st * a.n_chains + chain) * n4 : nullptr;
       float4* tr4 = snap ? reinterpret_cast<float4*>(a.trace) + (((st + 1) / a.keep_every - 1) * a.n_chains + chain) * n4
                          : nullptr;
       if (a.grad_out != nullptr && st == a.n_steps - 1)
         for (int q = tid; q < n4; q += NT)
           reinterpret_cast<float4*>(a.grad_out)[g0 + q] = reinterpret_cast<const float4*>(s.G)[q];
+      float sq = 0.0f;
       for (int q = tid; q < n4; q += NT) {
-        float zf[4], t[4], v[4], gr[4];
-        if (z4 != nullptr) rs_unpack(__ldcs(z4 + q), zf);
-        else normal4((uint64_t)(g0 + q) + a.group_offset, a.step0 + (uint64_t)st, a.seed, zf);
+        float t[4], v[4], gr[4];
         rs_unpack(reinterpret_cast<const float4*>(s.G)[q], gr);
         rs_unpack(reinterpret_cast<const float4*>(s.TH)[q], t);
         rs_unpack(reinterpret_cast<const float4*>(s.V)[q], v);
-        if (burn_in) {
-          float ta[4], g[4], h[4], mi[4];
-          rs_unpack(reinterpret_cast<const float4*>(s.TAU)[q], ta);
-          rs_unpack(reinterpret_cast<const float4*>(s.GG)[q], g);
-          rs_unpack(reinterpret_cast<const float4*>(s.VH)[q], h);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            mi[i] = adapt(ta[i], g[i], h[i], gr[i]);
-            sghmc_apply(t[i], v[i], mi[i], gr[i], zf[i], a.s);
-          }
-          reinterpret_cast<float4*>(s.TAU)[q] = make_float4(ta[0], ta[1], ta[2], ta[3]);
-          reinterpret_cast<float4*>(s.GG)[q] = make_float4(g[0], g[1], g[2], g[3]);
-          reinterpret_cast<float4*>(s.VH)[q] = make_float4(h[0], h[1], h[2], h[3]);
-          if (store_minv) reinterpret_cast<float4*>(s.MINV)[q] = make_float4(mi[0], mi[1], mi[2], mi[3]);
-        } else {
-          float mi[4];
+        if (pre) {
+          float ps[4], mi[4];
+          rs_unpack(reinterpret_cast<const float4*>(s.PS)[q], ps);
           rs_unpack(reinterpret_cast<const float4*>(s.MINV)[q], mi);
+          if (burn_in) {
+            float g[4], h[4], r[4];
+            rs_unpack(reinterpret_cast<const float4*>(s.GG)[q], g);
+            rs_unpack(reinterpret_cast<const float4*>(s.VH)[q], h);
+            rs_unpack(reinterpret_cast<const float4*>(s.PR)[q], r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rs_adapt_post(g[i], h[i], r[i], gr[i]);
+            reinterpret_cast<float4*>(s.GG)[q] = rs_pack(g);
+            reinterpret_cast<float4*>(s.VH)[q] = rs_pack(h);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rs_apply_post(t[i], v[i], mi[i], gr[i], ps[i], a.s);
+        } else {
+          float zf[4], mi[4];
+          if (z4 != nullptr) rs_unpack(__ldcs(z4 + q), zf);
+          else normal4((uint64_t)(g0 + q) + a.group_offset, a.step0 + (uint64_t)st, a.seed, zf);
+          if (burn_in) {
+            float ta[4], g[4], h[4];
+            rs_unpack(reinterpret_cast<const float4*>(s.TAU)[q], ta);
+            rs_unpack(reinterpret_cast<const float4*>(s.GG)[q], g);
+            rs_unpack(reinterpret_cast<const float4*>(s.VH)[q], h);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mi[i] = adapt(ta[i], g[i], h[i], gr[i]);
+            reinterpret_cast<float4*>(s.TAU)[q] = rs_pack(ta);
+            reinterpret_cast<float4*>(s.GG)[q] = rs_pack(g);
+            reinterpret_cast<float4*>(s.VH)[q] = rs_pack(h);
+            if (store_minv) reinterpret_cast<float4*>(s.MINV)[q] = rs_pack(mi);
+          } else {
+            rs_unpack(reinterpret_cast<const float4*>(s.MINV)[q], mi);
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) sghmc_apply(t[i], v[i], mi[i], gr[i], zf[i], a.s);
         }
-        const float4 tn = make_float4(t[0], t[1], t[2], t[3]);
+        sq = fmaf(t[0], t[0], sq); sq = fmaf(t[1], t[1], sq); sq = fmaf(t[2], t[2], sq); sq = fmaf(t[3], t[3], sq);
+        const float4 tn = rs_pack(t);
         reinterpret_cast<float4*>(s.TH)[q] = tn;
-        reinterpret_cast<float4*>(s.V)[q] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(s.V)[q] = rs_pack(v);
         if (snap) __stcs(tr4 + q, tn);
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0) s.scr[warp] = sq;               // sum(theta^2) of the next step's cost
     }
   }
   __syncthreads();
   // ---- the state goes back ----
   {
-    const int64_t g0 = chain * n4;
     float4 *t4 = reinterpret_cast<float4*>(a.theta) + g0, *v4 = reinterpret_cast<float4*>(a.v) + g0,
            *ta4 = reinterpret_cast<float4*>(a.tau) + g0, *g4 = reinterpret_cast<float4*>(a.g) + g0,
            *h4 = reinterpret_cast<float4*>(a.v_hat) + g0, *m4 = reinterpret_cast<float4*>(a.minv) + g0;
@@ -413,31 +551,36 @@ __global__ void __launch_bounds__(NT, 1) bnn_sghmc_resident_kernel(ResidentArgs 
   }
 }
 
-static int g_resident_threads = RS_T;
+constexpr size_t RS_SMEM_MAX = 227 * 1024;
 
-template <int NT>
+// 1: the gradient-free part of the update runs beside the gradient (two more D-float arrays); 0: it does not fit
+static int resident_pre_mode(int n_in, int batch) {
+  const BnnLayout L = make_layout(n_in);
+  return (size_t)resident_carve(nullptr, batch, n_in, L.D, 1).total * sizeof(float) <= RS_SMEM_MAX ? 1 : 0;
+}
+
+template <int BATCH_CT>
 static void launch_resident(const ResidentArgs& a, size_t smem, cudaStream_t st) {
-  auto k = bnn_sghmc_resident_kernel<NT>;
+  auto k = bnn_sghmc_resident_kernel<BATCH_CT>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<(unsigned)a.n_chains, NT, smem, st>>>(a);
+  k<<<(unsigned)a.n_chains, RS_T, smem, st>>>(a);
 }
 
 static bool resident_shape_ok(int n_in, int batch) {
   if (n_in < 1 || n_in > 64 || batch < 1 || batch > RS_MAX_BATCH) return false;
   const BnnLayout L = make_layout(n_in);
   if (L.D % 4 != 0) return false;                   // element groups of 4 must not straddle chains
-  const ResidentSmem s = resident_carve(nullptr, batch, n_in, L.D);
-  return (size_t)s.total * sizeof(float) <= 227 * 1024;
+  return (size_t)resident_carve(nullptr, batch, n_in, L.D, 0).total * sizeof(float) <= RS_SMEM_MAX;
 }
 
 }  // namespace sgmcmc
 
 using namespace sgmcmc;
 
-extern "C" int sgmcmc_set_bnn_resident_threads(int threads) {
-  SG_REQUIRE(threads == 0 || threads == 448 || threads == 672 || threads == 1024, SGMCMC_E_INVALID,
-             "bnn resident kernel: threads per chain must be 448, 672 or 1024 (0 = default)");
-  g_resident_threads = threads == 0 ? RS_T : threads;
+static int g_resident_overlap = 1;
+
+extern "C" int sgmcmc_set_bnn_resident_overlap(int on) {
+  g_resident_overlap = on != 0;
   return SGMCMC_OK;
 }
 
@@ -481,12 +624,9 @@ extern "C" int sgmcmc_bnn_sghmc_run_resident_f32(float* theta, float* v, float* 
              SGMCMC_E_ALIGN, "bnn_sghmc_run_resident: trace, z and grad_out must be 16-byte aligned");
   if (n_chains == 0 || n_steps == 0) return SGMCMC_OK;
   SG_REQUIRE(n_chains <= 0x7fffffff, SGMCMC_E_UNSUPPORTED, "bnn_sghmc_run_resident: at most 2^31 - 1 chains per launch");
-  const ResidentSmem sm = resident_carve(nullptr, batch, n_in, a.L.D);
-  const size_t smem = (size_t)sm.total * sizeof(float);
-  switch (g_resident_threads) {
-    case 448: launch_resident<448>(a, smem, (cudaStream_t)stream); break;
-    case 1024: launch_resident<1024>(a, smem, (cudaStream_t)stream); break;
-    default: launch_resident<RS_T>(a, smem, (cudaStream_t)stream); break;
-  }
+  a.pre = g_resident_overlap ? resident_pre_mode(n_in, batch) : 0;
+  const size_t smem = (size_t)resident_carve(nullptr, batch, n_in, a.L.D, a.pre).total * sizeof(float);
+  if (batch == 20) launch_resident<20>(a, smem, (cudaStream_t)stream);      // the reference's minibatch: strides fold
+  else launch_resident<0>(a, smem, (cudaStream_t)stream);
   return check_launch("bnn_sghmc_resident_kernel");
 }

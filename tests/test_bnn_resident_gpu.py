@@ -83,20 +83,24 @@ def ffma_k4(theta, X, y, starts, batch, N, n_in=1):
     return cost.cpu().numpy(), grad.cpu().numpy()
 
 
-@pytest.mark.parametrize("threads", [672, 448, 1024])
+@pytest.fixture(params=[1, 0], ids=["overlap", "no-overlap"])
+def overlap(request):
+    """The update's gradient-free part beside the gradient (default where it fits shared memory: batch <= 20),
+    or the whole update after the gradient; both must give the same bits."""
+    _native.call("sgmcmc_set_bnn_resident_overlap", request.param)
+    yield request.param
+    _native.call("sgmcmc_set_bnn_resident_overlap", 1)
+
+
 @pytest.mark.parametrize("batch", [20, 32, 7])
-def test_resident_gradient_equals_the_ffma_kernel_and_the_oracle(threads, batch):
+def test_resident_gradient_equals_the_ffma_kernel_and_the_oracle(overlap, batch):
     C, N = 5, 2000
     X, y = sinc_data(N)
     rng = np.random.RandomState(batch)
     starts = rng.randint(0, N - batch + 1, size=(1, C))
-    _native.call("sgmcmc_set_bnn_resident_threads", threads)
-    try:
-        st = fresh_state(C)
-        theta0 = st["theta"].clone()
-        out = run_resident(st, X, y, starts, np.zeros((1, C, D), np.float32), 1, 1, batch=batch, want_grad=True)
-    finally:
-        _native.call("sgmcmc_set_bnn_resident_threads", 0)
+    st = fresh_state(C)
+    theta0 = st["theta"].clone()
+    out = run_resident(st, X, y, starts, np.zeros((1, C, D), np.float32), 1, 1, batch=batch, want_grad=True)
     g = out["grad"].cpu().numpy()
     cost_ffma, g_ffma = ffma_k4(theta0, X, y, starts[0], batch, N)
     scalars = [D - 2, D - 1]            # b4 and rho: scalar expressions whose FMA contraction is the compiler's choice
@@ -111,7 +115,7 @@ def test_resident_gradient_equals_the_ffma_kernel_and_the_oracle(threads, batch)
     np.testing.assert_allclose(out["cost_last"].cpu().numpy(), c64, rtol=3e-6)
 
 
-def test_resident_update_is_the_oracle_update_on_its_own_gradient():
+def test_resident_update_is_the_oracle_update_on_its_own_gradient(overlap):
     """Teacher-forced, step by step, across the burn-in boundary: theta, V, tau, g, v_hat and the frozen
     inverse mass matrix after a one-step call == oracle step on the state before and the kernel's gradient."""
     C, N, batch, steps, burn = 4, 2000, 20, 12, 7
@@ -140,7 +144,7 @@ def test_resident_update_is_the_oracle_update_on_its_own_gradient():
 
 
 @pytest.mark.parametrize("use_z", [True, False])
-def test_resident_block_of_steps_equals_single_steps(use_z):
+def test_resident_block_of_steps_equals_single_steps(overlap, use_z):
     """n steps in one call (state on the SM throughout) == n calls of one step: states, thinned trace, costs;
     Philox noise (counter = element group, step) or injected noise; burn-in ends inside the block."""
     C, N, batch, steps, burn, keep = 7, 2000, 20, 24, 10, 4
@@ -165,7 +169,7 @@ def test_resident_block_of_steps_equals_single_steps(use_z):
     assert torch.isfinite(a["theta"]).all()
 
 
-def test_resident_noise_is_k1_noise():
+def test_resident_noise_is_k1_noise(overlap):
     """Without injected noise the kernel draws K1's Philox normals: one resident step == K1
     (sgmcmc_sghmc_step_f32) on the resident kernel's gradient, with a chain offset."""
     C, N, batch = 6, 2000, 20

@@ -2,7 +2,7 @@
 the benchmarked shapes (N = 20 000, minibatch 20, D = 5252): microseconds per step and chain-steps/s for
 1 ... 8192 chains, burn-in and sampling phase, for blocks of steps and for one step per call.
 
-    python tools/bench_resident.py [--chains 1,8,148,296,1184,8192] [--threads 672,448,1024] [--steps 64]
+    python tools/bench_resident.py [--chains 1,8,148,296,1184,8192] [--overlap 1,0] [--steps 64]
 """
 import argparse
 import json
@@ -20,7 +20,7 @@ from pysgmcmc_b200.models.bnn_cost import default_net_params  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--chains", default="1,8,148,296,1184,8192")
-ap.add_argument("--threads", default="672,448,1024")
+ap.add_argument("--overlap", default="1,0", help="update beside the gradient (1) / after it (0)")
 ap.add_argument("--steps", type=int, default=64)
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
@@ -68,14 +68,15 @@ for C in [int(c) for c in args.chains.split(",")]:
         ms = timed(lambda: k4k1(S, burn), args.reps)
         line = {"chains": C, "phase": "burn-in" if burn else "sampling", "steps_per_call": S,
                 "k4_then_k1_us_per_step": round(1e3 * ms / S, 3), "k4_then_k1_chain_steps_per_s": round(C * S / ms * 1e3)}
-        for T in [int(t) for t in args.threads.split(",")]:
-            _native.call("sgmcmc_set_bnn_resident_threads", T)
+        for ov in [int(t) for t in args.overlap.split(",")]:
+            _native.call("sgmcmc_set_bnn_resident_overlap", ov)
+            name = "resident" if ov else "resident_no_overlap"
             ms = timed(lambda: resident(S, burn), args.reps)
-            line["resident_%d_us_per_step" % T] = round(1e3 * ms / S, 3)
-            line["resident_%d_chain_steps_per_s" % T] = round(C * S / ms * 1e3)
+            line[name + "_us_per_step"] = round(1e3 * ms / S, 3)
+            line[name + "_chain_steps_per_s"] = round(C * S / ms * 1e3)
             ms1 = timed(lambda: resident(1, burn), args.reps * 4)
-            line["resident_%d_one_step_per_call_us" % T] = round(1e3 * ms1, 3)
-        _native.call("sgmcmc_set_bnn_resident_threads", 0)
+            line[name + "_one_step_per_call_us"] = round(1e3 * ms1, 3)
+        _native.call("sgmcmc_set_bnn_resident_overlap", 1)
         ms1 = timed(lambda: k4k1(1, burn), args.reps * 4)
         line["k4_then_k1_one_step_per_call_us"] = round(1e3 * ms1, 3)
         assert torch.isfinite(theta).all()
