@@ -260,17 +260,18 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def build(burn_in_steps=10 ** 9):
-        chain0 = rank * C                                   # global id of this rank's first chain
-        seeds = (np.arange(C, dtype=np.uint64) + np.uint64(chain0 + 1)) % np.uint64(2 ** 32)
+    def build(burn_in_steps=10 ** 9, n_chains=None):
+        Cn = C if n_chains is None else n_chains
+        chain0 = rank * Cn                                  # global id of this rank's first chain
+        seeds = (np.arange(Cn, dtype=np.uint64) + np.uint64(chain0 + 1)) % np.uint64(2 ** 32)
         gen = DeviceBatchGenerator(N_EXAMPLES, BATCH, seeds=seeds, device=dev, block=256)
         nll = BayesianNeuralNetworkNLL(N_EXAMPLES, BATCH, X=X, y=y,
                                        starts_placeholder=gen.starts_placeholder, device=dev)
-        params = default_net_params(N_IN, n_chains=C, seed=1 + rank, device=dev)
+        params = default_net_params(N_IN, n_chains=Cn, seed=1 + rank, device=dev)
         sampler = SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen,
                                stepsize_schedule=ConstantStepsizeSchedule(EPS),
                                burn_in_steps=burn_in_steps, mdecay=MDECAY, scale_grad=float(N_EXAMPLES),
-                               seed=1, session=Session(device=dev, n_chains=C, output="torch", chain_offset=chain0))
+                               seed=1, session=Session(device=dev, n_chains=Cn, output="torch", chain_offset=chain0))
         return sampler, gen, nll
 
     # ---- device-resident throughput: `value` -------------------------------------------
@@ -371,6 +372,13 @@ def run_b200(args):
         except Exception as exc:
             wide_net = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
+    few_chains = None
+    if world == 1:
+        try:
+            few_chains = few_chain_rates(torch, dev, build)
+        except Exception as exc:
+            few_chains = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -399,6 +407,7 @@ def run_b200(args):
         "sampling_phase": sampling_phase,
         "svgd": svgd,
         "wide_net": wide_net,
+        "few_chains": few_chains,
         "cpu_baseline": cpu,
     }
     emit(line)
@@ -450,6 +459,33 @@ def svgd_step_rates(torch, _native, dev, n=4096, D=5252, reps=10):
                               "peak": 0.5 * measured_bf16_peak(), "peak_source": "half of MEASURED_PEAKS.json "
                               "bf16_tflops (dense TF32 = half the bf16 rate)",
                               "frac": 3 * tf / (0.5 * measured_bf16_peak())}}
+
+
+def few_chain_rates(torch, dev, build, n_steps=2000):
+    """BASELINE.json configs[2] as the reference runs it: ONE BOHAMIANN chain (and one chain per SM), through
+    sampler.run() -- with few chains every chain is resident on an SM (csrc/bnn_resident.cu) instead of K4 then
+    K1 streaming all chains per step; both timed, burn-in and sampling phase."""
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = {"note": "sampler.run(%d), microseconds per step and chain-steps/s; 'resident' is the default for <= 4 "
+                   "chains per SM, 'k4_then_k1' the same sampler with RESIDENT_MAX_CHAINS = 0" % n_steps, "rows": []}
+    for C in (1, sms - 1):
+        for phase, burn in (("burn-in", 10 ** 9), ("sampling", 100)):
+            row = {"chains": C, "phase": phase}
+            for name, limit in (("resident", None), ("k4_then_k1", 0)):
+                sampler, gen, nll = build(burn_in_steps=burn, n_chains=C)
+                sampler.RESIDENT_MAX_CHAINS = limit
+                sampler.run(200, keep_every=200)            # (crosses the end of the 100-step burn-in)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                sampler.run(n_steps, keep_every=100)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                row[name + "_us_per_step"] = round(1e3 * ms / n_steps, 3)
+                row[name + "_chain_steps_per_s"] = round(C * n_steps / ms * 1e3)
+            out["rows"].append(row)
+    return out
 
 
 def wide_net_rates(torch, _native, dev, hidden=(1000, 512, 512), C=256, N=20000, B=20, reps=5):

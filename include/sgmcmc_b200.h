@@ -271,7 +271,9 @@ int sgmcmc_bnn_sghmc_run_resident_f32(float* theta, float* v, float* tau, float*
  * a ticket can be waited for until `depth` further steps were enqueued, and its host buffers
  * must stay untouched until then.  burn_in_left = burn-in steps left including this one
  * (0 = sampling phase; minv is written back only on the last burn-in step).  The handle owns
- * the copy streams, events and device-side slot buffers. */
+ * the copy streams, events and device-side slot buffers.  with_samples: bit 0 = allocate the sample
+ * stage, bit 1 = every step is one launch of the resident kernel (sgmcmc_bnn_sghmc_run_resident_f32,
+ * grad_scratch unused) instead of K4 then K1 -- the arithmetic a sampler with few chains uses everywhere. */
 typedef struct sgmcmc_bnn_host_pipeline sgmcmc_bnn_host_pipeline;
 int sgmcmc_bnn_host_pipeline_create(sgmcmc_bnn_host_pipeline** out, int64_t n_chains, int n_in,
                                     int depth, int with_samples);

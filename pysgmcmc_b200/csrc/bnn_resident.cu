@@ -3,41 +3,45 @@
 // `sample, cost = next(sampler)` of the BOHAMIANN configuration is, per chain, the cost + gradient of
 // pysgmcmc/models/bayesian_neural_network.py:28-69,337-388 followed by the update of
 // pysgmcmc/samplers/sghmc.py:165-251 -- and a chain never looks at another chain.  K4 + K1
-// (bnn.cu, update_kernels.cu) walk ALL chains once per step, so every step streams the whole state
-// through HBM (44 B per element during burn-in) and a single chain pays two kernel launches per step.
-// Here one CTA owns one chain for `n_steps` steps: theta, V, tau, g, v_hat and minv (7 x D floats =
-// 147 KB for D = 5252) are loaded into shared memory once, the minibatch rows of the next step arrive
-// by cp.async while the current step computes, and only costs and thinned samples leave.  HBM traffic
-// is 2 x 147 KB per chain and LAUNCH instead of 231 KB per chain and STEP; a single chain steps at the
-// latency of one SM instead of two launches.
+// (bnn.cu, update_kernels.cu) walk ALL chains once per step: the right shape for thousands of chains (every
+// step streams the state through HBM at the roofline), the wrong one for the reference's own use of the
+// sampler -- ONE chain (bayesian_neural_network.py:436-531), where a step is two launches of two-warp CTAs.
+// Here one CTA owns one chain for `n_steps` steps: theta, V, tau, g, v_hat and minv (7 x D floats = 147 KB
+// for D = 5252) are loaded into shared memory once, the minibatch rows of the next step arrive by cp.async
+// while the current step computes, and only costs and thinned samples leave.
 //
-// Arithmetic.  The cost + gradient is the FFMA formulation of bnn.cu (variant 0) spread over more
-// threads: every dot product is accumulated in the same order (bias first, k ascending; minibatch
-// rows ascending for the weight gradients), so the gradient equals that kernel's bit for bit except
-// d/d rho and the cost's prior term (sum of theta^2 in another order).  The update is sampler_math.cuh
-// with K1's (element group, step) -> Philox counter mapping, so given the same gradient the new state
-// is K1's bit for bit.
+// Arithmetic.  The cost + gradient is the FFMA formulation of bnn.cu (variant 0) spread over more threads:
+// every dot product is accumulated in the same order (bias first, k ascending; minibatch rows ascending for
+// the weight gradients), so the gradient equals that kernel's bit for bit except d/d rho, d/d b4 (scalar
+// expressions) and the cost's prior term (sum of theta^2 in another order).  The update is sampler_math.cuh's
+// arithmetic with K1's (element group, step) -> Philox counter mapping: given the same gradient the new state
+// is K1's (and the oracle's) bit for bit (tests/test_bnn_resident_gpu.py).
 //
-// Threads.  A step is a sequence of barrier-separated phases on one CTA of RS_T threads:
-//   A  sum(theta^2), W4 -> aligned copy, layer 1             B, C  layers 2, 3 (50 x rows/4 workers)
-//   D  head: f, d cost / d f, squared errors                 E  dZ3 | dW4 | the scalar tail (one thread)
-//   F  dW3, db3 | dZ2       G  dW2, db2 | dZ1                H  dW1, db1
-//   I  SGHMC update of the D/4 element groups by all threads (+ snapshot of the thinned sample)
-// A GEMM worker is (column j, group of 4 minibatch rows) in a 64-thread slot (50 active): the 4 rows'
-// activations come from a TRANSPOSED copy [unit][row] with one broadcast 128-bit load per k, the weight
-// column straight from the staged theta (consecutive j: conflict free).  The two halves of a backward
-// phase have no data dependence and run on different slots at the same time.
+// Two kinds of warps, side by side (672 threads, one CTA per SM):
+//   warps 0-7, the gradient: a step is eight phases separated by a named barrier of these 256 threads --
+//     A  layer 1, aligned copy of W4        B, C  layers 2, 3          D  head: f, d cost / d f, squared errors
+//     E  dZ3 | dW4                          F  dW3, db3 | dZ2          G  dW2, db2 | dZ1        H  dW1, db1
+//     A GEMM's workers own 2 units x 4 minibatch rows (8 accumulators, one 64-bit weight load and one 128-bit
+//     load of a TRANSPOSED activation copy [unit][row] per k) and are dealt to warps 0-3, one per SM
+//     sub-partition; the second GEMM of a backward phase (no data dependence) runs on warps 4-7.
+//   warps 8-20, the update: everything of the SGHMC step that does not need the gradient -- the Philox normals,
+//     r_t, tau_t, minv_t = 1 / sqrt(v_hat), sigma * z (5 of the 8 IEEE divisions / square roots per element) --
+//     WHILE the gradient warps compute; warp 20 then evaluates the scalar tail of the cost.
+//   After one CTA barrier all 21 warps finish the update (g_t, v_hat_t, v_t, theta_t: multiplies and adds) and
+//   sum theta^2 for the next step's prior.  When the two extra D-float arrays do not fit (minibatch > 20 rows)
+//   the whole update runs after the barrier instead (sgmcmc_set_bnn_resident_overlap(0) forces that; same bits).
 #include "bnn_common.cuh"
 
 namespace sgmcmc {
 
 constexpr int RS_T = 672;        // 21 warps: D/4 = 1313 update groups are 2 rounds of 672 (97.7 % of the slots)
-constexpr int RS_GW = 10;        // warps 0 .. 9: the gradient (320 threads); warps 10 .. 20: the update's gradient-free part
+constexpr int RS_GW = 8;         // warps 0 .. 7: the gradient (256 threads); warps 8 .. 20: the update's gradient-free part
 constexpr int RS_GT = 32 * RS_GW;
 constexpr int RS_UT = RS_T - RS_GT;
 constexpr int RS_KG = 12;        // k values per worker of a weight-gradient GEMM (5 warps cover 50 + 2 padding)
 constexpr int RS_NKG = 5;
 constexpr int RS_HALF = HID / 2; // a gradient worker owns 2 units: (2 jj, 2 jj + 1) or (kk, kk + 25)
+constexpr int RS_WT = 128;       // workers of a GEMM are dealt to 4 warps, one per SM sub-partition
 constexpr int RS_MAX_BATCH = 32;
 
 struct ResidentArgs {
@@ -285,14 +289,16 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
     for (int q = s.zero_from + tid; q < s.total - 64; q += NT) smem[q] = 0.0f;      // everything but scr
   }
   __syncthreads();
-  auto fetch_rows = [&](int64_t step, int buf) {     // X[start : start + B], y[start : start + B] of `step`
-    const int64_t start = a.starts != nullptr ? (int64_t)a.starts[step * a.n_chains + chain] : 0;
+  auto start_of = [&](int64_t step) -> int64_t {
+    return a.starts != nullptr ? (int64_t)__ldg(a.starts + step * a.n_chains + chain) : 0;
+  };
+  auto fetch_rows = [&](int64_t start, int buf) {    // X[start : start + B], y[start : start + B] -> buffer `buf`
     const float* xs = a.X + start * n_in;
     const float* ys = a.y + start;
     for (int t = tid; t < batch * n_in; t += RS_GT) cp_async4(s.X0 + buf * s.XB + t, xs + t);
     for (int t = tid; t < batch; t += RS_GT) cp_async4(s.Y0 + buf * s.YB + t, ys + t);
   };
-  if (tid < RS_GT && a.n_steps > 0) fetch_rows(0, 0);
+  if (tid < RS_GT && a.n_steps > 0) fetch_rows(start_of(0), 0);
 
   for (int64_t st = 0; st < a.n_steps; ++st) {
     const int cur = (int)(st & 1);
@@ -305,15 +311,20 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
 
     if (tid < RS_GT) {
       // =================== gradient warps: cost + gradient of this step into G ===================
-      const int jj = lane;                           // the worker's pair of units (active: jj < 25)
-      const bool act = jj < RS_HALF;
-      // ---- A: rows of the next step; aligned copy of W4; layer 1 ----
-      if (st + 1 < a.n_steps) fetch_rows(st + 1, cur ^ 1);
-      if (warp == RS_GW - 1)
+      // a GEMM's workers (pair of units, group of 4 rows) are dealt to warps 0-3; the second GEMM of a backward
+      // phase to warps 4-7: one (two) busy warps per SM sub-partition
+      const int wid = tid & (RS_WT - 1);
+      const bool first = tid < RS_WT;
+      const int n_fw = RS_HALF * nrg;                // workers of a forward / backward-data GEMM
+      // ---- A: start index of the next step (used in H); aligned copy of W4; layer 1 ----
+      const int64_t start_next = st + 1 < a.n_steps ? start_of(st + 1) : 0;
+      float fvi = 0.0f;
+      if (tid < batch) fvi = __fdiv_rn(1.0f, expf(s.TH[L.orho]) + 1e-16f);      // :368 (used in D)
+      if (warp == 4)
         for (int t = lane; t < 64; t += 32) s.sW4[t] = t < HID ? s.TH[L.oW4 + t] : 0.0f;
-      if (act)
-        for (int rg = warp; rg < nrg; rg += RS_GW) {
-          const int i0 = 4 * rg;
+      if (first)
+        for (int wk = wid; wk < n_fw; wk += RS_WT) {
+          const int rg = wk / RS_HALF, jj = wk - rg * RS_HALF, i0 = 4 * rg;
           const float2 b = ld2(s.TH + L.ob1 + 2 * jj);
           float z0[4], z1[4];
 #pragma unroll
@@ -336,15 +347,20 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
         }
       grad_sync();
       // ---- B, C: layers 2 and 3 ----
-      if (act)
-        for (int rg = warp; rg < nrg; rg += RS_GW) rs_forward(s.TH, L.oW2, L.ob2, s.H1t, s.H2, s.H2t, TS, 4 * rg, jj);
+      if (first)
+        for (int wk = wid; wk < n_fw; wk += RS_WT) {
+          const int rg = wk / RS_HALF;
+          rs_forward(s.TH, L.oW2, L.ob2, s.H1t, s.H2, s.H2t, TS, 4 * rg, wk - rg * RS_HALF);
+        }
       grad_sync();
-      if (act)
-        for (int rg = warp; rg < nrg; rg += RS_GW) rs_forward(s.TH, L.oW3, L.ob3, s.H2t, s.H3, nullptr, TS, 4 * rg, jj);
+      if (first)
+        for (int wk = wid; wk < n_fw; wk += RS_WT) {
+          const int rg = wk / RS_HALF;
+          rs_forward(s.TH, L.oW3, L.ob3, s.H2t, s.H3, nullptr, TS, 4 * rg, wk - rg * RS_HALF);
+        }
       grad_sync();
       // ---- D: head f_i = b4 + H3[i, :] . W4, one thread per row (k ascending) ----
       if (tid < batch) {
-        const float fvi = __fdiv_rn(1.0f, expf(s.TH[L.orho]) + 1e-16f);         // :368
         const float* hr = s.H3 + tid * HS;
         float f = s.TH[L.ob4];
 #pragma unroll
@@ -359,9 +375,9 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
       head_done_arrive();                            // warp 20 computes the scalar tail of the cost from here on
       grad_sync();
       // ---- E: dZ3 = (df W4^T) * (1 - H3^2) | dW4 ----
-      if (act)
-        for (int rg = warp; rg < nrg; rg += RS_GW) {
-          const int i0 = 4 * rg;
+      if (first)
+        for (int wk = wid; wk < n_fw; wk += RS_WT) {
+          const int rg = wk / RS_HALF, jj = wk - rg * RS_HALF, i0 = 4 * rg;
           const float2 w4 = ld2(s.sW4 + 2 * jj);
           float o0[4], o1[4];
 #pragma unroll
@@ -375,7 +391,8 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
           st4(s.Z3t + (2 * jj) * TS + i0, o0[0], o0[1], o0[2], o0[3]);
           st4(s.Z3t + (2 * jj + 1) * TS + i0, o1[0], o1[1], o1[2], o1[3]);
         }
-      if (warp == RS_GW - 1 && act) {                // nrg <= 8: this warp has no rows of dZ3
+      if (warp == 4 && lane < RS_HALF) {
+        const int jj = lane;
         const float2 w4 = ld2(s.sW4 + 2 * jj);
         float dw0 = 0.0f, dw1 = 0.0f;
         for (int i = 0; i < batch; ++i) {
@@ -386,18 +403,33 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
         st2(s.G + L.oW4 + 2 * jj, fmaf(w4.x, pscale, dw0), fmaf(w4.y, pscale, dw1));
       }
       grad_sync();
-      // ---- F: dW3, db3 (warps 0-4) | dZ2 (warps 5-9);   G: dW2, db2 | dZ1 ----
-      if (warp < RS_NKG) { if (act) rs_weight_grad<BATCH_CT>(s.TH, s.G, L.oW3, L.ob3, s.H2, s.Z3, batch, pscale, warp, jj); }
-      else if (act)
-        for (int rg = warp - RS_NKG; rg < nrg; rg += RS_GW - RS_NKG)
-          rs_backward_data(s.TH, L.oW3, s.Z3t, s.H2t, s.Z2, s.Z2t, TS, 4 * rg, jj);
+      // ---- F: dW3, db3 (warps 0-3) | dZ2 (warps 4-7);   G: dW2, db2 | dZ1 ----
+      if (first) {
+        if (wid < RS_HALF * RS_NKG) {
+          const int kg = wid / RS_HALF;
+          rs_weight_grad<BATCH_CT>(s.TH, s.G, L.oW3, L.ob3, s.H2, s.Z3, batch, pscale, kg, wid - kg * RS_HALF);
+        }
+      } else {
+        for (int wk = wid; wk < n_fw; wk += RS_WT) {
+          const int rg = wk / RS_HALF;
+          rs_backward_data(s.TH, L.oW3, s.Z3t, s.H2t, s.Z2, s.Z2t, TS, 4 * rg, wk - rg * RS_HALF);
+        }
+      }
       grad_sync();
-      if (warp < RS_NKG) { if (act) rs_weight_grad<BATCH_CT>(s.TH, s.G, L.oW2, L.ob2, s.H1, s.Z2, batch, pscale, warp, jj); }
-      else if (act)
-        for (int rg = warp - RS_NKG; rg < nrg; rg += RS_GW - RS_NKG)
-          rs_backward_data(s.TH, L.oW2, s.Z2t, s.H1t, s.Z1, nullptr, TS, 4 * rg, jj);
+      if (first) {
+        if (wid < RS_HALF * RS_NKG) {
+          const int kg = wid / RS_HALF;
+          rs_weight_grad<BATCH_CT>(s.TH, s.G, L.oW2, L.ob2, s.H1, s.Z2, batch, pscale, kg, wid - kg * RS_HALF);
+        }
+      } else {
+        for (int wk = wid; wk < n_fw; wk += RS_WT) {
+          const int rg = wk / RS_HALF;
+          rs_backward_data(s.TH, L.oW2, s.Z2t, s.H1t, s.Z1, nullptr, TS, 4 * rg, wk - rg * RS_HALF);
+        }
+      }
       grad_sync();
-      // ---- H: db1[j] = sum_i dZ1[i][j];  dW1[m][j] = sum_i X[i][m] dZ1[i][j] ----
+      // ---- H: db1[j] = sum_i dZ1[i][j];  dW1[m][j] = sum_i X[i][m] dZ1[i][j];  rows of the next step ----
+      if (st + 1 < a.n_steps) fetch_rows(start_next, cur ^ 1);
       for (int item = tid; item < (n_in + 1) * HID; item += RS_GT) {
         const int m = item / HID, j = item - m * HID;
         if (m == n_in) {

@@ -26,6 +26,7 @@ constexpr int MAX_DEPTH = 64;
 struct sgmcmc_bnn_host_pipeline {
   int64_t n_chains = 0, D = 0;
   int depth = 0;
+  int resident = 0;               // steps through the resident kernel (bnn_resident.cu) instead of K4 then K1
   int64_t next_ticket = 0;
   int64_t n_samples = 0;          // samples requested so far (stage buffer = n_samples % 2)
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -78,6 +79,7 @@ extern "C" int sgmcmc_bnn_host_pipeline_create(sgmcmc_bnn_host_pipeline** out, i
   p->n_chains = n_chains;
   p->D = make_layout(n_in).D;
   p->depth = depth;
+  p->resident = (with_samples & 2) != 0;
   int rc = SGMCMC_OK;
   auto ok = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess && rc == SGMCMC_OK) rc = set_error(SGMCMC_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -87,7 +89,7 @@ extern "C" int sgmcmc_bnn_host_pipeline_create(sgmcmc_bnn_host_pipeline** out, i
   ok(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking), "cudaStreamCreate");
   ok(cudaMalloc(&p->d_starts, sizeof(int32_t) * depth * n_chains), "cudaMalloc(starts)");
   ok(cudaMalloc(&p->d_cost, sizeof(float) * depth * n_chains), "cudaMalloc(cost)");
-  if (with_samples) ok(cudaMalloc(&p->d_stage, sizeof(float) * 2 * n_chains * p->D), "cudaMalloc(sample stage)");
+  if (with_samples & 1) ok(cudaMalloc(&p->d_stage, sizeof(float) * 2 * n_chains * p->D), "cudaMalloc(sample stage)");
   for (int b = 0; b < depth; ++b) {
     ok(cudaEventCreateWithFlags(&p->h2d[b], cudaEventDisableTiming), "cudaEventCreate");
     ok(cudaEventCreateWithFlags(&p->step_done[b], cudaEventDisableTiming), "cudaEventCreate");
@@ -131,7 +133,13 @@ extern "C" int sgmcmc_bnn_host_pipeline_step(sgmcmc_bnn_host_pipeline* p, float*
   // n_burn_in of the one-step run: 0 (sampling), 1 (the LAST burn-in step: minv is written
   // back and frozen) or 2 (burn-in goes on: no write-back)
   const int64_t n_burn_in = burn_in_left > 2 ? 2 : burn_in_left;
-  if (int rc = sgmcmc_bnn_sghmc_run_f32(theta, v, tau, g, v_hat, minv, X, y, d_starts, nullptr, nullptr, nullptr,
+  if (p->resident) {
+    if (int rc = sgmcmc_bnn_sghmc_run_resident_f32(theta, v, tau, g, v_hat, minv, X, y, d_starts, nullptr, nullptr,
+                                                   nullptr, nullptr, d_cost, nullptr, C, n_in, batch, batch_size_cfg,
+                                                   n_examples, 1, burn_in_left > 0 ? 1 : 0, adapt_forever, 1, epsilon,
+                                                   mdecay, scale_grad, seed, step, chain_offset, stream))
+      return rc;
+  } else if (int rc = sgmcmc_bnn_sghmc_run_f32(theta, v, tau, g, v_hat, minv, X, y, d_starts, nullptr, nullptr, nullptr,
                                         grad_scratch, d_cost, C, n_in, batch, batch_size_cfg, n_examples, 1,
                                         n_burn_in, adapt_forever, 1, epsilon, mdecay, scale_grad, seed, step,
                                         chain_offset, stream))

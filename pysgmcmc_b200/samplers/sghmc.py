@@ -8,6 +8,7 @@ import torch
 
 from .. import _native
 from ..stepsize_schedules import ConstantStepsizeSchedule
+from . import base_classes
 from .base_classes import BurnInMCMCSampler
 
 
@@ -89,14 +90,62 @@ class SGHMCSampler(BurnInMCMCSampler):
     def _can_run_fused(self):
         return super()._can_run_fused() or self._bnn_run_ok()
 
-    #: `run()` keeps every chain resident on one SM for a whole chunk of steps (csrc/bnn_resident.cu) when the
-    #: sampler has at most this many chains and the shape fits; otherwise K4 then K1 per step.  0 switches
-    #: the resident kernel off.
-    RESIDENT_MAX_CHAINS = 0
+    #: Few chains: every chain lives on one SM (csrc/bnn_resident.cu) -- the whole state in shared memory for a
+    #: block of `run()` steps, one launch per `next()` / `iter_host` step -- instead of K4 then K1 streaming all
+    #: chains through HBM every step.  Used when the sampler has at most this many chains (None: 4 per SM of
+    #: the device; 0: never) and the shape fits (float32, get_default_net, odd n_in, minibatch <= 32).  One
+    #: sampler uses ONE of the two arithmetics everywhere, so run(n) == n x next() == iter_host bit for bit
+    #: either way; the two differ from each other in the rounding of the gradient's dot products only
+    #: (both within 1e-5 of the oracle after 1000 steps, tests/test_bnn_resident_gpu.py, tests/test_bnn_gpu.py).
+    RESIDENT_MAX_CHAINS = None
+
+    _sm_count = {}
+
+    def _resident_limit(self):
+        if self.RESIDENT_MAX_CHAINS is not None:
+            return self.RESIDENT_MAX_CHAINS
+        key = str(self.device)
+        if key not in SGHMCSampler._sm_count:          # (a device query costs tens of microseconds: once)
+            SGHMCSampler._sm_count[key] = torch.cuda.get_device_properties(self.device).multi_processor_count
+        return 4 * SGHMCSampler._sm_count[key]
 
     def _resident_ok(self, batch):
-        return (0 < self.n_chains <= self.RESIDENT_MAX_CHAINS
-                and _native.load().sgmcmc_bnn_resident_supported(int(self.cost_fun.n_in), int(batch)) == 1)
+        cf = self.cost_fun
+        if not (getattr(cf, "bnn_native", False) and self.dtype == torch.float32 and self.session.fused
+                and 0 < self.n_chains <= self._resident_limit()):
+            return False
+        fits = self.__dict__.setdefault("_resident_fits", {})
+        key = (int(cf.n_in), int(batch))
+        if key not in fits:
+            fits[key] = _native.load().sgmcmc_bnn_resident_supported(*key) == 1
+        return fits[key]
+
+    def _advance(self, feed_dict, adapt=None, **kwargs):
+        """One `next()` step; with few chains the whole step is one launch of the resident kernel."""
+        cf = self.cost_fun
+        if not (getattr(cf, "bnn_native", False) and self.dtype == torch.float32 and self._native_target is None
+                and 0 < self.n_chains <= self._resident_limit() and self.session.fused):
+            return super()._advance(feed_dict, adapt=adapt, **kwargs)
+        base_classes.feed(feed_dict)
+        if adapt is None:
+            adapt = self._adapts
+        with self._on_device():
+            X, y, starts, batch = cf._device_batch()
+            if not self._resident_ok(batch):
+                return super()._advance({}, adapt=adapt, **kwargs)
+            epsilon = float(self.epsilon.value)
+            z = self._noise_tensor()
+            if self._grad is None:
+                self._grad = torch.empty_like(self._theta)
+            cost = torch.empty(self.n_chains, dtype=self.dtype, device=self.device)
+            _native.call("sgmcmc_bnn_sghmc_run_resident_f32", *[_native.ptr(a) for a in self._arrays()],
+                         _native.ptr(X), _native.ptr(y), _native.ptr(starts), _native.ptr(z), None, None, None,
+                         _native.ptr(cost), _native.ptr(self._grad), self.n_chains, cf.n_in, batch,
+                         float(cf.batch_size), cf.n_examples, 1, 1 if adapt else 0, 0, 1, epsilon, self.mdecay,
+                         self.scale_grad, self._noise_seed, self.n_iterations, self.session.chain_offset,
+                         self._stream())
+        self.cost = cost
+        return cost
 
     def _launch_fused_run(self, n_steps, keep_every, trace, costs):
         epsilon = float(next(self.stepsize_schedule))
@@ -137,7 +186,6 @@ class SGHMCSampler(BurnInMCMCSampler):
             starts = None
             if gen is not None:
                 starts, ready = pending
-                pending = gen.next_block_async(min(chunk, n_steps - done - n)) if done + n < n_steps else None
                 main.wait_event(ready)
                 starts.record_stream(main)
             k0 = done // keep_every                       # chunks start on a thinning boundary
@@ -152,6 +200,11 @@ class SGHMCSampler(BurnInMCMCSampler):
                          cf.n_examples, n, min(n, max(0, n_burn_in - done)), int(self.burn_in_steps == 0),
                          keep_every, epsilon, self.mdecay, self.scale_grad, self._noise_seed,
                          self.n_iterations, self.session.chain_offset, self._stream())
+            if gen is not None:
+                # the indices of the next chunk, on the side stream -- requested AFTER this chunk's launch so that
+                # its CTAs get their SMs first (a resident CTA fills an SM: with one chain per SM an index
+                # kernel that got there earlier would push chains into a second wave)
+                pending = gen.next_block_async(min(chunk, n_steps - done - n)) if done + n < n_steps else None
             self.n_iterations += n
             done += n
         self.cost = cost_scratch
@@ -195,7 +248,7 @@ class SGHMCSampler(BurnInMCMCSampler):
         # to s_k + depth are enqueued; slot k is re-used by sample k + n_slots, at step
         # s_k + n_slots * sample_every >= s_k + depth + sample_every
         n_slots = min(depth + 1, depth // sample_every + 2) if sample_every else 0
-        handle, h_cost, h_sample = self._host_pipeline(depth, n_slots)
+        handle, h_cost, h_sample = self._host_pipeline(depth, n_slots, self._resident_ok(cf.actual_batch))
         epsilon = float(next(self.stepsize_schedule))
         arrays = [_native.ptr(a) for a in self._arrays()]
         X, y, grad = _native.ptr(cf.X), _native.ptr(cf.y), _native.ptr(self._grad)
@@ -238,21 +291,21 @@ class SGHMCSampler(BurnInMCMCSampler):
 
     _host_samples = 0
 
-    def _host_pipeline(self, depth, n_sample_slots):
+    def _host_pipeline(self, depth, n_sample_slots, resident=False):
         """The native stepper of `iter_host` and its pinned result buffers, kept between calls
         (pinning [C, D] floats costs tens of milliseconds)."""
         cached = getattr(self, "_host_pipe", None)
-        if cached is not None and cached[0] == (depth, n_sample_slots):
+        if cached is not None and cached[0] == (depth, n_sample_slots, resident):
             return cached[1:]
         self.close_host_pipeline()
         C, D = self.n_chains, self.n_params_per_chain
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _native.call("sgmcmc_bnn_host_pipeline_create", ctypes.byref(handle), C, self.cost_fun.n_in, depth,
-                         int(n_sample_slots > 0))
+                         int(n_sample_slots > 0) | (2 if resident else 0))
         h_cost = torch.empty((depth, C), dtype=self.dtype).pin_memory()
         h_sample = torch.empty((n_sample_slots, C, D), dtype=self.dtype).pin_memory() if n_sample_slots else None
-        self._host_pipe = ((depth, n_sample_slots), handle, h_cost, h_sample)
+        self._host_pipe = ((depth, n_sample_slots, resident), handle, h_cost, h_sample)
         return handle, h_cost, h_sample
 
     def close_host_pipeline(self):

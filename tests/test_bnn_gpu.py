@@ -29,6 +29,13 @@ K4_DEFAULT = 16      # tensor-pipe kernel: rounded split, FP32-pipe accumulation
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+@pytest.fixture(autouse=True)
+def streaming_step_kernels(monkeypatch):
+    """This module tests K4 then K1 (all chains streamed through HBM every step).  Samplers with as few chains
+    as these tests use would run the resident kernel instead (tests/test_bnn_resident_gpu.py)."""
+    monkeypatch.setattr(SGHMCSampler, "RESIDENT_MAX_CHAINS", 0)
+
+
 def sinc_data(N, n_in=1, seed=1):
     rng = np.random.RandomState(seed)
     X = np.array([rng.uniform(0.0, 1.0, n_in) for _ in range(N)])      # tests/utils.py:24-29

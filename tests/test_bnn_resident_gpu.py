@@ -202,3 +202,77 @@ def test_resident_refuses_shapes_it_cannot_hold():
     X, y = sinc_data(100)
     with pytest.raises(_native.NativeError):
         run_resident(st, X, y, None, None, 1, 1, batch=64)
+
+
+# ---- the sampler classes on top: with few chains every entry point runs the resident kernel ----------------
+def _sampler(C, N, batch, burn, X, y, generator=True, seed=77, limit=None):
+    from pysgmcmc_b200 import Session
+    from pysgmcmc_b200.data_batches import DeviceBatchGenerator
+    from pysgmcmc_b200.models.bnn_cost import BayesianNeuralNetworkNLL, default_net_params
+    from pysgmcmc_b200.samplers import SGHMCSampler
+    gen = DeviceBatchGenerator(N, batch, n_chains=C, seed=5, device=DEV, block=16)
+    nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
+    params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+    s = SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen if generator else None, burn_in_steps=burn,
+                     scale_grad=float(N), seed=seed, session=Session(device=DEV, n_chains=C, output="torch"))
+    if limit is not None:
+        s.RESIDENT_MAX_CHAINS = limit
+    return s, gen.starts_placeholder
+
+
+@pytest.mark.parametrize("keep_every", [5, 7])
+def test_sampler_run_equals_next_with_the_resident_kernel(keep_every):
+    """run(n) (chunks of steps with the chains on their SMs) == n x next() (one launch per step), bit for bit:
+    states, thinned trace, costs; the burn-in ends inside; one launch per next() besides the index generator."""
+    C, N, batch, steps, burn = 10, 2000, 20, 60, 25
+    X, y = sinc_data(N)
+    a, _ = _sampler(C, N, batch, burn, X, y)
+    b, _ = _sampler(C, N, batch, burn, X, y)
+    assert a._resident_ok(batch)
+    trace, costs = a.run(steps, keep_every=keep_every)
+    assert a.n_iterations == steps and trace.shape == (steps // keep_every, C, D)
+    launches0 = _native.load().sgmcmc_launch_count()
+    for s in range(steps):
+        sample, cost = next(b)
+        if (s + 1) % keep_every == 0:
+            k = (s + 1) // keep_every - 1
+            assert torch.equal(trace[k], b._theta), "trace at step %d" % s
+            assert torch.equal(costs[k], cost), "cost at step %d" % s
+    n_launches = _native.load().sgmcmc_launch_count() - launches0
+    assert n_launches < 1.2 * steps, "%d launches for %d steps: K4 + K1 ran instead of the resident kernel" % (n_launches, steps)
+    for name in ("v", "tau", "g", "v_hat", "minv"):
+        assert torch.equal(a._state_array(name), b._state_array(name)), name
+    assert torch.equal(a._theta, b._theta) and torch.isfinite(a._theta).all() and not a.is_burning_in
+
+
+def test_sampler_iter_host_equals_next_with_the_resident_kernel():
+    C, N, batch, steps, burn, every = 6, 2000, 20, 40, 17, 8
+    X, y = sinc_data(N)
+    rng = np.random.RandomState(3)
+    host_starts = torch.from_numpy(rng.randint(0, N - batch + 1, size=(steps, C)).astype(np.int32)).pin_memory()
+    a, _ = _sampler(C, N, batch, burn, X, y, generator=False, seed=21)
+    b, ph = _sampler(C, N, batch, burn, X, y, generator=False, seed=21)
+    for s, (smp, cost) in enumerate(a.iter_host(host_starts, sample_every=every, lookahead=3)):
+        ph.value = host_starts[s].to(DEV)
+        _, want_cost = next(b)
+        assert np.array_equal(cost, want_cost.cpu().numpy()), "cost at step %d" % s
+        if (s + 1) % every == 0:
+            assert np.array_equal(smp, b._theta.cpu().numpy()), "sample at step %d" % s
+    for name in ("v", "tau", "g", "v_hat", "minv"):
+        assert torch.equal(a._state_array(name), b._state_array(name)), name
+    assert torch.equal(a._theta, b._theta)
+
+
+def test_resident_and_streaming_samplers_agree_to_rounding():
+    """The same sampler with the resident kernel and with K4 then K1: different rounding of the gradient's dot
+    products, nothing else -- 30 steps apart by ~1e-6 of max|theta|."""
+    C, N, batch, steps = 8, 2000, 20, 30
+    X, y = sinc_data(N)
+    a, _ = _sampler(C, N, batch, 20, X, y)
+    b, _ = _sampler(C, N, batch, 20, X, y, limit=0)
+    assert a._resident_ok(batch) and not b._resident_ok(batch)
+    a.run(steps, keep_every=steps)
+    b.run(steps, keep_every=steps)
+    ta, tb = a._theta.cpu().numpy(), b._theta.cpu().numpy()
+    assert np.abs(ta - tb).max() <= 1e-5 * np.abs(tb).max()
+    assert not np.array_equal(ta, tb)          # (they ARE two arithmetics; identical bits would mean one path ran twice)

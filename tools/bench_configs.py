@@ -119,20 +119,30 @@ Xd = ((Xd - Xd.mean(0)) / Xd.std(0)).astype(np.float32)
 yd = ((yd - yd.mean()) / yd.std()).astype(np.float32)
 
 
-def bnn_chain(C, prefetch=0, output="torch"):
+def bnn_chain(C, prefetch=0, output="torch", resident=True, burn_in_steps=1000):
     gen = DeviceBatchGenerator(N, B, n_chains=C, seed=1, device=DEV)
     nll = BayesianNeuralNetworkNLL(N, B, X=Xd, y=yd, starts_placeholder=gen.starts_placeholder, device=DEV)
-    return SGHMCSampler(params=default_net_params(1, n_chains=C, seed=1, device=DEV), cost_fun=nll,
-                        batch_generator=gen, burn_in_steps=1000, scale_grad=float(N), seed=1,
-                        session=Session(device=DEV, n_chains=C, output=output, prefetch=prefetch))
+    s = SGHMCSampler(params=default_net_params(1, n_chains=C, seed=1, device=DEV), cost_fun=nll,
+                     batch_generator=gen, burn_in_steps=burn_in_steps, scale_grad=float(N), seed=1,
+                     session=Session(device=DEV, n_chains=C, output=output, prefetch=prefetch))
+    if not resident:
+        s.RESIDENT_MAX_CHAINS = 0          # K4 then K1 per step instead of the resident kernel
+    return s
 
 
-for C in (1, 8, 148):
-    s = bnn_chain(C)
-    s.run(1100, keep_every=10 ** 9)
-    dt = gpu_timed(lambda: s.run(5000, keep_every=100))
-    emit(config="BNN-SGHMC (1-50-50-50-1, N=20000, batch 20), %d chain(s), sampler.run(5000) after burn-in" % C,
-         steps=5000, seconds=dt, chain_steps_per_s=C * 5000 / dt, us_per_step=1e6 * dt / 5000)
+for C in (1, 8, 148, 592):
+    for resident in (True, False):
+        kernels = "resident kernel (default for <= 4 chains per SM)" if resident else "K4 then K1 per step"
+        s = bnn_chain(C, resident=resident)
+        s.run(1100, keep_every=10 ** 9)
+        dt = gpu_timed(lambda: s.run(5000, keep_every=100))
+        emit(config="BNN-SGHMC (1-50-50-50-1, N=20000, batch 20), %d chain(s), sampler.run(5000) after burn-in, %s"
+             % (C, kernels), steps=5000, seconds=dt, chain_steps_per_s=C * 5000 / dt, us_per_step=1e6 * dt / 5000)
+        s = bnn_chain(C, resident=resident, burn_in_steps=10 ** 9)
+        s.run(200, keep_every=10 ** 9)
+        dt = gpu_timed(lambda: s.run(3000, keep_every=100))
+        emit(config="BNN-SGHMC (1-50-50-50-1, N=20000, batch 20), %d chain(s), sampler.run(3000) in burn-in, %s"
+             % (C, kernels), steps=3000, seconds=dt, chain_steps_per_s=C * 3000 / dt, us_per_step=1e6 * dt / 3000)
 s = bnn_chain(1)
 for _ in range(1100):
     next(s)

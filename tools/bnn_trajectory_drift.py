@@ -80,6 +80,7 @@ def gpu_run(theta0, X, y, seeds, steps, burn, z_seed, every, variant, dev="cuda:
         sampler = SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen, burn_in_steps=burn,
                                scale_grad=float(N), stepsize_schedule=ConstantStepsizeSchedule(0.01),
                                session=Session(device=dev, n_chains=C, output="torch"))
+        sampler.RESIDENT_MAX_CHAINS = 0          # K4 (this variant) then K1, not the resident kernel
         zr = np.random.RandomState(z_seed)
         out = []
         for s in range(steps):
