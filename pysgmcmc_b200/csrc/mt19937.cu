@@ -35,37 +35,46 @@ __device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t 
   return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
 
-__device__ void mt_twist(uint32_t* __restrict__ st, int64_t n_streams, int64_t j) {
-  // mt[i] = mt[(i+397) % 624] ^ f(mt[i], mt[i+1]); in-place, ascending i.
-  uint32_t first = st[j];
-  uint32_t cur = first;
-  for (int i = 0; i < MT_N - 1; ++i) {
-    const uint32_t nxt = st[(int64_t)(i + 1) * n_streams + j];
-    const int k = i + MT_M < MT_N ? i + MT_M : i + MT_M - MT_N;
-    const uint32_t far = st[(int64_t)k * n_streams + j];
-    const uint32_t nv = mt_mix(cur, nxt, far);
-    st[(int64_t)i * n_streams + j] = nv;
-    if (i == 0) first = nv;
-    cur = nxt;
+// The twist of ONE stream (mt[i] = mt[(i + 397) % 624] ^ f(mt[i], mt[(i + 1) % 624]), in place, ascending i) done
+// by a whole warp, 32 consecutive i per round: within a round every lane reads its three words before any lane
+// writes (mt[i + 1] is the neighbour's old word), and a round only depends on words written >= 195 positions
+// earlier (i - 227) or not yet written (i + 1, i + 397), so 20 rounds replace 624 dependent iterations.  Lanes
+// of a warp consume their streams at different rates (rejection sampling), so they reach a twist at different
+// steps: done one lane at a time, sequentially, a warp would walk the 624-iteration loop up to 32 times.
+__device__ void mt_twist_warp(uint32_t* __restrict__ st, int64_t n_streams, int64_t j, int lane) {
+  for (int i0 = 0; i0 < MT_N; i0 += 32) {
+    const int i = i0 + lane;
+    uint32_t nv = 0;
+    if (i < MT_N) {
+      const int i1 = i + 1 < MT_N ? i + 1 : 0;
+      const int k = i + MT_M < MT_N ? i + MT_M : i + MT_M - MT_N;
+      nv = mt_mix(st[(int64_t)i * n_streams + j], st[(int64_t)i1 * n_streams + j], st[(int64_t)k * n_streams + j]);
+    }
+    __syncwarp();
+    if (i < MT_N) st[(int64_t)i * n_streams + j] = nv;
+    __syncwarp();
   }
-  // i = 623 wraps to the already updated mt[0] and mt[396]
-  st[(int64_t)(MT_N - 1) * n_streams + j] = mt_mix(cur, first, st[(int64_t)(MT_M - 1) * n_streams + j]);
 }
 
 __global__ void mt19937_starts_kernel(uint32_t* __restrict__ state, int32_t* __restrict__ starts,
                                       int64_t n_streams, int64_t n_steps, uint32_t max_inclusive,
                                       uint32_t mask) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_streams) return;
-  uint32_t pos = state[(int64_t)MT_N * n_streams + j];
+  const int lane = threadIdx.x & 31;
+  const bool valid = j < n_streams;                   // whole warps stay: the twist is a warp-wide operation
+  uint32_t pos = valid ? state[(int64_t)MT_N * n_streams + j] : 0;
   for (int64_t s = 0; s < n_steps; ++s) {
     uint32_t v = 0;
-    if (max_inclusive != 0) {          // max == 0 consumes nothing (numpy legacy behaviour)
-      do {
-        if (pos >= MT_N) {
-          mt_twist(state, n_streams, j);
-          pos = 0;
-        }
+    bool done = !valid || max_inclusive == 0;         // max == 0 consumes nothing (numpy legacy behaviour)
+    while (!__all_sync(0xffffffffu, done)) {
+      unsigned need = __ballot_sync(0xffffffffu, !done && pos >= MT_N);
+      while (need != 0) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        mt_twist_warp(state, n_streams, __shfl_sync(0xffffffffu, j, src), lane);
+        if (lane == src) pos = 0;
+      }
+      if (!done) {
         uint32_t y = state[(int64_t)pos * n_streams + j];
         ++pos;
         y ^= y >> 11;
@@ -73,11 +82,12 @@ __global__ void mt19937_starts_kernel(uint32_t* __restrict__ state, int32_t* __r
         y ^= (y << 15) & 0xefc60000u;
         y ^= y >> 18;
         v = y & mask;
-      } while (v > max_inclusive);
+        done = v <= max_inclusive;
+      }
     }
-    starts[s * n_streams + j] = (int32_t)v;
+    if (valid) starts[s * n_streams + j] = (int32_t)v;
   }
-  state[(int64_t)MT_N * n_streams + j] = pos;
+  if (valid) state[(int64_t)MT_N * n_streams + j] = pos;
 }
 
 }  // namespace sgmcmc
