@@ -466,7 +466,7 @@ def few_chain_rates(torch, dev, build, n_steps=2000):
     sampler.run() -- with few chains every chain is resident on an SM (csrc/bnn_resident.cu) instead of K4 then
     K1 streaming all chains per step; both timed, burn-in and sampling phase."""
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    out = {"note": "sampler.run(%d), microseconds per step and chain-steps/s; 'resident' is the default for <= 4 "
+    out = {"note": "sampler.run(%d), microseconds per step and chain-steps/s; 'resident' is the default for <= 2 "
                    "chains per SM, 'k4_then_k1' the same sampler with RESIDENT_MAX_CHAINS = 0" % n_steps, "rows": []}
     for C in (1, sms - 1):
         for phase, burn in (("burn-in", 10 ** 9), ("sampling", 100)):

@@ -125,14 +125,14 @@ def bnn_chain(C, prefetch=0, output="torch", resident=True, burn_in_steps=1000):
     s = SGHMCSampler(params=default_net_params(1, n_chains=C, seed=1, device=DEV), cost_fun=nll,
                      batch_generator=gen, burn_in_steps=burn_in_steps, scale_grad=float(N), seed=1,
                      session=Session(device=DEV, n_chains=C, output=output, prefetch=prefetch))
-    if not resident:
-        s.RESIDENT_MAX_CHAINS = 0          # K4 then K1 per step instead of the resident kernel
+    # the resident kernel (the default up to 2 chains per SM) or K4 then K1 per step, at any chain count
+    s.RESIDENT_MAX_CHAINS = 10 ** 9 if resident else 0
     return s
 
 
 for C in (1, 8, 148, 592):
     for resident in (True, False):
-        kernels = "resident kernel (default for <= 4 chains per SM)" if resident else "K4 then K1 per step"
+        kernels = "resident kernel (the default up to 2 chains per SM)" if resident else "K4 then K1 per step"
         s = bnn_chain(C, resident=resident)
         s.run(1100, keep_every=10 ** 9)
         dt = gpu_timed(lambda: s.run(5000, keep_every=100))
