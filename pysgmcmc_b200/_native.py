@@ -148,7 +148,12 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream_ptr(stream=None):
+def stream_ptr(stream=None, device_index=None):
+    """cudaStream_t of `stream`, or of torch's current stream (on `device_index` if given)."""
     import torch
-    s = torch.cuda.current_stream() if stream is None else stream
-    return s.cuda_stream
+    if stream is not None:
+        return stream.cuda_stream
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)     # the handle without building a Stream object
+    if raw is not None:
+        return raw(torch.cuda.current_device() if device_index is None else device_index)
+    return (torch.cuda.current_stream() if device_index is None else torch.cuda.current_stream(device_index)).cuda_stream

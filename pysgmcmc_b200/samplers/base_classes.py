@@ -114,12 +114,13 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
     def _views(self, flat, vectorized=False):
         """Per-parameter views of a flat ``[C, D]`` buffer, in the user's shapes
         (or ``(n, 1)`` like tensor_utils.vectorize when `vectorized`)."""
-        out = []
-        for shp, off, n in zip(self._shapes, self._offsets, self._sizes):
-            v = flat[:, off:off + n]
-            tail = (n, 1) if vectorized else shp
-            out.append(v.view((self.n_chains,) + tail) if self.multi_chain else v[0].view(tail))
-        return out
+        # one split instead of a slice per parameter: this runs on every `next()`
+        if self.multi_chain:
+            pieces = flat.split(self._sizes, dim=1)
+            return [v.view((self.n_chains,) + ((n, 1) if vectorized else shp))
+                    for v, shp, n in zip(pieces, self._shapes, self._sizes)]
+        pieces = flat[0].split(self._sizes)
+        return [v.view((n, 1) if vectorized else shp) for v, shp, n in zip(pieces, self._shapes, self._sizes)]
 
     def _state_array(self, name):
         return self._state[self._STATE_NAMES.index(name)]
@@ -201,7 +202,14 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         return self.session.chain_offset * self.n_params_per_chain
 
     def _stream(self):
-        return _native.stream_ptr(self.session.stream)
+        return _native.stream_ptr(self.session.stream, self._device_index())
+
+    def _device_index(self):
+        idx = self.__dict__.get("_dev_idx")
+        if idx is None:
+            d = torch.device(self.device)
+            idx = self.__dict__["_dev_idx"] = d.index if d.index is not None else torch.cuda.current_device()
+        return idx
 
     @contextlib.contextmanager
     def _on_device(self):
@@ -210,8 +218,11 @@ class MCMCSampler(object, metaclass=abc.ABCMeta):
         and, when ``Session(stream=s)`` names one, on THAT stream (torch ops follow the current
         stream, the native calls get its handle), so the producers and consumers of `grad` and
         `theta` are ordered on one stream."""
+        stream = self.session.stream
+        if stream is None and torch.cuda.current_device() == self._device_index():
+            yield                      # already there (the nested uses inside one step): nothing to switch
+            return
         with torch.cuda.device(self.device):
-            stream = self.session.stream
             if stream is not None:
                 if not getattr(self, "_stream_joined", False):
                     # the constructor(s) filled the state on the stream that was current then
