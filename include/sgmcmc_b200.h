@@ -247,8 +247,10 @@ int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float
  * (odd n_in so that D % 4 == 0, batch <= 32, state + activations within 227 KB); E_UNSUPPORTED otherwise.
  * cost_last [C] receives the cost of the last step; cost_all (NULL or [n_steps, C]) the cost of every step;
  * grad_out (NULL or [C, D]) the gradient of the last step; the other arguments as in
- * sgmcmc_bnn_sghmc_run_f32.  sgmcmc_set_bnn_resident_threads: threads per chain (448, 672 or 1024; 0 = the
- * default 672), a tuning knob for the measurements in profiles/. */
+ * sgmcmc_bnn_sghmc_run_f32.  During burn-in `minv` holds the inverse mass matrix of the latest step (K1 with
+ * store_minv on every step), frozen from the last burn-in step on.  sgmcmc_set_bnn_resident_overlap(0): the whole
+ * update runs after the gradient instead of its gradient-free part beside it (what happens anyway when the two
+ * extra D-float arrays do not fit shared memory: minibatch > 20 rows); same bits, for the measurements in profiles/. */
 int sgmcmc_bnn_resident_supported(int n_in, int batch);
 int sgmcmc_set_bnn_resident_overlap(int on);
 int sgmcmc_bnn_sghmc_run_resident_f32(float* theta, float* v, float* tau, float* g, float* v_hat, float* minv,
