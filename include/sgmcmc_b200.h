@@ -242,13 +242,14 @@ int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float
  * gradient on the FP32 pipe in the accumulation order of K4's FFMA kernel, then K1's arithmetic with K1's
  * Philox counters) and writes the state back: HBM traffic per chain and CALL instead of per chain and step,
  * and no launch per step -- the path for few chains (the reference's single-chain BOHAMIANN runs,
- * bayesian_neural_network.py:436-531) and the faster one at any chain count.  Chains never interact, so the
+ * bayesian_neural_network.py:436-531); faster than K4 then K1 up to a few chains per SM, slower from ~1000
+ * chains on (DESIGN.md "K5r").  Chains never interact, so the
  * result does not depend on how a run is cut into calls.  Needs sgmcmc_bnn_resident_supported(n_in, batch)
  * (odd n_in so that D % 4 == 0, batch <= 32, state + activations within 227 KB); E_UNSUPPORTED otherwise.
  * cost_last [C] receives the cost of the last step; cost_all (NULL or [n_steps, C]) the cost of every step;
  * grad_out (NULL or [C, D]) the gradient of the last step; the other arguments as in
- * sgmcmc_bnn_sghmc_run_f32.  During burn-in `minv` holds the inverse mass matrix of the latest step (K1 with
- * store_minv on every step), frozen from the last burn-in step on.  sgmcmc_set_bnn_resident_overlap(0): the whole
+ * sgmcmc_bnn_sghmc_run_f32.  `minv` is defined from the last burn-in step on (frozen there); during burn-in it
+ * may already hold the inverse mass matrix of the latest step (it does with the overlap below).  sgmcmc_set_bnn_resident_overlap(0): the whole
  * update runs after the gradient instead of its gradient-free part beside it (what happens anyway when the two
  * extra D-float arrays do not fit shared memory: minibatch > 20 rows); same bits, for the measurements in profiles/. */
 int sgmcmc_bnn_resident_supported(int n_in, int batch);
