@@ -48,7 +48,12 @@ class SGHMCSampler(BurnInMCMCSampler):
             self._state_array(name).fill_(1.0)
 
     def _arrays(self):
-        return [self._theta] + [self._state_array(n) for n in self._STATE_NAMES]
+        # theta and the state rows are allocated once (load_state_dict copies into them): built once, this
+        # list is on the per-step path of `next()`
+        arrays = self.__dict__.get("_arrays_cache")
+        if arrays is None or arrays[0] is not self._theta:
+            arrays = self.__dict__["_arrays_cache"] = [self._theta] + [self._state_array(n) for n in self._STATE_NAMES]
+        return arrays
 
     def _launch_update(self, grad, z, epsilon, adapt=True):
         fn = "sgmcmc_sghmc_step_f32" if self.dtype == torch.float32 else "sgmcmc_sghmc_step_f64"
