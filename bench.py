@@ -484,6 +484,23 @@ def few_chain_rates(torch, dev, build, n_steps=2000):
                 ms = e0.elapsed_time(e1)
                 row[name + "_us_per_step"] = round(1e3 * ms / n_steps, 3)
                 row[name + "_chain_steps_per_s"] = round(C * n_steps / ms * 1e3)
+            if phase == "sampling":
+                # end to end like the headline's `e2e`: index rows from pinned host memory, the cost of every
+                # step and a sample per 100 steps back to the host (SGHMCSampler.iter_host, blocks of steps)
+                import time
+                sampler, gen, nll = build(burn_in_steps=burn, n_chains=C)
+                rows = np.random.RandomState(C).randint(0, N_EXAMPLES - BATCH + 1, size=(200 + n_steps, C))
+                host_starts = torch.from_numpy(rows.astype(np.int32)).pin_memory()
+                for _ in sampler.iter_host(host_starts[:200], sample_every=100, lookahead=24):
+                    pass
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in sampler.iter_host(host_starts[200:], sample_every=100, lookahead=24):
+                    pass
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                row["e2e_iter_host_us_per_step"] = round(1e6 * dt / n_steps, 3)
+                row["e2e_iter_host_chain_steps_per_s"] = round(C * n_steps / dt)
             out["rows"].append(row)
     return out
 

@@ -245,6 +245,9 @@ class SGHMCSampler(BurnInMCMCSampler):
         assert sample_every is None or sample_every >= 1
         cf, C, D = self.cost_fun, self.n_chains, self.n_params_per_chain
         n_steps, depth = host_starts.shape[0], lookahead + 1
+        if self.RESIDENT_HOST_BLOCKS and self._resident_ok(cf.actual_batch):
+            yield from self._iter_host_blocks(host_starts, sample_every, lookahead, sample_phase)
+            return
         if self._grad is None:
             with self._on_device():
                 self._grad = torch.empty_like(self._theta)
@@ -295,6 +298,103 @@ class SGHMCSampler(BurnInMCMCSampler):
             yield (h_sample[sample_slot[b]].numpy() if sample_slot[b] >= 0 else None), h_cost[b].numpy()
 
     _host_samples = 0
+
+    #: `iter_host` of a sampler on the resident kernel runs BLOCKS of up to lookahead + 1 steps per launch (a
+    #: block ends at a sample step) instead of one launch per step; False: one launch per step.
+    RESIDENT_HOST_BLOCKS = True
+
+    def _iter_host_blocks(self, host_starts, sample_every, lookahead, sample_phase):
+        """`iter_host` for few chains: the chains stay on their SMs (csrc/bnn_resident.cu) for a block of up to
+        lookahead + 1 steps -- one host-to-device copy of the block's index rows, one launch, one device-to-host
+        copy of its cost rows (and of the sample a block ends with) -- two blocks queued ahead of the one being
+        handed out.  Same pairs as stepping one by one, bit for bit; the buffer lifetimes promised by
+        `iter_host` hold (a cost row lives for lookahead + 1 further yields, a sample until the next one)."""
+        cf, C, D, dev = self.cost_fun, self.n_chains, self.n_params_per_chain, self.device
+        n_steps, S = host_starts.shape[0], lookahead + 1
+        bounds, s0 = [], 0
+        while s0 < n_steps:
+            s1 = min(s0 + S, n_steps)
+            if sample_every:
+                first_sample = s0 + (-(s0 + 1 + sample_phase)) % sample_every      # first sample step >= s0
+                s1 = min(s1, first_sample + 1)
+            bounds.append((s0, s1))
+            s0 = s1
+        shortest = min(S, sample_every) if sample_every else S
+        n_slots = -(-(S + 1) // shortest) + 3            # blocks a cost row has to outlive, + the two queued ahead
+        n_sample_slots = 4 if sample_every else 0
+        key = ("blocks", S, n_slots, n_sample_slots)
+        pipe = getattr(self, "_host_block_pipe", None)
+        if pipe is None or pipe["key"] != key:
+            with torch.cuda.device(dev):
+                pipe = self._host_block_pipe = {
+                    "key": key, "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev),
+                    "d_starts": torch.empty((n_slots, S, C), dtype=torch.int32, device=dev),
+                    "d_cost": torch.empty((n_slots, S, C), dtype=self.dtype, device=dev),
+                    "h_cost": torch.empty((n_slots, S, C), dtype=self.dtype).pin_memory(),
+                    "d_sample": torch.empty((n_sample_slots, C, D), dtype=self.dtype, device=dev),
+                    "h_sample": torch.empty((n_sample_slots, C, D), dtype=self.dtype).pin_memory() if n_sample_slots else None,
+                    "last": torch.empty(C, dtype=self.dtype, device=dev),
+                    "in": [torch.cuda.Event() for _ in range(n_slots)], "done": [torch.cuda.Event() for _ in range(n_slots)],
+                    "out": [torch.cuda.Event() for _ in range(n_slots)],
+                    "sample_out": [torch.cuda.Event() for _ in range(n_sample_slots)], "used": [False] * n_slots,
+                    "sample_used": [False] * n_sample_slots}
+        s_in, s_out = pipe["s_in"], pipe["s_out"]
+        epsilon = float(next(self.stepsize_schedule))
+        arrays = [_native.ptr(a) for a in self._arrays()]
+        sample_of_block = [-1] * len(bounds)
+
+        def enqueue(b):
+            s0, s1 = bounds[b]
+            n, slot = s1 - s0, b % n_slots
+            wants = bool(sample_every) and (s1 + sample_phase) % sample_every == 0     # step s1 - 1 is a sample step
+            ks = -1
+            with torch.cuda.device(dev):
+                main = self.session.stream if self.session.stream is not None else torch.cuda.current_stream(dev)
+                if pipe["used"][slot]:
+                    s_in.wait_event(pipe["done"][slot])        # the block that used this slot has read its rows
+                    main.wait_event(pipe["out"][slot])         # ... and its costs have left the device
+                with torch.cuda.stream(s_in):
+                    pipe["d_starts"][slot, :n].copy_(host_starts[s0:s1], non_blocking=True)
+                    pipe["in"][slot].record(s_in)
+                main.wait_event(pipe["in"][slot])
+                trace = None
+                if wants:
+                    ks = self._host_samples % n_sample_slots
+                    self._host_samples += 1
+                    if pipe["sample_used"][ks]:
+                        main.wait_event(pipe["sample_out"][ks])
+                    trace = pipe["d_sample"][ks]
+                    sample_of_block[b] = ks
+                burn_left = max(0, self.burn_in_steps - self.n_iterations)
+                _native.call("sgmcmc_bnn_sghmc_run_resident_f32", *arrays, _native.ptr(cf.X), _native.ptr(cf.y),
+                             _native.ptr(pipe["d_starts"][slot]), None, _native.ptr(trace), None,
+                             _native.ptr(pipe["d_cost"][slot]), _native.ptr(pipe["last"]), None, C, cf.n_in,
+                             cf.actual_batch, float(cf.batch_size), cf.n_examples, n, min(n, burn_left),
+                             int(self.burn_in_steps == 0), n if wants else 10 ** 9, epsilon, self.mdecay,
+                             self.scale_grad, self._noise_seed, self.n_iterations, self.session.chain_offset,
+                             main.cuda_stream)
+                pipe["done"][slot].record(main)
+                s_out.wait_event(pipe["done"][slot])
+                with torch.cuda.stream(s_out):
+                    pipe["h_cost"][slot, :n].copy_(pipe["d_cost"][slot, :n], non_blocking=True)
+                    if wants:
+                        pipe["h_sample"][ks].copy_(pipe["d_sample"][ks], non_blocking=True)
+                        pipe["sample_out"][ks].record(s_out)
+                        pipe["sample_used"][ks] = True
+                    pipe["out"][slot].record(s_out)
+                pipe["used"][slot] = True
+            self.n_iterations += n
+
+        queued = 0
+        for b, (s0, s1) in enumerate(bounds):
+            while queued < len(bounds) and queued <= b + 2:
+                enqueue(queued)
+                queued += 1
+            slot = b % n_slots
+            pipe["out"][slot].synchronize()                    # the block's costs (and sample) are in host memory
+            for s in range(s0, s1):
+                ks = sample_of_block[b] if s == s1 - 1 else -1
+                yield (pipe["h_sample"][ks].numpy() if ks >= 0 else None), pipe["h_cost"][slot, s - s0].numpy()
 
     def _host_pipeline(self, depth, n_sample_slots, resident=False):
         """The native stepper of `iter_host` and its pinned result buffers, kept between calls

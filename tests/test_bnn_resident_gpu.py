@@ -245,22 +245,35 @@ def test_sampler_run_equals_next_with_the_resident_kernel(keep_every):
     assert torch.equal(a._theta, b._theta) and torch.isfinite(a._theta).all() and not a.is_burning_in
 
 
-def test_sampler_iter_host_equals_next_with_the_resident_kernel():
-    C, N, batch, steps, burn, every = 6, 2000, 20, 40, 17, 8
+@pytest.mark.parametrize("blocks", [True, False], ids=["blocks", "per-step"])
+@pytest.mark.parametrize("lookahead,every", [(3, 8), (0, 8), (3, 1), (4, 2), (8, 3), (5, None)])
+def test_sampler_iter_host_equals_next_with_the_resident_kernel(lookahead, every, blocks):
+    """iter_host on the resident kernel -- blocks of up to lookahead + 1 steps per launch (ending at sample steps),
+    or one launch per step -- == next(sampler) fed the same index rows: costs of every step, thinned samples,
+    final state; crosses the end of burn-in; a call that continues a thinning period (sample_phase)."""
+    C, N, batch, steps, burn = 6, 2000, 20, 43, 17
     X, y = sinc_data(N)
     rng = np.random.RandomState(3)
     host_starts = torch.from_numpy(rng.randint(0, N - batch + 1, size=(steps, C)).astype(np.int32)).pin_memory()
     a, _ = _sampler(C, N, batch, burn, X, y, generator=False, seed=21)
     b, ph = _sampler(C, N, batch, burn, X, y, generator=False, seed=21)
-    for s, (smp, cost) in enumerate(a.iter_host(host_starts, sample_every=every, lookahead=3)):
+    a.RESIDENT_HOST_BLOCKS = blocks
+    phase = 3 if every == 8 else 0
+    n_got = 0
+    for s, (smp, cost) in enumerate(a.iter_host(host_starts, sample_every=every, lookahead=lookahead,
+                                                sample_phase=phase)):
         ph.value = host_starts[s].to(DEV)
         _, want_cost = next(b)
         assert np.array_equal(cost, want_cost.cpu().numpy()), "cost at step %d" % s
-        if (s + 1) % every == 0:
+        if every and (s + 1 + phase) % every == 0:
             assert np.array_equal(smp, b._theta.cpu().numpy()), "sample at step %d" % s
+        else:
+            assert smp is None
+        n_got += 1
+    assert n_got == steps and a.n_iterations == steps
     for name in ("v", "tau", "g", "v_hat", "minv"):
         assert torch.equal(a._state_array(name), b._state_array(name)), name
-    assert torch.equal(a._theta, b._theta)
+    assert torch.equal(a._theta, b._theta) and not a.is_burning_in
 
 
 def test_resident_and_streaming_samplers_agree_to_rounding():
