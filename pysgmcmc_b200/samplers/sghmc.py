@@ -303,6 +303,27 @@ class SGHMCSampler(BurnInMCMCSampler):
     #: block ends at a sample step) instead of one launch per step; False: one launch per step.
     RESIDENT_HOST_BLOCKS = True
 
+    @staticmethod
+    def _host_blocks(n_steps, max_steps, sample_every=None, sample_phase=0):
+        """Cut steps 0 .. n_steps - 1 into blocks ``[s0, s1)`` of at most `max_steps` steps such that every sample
+        step (``(s + 1 + sample_phase) % sample_every == 0``) is the LAST step of its block: the sample is the
+        state a block's launch leaves behind.
+
+        >>> SGHMCSampler._host_blocks(10, 4, sample_every=6, sample_phase=1)
+        [(0, 4), (4, 5), (5, 9), (9, 10)]
+        >>> SGHMCSampler._host_blocks(5, 2)
+        [(0, 2), (2, 4), (4, 5)]
+        """
+        bounds, s0 = [], 0
+        while s0 < n_steps:
+            s1 = min(s0 + max_steps, n_steps)
+            if sample_every:
+                first_sample = s0 + (-(s0 + 1 + sample_phase)) % sample_every      # first sample step >= s0
+                s1 = min(s1, first_sample + 1)
+            bounds.append((s0, s1))
+            s0 = s1
+        return bounds
+
     def _iter_host_blocks(self, host_starts, sample_every, lookahead, sample_phase):
         """`iter_host` for few chains: the chains stay on their SMs (csrc/bnn_resident.cu) for a block of up to
         lookahead + 1 steps -- one host-to-device copy of the block's index rows, one launch, one device-to-host
@@ -311,14 +332,7 @@ class SGHMCSampler(BurnInMCMCSampler):
         `iter_host` hold (a cost row lives for lookahead + 1 further yields, a sample until the next one)."""
         cf, C, D, dev = self.cost_fun, self.n_chains, self.n_params_per_chain, self.device
         n_steps, S = host_starts.shape[0], lookahead + 1
-        bounds, s0 = [], 0
-        while s0 < n_steps:
-            s1 = min(s0 + S, n_steps)
-            if sample_every:
-                first_sample = s0 + (-(s0 + 1 + sample_phase)) % sample_every      # first sample step >= s0
-                s1 = min(s1, first_sample + 1)
-            bounds.append((s0, s1))
-            s0 = s1
+        bounds = self._host_blocks(n_steps, S, sample_every, sample_phase)
         shortest = min(S, sample_every) if sample_every else S
         n_slots = -(-(S + 1) // shortest) + 3            # blocks a cost row has to outlive, + the two queued ahead
         n_sample_slots = 4 if sample_every else 0

@@ -12,6 +12,7 @@ MODULES = [
     "pysgmcmc_b200.diagnostics.objective_functions",
     "pysgmcmc_b200.samplers.base_classes",
     "pysgmcmc_b200.samplers.relativistic_sghmc",
+    "pysgmcmc_b200.samplers.sghmc",
 ]
 
 

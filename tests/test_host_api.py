@@ -239,3 +239,21 @@ def test_objective_functions_match_the_oracle_and_carry_native_tags():
     nll = to_negative_log_likelihood(banana_log_likelihood)
     assert nll.__name__ == "banana_log_likelihood" and nll((0.0, 0.0)) == 50.0
     assert np.allclose(sinc(np.array([[0.5]])), 1.0)
+
+
+@settings(max_examples=200, deadline=None)
+@given(n_steps=integers(min_value=0, max_value=300), max_steps=integers(min_value=1, max_value=65),
+       sample_every=one_of(integers(min_value=1, max_value=120)), sample_phase=integers(min_value=0, max_value=119),
+       thinned=integers(min_value=0, max_value=1))
+def test_iter_host_blocks_cover_the_steps_and_end_at_sample_steps(n_steps, max_steps, sample_every, sample_phase, thinned):
+    """The blocks `iter_host` launches for a sampler on the resident kernel: consecutive, non-empty, at most
+    lookahead + 1 steps, covering every step once, and a sample step is always the last step of its block."""
+    from pysgmcmc_b200.samplers import SGHMCSampler
+    every = sample_every if thinned else None
+    blocks = SGHMCSampler._host_blocks(n_steps, max_steps, every, sample_phase)
+    assert [b[0] for b in blocks] == [0] + [b[1] for b in blocks[:-1]] if blocks else n_steps == 0
+    assert (blocks[-1][1] if blocks else 0) == n_steps
+    assert all(0 < s1 - s0 <= max_steps for s0, s1 in blocks)
+    if every:
+        ends = {s1 - 1 for _, s1 in blocks}
+        assert all(s in ends for s in range(n_steps) if (s + 1 + sample_phase) % every == 0)
