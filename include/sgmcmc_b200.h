@@ -245,7 +245,8 @@ int sgmcmc_bnn_sghmc_run_f32(float* theta, float* v, float* tau, float* g, float
  * bayesian_neural_network.py:436-531); faster than K4 then K1 up to a few chains per SM, slower from ~1000
  * chains on (DESIGN.md "K5r").  Chains never interact, so the
  * result does not depend on how a run is cut into calls.  Needs sgmcmc_bnn_resident_supported(n_in, batch)
- * (odd n_in so that D % 4 == 0, batch <= 32, state + activations within 227 KB); E_UNSUPPORTED otherwise.
+ * (batch <= 32, state + activations within 227 KB); E_UNSUPPORTED otherwise.  The noise of element group q of
+ * chain c comes from Philox counter (chain_offset + c) * ceil(D / 4) + q: K1's counters when D % 4 == 0 (odd n_in).
  * cost_last [C] receives the cost of the last step; cost_all (NULL or [n_steps, C]) the cost of every step;
  * grad_out (NULL or [C, D]) the gradient of the last step; the other arguments as in
  * sgmcmc_bnn_sghmc_run_f32.  `minv` is defined from the last burn-in step on (frozen there); during burn-in it

@@ -220,6 +220,31 @@ __device__ __forceinline__ void rs_weight_grad(const float* __restrict__ TH, flo
   }
 }
 
+// Element group q of a chain row of D floats at `row` (D even: 8-byte aligned; D % 4 == 2: the last group holds two
+// elements and odd chains start on an 8-byte boundary only, so those rows move as 64-bit halves).
+__device__ __forceinline__ float4 rs_load_group(const float* __restrict__ row, int q, int D, float pad) {
+  const float* p = row + 4 * q;
+  if ((D & 3) == 0) return __ldcs(reinterpret_cast<const float4*>(p));
+  const float2 lo = __ldcs(reinterpret_cast<const float2*>(p));
+  if (4 * q + 2 < D) {
+    const float2 hi = __ldcs(reinterpret_cast<const float2*>(p + 2));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  return make_float4(lo.x, lo.y, pad, pad);
+}
+__device__ __forceinline__ void rs_store_group(float* __restrict__ row, int q, int D, const float4& v) {
+  float* p = row + 4 * q;
+  if ((D & 3) == 0) { __stcs(reinterpret_cast<float4*>(p), v); return; }
+  __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+  if (4 * q + 2 < D) __stcs(reinterpret_cast<float2*>(p + 2), make_float2(v.z, v.w));
+}
+// elements >= nv of a group are padding: keep their state at its neutral value
+__device__ __forceinline__ void rs_fix_pad(float (&x)[4], int nv, float value) {
+#pragma unroll
+  for (int i = 2; i < 4; ++i)
+    if (i >= nv) x[i] = value;
+}
+
 __device__ __forceinline__ void rs_unpack(const float4& q, float (&r)[4]) { r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
 __device__ __forceinline__ float4 rs_pack(const float (&r)[4]) { return make_float4(r[0], r[1], r[2], r[3]); }
 
@@ -259,29 +284,28 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t chain = blockIdx.x;
   const BnnLayout L = a.L;
-  const int D = L.D, n4 = D >> 2, n_in = L.n_in;
+  const int D = L.D, n4 = (D + 3) >> 2, n_in = L.n_in;    // groups of 4 elements; D % 4 == 2: the last one is half padding
   const int batch = BATCH_CT > 0 ? BATCH_CT : a.batch;
   const bool pre = a.pre != 0;
-  const ResidentSmem s = resident_carve(smem, batch, n_in, D, a.pre);
+  const ResidentSmem s = resident_carve(smem, batch, n_in, 4 * n4, a.pre);
   const int TS = s.TS, nrg = s.BP >> 2;
   const float pscale = a.prior_den_inv * a.inv_n;
-  const int64_t g0 = chain * n4;                    // first element group of this chain in the [C, D] arrays
+  const int64_t g0 = chain * n4;                    // first element group of this chain (Philox counter, with group_offset)
+  const int64_t row0 = chain * D;                   // the chain's row in the [C, D] arrays
 
   // ---- the chain's state -> shared memory; sum(theta^2); activation buffers and minibatch rows zeroed ----
   {
-    const float4 *t4 = reinterpret_cast<const float4*>(a.theta) + g0, *v4 = reinterpret_cast<const float4*>(a.v) + g0,
-                 *ta4 = reinterpret_cast<const float4*>(a.tau) + g0, *g4 = reinterpret_cast<const float4*>(a.g) + g0,
-                 *h4 = reinterpret_cast<const float4*>(a.v_hat) + g0, *m4 = reinterpret_cast<const float4*>(a.minv) + g0;
     float sq = 0.0f;
     for (int q = tid; q < n4; q += NT) {
-      const float4 t = __ldcs(t4 + q);
+      const float4 t = rs_load_group(a.theta + row0, q, D, 0.0f);
       sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
       reinterpret_cast<float4*>(s.TH)[q] = t;
-      reinterpret_cast<float4*>(s.V)[q] = __ldcs(v4 + q);
-      reinterpret_cast<float4*>(s.TAU)[q] = __ldcs(ta4 + q);
-      reinterpret_cast<float4*>(s.GG)[q] = __ldcs(g4 + q);
-      reinterpret_cast<float4*>(s.VH)[q] = __ldcs(h4 + q);
-      reinterpret_cast<float4*>(s.MINV)[q] = __ldcs(m4 + q);
+      reinterpret_cast<float4*>(s.V)[q] = rs_load_group(a.v + row0, q, D, 0.0f);
+      reinterpret_cast<float4*>(s.TAU)[q] = rs_load_group(a.tau + row0, q, D, 1.0f);
+      reinterpret_cast<float4*>(s.GG)[q] = rs_load_group(a.g + row0, q, D, 1.0f);
+      reinterpret_cast<float4*>(s.VH)[q] = rs_load_group(a.v_hat + row0, q, D, 1.0f);
+      reinterpret_cast<float4*>(s.MINV)[q] = rs_load_group(a.minv + row0, q, D, 1.0f);
+      reinterpret_cast<float4*>(s.G)[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);     // (the padding's gradient stays 0)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -305,7 +329,7 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
     const float* sX = s.X0 + cur * s.XB;
     const float* sY = s.Y0 + cur * s.YB;
     const bool burn_in = a.adapt_forever || st < a.n_burn_in;
-    const float4* z4 = a.z != nullptr ? reinterpret_cast<const float4*>(a.z) + (st * a.n_chains + chain) * n4 : nullptr;
+    const float* zrow = a.z != nullptr ? a.z + (st * a.n_chains + chain) * D : nullptr;
     cp_async_wait_all();
     __syncthreads();                                 // rows of this step landed; the last update is visible
 
@@ -447,7 +471,8 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
       if (pre) {
         for (int q = tid - RS_GT; q < n4; q += RS_UT) {
           float zf[4], ps[4];
-          if (z4 != nullptr) rs_unpack(__ldcs(z4 + q), zf);
+          const int nv = min(4, D - 4 * q);
+          if (zrow != nullptr) rs_unpack(rs_load_group(zrow, q, D, 0.0f), zf);
           else normal4((uint64_t)(g0 + q) + a.group_offset, a.step0 + (uint64_t)st, a.seed, zf);
           if (burn_in) {
             float ta[4], g[4], h[4], r[4], mi[4];
@@ -459,6 +484,7 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
               rs_adapt_pre(ta[i], g[i], h[i], r[i], mi[i]);
               ps[i] = rs_sample(mi[i], zf[i], a.s);
             }
+            rs_fix_pad(ta, nv, 1.0f); rs_fix_pad(mi, nv, 1.0f);
             reinterpret_cast<float4*>(s.TAU)[q] = rs_pack(ta);
             reinterpret_cast<float4*>(s.PR)[q] = rs_pack(r);
             reinterpret_cast<float4*>(s.MINV)[q] = rs_pack(mi);     // the inverse mass matrix of this step
@@ -507,14 +533,13 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
     {
       const bool store_minv = burn_in && (st == a.n_burn_in - 1 || (a.adapt_forever && st == a.n_steps - 1));
       const bool snap = a.trace != nullptr && (st + 1) % a.keep_every == 0;
-      float4* tr4 = snap ? reinterpret_cast<float4*>(a.trace) + (((st + 1) / a.keep_every - 1) * a.n_chains + chain) * n4
-                         : nullptr;
+      float* trow = snap ? a.trace + (((st + 1) / a.keep_every - 1) * a.n_chains + chain) * D : nullptr;
       if (a.grad_out != nullptr && st == a.n_steps - 1)
-        for (int q = tid; q < n4; q += NT)
-          reinterpret_cast<float4*>(a.grad_out)[g0 + q] = reinterpret_cast<const float4*>(s.G)[q];
+        for (int q = tid; q < n4; q += NT) rs_store_group(a.grad_out + row0, q, D, reinterpret_cast<const float4*>(s.G)[q]);
       float sq = 0.0f;
       for (int q = tid; q < n4; q += NT) {
         float t[4], v[4], gr[4];
+        const int nv = min(4, D - 4 * q);
         rs_unpack(reinterpret_cast<const float4*>(s.G)[q], gr);
         rs_unpack(reinterpret_cast<const float4*>(s.TH)[q], t);
         rs_unpack(reinterpret_cast<const float4*>(s.V)[q], v);
@@ -529,6 +554,7 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
             rs_unpack(reinterpret_cast<const float4*>(s.PR)[q], r);
 #pragma unroll
             for (int i = 0; i < 4; ++i) rs_adapt_post(g[i], h[i], r[i], gr[i]);
+            rs_fix_pad(g, nv, 1.0f); rs_fix_pad(h, nv, 1.0f);
             reinterpret_cast<float4*>(s.GG)[q] = rs_pack(g);
             reinterpret_cast<float4*>(s.VH)[q] = rs_pack(h);
           }
@@ -536,7 +562,7 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
           for (int i = 0; i < 4; ++i) rs_apply_post(t[i], v[i], mi[i], gr[i], ps[i], a.s);
         } else {
           float zf[4], mi[4];
-          if (z4 != nullptr) rs_unpack(__ldcs(z4 + q), zf);
+          if (zrow != nullptr) rs_unpack(rs_load_group(zrow, q, D, 0.0f), zf);
           else normal4((uint64_t)(g0 + q) + a.group_offset, a.step0 + (uint64_t)st, a.seed, zf);
           if (burn_in) {
             float ta[4], g[4], h[4];
@@ -545,6 +571,7 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
             rs_unpack(reinterpret_cast<const float4*>(s.VH)[q], h);
 #pragma unroll
             for (int i = 0; i < 4; ++i) mi[i] = adapt(ta[i], g[i], h[i], gr[i]);
+            rs_fix_pad(ta, nv, 1.0f); rs_fix_pad(g, nv, 1.0f); rs_fix_pad(h, nv, 1.0f); rs_fix_pad(mi, nv, 1.0f);
             reinterpret_cast<float4*>(s.TAU)[q] = rs_pack(ta);
             reinterpret_cast<float4*>(s.GG)[q] = rs_pack(g);
             reinterpret_cast<float4*>(s.VH)[q] = rs_pack(h);
@@ -555,11 +582,12 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
 #pragma unroll
           for (int i = 0; i < 4; ++i) sghmc_apply(t[i], v[i], mi[i], gr[i], zf[i], a.s);
         }
+        rs_fix_pad(t, nv, 0.0f); rs_fix_pad(v, nv, 0.0f);
         sq = fmaf(t[0], t[0], sq); sq = fmaf(t[1], t[1], sq); sq = fmaf(t[2], t[2], sq); sq = fmaf(t[3], t[3], sq);
         const float4 tn = rs_pack(t);
         reinterpret_cast<float4*>(s.TH)[q] = tn;
         reinterpret_cast<float4*>(s.V)[q] = rs_pack(v);
-        if (snap) __stcs(tr4 + q, tn);
+        if (snap) rs_store_group(trow, q, D, tn);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -569,16 +597,13 @@ __global__ void __launch_bounds__(RS_T, 1) bnn_sghmc_resident_kernel(ResidentArg
   __syncthreads();
   // ---- the state goes back ----
   {
-    float4 *t4 = reinterpret_cast<float4*>(a.theta) + g0, *v4 = reinterpret_cast<float4*>(a.v) + g0,
-           *ta4 = reinterpret_cast<float4*>(a.tau) + g0, *g4 = reinterpret_cast<float4*>(a.g) + g0,
-           *h4 = reinterpret_cast<float4*>(a.v_hat) + g0, *m4 = reinterpret_cast<float4*>(a.minv) + g0;
     for (int q = tid; q < n4; q += NT) {
-      __stcs(t4 + q, reinterpret_cast<const float4*>(s.TH)[q]);
-      __stcs(v4 + q, reinterpret_cast<const float4*>(s.V)[q]);
-      __stcs(ta4 + q, reinterpret_cast<const float4*>(s.TAU)[q]);
-      __stcs(g4 + q, reinterpret_cast<const float4*>(s.GG)[q]);
-      __stcs(h4 + q, reinterpret_cast<const float4*>(s.VH)[q]);
-      __stcs(m4 + q, reinterpret_cast<const float4*>(s.MINV)[q]);
+      rs_store_group(a.theta + row0, q, D, reinterpret_cast<const float4*>(s.TH)[q]);
+      rs_store_group(a.v + row0, q, D, reinterpret_cast<const float4*>(s.V)[q]);
+      rs_store_group(a.tau + row0, q, D, reinterpret_cast<const float4*>(s.TAU)[q]);
+      rs_store_group(a.g + row0, q, D, reinterpret_cast<const float4*>(s.GG)[q]);
+      rs_store_group(a.v_hat + row0, q, D, reinterpret_cast<const float4*>(s.VH)[q]);
+      rs_store_group(a.minv + row0, q, D, reinterpret_cast<const float4*>(s.MINV)[q]);
     }
   }
 }
@@ -587,8 +612,8 @@ constexpr size_t RS_SMEM_MAX = 227 * 1024;
 
 // 1: the gradient-free part of the update runs beside the gradient (two more D-float arrays); 0: it does not fit
 static int resident_pre_mode(int n_in, int batch) {
-  const BnnLayout L = make_layout(n_in);
-  return (size_t)resident_carve(nullptr, batch, n_in, L.D, 1).total * sizeof(float) <= RS_SMEM_MAX ? 1 : 0;
+  const int Dp = (make_layout(n_in).D + 3) & ~3;
+  return (size_t)resident_carve(nullptr, batch, n_in, Dp, 1).total * sizeof(float) <= RS_SMEM_MAX ? 1 : 0;
 }
 
 template <int BATCH_CT>
@@ -600,9 +625,8 @@ static void launch_resident(const ResidentArgs& a, size_t smem, cudaStream_t st)
 
 static bool resident_shape_ok(int n_in, int batch) {
   if (n_in < 1 || n_in > 64 || batch < 1 || batch > RS_MAX_BATCH) return false;
-  const BnnLayout L = make_layout(n_in);
-  if (L.D % 4 != 0) return false;                   // element groups of 4 must not straddle chains
-  return (size_t)resident_carve(nullptr, batch, n_in, L.D, 0).total * sizeof(float) <= RS_SMEM_MAX;
+  const int Dp = (make_layout(n_in).D + 3) & ~3;    // D is even; D % 4 == 2: every chain's last element group is half padding
+  return (size_t)resident_carve(nullptr, batch, n_in, Dp, 0).total * sizeof(float) <= RS_SMEM_MAX;
 }
 
 }  // namespace sgmcmc
@@ -632,8 +656,8 @@ extern "C" int sgmcmc_bnn_sghmc_run_resident_f32(float* theta, float* v, float* 
   SG_REQUIRE(theta && v && tau && g && v_hat && minv && X && y && cost_last, SGMCMC_E_INVALID,
              "bnn_sghmc_run_resident: state arrays, X, y and cost_last must not be NULL");
   SG_REQUIRE(resident_shape_ok(n_in, batch), SGMCMC_E_UNSUPPORTED,
-             "bnn_sghmc_run_resident: n_in = %d (must be odd, <= 64) / batch = %d (<= %d) does not fit an SM's shared "
-             "memory or the 4-element update groups; use sgmcmc_bnn_sghmc_run_f32", n_in, batch, RS_MAX_BATCH);
+             "bnn_sghmc_run_resident: n_in = %d (<= 64) / batch = %d (<= %d) does not fit an SM's shared memory; use "
+             "sgmcmc_bnn_sghmc_run_f32", n_in, batch, RS_MAX_BATCH);
   SG_REQUIRE(batch_size_cfg > 0 && n_examples >= 1 && scale_grad > 0, SGMCMC_E_INVALID,
              "bnn_sghmc_run_resident: batch_size_cfg, n_examples and scale_grad must be > 0");
   ResidentArgs a;
@@ -648,16 +672,17 @@ extern "C" int sgmcmc_bnn_sghmc_run_resident_f32(float* theta, float* v, float* 
   a.prior_den_inv = 1.0f / ((float)a.L.D + 3e-16f);
   a.s = make_sghmc_scalars<float>(epsilon, mdecay, scale_grad);
   a.seed = seed; a.step0 = step0;
-  SG_REQUIRE((chain_offset * (uint64_t)a.L.D) % 4 == 0, SGMCMC_E_INVALID, "chain_offset * D must be a multiple of 4");
-  a.group_offset = chain_offset * (uint64_t)a.L.D / 4;
+  // Philox counter of element group q of chain c: (chain_offset + c) * ceil(D / 4) + q -- K1's mapping when D % 4 == 0
+  a.group_offset = chain_offset * (uint64_t)((a.L.D + 3) / 4);
+  const size_t al = a.L.D % 4 == 0 ? 16 : 8;       // rows move as 128-bit groups, or as 64-bit halves when D % 4 == 2
   for (float* p : {theta, v, tau, g, v_hat, minv})
-    SG_REQUIRE(aligned_to(p, 16), SGMCMC_E_ALIGN, "bnn_sghmc_run_resident: state arrays must be 16-byte aligned");
-  SG_REQUIRE((!trace || aligned_to(trace, 16)) && (!z || aligned_to(z, 16)) && (!grad_out || aligned_to(grad_out, 16)),
-             SGMCMC_E_ALIGN, "bnn_sghmc_run_resident: trace, z and grad_out must be 16-byte aligned");
+    SG_REQUIRE(aligned_to(p, al), SGMCMC_E_ALIGN, "bnn_sghmc_run_resident: state arrays must be %zu-byte aligned", al);
+  SG_REQUIRE((!trace || aligned_to(trace, al)) && (!z || aligned_to(z, al)) && (!grad_out || aligned_to(grad_out, al)),
+             SGMCMC_E_ALIGN, "bnn_sghmc_run_resident: trace, z and grad_out must be %zu-byte aligned", al);
   if (n_chains == 0 || n_steps == 0) return SGMCMC_OK;
   SG_REQUIRE(n_chains <= 0x7fffffff, SGMCMC_E_UNSUPPORTED, "bnn_sghmc_run_resident: at most 2^31 - 1 chains per launch");
   a.pre = g_resident_overlap ? resident_pre_mode(n_in, batch) : 0;
-  const size_t smem = (size_t)resident_carve(nullptr, batch, n_in, a.L.D, a.pre).total * sizeof(float);
+  const size_t smem = (size_t)resident_carve(nullptr, batch, n_in, (a.L.D + 3) & ~3, a.pre).total * sizeof(float);
   if (batch == 20) launch_resident<20>(a, smem, (cudaStream_t)stream);      // the reference's minibatch: strides fold
   else launch_resident<0>(a, smem, (cudaStream_t)stream);
   return check_launch("bnn_sghmc_resident_kernel");

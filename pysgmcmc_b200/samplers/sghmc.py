@@ -98,7 +98,7 @@ class SGHMCSampler(BurnInMCMCSampler):
     #: Few chains: every chain lives on one SM (csrc/bnn_resident.cu) -- the whole state in shared memory for a
     #: block of `run()` steps, one launch per `next()` / `iter_host` step -- instead of K4 then K1 streaming all
     #: chains through HBM every step.  Used when the sampler has at most this many chains (None: 2 per SM of
-    #: the device -- beyond that a one-step call, which loads and stores the whole state, loses to K4 + K1; 0: never) and the shape fits (float32, get_default_net, odd n_in, minibatch <= 32).  One
+    #: the device -- beyond that a one-step call, which loads and stores the whole state, loses to K4 + K1; 0: never) and the shape fits (float32, get_default_net, minibatch <= 32).  One
     #: sampler uses ONE of the two arithmetics everywhere, so run(n) == n x next() == iter_host bit for bit
     #: either way; the two differ from each other in the rounding of the gradient's dot products only
     #: (both within 1e-5 of the oracle after 1000 steps, tests/test_bnn_resident_gpu.py, tests/test_bnn_gpu.py).

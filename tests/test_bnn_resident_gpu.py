@@ -42,11 +42,12 @@ def fresh_state(C, seed=11, n_in=1):
 
 
 def run_resident(state, X, y, starts, z, n_steps, n_burn_in, keep_every=1, batch=20, N=None, eps=0.01,
-                 want_trace=False, want_grad=False, want_all=False, seed=5, step0=0, chain_offset=0, n_in=1,
+                 want_trace=False, want_grad=False, want_all=False, seed=5, step0=0, chain_offset=0, n_in=None,
                  adapt_forever=0):
     """One call of the C entry point on device copies of `state` (dict of [C, D] tensors, updated in place)."""
     C, Dn = state["theta"].shape
     N = N if N is not None else X.shape[0]
+    n_in = X.shape[1] if n_in is None else n_in
     Xd = torch.as_tensor(X, dtype=torch.float32, device=DEV).contiguous()
     yd = torch.as_tensor(y, dtype=torch.float32, device=DEV).contiguous()
     sd = None if starts is None else torch.as_tensor(np.ascontiguousarray(starts), dtype=torch.int32, device=DEV)
@@ -66,8 +67,8 @@ def run_resident(state, X, y, starts, z, n_steps, n_burn_in, keep_every=1, batch
     return {"trace": trace, "cost_trace": cost_trace, "cost_all": cost_all, "cost_last": cost_last, "grad": grad}
 
 
-def ffma_k4(theta, X, y, starts, batch, N, n_in=1):
-    C = theta.shape[0]
+def ffma_k4(theta, X, y, starts, batch, N):
+    C, n_in = theta.shape[0], X.shape[1]
     t = theta.contiguous()
     Xd = torch.as_tensor(X, dtype=torch.float32, device=DEV).contiguous()
     yd = torch.as_tensor(y, dtype=torch.float32, device=DEV).contiguous()
@@ -92,13 +93,15 @@ def overlap(request):
     _native.call("sgmcmc_set_bnn_resident_overlap", 1)
 
 
+@pytest.mark.parametrize("n_in", [1, 2, 5])       # D % 4 == 0 / 2 / 0: every chain's last element group full or half padding
 @pytest.mark.parametrize("batch", [20, 32, 7])
-def test_resident_gradient_equals_the_ffma_kernel_and_the_oracle(overlap, batch):
+def test_resident_gradient_equals_the_ffma_kernel_and_the_oracle(overlap, batch, n_in):
     C, N = 5, 2000
-    X, y = sinc_data(N)
+    X, y = sinc_data(N, n_in=n_in)
+    D = 50 * n_in + 5202
     rng = np.random.RandomState(batch)
     starts = rng.randint(0, N - batch + 1, size=(1, C))
-    st = fresh_state(C)
+    st = fresh_state(C, n_in=n_in)
     theta0 = st["theta"].clone()
     out = run_resident(st, X, y, starts, np.zeros((1, C, D), np.float32), 1, 1, batch=batch, want_grad=True)
     g = out["grad"].cpu().numpy()
@@ -110,18 +113,21 @@ def test_resident_gradient_equals_the_ffma_kernel_and_the_oracle(overlap, batch)
     np.testing.assert_allclose(g[:, scalars], g_ffma[:, scalars], rtol=1e-5)
     np.testing.assert_allclose(out["cost_last"].cpu().numpy(), cost_ffma, rtol=3e-6)
     Xb, yb = obnn.gather_minibatch(X.astype(np.float64), y.astype(np.float64), starts[0], batch)
-    c64, g64, _ = obnn.nll_and_grad(theta0.cpu().numpy().astype(np.float64), Xb, yb, n_examples=N, batch_size=batch)
+    c64, g64, _ = obnn.nll_and_grad(theta0.cpu().numpy().astype(np.float64), Xb, yb, n_examples=N, batch_size=batch,
+                                    n_in=n_in)
     assert (np.abs(g - g64) / np.abs(g64).max(axis=1, keepdims=True)).max() <= 2e-5
     np.testing.assert_allclose(out["cost_last"].cpu().numpy(), c64, rtol=3e-6)
 
 
-def test_resident_update_is_the_oracle_update_on_its_own_gradient(overlap):
+@pytest.mark.parametrize("n_in", [1, 2])
+def test_resident_update_is_the_oracle_update_on_its_own_gradient(overlap, n_in):
     """Teacher-forced, step by step, across the burn-in boundary: theta, V, tau, g, v_hat and the frozen
     inverse mass matrix after a one-step call == oracle step on the state before and the kernel's gradient."""
-    C, N, batch, steps, burn = 4, 2000, 20, 12, 7
-    X, y = sinc_data(N)
+    C, N, batch, steps, burn = 5, 2000, 20, 12, 7
+    X, y = sinc_data(N, n_in=n_in)
+    D = 50 * n_in + 5202
     rng = np.random.RandomState(2)
-    st = fresh_state(C)
+    st = fresh_state(C, n_in=n_in)
     frozen = None
     for s in range(steps):
         before = {k: v.cpu().numpy() for k, v in st.items()}
@@ -143,16 +149,18 @@ def test_resident_update_is_the_oracle_update_on_its_own_gradient(overlap):
                 assert np.array_equal(st[n].cpu().numpy(), before[n]), "%s must not change after burn-in" % n
 
 
+@pytest.mark.parametrize("n_in", [1, 2])
 @pytest.mark.parametrize("use_z", [True, False])
-def test_resident_block_of_steps_equals_single_steps(overlap, use_z):
+def test_resident_block_of_steps_equals_single_steps(overlap, use_z, n_in):
     """n steps in one call (state on the SM throughout) == n calls of one step: states, thinned trace, costs;
     Philox noise (counter = element group, step) or injected noise; burn-in ends inside the block."""
     C, N, batch, steps, burn, keep = 7, 2000, 20, 24, 10, 4
-    X, y = sinc_data(N)
+    X, y = sinc_data(N, n_in=n_in)
+    D = 50 * n_in + 5202
     rng = np.random.RandomState(4)
     starts = rng.randint(0, N - batch + 1, size=(steps, C))
     z = rng.standard_normal((steps, C, D)).astype(np.float32) if use_z else None
-    a, b = fresh_state(C), fresh_state(C)
+    a, b = fresh_state(C, n_in=n_in), fresh_state(C, n_in=n_in)
     out = run_resident(a, X, y, starts, z, steps, burn, keep_every=keep, want_trace=True, want_all=True, step0=100,
                        chain_offset=8)
     for s in range(steps):
@@ -196,7 +204,7 @@ def test_resident_1000_step_trajectory_at_the_benchmarked_shapes():
 def test_resident_refuses_shapes_it_cannot_hold():
     assert _native.load().sgmcmc_bnn_resident_supported(1, 20) == 1
     assert _native.load().sgmcmc_bnn_resident_supported(3, 32) == 1
-    assert _native.load().sgmcmc_bnn_resident_supported(2, 20) == 0      # D % 4 != 0
+    assert _native.load().sgmcmc_bnn_resident_supported(2, 20) == 1      # D % 4 == 2: half-padded last groups
     assert _native.load().sgmcmc_bnn_resident_supported(1, 33) == 0
     st = fresh_state(2)
     X, y = sinc_data(100)
@@ -212,7 +220,7 @@ def _sampler(C, N, batch, burn, X, y, generator=True, seed=77, limit=None):
     from pysgmcmc_b200.samplers import SGHMCSampler
     gen = DeviceBatchGenerator(N, batch, n_chains=C, seed=5, device=DEV, block=16)
     nll = BayesianNeuralNetworkNLL(N, batch, X=X, y=y, starts_placeholder=gen.starts_placeholder, device=DEV)
-    params = default_net_params(1, n_chains=C, seed=3, device=DEV)
+    params = default_net_params(X.shape[1], n_chains=C, seed=3, device=DEV)
     s = SGHMCSampler(params=params, cost_fun=nll, batch_generator=gen if generator else None, burn_in_steps=burn,
                      scale_grad=float(N), seed=seed, session=Session(device=DEV, n_chains=C, output="torch"))
     if limit is not None:
@@ -220,17 +228,18 @@ def _sampler(C, N, batch, burn, X, y, generator=True, seed=77, limit=None):
     return s, gen.starts_placeholder
 
 
+@pytest.mark.parametrize("n_in", [1, 2])
 @pytest.mark.parametrize("keep_every", [5, 7])
-def test_sampler_run_equals_next_with_the_resident_kernel(keep_every):
+def test_sampler_run_equals_next_with_the_resident_kernel(keep_every, n_in):
     """run(n) (chunks of steps with the chains on their SMs) == n x next() (one launch per step), bit for bit:
     states, thinned trace, costs; the burn-in ends inside; one launch per next() besides the index generator."""
-    C, N, batch, steps, burn = 10, 2000, 20, 60, 25
-    X, y = sinc_data(N)
+    C, N, batch, steps, burn = 11, 2000, 20, 60, 25
+    X, y = sinc_data(N, n_in=n_in)
     a, _ = _sampler(C, N, batch, burn, X, y)
     b, _ = _sampler(C, N, batch, burn, X, y)
     assert a._resident_ok(batch)
     trace, costs = a.run(steps, keep_every=keep_every)
-    assert a.n_iterations == steps and trace.shape == (steps // keep_every, C, D)
+    assert a.n_iterations == steps and trace.shape == (steps // keep_every, C, 50 * n_in + 5202)
     launches0 = _native.load().sgmcmc_launch_count()
     for s in range(steps):
         sample, cost = next(b)
