@@ -97,3 +97,20 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_resident_kernel_shape_query_is_host_arithmetic():
+    """Which BOHAMIANN shapes the resident kernel (csrc/bnn_resident.cu) can hold on one SM: 7 state arrays of
+    ceil(D / 4) * 4 floats plus the activation buffers of the minibatch within 227 KB of shared memory."""
+    lib = _native.load()
+    assert lib.sgmcmc_bnn_resident_supported(1, 20) == 1          # the reference's configuration (D = 5252)
+    assert lib.sgmcmc_bnn_resident_supported(2, 20) == 1          # D % 4 == 2: half-padded last element groups
+    assert lib.sgmcmc_bnn_resident_supported(13, 20) == 1
+    assert lib.sgmcmc_bnn_resident_supported(13, 32) == 0         # 32-row activation buffers no longer fit beside D = 5852
+    assert lib.sgmcmc_bnn_resident_supported(1, 33) == 0          # minibatch rows are held in 32-row buffers
+    assert lib.sgmcmc_bnn_resident_supported(64, 20) == 0         # D = 8402: the state alone is 235 KB
+    assert lib.sgmcmc_bnn_resident_supported(0, 20) == 0 and lib.sgmcmc_bnn_resident_supported(1, 0) == 0
+    # calls with a shape it cannot hold are refused before any device work
+    rc = lib.sgmcmc_bnn_sghmc_run_resident_f32(*([None] * 15), 1, 64, 20, 20.0, 100, 1, 1, 0, 1, 0.01, 0.05, 100.0,
+                                               0, 0, 0, None)
+    assert rc != 0 and lib.sgmcmc_last_error()
